@@ -1,0 +1,218 @@
+/*
+ * nsig.h — C ABI of libnsig_b200.so: the B200 (sm_100a) native replacement for the
+ * ray-batch render/train hot path of luo-ziyuan/NeRF_Signature.
+ *
+ * Every entry point
+ *   - takes raw DEVICE pointers, sizes and scalars, and the CUDA stream to run on;
+ *   - never allocates, frees or synchronises (stream-ordered, re-entrant);
+ *   - returns 0 on success, a cudaError_t (>0) from the launch, or NSIG_EINVAL (-1)
+ *     for arguments the kernels cannot honour.
+ * All tensors are contiguous row-major; float = IEEE fp32, int = int32.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef NSIG_H_
+#define NSIG_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSIG_EINVAL (-1)
+#define NSIG_MAX_LEVELS 16      /* base encoder levels (hash_encoding.py:49)            */
+#define NSIG_MAX_MSG_TABLES 256 /* 2*message_dim tables (hash_encoding_wtmk_bit.py:64)  */
+
+typedef void* nsig_stream_t; /* cudaStream_t */
+
+/* library identity: "nsig_b200 <version> sm_100a" */
+const char* nsig_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* raymarching utilities — raymarching/src/raymarching.h:7-11                 */
+/* ------------------------------------------------------------------------- */
+
+/* raymarching.h:7  near_far_from_aabb (kernel raymarching.cu:92-145) */
+int nsig_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                            uint32_t N, float min_near, float* nears, float* fars,
+                            nsig_stream_t stream);
+
+/* raymarching.h:8  sph_from_ray (raymarching.cu:163-198) */
+int nsig_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                      float* coords, nsig_stream_t stream);
+
+/* raymarching.h:9  morton3D (raymarching.cu:214-226) */
+int nsig_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, nsig_stream_t stream);
+
+/* raymarching.h:10 morton3D_invert (raymarching.cu:237-254) */
+int nsig_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords,
+                         nsig_stream_t stream);
+
+/* raymarching.h:11 packbits (raymarching.cu:268-289); N = number of output BYTES */
+int nsig_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                  nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* training march / composite — raymarching/src/raymarching.h:13-15           */
+/* ------------------------------------------------------------------------- */
+
+/* Scratch (bytes) nsig_march_rays_train needs for N rays (per-ray counts + scan state). */
+size_t nsig_march_rays_train_scratch_bytes(uint32_t N);
+
+/* raymarching.h:13 march_rays_train (raymarching.cu:312-480).
+ * Same arguments as the reference plus `scratch`.  Differences that are allowed by the
+ * reference's own nondeterminism (atomicAdd order): ray n always owns row n of
+ * `rays` and sample offsets are the exclusive prefix sum of the per-ray counts in ray
+ * order, starting at counter[0]'s value on entry.  counter[0] += total samples,
+ * counter[1] += N, exactly as the reference's atomics leave them.
+ * xyzs/dirs/deltas rows past counter[0] are NOT touched (the reference wrapper zero-fills
+ * them before the call, raymarching.py:205-207; use nsig_zero_sample_padding), except that
+ * when rays are dropped for lack of room the rows after the last kept ray are cleared. */
+int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                          float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                          uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                          const float* fars, float* xyzs, float* dirs, float* deltas,
+                          int32_t* rays, int32_t* counter, const float* noises,
+                          void* scratch, nsig_stream_t stream);
+
+/* Zero rows [counter[0], end) of the three sample buffers — the rows the reference gets from
+ * torch.zeros (raymarching.py:205-207): end = min(align_up(counter[0]), M) with
+ * align_up(m) = m + align - m % align (adds a full `align` when already aligned,
+ * raymarching.py:224-229), or end = M when align == 0 (mean_count mode returns all M rows). */
+int nsig_zero_sample_padding(float* xyzs, float* dirs, float* deltas, const int32_t* counter,
+                             uint32_t align, uint32_t M, nsig_stream_t stream);
+
+/* raymarching.h:14 composite_rays_train_forward (raymarching.cu:501-577) */
+int nsig_composite_rays_train_forward(const float* sigmas, const float* rgbs,
+                                      const float* deltas, const int32_t* rays, uint32_t M,
+                                      uint32_t N, float T_thresh, float* weights_sum,
+                                      float* depth, float* image, nsig_stream_t stream);
+
+/* raymarching.h:15 composite_rays_train_backward (raymarching.cu:602-682).
+ * Every sample row owned by a (non-dropped) ray is written, zeros after early termination;
+ * rows owned by no ray (padding, dropped rays) are left untouched — the reference wrapper
+ * zero-fills the buffers first (raymarching.py:283-284). */
+int nsig_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                       const float* sigmas, const float* rgbs,
+                                       const float* deltas, const int32_t* rays,
+                                       const float* weights_sum, const float* image,
+                                       uint32_t M, uint32_t N, float T_thresh,
+                                       float* grad_sigmas, float* grad_rgbs,
+                                       nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* inference march / composite — raymarching/src/raymarching.h:17-18          */
+/* ------------------------------------------------------------------------- */
+
+/* raymarching.h:17 march_rays (raymarching.cu:701-805). xyzs/dirs/deltas must be
+ * zero-filled by the caller (raymarching.py:333-335). */
+int nsig_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                    const float* rays_t, const float* rays_o, const float* rays_d,
+                    float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                    const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                    float* dirs, float* deltas, const float* noises, nsig_stream_t stream);
+
+/* raymarching.h:18 composite_rays (raymarching.cu:819-905); in-place on rays_alive,
+ * rays_t, weights_sum, depth, image. */
+int nsig_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                        float* rays_t, const float* sigmas, const float* rgbs,
+                        const float* deltas, float* weights_sum, float* depth, float* image,
+                        nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* hash encoders — hash_encoding.py:48-111, hash_encoding_wtmk_bit.py:51-116   */
+/* ------------------------------------------------------------------------- */
+
+/* HashEmbedder.forward (hash_encoding.py:96-111): x[B,3] (already normalised to the
+ * bounding box [0,1]) -> out[B, 2*n_levels] fp32.  tables[l] is embeddings[l].weight
+ * ([2^log2_T, 2] fp32, device pointer; the array itself is a HOST array).
+ * resolutions[l] is floor(base*b**l) computed by the caller with the reference's torch
+ * fp32 expression (hash_encoding.py:100).  slots (optional, may be NULL):
+ * int32 [B, n_levels, 8] hashed voxel indices (hash_encoding.py:43-44) for parity tests. */
+int nsig_hash_encode_forward(const float* x, uint32_t B, const float* const* tables,
+                             const float* resolutions, uint32_t n_levels, uint32_t log2_T,
+                             float* out, int32_t* slots, nsig_stream_t stream);
+
+/* d(loss)/d(embeddings[l].weight) of the above: scatter-add of grad_out[B, 2*n_levels]
+ * into grad_tables[l] ([2^log2_T, 2] fp32, accumulated, caller zero-fills). */
+int nsig_hash_encode_backward(const float* x, const float* grad_out, uint32_t B,
+                              float* const* grad_tables, const float* resolutions,
+                              uint32_t n_levels, uint32_t log2_T, nsig_stream_t stream);
+
+/* Watermark-bit encoder, hash_encoding_wtmk_bit.py:99-116, in its algebraically equal
+ * pre-summed form: all message_dim "levels" share one resolution, so
+ *   out = trilerp(S)[x],  S = sum_i embeddings[2*i + bit_i].weight.
+ * nsig_msg_table_sum builds S ([2^log2_T,2] fp32) from the DEVICE message vector
+ * (float 0/1, read on device: no .item() sync, cf. hash_encoding_wtmk_bit.py:110). */
+int nsig_msg_table_sum(const float* const* tables, uint32_t message_dim, const float* message,
+                       uint32_t log2_T, float* S, nsig_stream_t stream);
+
+/* The same encoder in the reference's literal per-bit form (message_dim gathers per
+ * corner, summed in bit order) — kept for parity tests against the pre-summed form. */
+int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* const* tables,
+                                   uint32_t message_dim, const float* message,
+                                   float resolution, uint32_t log2_T, float* out,
+                                   nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* field network — nerf/network_wtmk_tcnn.py:97-124, nerf/network_hash.py:77-110 */
+/* ------------------------------------------------------------------------- */
+
+/* Weights of the two bias-free 64-wide MLPs that the reference instantiates through
+ * tiny-cuda-nn (network_wtmk_tcnn.py:52-62, 78-88), fp16, row-major [out, in]:
+ *   sigma: W0[64,32] W1[16,64]            (3072 halfs)
+ *   color: W0[64,32] W1[64,64] W2[16,64]  (7168 halfs; input col 31 and output rows 3..15
+ *                                           are padding)                                  */
+#define NSIG_SIGMA_PARAMS 3072
+#define NSIG_COLOR_PARAMS 7168
+
+/* Fused field forward: NeRFNetwork.forward(x, d, message) (network_wtmk_tcnn.py:97-124).
+ *   xyzs[M,3] in [-bound,bound], dirs[M,3] unit vectors
+ *   base tables/resolutions as in nsig_hash_encode_forward (16 levels, F=2)
+ *   S: pre-summed message table or NULL (message=None / clean network_hash.py)
+ *   sigma_w / color_w: fp16 weights (layout above)
+ *   density_scale: sigmas = density_scale * trunc_exp(h0)  (renderer_wtmk.py:294; pass 1 for the
+ *          bare network output)
+ *   M_dev (optional): device int32 holding the live sample count (the march counter); the
+ *          kernel processes min(M, *M_dev) rows, so no host sync is needed to size the launch
+ * outputs: sigmas[M] fp32, rgbs[M,3] fp32 (sigmoid applied)
+ *          feat_out (optional) [M,32] fp16: encoder output incl. message feature, saved for
+ *          the backward pass. */
+int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float bound,
+                       const float* const* tables, const float* resolutions, uint32_t log2_T,
+                       const float* S, float msg_resolution, const void* sigma_w,
+                       const void* color_w, float density_scale, const int32_t* M_dev,
+                       float* sigmas, float* rgbs, void* feat_out, nsig_stream_t stream);
+
+/* Density-only variant: NeRFNetwork.density (network_wtmk_tcnn.py:126-143);
+ * geo_feat (optional) [M,15] fp16. */
+int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* const* tables,
+                       const float* resolutions, uint32_t log2_T, const float* S,
+                       float msg_resolution, const void* sigma_w, float density_scale,
+                       float* sigmas, void* geo_feat, nsig_stream_t stream);
+
+/* Colour branch only: NeRFNetwork.color (network_wtmk_tcnn.py:146-176): SH4(dirs) ++ geo_feat
+ * ([M,15] fp16 from nsig_field_density) -> colour MLP -> sigmoid -> rgbs[M,3] fp32. */
+int nsig_color_forward(const float* dirs, const void* geo_feat, uint32_t M, const void* color_w,
+                       float* rgbs, nsig_stream_t stream);
+
+/* Fused field backward (watermark mode: MLP dgrad only):
+ * given dL/dsigma[M], dL/drgb[M,3] and the saved feat[M,32], recompute the MLP
+ * activations, back-propagate to the encoder output and scatter-add the gradient of
+ * channels 30,31 into G ([2^log2_T,2] fp32 = gradient of the pre-summed table S,
+ * caller zero-fills).  grad_feat (optional) [M,32] fp32 receives the full encoder-output
+ * gradient (needed for base-table training in clean mode). */
+int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float bound,
+                        const void* feat, const float* grad_sigmas, const float* grad_rgbs,
+                        const void* sigma_w, const void* color_w, float density_scale,
+                        const int32_t* M_dev, float msg_resolution, uint32_t log2_T, float* G,
+                        float* grad_feat, float* grad_sigma_w, float* grad_color_w,
+                        nsig_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSIG_H_ */

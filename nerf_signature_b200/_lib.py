@@ -1,0 +1,121 @@
+"""ctypes binding of libnsig_b200.so — the thin layer between PyTorch tensors and the C ABI
+declared in include/nsig.h.
+
+There is NO fallback: if the shared library is missing or a kernel launch fails this module
+raises.  Tensors are passed as raw device pointers together with torch's current CUDA stream.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnsig_b200.so")
+
+_c = ctypes
+_vp, _u32, _f32, _sz = _c.c_void_p, _c.c_uint32, _c.c_float, _c.c_size_t
+
+# name -> (argtypes, number of kernel launches one call performs)
+_SIGNATURES = {
+    "nsig_near_far_from_aabb": ([_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp], 1),
+    "nsig_sph_from_ray": ([_vp, _vp, _f32, _u32, _vp, _vp], 1),
+    "nsig_morton3D": ([_vp, _u32, _vp, _vp], 1),
+    "nsig_morton3D_invert": ([_vp, _u32, _vp, _vp], 1),
+    "nsig_packbits": ([_vp, _u32, _f32, _vp, _vp], 1),
+    "nsig_march_rays_train": ([_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _vp, _vp], 3),
+    "nsig_zero_sample_padding": ([_vp, _vp, _vp, _vp, _u32, _u32, _vp], 1),
+    "nsig_composite_rays_train_forward": ([_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp], 1),
+    "nsig_composite_rays_train_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp,
+                                            _vp], 1),
+    "nsig_march_rays": ([_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
+                         _vp, _vp, _vp], 1),
+    "nsig_composite_rays": ([_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
+    "nsig_hash_encode_forward": ([_vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp, _vp], 1),
+    "nsig_hash_encode_backward": ([_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp], 1),
+    "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _vp], 1),
+    "nsig_msg_encode_forward_perbit": ([_vp, _u32, _vp, _u32, _vp, _f32, _u32, _vp, _vp], 1),
+    "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp,
+                            _vp], 1),
+    "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp], 1),
+    "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
+    "nsig_field_backward": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp, _vp,
+                             _vp, _vp], 1),
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes"])
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+class NsigError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (once).  Raises NsigError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NsigError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  nerf_signature_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, _) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _c.c_int
+        lib.nsig_version.restype = _c.c_char_p
+        lib.nsig_version.argtypes = []
+        lib.nsig_march_rays_train_scratch_bytes.restype = _sz
+        lib.nsig_march_rays_train_scratch_bytes.argtypes = [_u32]
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA and contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NsigError("nerf_signature_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise NsigError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on torch's current stream and check its status."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    if rc != 0:
+        if rc == -1:
+            raise NsigError(f"{name}: invalid argument (NSIG_EINVAL)")
+        raise NsigError(f"{name}: CUDA error {rc}")
+    launch_count += _SIGNATURES[name][1]
+
+
+def pointer_array(tensors):
+    """Host array of device pointers (const float* const*) for a list of tensors."""
+    arr = (_vp * len(tensors))(*[ptr(t) for t in tensors])
+    return arr
+
+
+def float_array(values):
+    return (_f32 * len(values))(*[float(v) for v in values])
+
+
+def version():
+    return load().nsig_version().decode()

@@ -1,0 +1,834 @@
+// field.cu — fused NeRFNetwork.forward / density and the watermark-mode backward for B200.
+//
+// Reference path (nerf/network_wtmk_tcnn.py:97-124): normalise x -> 16-level hash encode
+// (hash_encoding.py) -> add message feature to channels 30,31 -> sigma MLP 32-64-16 ->
+// trunc_exp -> SH4(d) ++ geo(15) -> colour MLP 32-64-64-16 -> sigmoid; ~400 torch kernels, a
+// [M,32] fp32 feature tensor and several [M,16..64] activations round-tripping through HBM.
+//
+// Here one kernel does all of it.  A warp owns 32 samples (two 16-row MMA tiles).  The thread
+// with quad coordinates (g, tig) gathers exactly the levels {tig, tig+4, tig+8, tig+12} of rows
+// {g, g+8} of each tile, which is precisely the set of elements it owns in the m16n8k16
+// A-fragment, so hash features go from the gather straight into tensor-core operand registers
+// - no shared-memory transpose, no feature tensor in HBM.  Accumulator fragments of one layer
+// are re-packed (ReLU, fp32->fp16) into the A fragments of the next layer in registers; weights
+// (fp16, 10 240 values) sit in padded shared memory and every B fragment is reused by both row
+// tiles.  The sigma net's output rows are permuted to [geo0..geo14, logit] so the geo features
+// land in the colour net's second k-step without any data movement.
+//
+// Precision: fp16 operands, fp32 accumulation (tcnn's FullyFusedMLP accumulates in fp16 - the
+// reference's own MLP arithmetic is unpinned); encoder arithmetic is the exact
+// fp32 restatement in hash_common.cuh.
+#include "hash_common.cuh"
+
+namespace nsig {
+
+// ---- shared-memory weight layout (halfs); row strides padded by 8 halfs: conflict-free B loads
+constexpr int kS32 = 40;  // stride of a [*,32] matrix
+constexpr int kS64 = 72;  // stride of a [*,64] matrix
+constexpr int kS16 = 24;  // stride of a [*,16] matrix
+// forward copies, [out][in]
+constexpr int oWs0 = 0;                    // [64][32]
+constexpr int oWs1 = oWs0 + 64 * kS32;     // [16][64] rows permuted: r' <- (r'+1)%16
+constexpr int oWc0 = oWs1 + 16 * kS64;     // [64][32] (input column 31 zeroed)
+constexpr int oWc1 = oWc0 + 64 * kS32;     // [64][64]
+constexpr int oWc2 = oWc1 + 64 * kS64;     // [8][64]  (outputs 0..7; 3..7 are padding)
+constexpr int kFwdHalfs = oWc2 + 8 * kS64;
+// transposed copies for dgrad, [in][out]
+constexpr int oWc2T = kFwdHalfs;           // [64][16] (outputs >= 3 zeroed)
+constexpr int oWc1T = oWc2T + 64 * kS16;   // [64][64]
+constexpr int oWc0T = oWc1T + 64 * kS64;   // [16][64] inputs 16..31 (geo part)
+constexpr int oWs1T = oWc0T + 16 * kS64;   // [64][16] outputs permuted like oWs1
+constexpr int oWs0T = oWs1T + 64 * kS16;   // [32][64]
+constexpr int kBwdHalfs = oWs0T + 32 * kS64;
+
+constexpr int kFieldWarps = 4;
+constexpr int kFieldThreads = kFieldWarps * 32;
+
+struct FieldParams {
+    const float* xyzs;
+    const float* dirs;
+    uint32_t M;
+    float bound_add;   // bound
+    float bound_mul;   // fl(1 / (2*bound)): torch divides by a scalar as x * (1/s) on CUDA
+    TablePtrs base;    // 16 levels
+    const float2* S;   // pre-summed message table or null
+    float msg_grid_size;
+    uint32_t mask;
+    const __half* sigma_w;
+    const __half* color_w;
+    const int32_t* M_dev;  // optional device-side sample count (march counter): M = min(M, *M_dev)
+    float density_scale;   // sigma = density_scale * exp(logit)  (renderer_wtmk.py:294)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+    return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C[MT][NT] (+)= A[MT][KS] x W^T, W in shared memory as [n][k] with `stride` halfs per row.
+// NT0 = first n-tile computed (lets the caller skip unused output columns).
+template <int MT, int KS, int NT, int NT0 = 0>
+__device__ __forceinline__ void layer(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KS][4],
+                                      const __half* __restrict__ W, int stride, int g, int tig) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.f; }
+        const __half* wrow = W + ((NT0 + nt) * 8 + g) * stride + 2 * tig;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + ks * 16);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma16816(c[mt][nt], a[mt][ks], b0, b1);
+        }
+    }
+}
+
+// accumulators of a 16 x (NT*8) layer output -> A fragments of the next layer (ReLU, fp16)
+template <int MT, int NT>
+__device__ __forceinline__ void relu_to_a(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            a[mt][ks][0] = pack_relu_h2(c[mt][2 * ks][0], c[mt][2 * ks][1]);
+            a[mt][ks][1] = pack_relu_h2(c[mt][2 * ks][2], c[mt][2 * ks][3]);
+            a[mt][ks][2] = pack_relu_h2(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1]);
+            a[mt][ks][3] = pack_relu_h2(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3]);
+        }
+}
+
+// gradient accumulators -> A fragments, masked by the forward activation (ReLU'(h) = h > 0)
+__device__ __forceinline__ uint32_t pack_masked(float a, float b, uint32_t act) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&act);
+    const __half2 m = __hgt2(h, __float2half2_rn(0.0f));  // 1.0 where h > 0
+    __half2 v = __hmul2(__floats2half2_rn(a, b), m);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int MT, int NT>
+__device__ __forceinline__ void grad_to_a(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4],
+                                          const uint32_t (&act)[MT][NT / 2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            a[mt][ks][0] = pack_masked(c[mt][2 * ks][0], c[mt][2 * ks][1], act[mt][ks][0]);
+            a[mt][ks][1] = pack_masked(c[mt][2 * ks][2], c[mt][2 * ks][3], act[mt][ks][1]);
+            a[mt][ks][2] = pack_masked(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1], act[mt][ks][2]);
+            a[mt][ks][3] = pack_masked(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3], act[mt][ks][3]);
+        }
+}
+
+// ---- weight staging ---------------------------------------------------------------------
+__device__ __forceinline__ void stage_forward_weights(__half* sm, const __half* __restrict__ sw,
+                                                      const __half* __restrict__ cw, bool color) {
+    const __half zero = __float2half(0.0f);
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int r = i >> 5, c = i & 31;
+        sm[oWs0 + r * kS32 + c] = sw[i];
+        if (color) sm[oWc0 + r * kS32 + c] = (c == 31) ? zero : cw[i];
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        const int r = i >> 6, c = i & 63;  // smem row r holds param row (r+1)%16: [geo0..14, logit]
+        sm[oWs1 + r * kS64 + c] = sw[2048 + ((r + 1) & 15) * 64 + c];
+    }
+    if (color) {
+        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+            const int r = i >> 6, c = i & 63;
+            sm[oWc1 + r * kS64 + c] = cw[2048 + i];
+        }
+        for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) {
+            const int r = i >> 6, c = i & 63;
+            sm[oWc2 + r * kS64 + c] = cw[2048 + 4096 + i];
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_backward_weights(__half* sm, const __half* __restrict__ sw,
+                                                       const __half* __restrict__ cw) {
+    const __half zero = __float2half(0.0f);
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+        const int n = i >> 4, k = i & 15;  // n = hidden (in) index, k = output index
+        sm[oWc2T + n * kS16 + k] = (k < 3) ? cw[2048 + 4096 + k * 64 + n] : zero;
+        sm[oWs1T + n * kS16 + k] = sw[2048 + ((k + 1) & 15) * 64 + n];
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        sm[oWc1T + n * kS64 + k] = cw[2048 + k * 64 + n];
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;  // n = colour-net input 16+n (geo part; input 31 is padding)
+        sm[oWc0T + n * kS64 + k] = (n == 15) ? zero : cw[k * 32 + 16 + n];
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        sm[oWs0T + n * kS64 + k] = sw[k * 32 + n];
+    }
+}
+
+// ---- SH degree 4 at v = ((d+1)/2)*2-1 (network_wtmk_tcnn.py:114 + tcnn's [0,1] convention);
+//      formulas of hash_encoding.py:162-193 -----------------------------------------------------
+__device__ __forceinline__ void sh4(float dx, float dy, float dz, float (&o)[16]) {
+    const float x = __fmaf_rn(__fmul_rn(__fadd_rn(dx, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float y = __fmaf_rn(__fmul_rn(__fadd_rn(dy, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float z = __fmaf_rn(__fmul_rn(__fadd_rn(dz, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.4886025119029199f * y;
+    o[2] = 0.4886025119029199f * z;
+    o[3] = -0.4886025119029199f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.5462742152960396f * (xx - yy);
+    o[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
+    o[10] = 2.890611442640554f * xy * z;
+    o[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
+    o[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    o[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
+    o[14] = 1.445305721320277f * z * (xx - yy);
+    o[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+
+// row index helpers: a warp owns rows [row0, row0 + 16*MT); thread (g,tig) owns rows
+// row0 + mt*16 + h*8 + g for mt < MT, h in {0,1}; fragment register index is 2*half_k + h.
+template <int MT>
+__device__ __forceinline__ uint32_t frag_row(uint32_t row0, int mt, int h, int g) {
+    return row0 + mt * 16 + h * 8 + g;
+}
+
+// Encode the rows of this thread: A fragments of the sigma net's first layer.
+// fa[mt][ks][2*hk + h]: level = 8*ks + 4*hk + tig, row half h.
+template <int MT>
+__device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
+                                            uint32_t row0, int g, int tig) {
+    float xn[MT][2][3];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
+                xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
+        }
+    float2 f[MT][2][4];  // [mt][h][j]: level tig + 4j
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int level = tig + 4 * j;
+        const float2* tab = p.base.t[level];
+        const float gs = p.base.grid_size[level];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const Voxel v = locate(xn[mt][h][0], xn[mt][h][1], xn[mt][h][2], gs);
+                f[mt][h][j] = encode_level(tab, v, p.mask);
+            }
+    }
+    if (p.S != nullptr) {
+        // message feature (hash_encoding_wtmk_bit.py, pre-summed form): quad thread `tig` evaluates row
+        // (mt = tig>>1, h = tig&1) of each 2-tile group, thread tig==3 (owner of channels 30,31) collects.
+#pragma unroll
+        for (int q = 0; q < (MT * 2 + 3) / 4; ++q) {
+            const int sel = q * 4 + tig;  // which (mt,h) this thread evaluates
+            float2 mine = make_float2(0.f, 0.f);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (mt * 2 + h == sel) { sx = xn[mt][h][0]; sy = xn[mt][h][1]; sz = xn[mt][h][2]; }
+            if (sel < MT * 2) {
+                const Voxel v = locate(sx, sy, sz, p.msg_grid_size);
+                mine = encode_level(p.S, v, p.mask);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int src = mt * 2 + h - q * 4;  // quad lane that evaluated this row
+                    if (src >= 0 && src < 4) {
+                        const float mx = __shfl_sync(NSIG_FULL_MASK, mine.x, (g << 2) | src);
+                        const float my = __shfl_sync(NSIG_FULL_MASK, mine.y, (g << 2) | src);
+                        if (tig == 3) {  // x_feature[:, -2:] += msg_feature (network_wtmk_tcnn.py:106)
+                            f[mt][h][3].x = __fadd_rn(f[mt][h][3].x, mx);
+                            f[mt][h][3].y = __fadd_rn(f[mt][h][3].y, my);
+                        }
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // level tig+4j -> k-step j>>1, half-k j&1
+                fa[mt][j >> 1][2 * (j & 1) + h] = pack_h2(f[mt][h][j].x, f[mt][h][j].y);
+}
+
+// A fragments of the colour net's first k-step: SH(d) columns {2tig,2tig+1,2tig+8,2tig+9}
+template <int MT>
+__device__ __forceinline__ void sh_rows(uint32_t (&ca)[MT][2][4], const float* __restrict__ dirs, uint32_t M,
+                                        uint32_t row0, int g, int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+            float o[16];
+            sh4(__ldg(dirs + (size_t)r * 3), __ldg(dirs + (size_t)r * 3 + 1), __ldg(dirs + (size_t)r * 3 + 2), o);
+            float lo0 = o[0], lo1 = o[1], hi0 = o[8], hi1 = o[9];
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (tig == t) { lo0 = o[2 * t]; lo1 = o[2 * t + 1]; hi0 = o[2 * t + 8]; hi1 = o[2 * t + 9]; }
+            ca[mt][0][h] = pack_h2(lo0, lo1);
+            ca[mt][0][2 + h] = pack_h2(hi0, hi1);
+        }
+}
+
+// geo features (sigma net outputs in the permuted order [geo0..14, logit]) -> colour k-step 1;
+// column 15 (the logit; the colour net's padded input 31) is cleared.
+template <int MT>
+__device__ __forceinline__ void geo_to_a(uint32_t (&ca)[MT][2][4], const float (&so)[MT][2][4], int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        ca[mt][1][0] = pack_h2(so[mt][0][0], so[mt][0][1]);
+        ca[mt][1][1] = pack_h2(so[mt][0][2], so[mt][0][3]);
+        ca[mt][1][2] = pack_h2(so[mt][1][0], (tig == 3) ? 0.0f : so[mt][1][1]);
+        ca[mt][1][3] = pack_h2(so[mt][1][2], (tig == 3) ? 0.0f : so[mt][1][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+template <bool COLOR>
+__global__ void __launch_bounds__(kFieldThreads)
+k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__ rgbs, __half* __restrict__ feat_out,
+            __half* __restrict__ geo_out) {
+    constexpr int MT = 2;
+    extern __shared__ __align__(16) __half sm[];
+    uint32_t M = p.M;
+    if (p.M_dev) M = min(M, (uint32_t)max(*p.M_dev, 0));
+    if (M == 0) return;
+    stage_forward_weights(sm, p.sigma_w, p.color_w, COLOR);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
+    const uint32_t n_tiles = div_up(M, rows_per_cta);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
+        if (row0 >= M) continue;
+        uint32_t fa[MT][2][4];
+        encode_rows<MT>(fa, p, M, row0, g, tig);
+        if (feat_out) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                    if (r < M) {
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(feat_out + (size_t)r * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[tig + 4 * j] = fa[mt][j >> 1][2 * (j & 1) + h];
+                    }
+                }
+        }
+        // sigma net: 32 -> 64 (ReLU) -> 16
+        uint32_t h1[MT][4][4];
+        {
+            float c[MT][8][4];
+            layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
+            relu_to_a<MT, 8>(h1, c);
+        }
+        float so[MT][2][4];
+        layer<MT, 4, 2>(so, h1, sm + oWs1, kS64, g, tig);
+        // logit = permuted column 15: thread tig==3, second element of n-tile 1
+        if (tig == 3) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                    if (r < M) sigmas[r] = __fmul_rn(p.density_scale, expf(so[mt][1][2 * h + 1]));  // trunc_exp (activation.py:8-10)
+                }
+        }
+        if (geo_out) {  // density(): geo_feat [M,15] fp16
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                    if (r < M) {
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = nt * 8 + 2 * tig + e;
+                                if (col < 15) geo_out[(size_t)r * 15 + col] = __float2half_rn(so[mt][nt][2 * h + e]);
+                            }
+                    }
+                }
+        }
+        if (COLOR) {
+            uint32_t ca[MT][2][4];
+            sh_rows<MT>(ca, p.dirs, M, row0, g, tig);
+            geo_to_a<MT>(ca, so, tig);
+            uint32_t h2[MT][4][4];
+            {
+                float c[MT][8][4];
+                layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
+                relu_to_a<MT, 8>(h1, c);
+                layer<MT, 4, 8>(c, h1, sm + oWc1, kS64, g, tig);
+                relu_to_a<MT, 8>(h2, c);
+            }
+            float co[MT][1][4];
+            layer<MT, 4, 1>(co, h2, sm + oWc2, kS64, g, tig);
+            if (tig < 2) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                        if (r < M) {
+                            const float s0 = 1.0f / (1.0f + expf(-co[mt][0][2 * h]));
+                            if (tig == 0) {
+                                rgbs[(size_t)r * 3] = s0;
+                                rgbs[(size_t)r * 3 + 1] = 1.0f / (1.0f + expf(-co[mt][0][2 * h + 1]));
+                            } else {
+                                rgbs[(size_t)r * 3 + 2] = s0;
+                            }
+                        }
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// colour branch only: NeRFNetwork.color(x, d, geo_feat) (network_wtmk_tcnn.py:146-176), used by the
+// non-cuda_ray renderer.  geo_feat [M,15] fp16 comes from nsig_field_density.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFieldThreads)
+k_color_fwd(const float* __restrict__ dirs, const __half* __restrict__ geo, uint32_t M,
+            const __half* __restrict__ color_w, float* __restrict__ rgbs) {
+    constexpr int MT = 2;
+    extern __shared__ __align__(16) __half sm[];
+    {   // only the colour matrices are needed; the sigma slots are left unused
+        const __half zero = __float2half(0.0f);
+        for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+            const int r = i >> 5, c = i & 31;
+            sm[oWc0 + r * kS32 + c] = (c == 31) ? zero : color_w[i];
+        }
+        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) sm[oWc1 + (i >> 6) * kS64 + (i & 63)] = color_w[2048 + i];
+        for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) sm[oWc2 + (i >> 6) * kS64 + (i & 63)] = color_w[2048 + 4096 + i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
+    const uint32_t n_tiles = div_up(M, rows_per_cta);
+    const float* dirs_ = dirs;
+    const uint32_t M_ = M;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
+        if (row0 >= M) continue;
+        uint32_t ca[MT][2][4];
+        sh_rows<MT>(ca, dirs_, M_, row0, g, tig);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+                const __half* gr = geo + (size_t)r * 15;
+                const __half z = __float2half(0.0f);
+                __half2 lo = __halves2half2(gr[2 * tig], gr[2 * tig + 1]);
+                __half2 hi = __halves2half2(gr[2 * tig + 8], (tig == 3) ? z : gr[2 * tig + 9]);
+                ca[mt][1][h] = *reinterpret_cast<uint32_t*>(&lo);
+                ca[mt][1][2 + h] = *reinterpret_cast<uint32_t*>(&hi);
+            }
+        uint32_t h1[MT][4][4], h2[MT][4][4];
+        {
+            float c[MT][8][4];
+            layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
+            relu_to_a<MT, 8>(h1, c);
+            layer<MT, 4, 8>(c, h1, sm + oWc1, kS64, g, tig);
+            relu_to_a<MT, 8>(h2, c);
+        }
+        float co[MT][1][4];
+        layer<MT, 4, 1>(co, h2, sm + oWc2, kS64, g, tig);
+        if (tig < 2) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                    if (r < M) {
+                        const float s0 = 1.0f / (1.0f + expf(-co[mt][0][2 * h]));
+                        if (tig == 0) {
+                            rgbs[(size_t)r * 3] = s0;
+                            rgbs[(size_t)r * 3 + 1] = 1.0f / (1.0f + expf(-co[mt][0][2 * h + 1]));
+                        } else {
+                            rgbs[(size_t)r * 3 + 2] = s0;
+                        }
+                    }
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward (dgrad through both MLPs, scatter of the message-table gradient)
+// ---------------------------------------------------------------------------------------
+struct FieldBwdParams {
+    const float* xyzs;
+    const float* dirs;
+    uint32_t M;
+    float bound_add, bound_mul;
+    const __half* feat;        // [M,32] saved by the forward
+    const float* grad_sigmas;  // [M]
+    const float* grad_rgbs;    // [M,3]
+    const __half* sigma_w;
+    const __half* color_w;
+    float msg_grid_size;
+    uint32_t mask;
+    float* G;          // [T,2] gradient of the pre-summed message table (may be null)
+    float* grad_feat;  // [M,32] fp32 full encoder-output gradient (may be null)
+    const int32_t* M_dev;
+    float density_scale;
+};
+
+// power-of-two scale that brings |v| into [0.5, 1): keeps the fp16 gradient chain in range
+__device__ __forceinline__ float pow2_scale(float vmax) {
+    if (!(vmax > 0.0f) || !isfinite(vmax)) return 1.0f;
+    int e;
+    frexpf(vmax, &e);
+    e = max(-100, min(100, e));
+    return scalbnf(1.0f, -e);
+}
+
+template <bool FULL_GRAD>
+__global__ void __launch_bounds__(kFieldThreads)
+k_field_bwd(const FieldBwdParams p) {
+    constexpr int MT = 1;
+    extern __shared__ __align__(16) __half sm[];
+    uint32_t M = p.M;
+    if (p.M_dev) M = min(M, (uint32_t)max(*p.M_dev, 0));
+    if (M == 0) return;
+    stage_forward_weights(sm, p.sigma_w, p.color_w, true);
+    stage_backward_weights(sm, p.sigma_w, p.color_w);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
+    const uint32_t n_tiles = div_up(M, rows_per_cta);
+    const float* dirs_ = p.dirs;
+    const uint32_t M_ = M;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
+        if (row0 >= M) continue;
+        // incoming gradients of this thread's rows; skip the tile when the whole warp has none
+        float gs_in[MT][2], gc_in[MT][2][2];
+        bool any = false;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                gs_in[mt][h] = 0.f; gc_in[mt][h][0] = gc_in[mt][h][1] = 0.f;
+                if (r < M) {
+                    if (tig == 3) gs_in[mt][h] = __ldg(p.grad_sigmas + r);
+                    if (tig == 0) { gc_in[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3); gc_in[mt][h][1] = __ldg(p.grad_rgbs + (size_t)r * 3 + 1); }
+                    if (tig == 1) gc_in[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3 + 2);
+                }
+                any |= (gs_in[mt][h] != 0.f) | (gc_in[mt][h][0] != 0.f) | (gc_in[mt][h][1] != 0.f);
+            }
+        if (!__any_sync(NSIG_FULL_MASK, any)) {
+            if (FULL_GRAD && p.grad_feat) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                        if (r < M)
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt)
+                                *reinterpret_cast<float2*>(p.grad_feat + (size_t)r * 32 + nt * 8 + 2 * tig) = make_float2(0.f, 0.f);
+                    }
+            }
+            continue;
+        }
+        // ---- recompute the forward activations from the saved encoder output ----
+        uint32_t fa[MT][2][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.feat + (size_t)r * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fa[mt][j >> 1][2 * (j & 1) + h] = __ldg(src + tig + 4 * j);
+            }
+        uint32_t h1s[MT][4][4], h1c[MT][4][4], h2c[MT][4][4];
+        float so[MT][2][4], co[MT][1][4];
+        {
+            float c[MT][8][4];
+            layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
+            relu_to_a<MT, 8>(h1s, c);
+            layer<MT, 4, 2>(so, h1s, sm + oWs1, kS64, g, tig);
+            uint32_t ca[MT][2][4];
+            sh_rows<MT>(ca, dirs_, M_, row0, g, tig);
+            geo_to_a<MT>(ca, so, tig);
+            layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
+            relu_to_a<MT, 8>(h1c, c);
+            layer<MT, 4, 8>(c, h1c, sm + oWc1, kS64, g, tig);
+            relu_to_a<MT, 8>(h2c, c);
+            layer<MT, 4, 1>(co, h2c, sm + oWc2, kS64, g, tig);
+        }
+        // ---- output-activation gradients, normalised per row by a power of two ----
+        float d_rgb[MT][2][2], d_logit[MT][2], inv_scale[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // sigmoid'(z) = s(1-s)
+                const float s0 = 1.0f / (1.0f + expf(-co[mt][0][2 * h])), s1 = 1.0f / (1.0f + expf(-co[mt][0][2 * h + 1]));
+                d_rgb[mt][h][0] = (tig < 2) ? gc_in[mt][h][0] * s0 * (1.0f - s0) : 0.f;
+                d_rgb[mt][h][1] = (tig == 0) ? gc_in[mt][h][1] * s1 * (1.0f - s1) : 0.f;
+                // trunc_exp backward: g * exp(clamp(x, -15, 15))  (activation.py:14-16)
+                const float logit = so[mt][1][2 * h + 1];
+                d_logit[mt][h] = (tig == 3) ? gs_in[mt][h] * p.density_scale * expf(fminf(fmaxf(logit, -15.0f), 15.0f)) : 0.f;
+                float vmax = fmaxf(fmaxf(fabsf(d_rgb[mt][h][0]), fabsf(d_rgb[mt][h][1])), fabsf(d_logit[mt][h]));
+                vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 1));
+                vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 2));
+                const float sc = pow2_scale(vmax);
+                inv_scale[mt][h] = 1.0f / sc;
+                d_rgb[mt][h][0] *= sc; d_rgb[mt][h][1] *= sc; d_logit[mt][h] *= sc;
+            }
+        // ---- colour net dgrad ----
+        uint32_t da[MT][1][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            da[mt][0][0] = pack_h2(d_rgb[mt][0][0], d_rgb[mt][0][1]);
+            da[mt][0][1] = pack_h2(d_rgb[mt][1][0], d_rgb[mt][1][1]);
+            da[mt][0][2] = 0u; da[mt][0][3] = 0u;
+        }
+        uint32_t dh[MT][4][4];
+        float dgeo[MT][2][4];
+        {
+            float c[MT][8][4];
+            layer<MT, 1, 8>(c, da, sm + oWc2T, kS16, g, tig);        // d h2 = d out x W2
+            grad_to_a<MT, 8>(dh, c, h2c);
+            layer<MT, 4, 8>(c, dh, sm + oWc1T, kS64, g, tig);        // d h1 = d h2 x W1
+            grad_to_a<MT, 8>(dh, c, h1c);
+            layer<MT, 4, 2>(dgeo, dh, sm + oWc0T, kS64, g, tig);     // d geo = (d h1 x W0)[:, 16:32]
+        }
+        // ---- sigma net dgrad: d out' = [d geo0..14, d logit] ----
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            da[mt][0][0] = pack_h2(dgeo[mt][0][0], dgeo[mt][0][1]);
+            da[mt][0][1] = pack_h2(dgeo[mt][0][2], dgeo[mt][0][3]);
+            da[mt][0][2] = pack_h2(dgeo[mt][1][0], (tig == 3) ? d_logit[mt][0] : dgeo[mt][1][1]);
+            da[mt][0][3] = pack_h2(dgeo[mt][1][2], (tig == 3) ? d_logit[mt][1] : dgeo[mt][1][3]);
+        }
+        {
+            float c[MT][8][4];
+            layer<MT, 1, 8>(c, da, sm + oWs1T, kS16, g, tig);        // d h1s = d out' x W1'
+            grad_to_a<MT, 8>(dh, c, h1s);
+        }
+        float gmsg[MT][2][2];  // d feature 30,31 (valid on tig == 3)
+        if (FULL_GRAD) {
+            float c[MT][4][4];
+            layer<MT, 4, 4>(c, dh, sm + oWs0T, kS64, g, tig);        // d feat = d h1s x W0
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                    gmsg[mt][h][0] = c[mt][3][2 * h] * inv_scale[mt][h];
+                    gmsg[mt][h][1] = c[mt][3][2 * h + 1] * inv_scale[mt][h];
+                    if (r < M && p.grad_feat)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt)
+                            *reinterpret_cast<float2*>(p.grad_feat + (size_t)r * 32 + nt * 8 + 2 * tig) =
+                                make_float2(c[mt][nt][2 * h] * inv_scale[mt][h], c[mt][nt][2 * h + 1] * inv_scale[mt][h]);
+                }
+        } else {
+            float c[MT][1][4];
+            layer<MT, 4, 1, 3>(c, dh, sm + oWs0T, kS64, g, tig);     // only channels 24..31
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    gmsg[mt][h][0] = c[mt][0][2 * h] * inv_scale[mt][h];
+                    gmsg[mt][h][1] = c[mt][0][2 * h + 1] * inv_scale[mt][h];
+                }
+        }
+        // ---- scatter into G: quad thread `tig` handles all 8 corners of row (mt,h) = tig ----
+        if (p.G) {
+#pragma unroll
+            for (int q = 0; q < (MT * 2 + 3) / 4; ++q) {
+                float gx = 0.f, gy = 0.f;
+                uint32_t myrow = 0xffffffffu;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int dst = mt * 2 + h - q * 4;
+                        if (dst >= 0 && dst < 4) {
+                            const float vx = __shfl_sync(NSIG_FULL_MASK, gmsg[mt][h][0], (g << 2) | 3);
+                            const float vy = __shfl_sync(NSIG_FULL_MASK, gmsg[mt][h][1], (g << 2) | 3);
+                            if (tig == dst) { gx = vx; gy = vy; myrow = frag_row<MT>(row0, mt, h, g); }
+                        }
+                    }
+                if (myrow < M && (gx != 0.f || gy != 0.f)) {
+                    float xn[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        xn[a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)myrow * 3 + a), p.bound_add), p.bound_mul);
+                    const Voxel v = locate(xn[0], xn[1], xn[2], p.msg_grid_size);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        red_add_v2(p.G + (size_t)corner_slot(v, k, p.mask) * 2, corner_grad(v, k, gx), corner_grad(v, k, gy));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace nsig
+
+using namespace nsig;
+
+static int fill_field_params(FieldParams& p, const float* xyzs, const float* dirs, uint32_t M, float bound,
+                             const float* const* tables, const float* resolutions, uint32_t log2_T,
+                             const float* S, float msg_resolution, const void* sigma_w, const void* color_w,
+                             const int32_t* M_dev, float density_scale) {
+    if (!xyzs || !tables || !resolutions || !sigma_w) return NSIG_EINVAL;
+    if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
+    p.xyzs = xyzs;
+    p.dirs = dirs;
+    p.M = M;
+    p.bound_add = bound;
+    p.bound_mul = 1.0f / (2.0f * bound);
+    for (int l = 0; l < NSIG_MAX_LEVELS; ++l) {
+        if (!tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
+        p.base.t[l] = reinterpret_cast<const float2*>(tables[l]);
+        p.base.grid_size[l] = 1.0f / resolutions[l];
+    }
+    p.S = reinterpret_cast<const float2*>(S);
+    p.msg_grid_size = (msg_resolution > 0.0f) ? 1.0f / msg_resolution : 0.0f;
+    if (S && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
+    p.mask = (1u << log2_T) - 1u;
+    p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
+    p.color_w = reinterpret_cast<const __half*>(color_w);
+    p.M_dev = M_dev;
+    p.density_scale = density_scale;
+    return 0;
+}
+
+static int field_grid(uint32_t M, uint32_t rows_per_cta, int ctas_per_sm) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t tiles = div_up(M, rows_per_cta);
+    const uint32_t cap = (uint32_t)(sms * ctas_per_sm);
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+extern "C" {
+
+int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float bound, const float* const* tables,
+                       const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
+                       const void* sigma_w, const void* color_w, float density_scale, const int32_t* M_dev,
+                       float* sigmas, float* rgbs, void* feat_out, nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!dirs || !color_w || !sigmas || !rgbs) return NSIG_EINVAL;
+    FieldParams p;
+    const int rc = fill_field_params(p, xyzs, dirs, M, bound, tables, resolutions, log2_T, S, msg_resolution,
+                                     sigma_w, color_w, M_dev, density_scale);
+    if (rc) return rc;
+    const size_t smem = kFwdHalfs * sizeof(__half);
+    k_field_fwd<true><<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+        p, sigmas, rgbs, reinterpret_cast<__half*>(feat_out), nullptr);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* const* tables,
+                       const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
+                       const void* sigma_w, float density_scale, float* sigmas, void* geo_feat,
+                       nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!sigmas) return NSIG_EINVAL;
+    FieldParams p;
+    const int rc = fill_field_params(p, xyzs, nullptr, M, bound, tables, resolutions, log2_T, S, msg_resolution,
+                                     sigma_w, nullptr, nullptr, density_scale);
+    if (rc) return rc;
+    const size_t smem = kFwdHalfs * sizeof(__half);
+    k_field_fwd<false><<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+        p, sigmas, nullptr, nullptr, reinterpret_cast<__half*>(geo_feat));
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_color_forward(const float* dirs, const void* geo_feat, uint32_t M, const void* color_w, float* rgbs,
+                       nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!dirs || !geo_feat || !color_w || !rgbs) return NSIG_EINVAL;
+    const size_t smem = kFwdHalfs * sizeof(__half);
+    k_color_fwd<<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+        dirs, reinterpret_cast<const __half*>(geo_feat), M, reinterpret_cast<const __half*>(color_w), rgbs);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float bound, const void* feat,
+                        const float* grad_sigmas, const float* grad_rgbs, const void* sigma_w, const void* color_w,
+                        float density_scale, const int32_t* M_dev, float msg_resolution, uint32_t log2_T,
+                        float* G, float* grad_feat, float* grad_sigma_w, float* grad_color_w,
+                        nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyzs || !dirs || !feat || !grad_sigmas || !grad_rgbs || !sigma_w || !color_w) return NSIG_EINVAL;
+    if (grad_sigma_w || grad_color_w) return NSIG_EINVAL;  // weight gradients: see nsig_mlp_wgrad
+    if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
+    if (G && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
+    FieldBwdParams p;
+    p.xyzs = xyzs; p.dirs = dirs; p.M = M;
+    p.bound_add = bound; p.bound_mul = 1.0f / (2.0f * bound);
+    p.feat = reinterpret_cast<const __half*>(feat);
+    p.grad_sigmas = grad_sigmas; p.grad_rgbs = grad_rgbs;
+    p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
+    p.color_w = reinterpret_cast<const __half*>(color_w);
+    p.msg_grid_size = (msg_resolution > 0.0f) ? 1.0f / msg_resolution : 0.0f;
+    p.mask = (1u << log2_T) - 1u;
+    p.G = G; p.grad_feat = grad_feat;
+    p.M_dev = M_dev; p.density_scale = density_scale;
+    const size_t smem = kBwdHalfs * sizeof(__half);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_field_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_field_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int grid = field_grid(M, kFieldWarps * 16, 4);
+    if (grad_feat)
+        k_field_bwd<true><<<grid, kFieldThreads, smem, (cudaStream_t)stream>>>(p);
+    else
+        k_field_bwd<false><<<grid, kFieldThreads, smem, (cudaStream_t)stream>>>(p);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

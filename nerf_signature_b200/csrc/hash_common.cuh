@@ -1,0 +1,97 @@
+// Per-level voxel location, hashing and trilinear interpolation shared by the stand-alone
+// hash-encoder kernels (hashenc.cu) and the fused field kernels (field.cu).
+//
+// The arithmetic restates hash_encoding.py:24-46,78-94 of the reference one torch op per
+// rounded fp32 operation (explicit __f*_rn intrinsics: no contraction, no fast reciprocal):
+// integer slots are bit-exact by construction and so are the interpolated features.
+#pragma once
+#include "nsig_common.cuh"
+
+namespace nsig {
+
+constexpr uint32_t kPrimeY = 2654435761u;  // hash_encoding.py:16
+constexpr uint32_t kPrimeZ = 805459861u;
+
+struct Voxel {
+    uint32_t hx0, hx1, hy0, hy1, hz0, hz1;  // per-axis hash terms of the lower / upper corner
+    float wx, wy, wz;                       // interpolation weights
+};
+
+// x in the unit box; grid_size = fl(1/resolution) computed by the host in IEEE fp32.
+__device__ __forceinline__ void locate_axis(float x, float grid_size, uint32_t& idx, float& w) {
+    const float xc = fminf(fmaxf(x, 0.0f), 1.0f);            // hash_encoding.py:33-35
+    const float fi = floorf(__fdiv_rn(xc, grid_size));       // :39  floor((x - 0)/grid_size)
+    idx = (uint32_t)(int)fi;
+    const float vmin = __fmul_rn(fi, grid_size);             // :40
+    const float vmax = __fadd_rn(vmin, grid_size);           // :41
+    w = __fdiv_rn(__fsub_rn(x, vmin), __fsub_rn(vmax, vmin)); // :87 (x unclamped)
+}
+
+__device__ __forceinline__ Voxel locate(float x, float y, float z, float grid_size) {
+    Voxel v;
+    uint32_t ix, iy, iz;
+    locate_axis(x, grid_size, ix, v.wx);
+    locate_axis(y, grid_size, iy, v.wy);
+    locate_axis(z, grid_size, iz, v.wz);
+    v.hx0 = ix;            v.hx1 = ix + 1u;
+    v.hy0 = iy * kPrimeY;  v.hy1 = v.hy0 + kPrimeY;
+    v.hz0 = iz * kPrimeZ;  v.hz1 = v.hz0 + kPrimeZ;
+    return v;
+}
+
+// corner k = i*4 + j*2 + l with x the most significant bit (hash_encoding.py:8)
+__device__ __forceinline__ uint32_t corner_slot(const Voxel& v, int k, uint32_t mask) {
+    return (((k & 4) ? v.hx1 : v.hx0) ^ ((k & 2) ? v.hy1 : v.hy0) ^ ((k & 1) ? v.hz1 : v.hz0)) & mask;
+}
+
+__device__ __forceinline__ float lerp_ref(float a, float b, float w, float omw) {
+    return __fadd_rn(__fmul_rn(a, omw), __fmul_rn(b, w));
+}
+
+// trilinear interpolation in the reference's order: x, then y, then z (hash_encoding.py:89-104)
+__device__ __forceinline__ float2 trilerp(const float2 e[8], const Voxel& v) {
+    const float ox = __fsub_rn(1.0f, v.wx), oy = __fsub_rn(1.0f, v.wy), oz = __fsub_rn(1.0f, v.wz);
+    float2 r;
+    {
+        const float c00 = lerp_ref(e[0].x, e[4].x, v.wx, ox), c01 = lerp_ref(e[1].x, e[5].x, v.wx, ox);
+        const float c10 = lerp_ref(e[2].x, e[6].x, v.wx, ox), c11 = lerp_ref(e[3].x, e[7].x, v.wx, ox);
+        const float c0 = lerp_ref(c00, c10, v.wy, oy), c1 = lerp_ref(c01, c11, v.wy, oy);
+        r.x = lerp_ref(c0, c1, v.wz, oz);
+    }
+    {
+        const float c00 = lerp_ref(e[0].y, e[4].y, v.wx, ox), c01 = lerp_ref(e[1].y, e[5].y, v.wx, ox);
+        const float c10 = lerp_ref(e[2].y, e[6].y, v.wx, ox), c11 = lerp_ref(e[3].y, e[7].y, v.wx, ox);
+        const float c0 = lerp_ref(c00, c10, v.wy, oy), c1 = lerp_ref(c01, c11, v.wy, oy);
+        r.y = lerp_ref(c0, c1, v.wz, oz);
+    }
+    return r;
+}
+
+// gather the 8 corners of one level and interpolate
+__device__ __forceinline__ float2 encode_level(const float2* __restrict__ table, const Voxel& v, uint32_t mask) {
+    float2 e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = __ldg(table + corner_slot(v, k, mask));
+    return trilerp(e, v);
+}
+
+// d(loss)/d(table[slot_k]) contribution of output gradient g, in autograd's association order
+// through hash_encoding.py:89-104: ((g * z-factor) * y-factor) * x-factor
+__device__ __forceinline__ float corner_grad(const Voxel& v, int k, float g) {
+    const float fz = (k & 1) ? v.wz : __fsub_rn(1.0f, v.wz);
+    const float fy = (k & 2) ? v.wy : __fsub_rn(1.0f, v.wy);
+    const float fx = (k & 4) ? v.wx : __fsub_rn(1.0f, v.wx);
+    return __fmul_rn(__fmul_rn(__fmul_rn(g, fz), fy), fx);
+}
+
+// vectorised fp32 reduction into global memory (sm_90+): one L2 atomic for both features
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+struct TablePtrs {
+    const float2* t[NSIG_MAX_LEVELS];
+    float grid_size[NSIG_MAX_LEVELS];  // fl(1/resolution)
+};
+
+}  // namespace nsig

@@ -1,0 +1,215 @@
+// hashenc.cu — stand-alone multiresolution hash encoders (HashEmbedder.forward and its table
+// gradient), the message-table pre-sum and the reference-form per-bit message encoder.
+//
+// These back the drop-in `HashEmbedder` modules.  The render/train hot path uses the fused
+// field kernels (field.cu), which share the per-level arithmetic in hash_common.cuh.
+#include "hash_common.cuh"
+
+namespace nsig {
+
+// ---------------------------------------------------------------------------------------
+// forward: one thread per (sample, level); the 2*n_levels outputs of a sample are written by
+// n_levels consecutive lanes => each warp stores 256 contiguous bytes.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_hash_encode_fwd(const float* __restrict__ x, uint32_t B, TablePtrs tp, uint32_t n_levels, uint32_t mask,
+                  float* __restrict__ out, int32_t* __restrict__ slots) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)B * n_levels;
+    if (gid >= total) return;
+    const uint32_t b = (uint32_t)(gid / n_levels), l = (uint32_t)(gid % n_levels);
+    const float px = x[(size_t)b * 3], py = x[(size_t)b * 3 + 1], pz = x[(size_t)b * 3 + 2];
+    const Voxel v = locate(px, py, pz, tp.grid_size[l]);
+    float2 e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t s = corner_slot(v, k, mask);
+        e[k] = __ldg(tp.t[l] + s);
+        if (slots) slots[gid * 8 + k] = (int32_t)s;
+    }
+    const float2 r = trilerp(e, v);
+    *reinterpret_cast<float2*>(out + gid * 2) = r;
+}
+
+struct GradTablePtrs {
+    float* t[NSIG_MAX_LEVELS];
+    float grid_size[NSIG_MAX_LEVELS];
+};
+
+// backward: scatter-add into the tables, one thread per (sample, level), 8 vector reductions
+__global__ void __launch_bounds__(256)
+k_hash_encode_bwd(const float* __restrict__ x, const float* __restrict__ grad_out, uint32_t B,
+                  GradTablePtrs tp, uint32_t n_levels, uint32_t mask) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)B * n_levels;
+    if (gid >= total) return;
+    const uint32_t b = (uint32_t)(gid / n_levels), l = (uint32_t)(gid % n_levels);
+    const float2 g = *reinterpret_cast<const float2*>(grad_out + gid * 2);
+    if (g.x == 0.0f && g.y == 0.0f) return;  // padding rows / terminated samples
+    const float px = x[(size_t)b * 3], py = x[(size_t)b * 3 + 1], pz = x[(size_t)b * 3 + 2];
+    const Voxel v = locate(px, py, pz, tp.grid_size[l]);
+    float* tab = tp.t[l];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t s = corner_slot(v, k, mask);
+        red_add_v2(tab + (size_t)s * 2, corner_grad(v, k, g.x), corner_grad(v, k, g.y));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// S = sum_i tables[2i + bit_i]  (message read on device).  Pure streaming: message_dim x 4 MiB
+// read once, 4 MiB written; loads bypass L1 and are marked evict-first in L2 so they do not
+// push the base tables out.
+// ---------------------------------------------------------------------------------------
+struct MsgTablePtrs {
+    const float* t[NSIG_MAX_MSG_TABLES];
+};
+
+struct f8 { float v[8]; };
+
+// 256-bit streaming load (sm_100): no L1 allocation, evict-first in L2
+__device__ __forceinline__ f8 ld_evict_first8(const float* p) {
+    f8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),
+                   "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_msg_table_sum(MsgTablePtrs tp, uint32_t message_dim, const float* __restrict__ message, uint32_t n_vec8,
+                float* __restrict__ S) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec8) return;
+    const size_t off = (size_t)i * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    uint32_t m = 0;
+    for (; m + 4 <= message_dim; m += 4) {  // 4 independent 32-byte loads in flight
+        f8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t bit = (uint32_t)(int)__ldg(message + m + u);
+            v[u] = ld_evict_first8(tp.t[2 * (m + u) + (bit & 1u)] + off);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[u].v[j];
+    }
+    for (; m < message_dim; ++m) {
+        const uint32_t bit = (uint32_t)(int)__ldg(message + m);
+        const f8 v = ld_evict_first8(tp.t[2 * m + (bit & 1u)] + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
+    }
+    float4* dst = reinterpret_cast<float4*>(S + off);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// reference-form message encoder: per bit gather + trilerp, summed in bit order
+__global__ void __launch_bounds__(256)
+k_msg_encode_perbit(const float* __restrict__ x, uint32_t B, MsgTablePtrs tp, uint32_t message_dim,
+                    const float* __restrict__ message, float grid_size, uint32_t mask, float* __restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Voxel v = locate(x[(size_t)b * 3], x[(size_t)b * 3 + 1], x[(size_t)b * 3 + 2], grid_size);
+    uint32_t s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = corner_slot(v, k, mask);
+    float a0 = 0.f, a1 = 0.f;
+    for (uint32_t m = 0; m < message_dim; ++m) {
+        const uint32_t bit = (uint32_t)(int)__ldg(message + m);
+        const float2* tab = reinterpret_cast<const float2*>(tp.t[2 * m + (bit & 1u)]);
+        float2 e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + s[k]);
+        const float2 r = trilerp(e, v);
+        a0 = __fadd_rn(a0, r.x);
+        a1 = __fadd_rn(a1, r.y);
+    }
+    out[(size_t)b * 2] = a0;
+    out[(size_t)b * 2 + 1] = a1;
+}
+
+}  // namespace nsig
+
+using namespace nsig;
+
+extern "C" {
+
+int nsig_hash_encode_forward(const float* x, uint32_t B, const float* const* tables, const float* resolutions,
+                             uint32_t n_levels, uint32_t log2_T, float* out, int32_t* slots,
+                             nsig_stream_t stream) {
+    if (B == 0) return 0;
+    if (!x || !tables || !resolutions || !out) return NSIG_EINVAL;
+    if (n_levels == 0 || n_levels > NSIG_MAX_LEVELS || log2_T == 0 || log2_T > 30) return NSIG_EINVAL;
+    TablePtrs tp;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        if (!tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
+        tp.t[l] = reinterpret_cast<const float2*>(tables[l]);
+        tp.grid_size[l] = 1.0f / resolutions[l];  // IEEE fp32 division, hash_encoding.py:37
+    }
+    const uint64_t total = (uint64_t)B * n_levels;
+    k_hash_encode_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, tp, n_levels, (1u << log2_T) - 1u, out, slots);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_hash_encode_backward(const float* x, const float* grad_out, uint32_t B, float* const* grad_tables,
+                              const float* resolutions, uint32_t n_levels, uint32_t log2_T,
+                              nsig_stream_t stream) {
+    if (B == 0) return 0;
+    if (!x || !grad_out || !grad_tables || !resolutions) return NSIG_EINVAL;
+    if (n_levels == 0 || n_levels > NSIG_MAX_LEVELS || log2_T == 0 || log2_T > 30) return NSIG_EINVAL;
+    GradTablePtrs tp;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        if (!grad_tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
+        tp.t[l] = grad_tables[l];
+        tp.grid_size[l] = 1.0f / resolutions[l];
+    }
+    const uint64_t total = (uint64_t)B * n_levels;
+    k_hash_encode_bwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, grad_out, B, tp, n_levels, (1u << log2_T) - 1u);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_msg_table_sum(const float* const* tables, uint32_t message_dim, const float* message, uint32_t log2_T,
+                       float* S, nsig_stream_t stream) {
+    if (!tables || !message || !S) return NSIG_EINVAL;
+    if (message_dim == 0 || 2 * message_dim > NSIG_MAX_MSG_TABLES || log2_T < 1 || log2_T > 30) return NSIG_EINVAL;
+    MsgTablePtrs tp;
+    for (uint32_t i = 0; i < 2 * message_dim; ++i) {
+        if (!tables[i] || (((uintptr_t)tables[i]) & 31)) return NSIG_EINVAL;
+        tp.t[i] = tables[i];
+    }
+    if (log2_T < 2 || (((uintptr_t)S) & 31)) return NSIG_EINVAL;
+    const uint32_t n_vec8 = (1u << log2_T) / 4;  // T entries x 2 floats / 8
+    k_msg_table_sum<<<div_up(n_vec8, 256), 256, 0, (cudaStream_t)stream>>>(tp, message_dim, message, n_vec8, S);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* const* tables, uint32_t message_dim,
+                                   const float* message, float resolution, uint32_t log2_T, float* out,
+                                   nsig_stream_t stream) {
+    if (B == 0) return 0;
+    if (!x || !tables || !message || !out) return NSIG_EINVAL;
+    if (message_dim == 0 || 2 * message_dim > NSIG_MAX_MSG_TABLES || log2_T < 1 || log2_T > 30) return NSIG_EINVAL;
+    MsgTablePtrs tp;
+    for (uint32_t i = 0; i < 2 * message_dim; ++i) {
+        if (!tables[i]) return NSIG_EINVAL;
+        tp.t[i] = tables[i];
+    }
+    k_msg_encode_perbit<<<div_up(B, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, tp, message_dim, message, 1.0f / resolution, (1u << log2_T) - 1u, out);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

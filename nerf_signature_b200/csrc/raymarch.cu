@@ -1,0 +1,818 @@
+// raymarch.cu — occupancy-grid ray marching and compositing for B200 (sm_100a).
+//
+// Replaces the reference's raymarching/src/raymarching.cu (10 thread-per-ray kernels) with a
+// warp-per-ray design:
+//   * march: a warp tests 32 lattice points of one ray per iteration (the sequence
+//     of candidate t values is a fixed per-ray lattice), resolves which of them the reference's
+//     sequential loop would actually visit with a pointer-doubling pass over warp shuffles, and
+//     compacts the occupied ones with ballot/popc.  Sample offsets come from a deterministic
+//     prefix sum over rays instead of the reference's atomicAdd (raymarching.cu:405-406).
+//   * composite: a warp owns a ray, streams 32 samples per iteration with coalesced loads and
+//     carries transmittance / colour with warp scans; early termination is decided per chunk.
+//
+// Bit-exactness: every float operation that feeds an integer decision (grid cell, occupancy,
+// skip distance, loop exit) is written with explicit __f*_rn intrinsics in the operation order
+// and FMA contraction the reference build produces (nvcc default -fmad=true, IEEE div), so the
+// compiler cannot re-associate or re-contract it.
+#include "nsig_common.cuh"
+
+namespace nsig {
+
+constexpr float kSqrt3 = 1.7320508075688772f;
+constexpr float kRPi = 0.3183098861837907f;
+
+// ---------------------------------------------------------------------------------------
+// K1 near/far — reference raymarching.cu:92-145
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void near_far_one(float ox, float oy, float oz, float dx, float dy,
+                                             float dz, const float* __restrict__ aabb,
+                                             float min_near, float& near_out, float& far_out) {
+    const float rdx = __fdiv_rn(1.0f, dx), rdy = __fdiv_rn(1.0f, dy), rdz = __fdiv_rn(1.0f, dz);
+    float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx);
+    float far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx);
+    if (near > far) { float c = near; near = far; far = c; }
+    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy);
+    float far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (near_y > far_y) { float c = near_y; near_y = far_y; far_y = c; }
+    if (near > far_y || near_y > far) { near_out = far_out = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz);
+    float far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+    if (near_z > far_z) { float c = near_z; near_z = far_z; far_z = c; }
+    if (near > far_z || near_z > far) { near_out = far_out = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    near_out = near;
+    far_out = far;
+}
+
+__global__ void __launch_bounds__(256)
+k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+           const float* __restrict__ aabb, uint32_t N, float min_near,
+           float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    float nr, fr;
+    near_far_one(rays_o[n * 3], rays_o[n * 3 + 1], rays_o[n * 3 + 2], rays_d[n * 3],
+                 rays_d[n * 3 + 1], rays_d[n * 3 + 2], aabb, min_near, nr, fr);
+    nears[n] = nr;
+    fars[n] = fr;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 sph_from_ray — reference raymarching.cu:163-198 (API compatibility; bg_radius > 0 only)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+               uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float C = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * C)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    coords[n * 2] = 2 * theta * kRPi - 1;
+    coords[n * 2 + 1] = phi * kRPi;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3/K4 Morton — reference raymarching.cu:214-254
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_morton3D(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    indices[n] = (int)morton3D(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+
+__global__ void __launch_bounds__(256)
+k_morton3D_invert(const int* __restrict__ indices, uint32_t N, int* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const int ind = indices[n];  // arithmetic shifts of the signed value, as in the reference
+    coords[n * 3] = (int)morton3D_invert((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int)morton3D_invert((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int)morton3D_invert((uint32_t)(ind >> 2));
+}
+
+// ---------------------------------------------------------------------------------------
+// K5 packbits — reference raymarching.cu:268-289.  One thread packs 4 output bytes from
+// 8 float4 loads (128 contiguous bytes per thread) and stores them with one 32-bit store.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_packbits(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t q = threadIdx.x + blockIdx.x * blockDim.x;  // group of 4 bytes
+    const uint32_t n0 = q * 4;
+    if (n0 >= N) return;
+    const bool vec_ok = (n0 + 4 <= N) && ((((uintptr_t)grid) & 15) == 0) && ((((uintptr_t)bitfield) & 3) == 0);
+    if (vec_ok) {
+        const float4* g4 = reinterpret_cast<const float4*>(grid + (size_t)n0 * 8);
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float4 lo = ld_stream4(g4 + 2 * b), hi = ld_stream4(g4 + 2 * b + 1);
+            uint32_t bits = (lo.x > thresh ? 1u : 0u) | (lo.y > thresh ? 2u : 0u) |
+                            (lo.z > thresh ? 4u : 0u) | (lo.w > thresh ? 8u : 0u) |
+                            (hi.x > thresh ? 16u : 0u) | (hi.y > thresh ? 32u : 0u) |
+                            (hi.z > thresh ? 64u : 0u) | (hi.w > thresh ? 128u : 0u);
+            word |= bits << (8 * b);
+        }
+        *reinterpret_cast<uint32_t*>(bitfield + n0) = word;
+    } else {
+        for (uint32_t n = n0; n < N && n < n0 + 4; ++n) {
+            uint32_t bits = 0;
+            for (int i = 0; i < 8; ++i) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (1u << i) : 0u;
+            bitfield[n] = (uint8_t)bits;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Marching core
+// ---------------------------------------------------------------------------------------
+struct MarchCfg {
+    float bound, dt_gamma, dt_min, dt_max;
+    float rH;    // 1 / (float)H            (raymarching.cu:338)
+    float H3f;   // (float)(H*H*H)          (raymarching.cu:339)
+    float Hf;    // (float)H
+    float Hm1f;  // (float)(H-1)
+    float Cf;    // (float)C
+    double Hd;   // (double)H
+};
+
+__device__ __forceinline__ MarchCfg make_cfg(float bound, float dt_gamma, uint32_t max_steps,
+                                             uint32_t C, uint32_t H) {
+    MarchCfg c;
+    c.bound = bound;
+    c.dt_gamma = dt_gamma;
+    // dt_min = 2*SQRT3()/max_steps ; dt_max = 2*SQRT3()*(1<<(C-1))/H   (raymarching.cu:345-346)
+    const float two_s3 = __fmul_rn(2.0f, kSqrt3);
+    c.dt_min = __fdiv_rn(two_s3, (float)max_steps);
+    c.dt_max = __fdiv_rn(__fmul_rn(two_s3, (float)(1 << (C - 1))), (float)H);
+    c.rH = __fdiv_rn(1.0f, (float)H);
+    c.H3f = (float)(H * H * H);
+    c.Hf = (float)H;
+    c.Hm1f = (float)(H - 1);
+    c.Cf = (float)C;
+    c.Hd = (double)H;
+    return c;
+}
+
+struct RayConst {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float hsx, hsy, hsz;  // 0.5f * signf(d)
+};
+
+__device__ __forceinline__ RayConst load_ray(const float* __restrict__ rays_o,
+                                             const float* __restrict__ rays_d, uint32_t n) {
+    RayConst r;
+    r.ox = rays_o[n * 3]; r.oy = rays_o[n * 3 + 1]; r.oz = rays_o[n * 3 + 2];
+    r.dx = rays_d[n * 3]; r.dy = rays_d[n * 3 + 1]; r.dz = rays_d[n * 3 + 2];
+    r.rdx = __fdiv_rn(1.0f, r.dx); r.rdy = __fdiv_rn(1.0f, r.dy); r.rdz = __fdiv_rn(1.0f, r.dz);
+    r.hsx = __fmul_rn(0.5f, copysignf(1.0f, r.dx));
+    r.hsy = __fmul_rn(0.5f, copysignf(1.0f, r.dy));
+    r.hsz = __fmul_rn(0.5f, copysignf(1.0f, r.dz));
+    return r;
+}
+
+// dt(t) = clamp(t*dt_gamma, dt_min, dt_max)   (raymarching.cu:365,396)
+__device__ __forceinline__ float step_dt(float t, const MarchCfg& c) {
+    return clampf(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
+}
+
+// (int) clamp(0.5 * (p * mip_rbound + 1) * H, 0.0f, (float)(H - 1))   (raymarching.cu:374-376):
+// fp32 FMA, then two fp64 multiplies (the literal 0.5 is a double), rounded to fp32, clamped,
+// truncated.
+__device__ __forceinline__ int grid_coord(float p, float mip_rbound, const MarchCfg& c) {
+    const float v = __fmaf_rn(p, mip_rbound, 1.0f);
+    const double d = __dmul_rn(__dmul_rn(0.5, (double)v), c.Hd);
+    return (int)clampf(__double2float_rn(d), 0.0f, c.Hm1f);
+}
+
+// distance along the ray to the exit face of cell `n` on one axis (raymarching.cu:389-391):
+// (((n + 0.5f + 0.5f*sign(d)) * rH * 2 - 1) * mip_bound - p) * rd
+__device__ __forceinline__ float exit_dist(int n, float hs, float p, float rd, float mip_bound,
+                                           const MarchCfg& c) {
+    const float a = __fadd_rn(__fadd_rn((float)n, 0.5f), hs);
+    const float b = __fmul_rn(a, c.rH);
+    const float e = __fadd_rn(__fmul_rn(b, 2.0f), -1.0f);  // b*2 is exact: FMA or not, same bits
+    const float f = __fmaf_rn(e, mip_bound, -p);
+    return __fmul_rn(f, rd);
+}
+
+struct Point {
+    float x, y, z, dt;
+    float tt;  // skip target when not occupied
+    bool occ;
+};
+
+// One iteration body of the reference loop (raymarching.cu:357-399) evaluated at lattice point t.
+__device__ __forceinline__ Point eval_point(float t, const RayConst& r, const MarchCfg& c,
+                                            const uint8_t* __restrict__ grid) {
+    Point p;
+    p.x = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
+    p.y = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
+    p.z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
+    p.dt = step_dt(t, c);
+
+    // mip_from_pos / mip_from_dt (raymarching.cu:42-54)
+    int ep, ed;
+    frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &ep);
+    const int lp = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ep));
+    const float mxd = __double2float_rn(__dmul_rn((double)__fmul_rn(p.dt, c.Hf), 0.5));
+    frexpf(mxd, &ed);
+    const int ld = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ed));
+    const int level = max(lp, ld);
+
+    const float mip_bound = fminf(scalbnf(1.0f, level), c.bound);
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+
+    const int nx = grid_coord(p.x, mip_rbound, c);
+    const int ny = grid_coord(p.y, mip_rbound, c);
+    const int nz = grid_coord(p.z, mip_rbound, c);
+
+    // index = level * H3 + morton: evaluated in fp32 like the reference (H3 is a float there)
+    const uint32_t m = morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const uint32_t index = (uint32_t)__fmaf_rn((float)level, c.H3f, (float)m);
+    p.occ = (__ldg(grid + (index >> 3)) & (1u << (index & 7u))) != 0;
+
+    const float tx = exit_dist(nx, r.hsx, p.x, r.rdx, mip_bound, c);
+    const float ty = exit_dist(ny, r.hsy, p.y, r.rdy, mip_bound, c);
+    const float tz = exit_dist(nz, r.hsz, p.z, r.rdz, mip_bound, c);
+    p.tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return p;
+}
+
+// Warp-cooperative march of one ray.  Emits (at most `limit`) samples in the exact order and with
+// the exact values of the reference's sequential loop `while (t < far && step < limit)`.
+// When WRITE, sample k goes to row k of xyzs/dirs/deltas (already offset to the ray's first row).
+// Returns the number of samples; t_end receives nothing (inference keeps t via deltas).
+template <bool WRITE>
+__device__ __forceinline__ uint32_t warp_march(const RayConst& r, const MarchCfg& c,
+                                               const uint8_t* __restrict__ grid, float t0, float far,
+                                               uint32_t limit, float* __restrict__ xyzs,
+                                               float* __restrict__ dirs, float* __restrict__ deltas,
+                                               int lane) {
+    float t = t0;                 // first lattice point of the current 32-point window
+    float carry_tt = -INFINITY;   // pending skip target of the last visited, unoccupied point
+    float last_t = t0;            // t after the previous emitted sample (raymarching.cu:424)
+    uint32_t count = 0;
+    const uint32_t lt_mask = lanemask_lt();
+
+    while (t < far && count < limit) {
+        // lattice: t_{k+1} = t_k + dt(t_k), sequential fp32 adds exactly like the reference
+        float my_t = t, tc = t;
+        if (c.dt_gamma == 0.0f) {  // dt(t) == dt_min for every finite t: skip the clamp chain
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k == lane) my_t = tc;
+                tc = __fadd_rn(tc, c.dt_min);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k == lane) my_t = tc;
+                tc = __fadd_rn(tc, step_dt(tc, c));
+            }
+        }
+        const bool inr = my_t < far;
+        Point p;
+        p.occ = false; p.tt = -INFINITY; p.dt = 0.f; p.x = p.y = p.z = 0.f;
+        if (inr) p = eval_point(my_t, r, c, grid);
+
+        // successor of this lattice point if the sequential loop visits it:
+        //   occupied  -> next lattice point
+        //   otherwise -> first lattice point with t >= tt (do { t += dt } while (t < tt))
+        int nxt = lane + 1;
+        // binary search (all lanes participate in the shuffles)
+        {
+            const float key = (inr && !p.occ) ? p.tt : -INFINITY;
+            const float t31 = __shfl_sync(NSIG_FULL_MASK, my_t, 31);
+            int pos = 0;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const float tv = __shfl_sync(NSIG_FULL_MASK, my_t, pos + s - 1);
+                if (tv < key) pos += s;
+            }
+            if (t31 < key) pos = 32;
+            if (inr && !p.occ) nxt = max(lane + 1, pos);
+        }
+
+        // entry point of this window: first lattice point with t >= carry_tt
+        const int entry = __popc(__ballot_sync(NSIG_FULL_MASK, my_t < carry_tt));
+
+        // visited set = orbit of `entry` under nxt; pointer doubling over 5 rounds
+        uint32_t reach = 1u << lane;
+        int jump = nxt;
+#pragma unroll
+        for (int rnd = 0; rnd < 5; ++rnd) {
+            const uint32_t m2 = __shfl_sync(NSIG_FULL_MASK, reach, jump & 31);
+            const int j2 = __shfl_sync(NSIG_FULL_MASK, jump, jump & 31);
+            if (jump < 32) { reach |= m2; jump = j2; }
+        }
+        const uint32_t visited = (entry < 32) ? __shfl_sync(NSIG_FULL_MASK, reach, entry & 31) : 0u;
+        const uint32_t occ_mask = __ballot_sync(NSIG_FULL_MASK, inr && p.occ);
+        const uint32_t emitted = visited & occ_mask;
+
+        if (visited) {
+            const int last = 31 - __clz(visited);
+            const float tt_last = __shfl_sync(NSIG_FULL_MASK, p.tt, last);
+            carry_tt = ((occ_mask >> last) & 1u) ? -INFINITY : tt_last;
+        }
+
+        if (WRITE) {
+            const float tnext = __fadd_rn(my_t, p.dt);
+            const uint32_t before = emitted & lt_mask;
+            const int prev = before ? (31 - __clz(before)) : 0;
+            float lt = __shfl_sync(NSIG_FULL_MASK, tnext, prev);
+            if (!before) lt = last_t;
+            const uint32_t rank = count + __popc(before);
+            if (((emitted >> lane) & 1u) && rank < limit) {
+                float* px = xyzs + (size_t)rank * 3;
+                float* pd = dirs + (size_t)rank * 3;
+                float* pl = deltas + (size_t)rank * 2;
+                px[0] = p.x; px[1] = p.y; px[2] = p.z;
+                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                pl[0] = p.dt;
+                pl[1] = __fsub_rn(tnext, lt);
+            }
+            if (emitted) last_t = __shfl_sync(NSIG_FULL_MASK, tnext, 31 - __clz(emitted));
+        }
+        count = min(limit, count + (uint32_t)__popc(emitted));
+        t = tc;
+    }
+    return count;
+}
+
+// t0 = near + clamp(near*dt_gamma, dt_min, dt_max) * noise   (raymarching.cu:348-351; FMA-contracted)
+__device__ __forceinline__ float perturbed_start(float t, float noise, const MarchCfg& c) {
+    return __fmaf_rn(step_dt(t, c), noise, t);
+}
+
+constexpr int kMarchWarps = 8;  // rays per CTA
+
+// pass 1: per-ray sample counts
+__global__ void __launch_bounds__(kMarchWarps * 32)
+k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
+              uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
+              const float* __restrict__ fars, const float* __restrict__ noises,
+              uint32_t* __restrict__ counts) {
+    const uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
+    const RayConst r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
+    const uint32_t cnt = warp_march<false>(r, c, grid, t0, fars[n], max_steps, nullptr, nullptr, nullptr, lane);
+    if (lane == 0) counts[n] = cnt;
+}
+
+// exclusive scan of counts (single CTA of 1024 threads); updates the global counters the way the
+// reference's atomics do: counter[0] += sum(counts), counter[1] += N.
+__global__ void __launch_bounds__(1024)
+k_march_scan(const uint32_t* __restrict__ counts, uint32_t N, uint32_t* __restrict__ offsets,
+             int* __restrict__ counter) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t running;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = (uint32_t)counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < N; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < N) ? counts[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(NSIG_FULL_MASK, s, d);
+            if (lane >= d) s += o;
+        }
+        if (lane == 31) warp_sums[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(NSIG_FULL_MASK, ws, d);
+                if (lane >= d) ws += o;
+            }
+            warp_sums[lane] = ws;  // inclusive
+        }
+        __syncthreads();
+        const uint32_t warp_excl = (wid == 0) ? 0u : warp_sums[wid - 1];
+        const uint32_t start = running;
+        if (i < N) offsets[i] = start + warp_excl + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) running = start + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counter[0] = (int)running;
+        counter[1] += (int)N;
+    }
+}
+
+// pass 2: write samples and the rays table (id, offset, count)
+__global__ void __launch_bounds__(kMarchWarps * 32)
+k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
+              uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
+              const float* __restrict__ fars, const float* __restrict__ noises,
+              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+              float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+              int* __restrict__ rays) {
+    const uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t num_steps = counts[n], off = offsets[n];
+    if (lane == 0) {
+        rays[n * 3] = (int)n;
+        rays[n * 3 + 1] = (int)off;
+        rays[n * 3 + 2] = (int)num_steps;
+    }
+    if (num_steps == 0) return;
+    if (off + num_steps > M) {
+        // reservation overflow: ray dropped (raymarching.cu:416).  Offsets only grow, so exactly one
+        // dropped ray starts inside the buffer; it clears the tail the reference leaves zero-filled.
+        for (uint32_t i = off + lane; i < M; i += 32) {
+            xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
+            dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
+            deltas[(size_t)i * 2] = deltas[(size_t)i * 2 + 1] = 0.f;
+        }
+        return;
+    }
+    const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
+    const RayConst r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
+    warp_march<true>(r, c, grid, t0, fars[n], num_steps, xyzs + (size_t)off * 3,
+                     dirs + (size_t)off * 3, deltas + (size_t)off * 2, lane);
+}
+
+// zero rows [counter[0], end) with end = min(align_up(counter[0]), M), or M when align == 0
+__global__ void __launch_bounds__(256)
+k_zero_padding(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+               const int* __restrict__ counter, uint32_t align, uint32_t M) {
+    const uint32_t m = (uint32_t)counter[0];
+    uint32_t end = M;
+    if (align) { end = m + align - m % align; if (end > M) end = M; }
+    for (uint32_t i = m + threadIdx.x + blockIdx.x * blockDim.x; i < end; i += blockDim.x * gridDim.x) {
+        xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
+        dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
+        deltas[(size_t)i * 2] = deltas[(size_t)i * 2 + 1] = 0.f;
+    }
+}
+
+// K9 inference march — reference raymarching.cu:701-805
+__global__ void __launch_bounds__(kMarchWarps * 32)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
+             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+             const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+             uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+             const float* __restrict__ nears, const float* __restrict__ fars,
+             float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+             const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+    if (n >= n_alive) return;
+    const int lane = threadIdx.x & 31;
+    const int index = rays_alive[n];
+    const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
+    const RayConst r = load_ray(rays_o, rays_d, (uint32_t)index);
+    const float t0 = perturbed_start(rays_t[index], noises ? noises[n] : 0.0f, c);
+    const size_t row = (size_t)n * n_step;
+    warp_march<true>(r, c, grid, t0, fars[index], n_step, xyzs + row * 3, dirs + row * 3,
+                     deltas + row * 2, lane);
+}
+
+// ---------------------------------------------------------------------------------------
+// K7 composite forward (training) — reference raymarching.cu:501-577, warp per ray
+// ---------------------------------------------------------------------------------------
+constexpr int kCompWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(NSIG_FULL_MASK, v, d);
+    return v;
+}
+// inclusive scans across the warp
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(NSIG_FULL_MASK, v, d);
+        if (lane >= d) v *= o;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(NSIG_FULL_MASK, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                      const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M,
+                      uint32_t N, float T_thresh, float* __restrict__ weights_sum,
+                      float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1],
+                   num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) {
+        if (lane == 0) {
+            weights_sum[index] = 0; depth[index] = 0;
+            image[index * 3] = 0; image[index * 3 + 1] = 0; image[index * 3 + 2] = 0;
+        }
+        return;
+    }
+    float T = 1.0f, t_acc = 0.f;           // transmittance / accumulated real delta before the chunk
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t s = base + lane;
+        const bool valid = s < num_steps;
+        const size_t i = (size_t)offset + s;
+        const float sigma = valid ? sigmas[i] : 0.f;
+        const float2 dl = valid ? *reinterpret_cast<const float2*>(deltas + i * 2) : make_float2(0.f, 0.f);
+        const float alpha = 1.0f - __expf(-sigma * dl.x);
+        const float one_m = valid ? (1.0f - alpha) : 1.0f;
+        const float Tincl = T * warp_scan_mul(one_m, lane);       // T after this sample
+        float Tbefore = __shfl_up_sync(NSIG_FULL_MASK, Tincl, 1);
+        if (lane == 0) Tbefore = T;
+        const float tcum = t_acc + warp_scan_add(dl.y, lane);
+        // the reference accumulates sample k iff every earlier sample left T >= T_thresh
+        const uint32_t dead = __ballot_sync(NSIG_FULL_MASK, valid && (Tincl < T_thresh));
+        const int stop = dead ? (__ffs(dead) - 1) : 32;  // first lane that triggers the break
+        if (valid && lane <= stop) {
+            const float w = alpha * Tbefore;
+            r += w * rgbs[i * 3]; g += w * rgbs[i * 3 + 1]; b += w * rgbs[i * 3 + 2];
+            d += w * tcum;
+            ws += w;
+        }
+        if (dead) break;
+        T = __shfl_sync(NSIG_FULL_MASK, Tincl, 31);
+        t_acc = __shfl_sync(NSIG_FULL_MASK, tcum, 31);
+    }
+    r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    if (lane == 0) {
+        weights_sum[index] = ws; depth[index] = d;
+        image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K8 composite backward (training) — reference raymarching.cu:602-682, warp per ray
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                      const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                      const float* __restrict__ deltas, const int* __restrict__ rays,
+                      const float* __restrict__ weights_sum, const float* __restrict__ image,
+                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas,
+                      float* __restrict__ grad_rgbs) {
+    const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1],
+                   num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+    const float gws = grad_weights_sum[index];
+    const float gr = grad_image[index * 3], gg = grad_image[index * 3 + 1], gb = grad_image[index * 3 + 2];
+    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
+    const float ws_term = gws * (1.0f - weights_sum[index]);
+    float T = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f;  // state before the chunk
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t s = base + lane;
+        const bool valid = s < num_steps;
+        const size_t i = (size_t)offset + s;
+        const float sigma = valid ? sigmas[i] : 0.f;
+        const float d0 = valid ? deltas[i * 2] : 0.f;
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) { cr = rgbs[i * 3]; cg = rgbs[i * 3 + 1]; cb = rgbs[i * 3 + 2]; }
+        const float alpha = 1.0f - __expf(-sigma * d0);
+        const float one_m = valid ? (1.0f - alpha) : 1.0f;
+        const float Tincl = T * warp_scan_mul(one_m, lane);
+        float Tbefore = __shfl_up_sync(NSIG_FULL_MASK, Tincl, 1);
+        if (lane == 0) Tbefore = T;
+        const float w = valid ? alpha * Tbefore : 0.f;
+        const float racc = r0 + warp_scan_add(w * cr, lane);   // inclusive running colour
+        const float gacc = g0 + warp_scan_add(w * cg, lane);
+        const float bacc = b0 + warp_scan_add(w * cb, lane);
+        const uint32_t dead = __ballot_sync(NSIG_FULL_MASK, valid && (Tincl < T_thresh));
+        const int stop = dead ? (__ffs(dead) - 1) : 32;
+        if (valid && lane <= stop) {
+            grad_rgbs[i * 3] = gr * w; grad_rgbs[i * 3 + 1] = gg * w; grad_rgbs[i * 3 + 2] = gb * w;
+            grad_sigmas[i] = d0 * (gr * (Tincl * cr - (r_final - racc)) +
+                                   gg * (Tincl * cg - (g_final - gacc)) +
+                                   gb * (Tincl * cb - (b_final - bacc)) + ws_term);
+        }
+        if (dead) {
+            // samples after the terminating one get zero gradient (the reference relies on the caller's
+            // zero-fill, raymarching.py:283-284; writing them here makes that fill unnecessary)
+            for (uint32_t z = base + stop + 1 + lane; z < num_steps; z += 32) {
+                const size_t zi = (size_t)offset + z;
+                grad_sigmas[zi] = 0.f;
+                grad_rgbs[zi * 3] = 0.f; grad_rgbs[zi * 3 + 1] = 0.f; grad_rgbs[zi * 3 + 2] = 0.f;
+            }
+            break;
+        }
+        T = __shfl_sync(NSIG_FULL_MASK, Tincl, 31);
+        r0 = __shfl_sync(NSIG_FULL_MASK, racc, 31);
+        g0 = __shfl_sync(NSIG_FULL_MASK, gacc, 31);
+        b0 = __shfl_sync(NSIG_FULL_MASK, bacc, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K10 inference composite — reference raymarching.cu:819-905 (n_step <= 8: thread per ray)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restrict__ rays_alive,
+                 float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                 const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                 float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    sigmas += (size_t)n * n_step;
+    rgbs += (size_t)n * n_step * 3;
+    deltas += (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (deltas[0] == 0) break;  // ray ran out of samples
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += deltas[1];
+        d += weight * t;
+        r += weight * rgbs[0]; g += weight * rgbs[1]; b += weight * rgbs[2];
+        if (T < T_thresh) break;
+        sigmas++; rgbs += 3; deltas += 2; step++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else rays_t[index] = t;
+    weights_sum[index] = weight_sum; depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+}  // namespace nsig
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+using namespace nsig;
+
+extern "C" {
+
+int nsig_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                            float min_near, float* nears, float* fars, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NSIG_EINVAL;
+    k_near_far<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                      nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !coords) return NSIG_EINVAL;
+    k_sph_from_ray<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!coords || !indices) return NSIG_EINVAL;
+    k_morton3D<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!coords || !indices) return NSIG_EINVAL;
+    k_morton3D_invert<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                  nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!grid || !bitfield) return NSIG_EINVAL;
+    k_packbits<<<div_up(div_up(N, 4), 256), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t nsig_march_rays_train_scratch_bytes(uint32_t N) { return (size_t)N * 2 * sizeof(uint32_t); }
+
+int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                          uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                          float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                          void* scratch, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !rays ||
+        !counter || !scratch)
+        return NSIG_EINVAL;
+    if (C == 0 || C > 31 || H == 0 || H > 1024 || max_steps == 0) return NSIG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* counts = (uint32_t*)scratch;
+    uint32_t* offsets = counts + N;
+    const uint32_t blocks = div_up(N, kMarchWarps);
+    k_march_count<<<blocks, kMarchWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
+                                                       C, H, nears, fars, noises, counts);
+    NSIG_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, st>>>(counts, N, offsets, counter);
+    NSIG_LAUNCH_CHECK();
+    k_march_write<<<blocks, kMarchWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
+                                                       C, H, M, nears, fars, noises, counts, offsets,
+                                                       xyzs, dirs, deltas, rays);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_zero_sample_padding(float* xyzs, float* dirs, float* deltas, const int32_t* counter,
+                             uint32_t align, uint32_t M, nsig_stream_t stream) {
+    if (!xyzs || !dirs || !deltas || !counter) return NSIG_EINVAL;
+    const uint32_t span = align ? align : M;
+    const uint32_t blocks = div_up(span, 256) < 1184u ? div_up(span, 256) : 1184u;
+    if (blocks == 0) return 0;
+    k_zero_padding<<<blocks, 256, 0, (cudaStream_t)stream>>>(xyzs, dirs, deltas, counter, align, M);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                      const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                      float* weights_sum, float* depth, float* image,
+                                      nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!sigmas || !rgbs || !deltas || !rays || !weights_sum || !depth || !image) return NSIG_EINVAL;
+    k_composite_train_fwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                       const float* sigmas, const float* rgbs, const float* deltas,
+                                       const int32_t* rays, const float* weights_sum, const float* image,
+                                       uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                       float* grad_rgbs, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum ||
+        !image || !grad_sigmas || !grad_rgbs)
+        return NSIG_EINVAL;
+    k_composite_train_bwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh,
+        grad_sigmas, grad_rgbs);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                    const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                    uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                    const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                    nsig_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return 0;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas)
+        return NSIG_EINVAL;
+    if (C == 0 || C > 31 || H == 0 || H > 1024 || max_steps == 0) return NSIG_EINVAL;
+    k_march_rays<<<div_up(n_alive, kMarchWarps), kMarchWarps * 32, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears,
+        fars, xyzs, dirs, deltas, noises);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                        float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                        float* weights_sum, float* depth, float* image, nsig_stream_t stream) {
+    if (n_alive == 0) return 0;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image)
+        return NSIG_EINVAL;
+    k_composite_rays<<<div_up(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+"""Watermark-bit hash encoder with the reference's interface (hash_encoding_wtmk_bit.py:51-116).
+
+The reference evaluates, for every message bit i, a full gather + trilinear interpolation from table
+`2*i + bit_i` and sums the message_dim results.  All "levels" share one resolution
+(base == finest == 2048 at the only call site, nerf/network_wtmk_tcnn.py:43-44), hence
+identical hash slots and weights, so
+    forward(x, message) == trilerp(S)[x],   S = sum_i embeddings[2*i + bit_i].weight
+and d(loss)/d(embeddings[2*i + bit_i].weight) == d(loss)/dS for every selected table.
+This module builds S with one streaming kernel (message read on the device: no .item() per bit) and
+gathers 8 corners per sample instead of 8*message_dim.  Parameters stay 2*message_dim separate
+`embeddings.{i}.weight` tensors, unselected tables keep `grad is None` exactly like the reference.
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib
+from .hash_encoding import _hash_encode, level_resolutions
+
+_P = _lib.ptr
+
+
+def message_bits(message):
+    """Host copy of the bits as a tuple of ints (one D2H transfer; the reference does one per bit)."""
+    if isinstance(message, torch.Tensor):
+        return tuple(int(v) for v in message.detach().to("cpu", torch.float32).tolist())
+    return tuple(int(v) for v in message)
+
+
+class _msg_table_sum(Function):
+    """S = sum_i tables[2i + bit_i]; backward hands dS to every selected table."""
+
+    @staticmethod
+    def forward(ctx, message, bits, log2_T, *tables):
+        md = len(bits)
+        dev = tables[0].device
+        msg = message.to(device=dev, dtype=torch.float32).contiguous()
+        S = torch.empty_like(tables[0])
+        tabs = [t.contiguous() for t in tables]
+        _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S))
+        ctx.bits = bits
+        ctx.n = len(tables)
+        return S
+
+    @staticmethod
+    def backward(ctx, grad_S):
+        grads = [None] * ctx.n
+        for i, b in enumerate(ctx.bits):
+            if ctx.needs_input_grad[3 + 2 * i + b]:
+                grads[2 * i + b] = grad_S
+        return (None, None, None) + tuple(grads)
+
+
+class HashEmbedder(nn.Module):
+    def __init__(self, bounding_box, n_levels=16, n_features_per_level=2,
+                 log2_hashmap_size=19, base_resolution=16, finest_resolution=512, message_dim=16):
+        super(HashEmbedder, self).__init__()
+        if n_features_per_level != 2:
+            raise NotImplementedError("the sm_100a kernels are specialised for 2 features per level")
+        self.bounding_box = bounding_box
+        self.n_levels = n_levels
+        self.n_features_per_level = n_features_per_level
+        self.log2_hashmap_size = log2_hashmap_size
+        self.base_resolution = torch.tensor(base_resolution)
+        self.finest_resolution = torch.tensor(finest_resolution)
+        self.out_dim = self.n_levels * self.n_features_per_level
+
+        self.b = torch.exp((torch.log(self.finest_resolution) - torch.log(self.base_resolution)) / (n_levels - 1))
+        self.message_dim = message_dim
+        if n_levels < 2 * message_dim:
+            raise ValueError("need 2*message_dim tables (embeddings[2*i + bit])")
+        self.embeddings = nn.ModuleList([nn.Embedding(2 ** self.log2_hashmap_size,
+                                                      self.n_features_per_level) for i in range(n_levels)])
+        for i in range(n_levels):
+            nn.init.uniform_(self.embeddings[i].weight, a=-0.0001, b=0.0001)
+        res = level_resolutions(self.base_resolution, self.b, message_dim)
+        if any(r != res[0] for r in res):
+            raise NotImplementedError(
+                "the pre-summed form needs one resolution for every bit (base_resolution == finest_resolution, "
+                "as in nerf/network_wtmk_tcnn.py:43-44)")
+        self.resolution = res[0]
+
+    def tables(self):
+        return [e.weight for e in self.embeddings[:2 * self.message_dim]]
+
+    def summed_table(self, message, bits=None):
+        """S [T,2] (differentiable w.r.t. the selected tables)."""
+        if bits is None:
+            bits = message_bits(message)
+        if len(bits) != self.message_dim:
+            raise ValueError(f"message has {len(bits)} bits, encoder was built for {self.message_dim}")
+        if not isinstance(message, torch.Tensor):
+            message = torch.tensor(bits, dtype=torch.float32)
+        return _msg_table_sum.apply(message, bits, self.log2_hashmap_size, *self.tables())
+
+    def forward(self, x, message):
+        S = self.summed_table(message)
+        return _hash_encode.apply(x, [self.resolution], self.log2_hashmap_size, S)
+
+    @torch.no_grad()
+    def forward_perbit(self, x, message):
+        """The reference's literal per-bit evaluation order (for parity tests)."""
+        x = x.contiguous().float()
+        msg = message.to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty(x.shape[0], 2, dtype=torch.float32, device=x.device)
+        tabs = [t.contiguous() for t in self.tables()]
+        _lib.call("nsig_msg_encode_forward_perbit", _P(x), x.shape[0], _lib.pointer_array(tabs), self.message_dim,
+                  _P(msg), self.resolution, self.log2_hashmap_size, _P(out))
+        return out

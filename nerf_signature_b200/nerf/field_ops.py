@@ -1,0 +1,195 @@
+"""Host side of the fused field kernels (csrc/field.cu): parameter containers that stand in for the
+tiny-cuda-nn modules the reference instantiates, and the autograd functions that launch
+nsig_field_forward / nsig_field_density / nsig_field_backward.
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .. import _lib
+
+_P = _lib.ptr
+
+
+class FusedMLP(nn.Module):
+    """Parameter container replacing `tcnn.Network(otype=FullyFusedMLP, activation=ReLU,
+    output_activation=None, n_neurons=64)` (nerf/network_wtmk_tcnn.py:52-62,78-88).
+
+    `params` is one flat fp32 vector like tcnn's (state-dict key `<name>.params`): the bias-free
+    weight matrices in layer order, each row-major [out, in], with the input width padded to a multiple
+    of 16 and the output width padded to 16.  (tcnn's exact flat layout is not verifiable offline —
+    SURVEY.md 8c; this is the documented layout of this implementation.)  Initialisation is Xavier
+    uniform per matrix, tcnn's default.  The kernels consume an fp16 copy, refreshed when `params`
+    changes; arithmetic is fp16 operands with fp32 accumulation.
+    """
+
+    def __init__(self, n_input_dims, n_output_dims, n_neurons=64, n_hidden_layers=1, seed=1337):
+        super().__init__()
+        if n_neurons != 64:
+            raise NotImplementedError("the fused kernels are specialised for 64 neurons")
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = n_output_dims
+        self.n_neurons = n_neurons
+        self.n_hidden_layers = n_hidden_layers
+        self.padded_input = (n_input_dims + 15) // 16 * 16
+        self.padded_output = (n_output_dims + 15) // 16 * 16
+        shapes = [(n_neurons, self.padded_input)]
+        shapes += [(n_neurons, n_neurons)] * (n_hidden_layers - 1)
+        shapes += [(self.padded_output, n_neurons)]
+        self.shapes = shapes
+        gen = torch.Generator().manual_seed(seed)
+        chunks = []
+        for (fo, fi) in shapes:
+            s = math.sqrt(6.0 / (fi + fo))
+            chunks.append(((torch.rand(fo * fi, generator=gen) * 2 - 1) * s))
+        self.params = nn.Parameter(torch.cat(chunks).float())
+        self._half = None
+        self._half_key = None
+
+    def matrices(self, params=None):
+        """List of [out, in] views of the flat vector (fp32)."""
+        p = self.params if params is None else params
+        out, o = [], 0
+        for (fo, fi) in self.shapes:
+            out.append(p[o:o + fo * fi].view(fo, fi))
+            o += fo * fi
+        return out
+
+    def half_weights(self):
+        key = (self.params.data_ptr(), self.params._version, self.params.device)
+        if self._half is None or self._half_key != key:
+            self._half = self.params.detach().to(torch.float16).contiguous()
+            self._half_key = key
+        return self._half
+
+    def forward(self, x):  # pragma: no cover - the networks call the fused kernels instead
+        raise NotImplementedError("FusedMLP is evaluated inside the fused field kernels; call NeRFNetwork.forward/"
+                                  "density/color")
+
+
+class SHEncoding(nn.Module):
+    """Stands in for `tcnn.Encoding(3, SphericalHarmonics degree 4)` (network_wtmk_tcnn.py:68-74); the
+    16 basis values are computed inside the fused kernels (formulas of hash_encoding.py:162-193)."""
+
+    def __init__(self, n_input_dims=3, degree=4):
+        super().__init__()
+        if n_input_dims != 3 or degree != 4:
+            raise NotImplementedError("SH degree 4 on 3-D directions only")
+        self.n_input_dims = n_input_dims
+        self.degree = degree
+        self.n_output_dims = degree ** 2
+
+
+class FieldConfig:
+    """Everything the field kernels need besides tensors."""
+
+    def __init__(self, bound, resolutions, log2_T, msg_resolution, density_scale=1.0):
+        self.bound = float(bound)
+        self.resolutions = list(resolutions)
+        self.log2_T = int(log2_T)
+        self.msg_resolution = float(msg_resolution)
+        self.density_scale = float(density_scale)
+
+
+class _field_forward(Function):
+    """(sigmas [M], rgbs [M,3]) = field(xyzs, dirs; S, base tables, MLP weights).
+
+    Differentiable w.r.t. S (the pre-summed message table) and, for the clean model, the base tables.
+    MLP weight gradients are not produced here (frozen in watermark training).
+    `count` is an optional device int32 holding the live row count (the march counter).
+    """
+
+    @staticmethod
+    def forward(ctx, xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, *tables):
+        xyzs = xyzs.contiguous().float()
+        dirs = dirs.contiguous().float()
+        M = xyzs.shape[0]
+        dev = xyzs.device
+        sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        need_S = S is not None and ctx.needs_input_grad[2]
+        need_tab = any(ctx.needs_input_grad[7:])
+        if torch.is_grad_enabled() and (sigma_mlp.params.requires_grad or color_mlp.params.requires_grad):
+            raise NotImplementedError(
+                "MLP weight gradients (clean-model training, main_nerf.py) are not implemented in this round: "
+                "freeze sigma_net/color_net (as watermark training does, network_wtmk_tcnn.py:90-95) or run under "
+                "torch.no_grad()")
+        save = need_S or need_tab
+        feat = torch.empty(M, 32, dtype=torch.float16, device=dev) if save else None
+        tabs = [t.contiguous() for t in tables]
+        sw, cw = sigma_mlp.half_weights(), color_mlp.half_weights()
+        Sc = S.contiguous() if S is not None else None
+        _lib.call("nsig_field_forward", _P(xyzs), _P(dirs), M, cfg.bound, _lib.pointer_array(tabs),
+                  _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc), cfg.msg_resolution, _P(sw), _P(cw),
+                  cfg.density_scale, _P(count), _P(sigmas), _P(rgbs), _P(feat))
+        if save:
+            ctx.save_for_backward(xyzs, dirs, feat, sw, cw)
+            ctx.cfg = cfg
+            ctx.count = count
+            ctx.S_shape = tuple(S.shape) if S is not None else None
+            ctx.tab_shapes = [tuple(t.shape) for t in tables]
+        ctx.has_graph = save
+        return sigmas, rgbs
+
+    @staticmethod
+    def backward(ctx, grad_sigmas, grad_rgbs):
+        n_in = 7 + len(getattr(ctx, "tab_shapes", []))
+        if not ctx.has_graph:
+            return (None,) * n_in
+        xyzs, dirs, feat, sw, cw = ctx.saved_tensors
+        cfg = ctx.cfg
+        M = xyzs.shape[0]
+        dev = xyzs.device
+        grad_sigmas = grad_sigmas.contiguous().float()
+        grad_rgbs = grad_rgbs.contiguous().float()
+        need_S = ctx.S_shape is not None and ctx.needs_input_grad[2]
+        need_tab = ctx.needs_input_grad[7:]
+        G = torch.zeros(ctx.S_shape, dtype=torch.float32, device=dev) if need_S else None
+        # rows past the live count are not written by the kernel: start from zeros in that case
+        alloc = torch.zeros if ctx.count is not None else torch.empty
+        grad_feat = alloc(M, 32, dtype=torch.float32, device=dev) if any(need_tab) else None
+        _lib.call("nsig_field_backward", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
+                  _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G),
+                  _P(grad_feat), None, None)
+        tab_grads = [None] * len(ctx.tab_shapes)
+        if any(need_tab):
+            xn = (xyzs + cfg.bound) * (1.0 / (2.0 * cfg.bound))  # network_wtmk_tcnn.py:101
+            gt = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.tab_shapes]
+            _lib.call("nsig_hash_encode_backward", _P(xn.contiguous()), _P(grad_feat.contiguous()), M,
+                      _lib.pointer_array(gt), _lib.float_array(cfg.resolutions), len(gt), cfg.log2_T)
+            tab_grads = [g if n else None for g, n in zip(gt, need_tab)]
+        return (None, None, G, None, None, None, None) + tuple(tab_grads)
+
+
+def field_forward(xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, tables):
+    return _field_forward.apply(xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, *tables)
+
+
+@torch.no_grad()
+def field_density(xyzs, S, cfg, sigma_mlp, tables, want_geo=True):
+    """sigma [M] fp32 (and geo_feat [M,15] fp16) — NeRFNetwork.density, no gradient (it is only used by
+    update_extra_state and the non-cuda_ray renderer's sampling passes)."""
+    xyzs = xyzs.contiguous().float()
+    M = xyzs.shape[0]
+    dev = xyzs.device
+    sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+    geo = torch.empty(M, 15, dtype=torch.float16, device=dev) if want_geo else None
+    tabs = [t.contiguous() for t in tables]
+    Sc = S.contiguous() if S is not None else None
+    _lib.call("nsig_field_density", _P(xyzs), M, cfg.bound, _lib.pointer_array(tabs), _lib.float_array(cfg.resolutions),
+              cfg.log2_T, _P(Sc), cfg.msg_resolution, _P(sigma_mlp.half_weights()), cfg.density_scale, _P(sigmas),
+              _P(geo))
+    return sigmas, geo
+
+
+@torch.no_grad()
+def color_forward(dirs, geo_feat, color_mlp):
+    """rgb [M,3] fp32 from view directions and geo features (NeRFNetwork.color)."""
+    dirs = dirs.contiguous().float()
+    geo = geo_feat.contiguous().to(torch.float16)
+    M = dirs.shape[0]
+    rgbs = torch.empty(M, 3, dtype=torch.float32, device=dirs.device)
+    _lib.call("nsig_color_forward", _P(dirs), _P(geo), M, _P(color_mlp.half_weights()), _P(rgbs))
+    return rgbs

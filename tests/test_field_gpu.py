@@ -1,0 +1,103 @@
+"""-m gpu parity tests of the fused field kernels (NeRFNetwork.forward / density / color and the
+watermark-mode backward) against oracle/hash_oracle.c (features) + oracle/field_oracle.py (torch fp32
+restatement of the tcnn part).  Tolerances (MLP parity is unpinned): fp16 operands with fp32
+accumulation on both sides -> sigma 2e-3 relative, rgb 2e-3 absolute, table gradients 1e-2 of their max
+(fp16 gradient activations, per-row power-of-two scaled)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _points(M, bound, seed):
+    rs = np.random.RandomState(seed)
+    o = rs.uniform(-0.6 * bound, 0.6 * bound, size=(M // 50 + 1, 1, 3))
+    d = rs.normal(size=(M // 50 + 1, 1, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    t = np.arange(50).reshape(1, -1, 1) * 0.0034 * bound
+    x = np.clip(o + d * t, -bound, bound).reshape(-1, 3)[:M].astype(np.float32)
+    dirs = np.broadcast_to(d, (M // 50 + 1, 50, 3)).reshape(-1, 3)[:M].astype(np.float32)
+    x[0] = bound; x[1] = -bound; x[2] = 0.0
+    return x, np.ascontiguousarray(dirs)
+
+
+def _net(bound, md, scale_tables=300.0, seed=0):
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+    torch.manual_seed(seed)
+    net = NeRFNetwork(bound=bound, cuda_ray=True, message_dim=md)
+    with torch.no_grad():  # make features O(0.03) so that the MLP output is not trivially constant
+        for e in list(net.encoder.embeddings) + list(net.msg_encoder.embeddings):
+            e.weight.mul_(scale_tables)
+    return net.cuda()
+
+
+def _oracle_forward(net, x, dirs, msg, oracle_cpu, density_scale=1.0):
+    from oracle import field_oracle as fo
+    bound = float(net.bound)
+    xn = ((x + np.float32(bound)) * np.float32(1.0 / (2.0 * bound))).astype(np.float32)
+    tabs = [e.weight.detach().cpu().numpy() for e in net.encoder.embeddings]
+    feat = oracle_cpu.hash_encode_forward(xn, tabs, net.encoder.resolutions, 19)
+    if msg is not None:
+        mt = [e.weight.detach().cpu().numpy() for e in net.msg_encoder.embeddings]
+        feat[:, 30:32] += oracle_cpu.msg_encode_forward(xn, mt, msg, net.msg_encoder.resolution, 19)
+    featt = torch.from_numpy(feat).requires_grad_(True)
+    sigma, rgb, logit, geo = fo.mlp_forward(featt, torch.from_numpy(dirs), net.sigma_net.params.detach().cpu(),
+                                            net.color_net.params.detach().cpu(), density_scale)
+    return xn, featt, sigma, rgb, geo
+
+
+@pytest.mark.parametrize("bound,md,M", [(1.0, 32, 5000), (2.0, 48, 3001), (1.0, 4, 97)])
+def test_field_forward_and_density(oracle_cpu, bound, md, M):
+    net = _net(bound, md)
+    x, dirs = _points(M, bound, 1)
+    msg = np.random.RandomState(2).randint(0, 2, size=md).astype(np.float32)
+    xt, dt, mt = torch.from_numpy(x).cuda(), torch.from_numpy(dirs).cuda(), torch.from_numpy(msg).cuda()
+    with torch.no_grad():
+        sigma, rgb = net(xt, dt, mt)
+        sigma0, rgb0 = net(xt, dt, None)
+        dens = net.density(xt, mt)
+        col = net.color(xt, dt, geo_feat=dens["geo_feat"])
+        mask = torch.zeros(M, dtype=torch.bool, device="cuda"); mask[::3] = True
+        colm = net.color(xt, dt, mask=mask, geo_feat=dens["geo_feat"])
+    for m_, (s_, c_) in ((msg, (sigma, rgb)), (None, (sigma0, rgb0))):
+        _, _, osig, orgb, ogeo = _oracle_forward(net, x, dirs, m_, oracle_cpu)
+        np.testing.assert_allclose(s_.cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
+        np.testing.assert_allclose(c_.cpu().numpy(), orgb.detach().numpy(), rtol=0, atol=2e-3)
+    assert float((sigma - sigma0).abs().max()) > 0  # the message does change the field
+    _, _, osig, orgb, ogeo = _oracle_forward(net, x, dirs, msg, oracle_cpu)
+    np.testing.assert_allclose(dens["sigma"].cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(dens["geo_feat"].float().cpu().numpy(), ogeo.detach().numpy(), rtol=0, atol=3e-3)
+    np.testing.assert_allclose(col.cpu().numpy(), rgb.cpu().numpy(), rtol=0, atol=1e-5)
+    assert torch.equal(colm[mask], col[mask]) and float(colm[~mask].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("bound,md,M", [(1.0, 32, 4000), (2.0, 8, 1500)])
+def test_field_backward_message_tables(oracle_cpu, bound, md, M):
+    net = _net(bound, md)
+    net.density_scale = 1.0
+    x, dirs = _points(M, bound, 3)
+    rs = np.random.RandomState(4)
+    msg = rs.randint(0, 2, size=md).astype(np.float32)
+    gs = (rs.normal(size=M) * np.exp(rs.normal(0, 3, size=M))).astype(np.float32)   # wide dynamic range
+    gc = (rs.normal(size=(M, 3)) * np.exp(rs.normal(0, 3, size=(M, 1)))).astype(np.float32)
+    gs[::7] = 0; gc[::7] = 0   # samples after early termination receive exactly zero
+    xt, dt, mt = torch.from_numpy(x).cuda(), torch.from_numpy(dirs).cuda(), torch.from_numpy(msg).cuda()
+    sigma, rgb = net(xt, dt, mt)
+    ((sigma * torch.from_numpy(gs).cuda()).sum() + (rgb * torch.from_numpy(gc).cuda()).sum()).backward()
+    # oracle gradient wrt the encoder output, channels 30:32, scattered into G
+    xn, featt, osig, orgb, _ = _oracle_forward(net, x, dirs, msg, oracle_cpu)
+    ((osig * torch.from_numpy(gs)).sum() + (orgb * torch.from_numpy(gc)).sum()).backward()
+    G = oracle_cpu.msg_encode_backward(xn, featt.grad[:, 30:32].numpy(), net.msg_encoder.resolution, 19)
+    gmax = np.abs(G).max()
+    assert gmax > 0
+    for i in range(md):
+        sel = net.msg_encoder.embeddings[2 * i + int(msg[i])].weight
+        uns = net.msg_encoder.embeddings[2 * i + 1 - int(msg[i])].weight
+        assert uns.grad is None
+        np.testing.assert_allclose(sel.grad.cpu().numpy(), G, rtol=0, atol=1e-2 * gmax)
+    got = net.msg_encoder.embeddings[int(msg[0])].weight.grad.cpu().numpy()
+    rel_l2 = np.linalg.norm(got - G) / np.linalg.norm(G)
+    assert rel_l2 < 5e-3, rel_l2
+    # frozen parts stay grad-free
+    assert all(e.weight.grad is None for e in net.encoder.embeddings)
+    assert net.sigma_net.params.grad is None and net.color_net.params.grad is None

@@ -1,0 +1,302 @@
+"""-m gpu parity tests for the raymarching kernels, called through the drop-in Python API
+(nerf_signature_b200.raymarching -> ctypes -> C ABI), against
+  (1) the C oracle (oracle/raymarch_oracle.c) and
+  (2) the UNMODIFIED reference CUDA extension built into oracle/_ref/ (when it travelled with the snapshot).
+Integer outputs (ray sample counts, offsets in canonical order, Morton codes, occupancy bits) and every
+float the march emits must be BIT-EXACT; composite outputs within 1e-5 relative (fast-math exp,
+scan-ordered products; north_star allows 1e-3).
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from nerf_signature_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rm():
+    from nerf_signature_b200 import raymarching
+    return raymarching
+
+
+@pytest.fixture(scope="module")
+def ref_cuda():
+    """The reference's own `_raymarching` pybind module, or None."""
+    so = os.path.join(ROOT, "oracle", "_ref", "_raymarching.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("_raymarching", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+CASES = [
+    # name, rays fn, bound, C, grid kind, dt_gamma, perturb
+    ("blender_sphere", syn.blender_rays, 1.0, 1, "sphere", 0.0, False),
+    ("blender_bernoulli", syn.blender_rays, 1.0, 1, "bernoulli", 0.0, False),
+    ("blender_perturb_gamma", syn.blender_rays, 1.0, 1, "bernoulli", 1.0 / 128, True),
+    ("360_sphere", syn.rays_360, 2.0, 2, "sphere", 0.0, False),
+    ("360_bernoulli_gamma", syn.rays_360, 2.0, 2, "bernoulli", 1.0 / 128, True),
+    ("bound1p5_bernoulli", syn.rays_360, 1.5, 2, "bernoulli", 0.0, True),   # non power-of-two bound: FMA contraction matters
+    ("bound4_bernoulli", syn.rays_360, 4.0, 3, "bernoulli", 1.0 / 256, False),
+]
+
+
+def make_case(case, n_rays=1024, seed=3):
+    name, rays_fn, bound, C, kind, dt_gamma, perturb = case
+    rays_o, rays_d = rays_fn(n_rays, seed=seed)
+    if kind == "sphere":
+        grid = syn.sphere_grid(C)
+    else:
+        grid = syn.bernoulli_grid(C, p=0.3, seed=seed)
+    bitfield = syn.packbits_np(grid, 0.5)
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    noises = np.random.RandomState(seed + 1).uniform(size=n_rays).astype(np.float32) if perturb else None
+    return rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises
+
+
+def canon(xyzs, dirs, deltas, rays):
+    """canonical form: per-ray count + the ray's sample rows, in ray-id order."""
+    rays = rays[np.argsort(rays[:, 0], kind="stable")]
+    out = []
+    for rid, off, cnt in rays:
+        out.append((int(rid), int(cnt), xyzs[off:off + cnt], dirs[off:off + cnt], deltas[off:off + cnt]))
+    return out
+
+
+def test_near_far_bit_exact(rm, oracle_cpu, ref_cuda):
+    for case in CASES:
+        rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(case, 4096)
+        # add rays that miss the box and axis-parallel rays (division by zero paths)
+        rays_d[:8] = np.array([0, 0, 1], np.float32)
+        rays_o[:4] = np.array([5, 5, -3], np.float32)
+        nears, fars = rm.near_far_from_aabb(cu(rays_o), cu(rays_d), cu(aabb), 0.2)
+        on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+        assert np.array_equal(nears.cpu().numpy().view(np.uint32), on.view(np.uint32)), case[0]
+        assert np.array_equal(fars.cpu().numpy().view(np.uint32), of.view(np.uint32)), case[0]
+        if ref_cuda is not None:
+            rn = torch.empty_like(nears); rf = torch.empty_like(fars)
+            ref_cuda.near_far_from_aabb(cu(rays_o), cu(rays_d), cu(aabb), rays_o.shape[0], 0.2, rn, rf)
+            assert torch.equal(rn.view(torch.int32), nears.view(torch.int32))
+            assert torch.equal(rf.view(torch.int32), fars.view(torch.int32))
+
+
+def test_morton_and_packbits(rm, oracle_cpu, ref_cuda):
+    rs = np.random.RandomState(0)
+    coords = rs.randint(0, 128, size=(100003, 3)).astype(np.int32)
+    idx = rm.morton3D(cu(coords))
+    assert np.array_equal(idx.cpu().numpy(), oracle_cpu.morton3D(coords))
+    back = rm.morton3D_invert(idx)
+    assert np.array_equal(back.cpu().numpy(), coords)
+    assert np.array_equal(back.cpu().numpy(), oracle_cpu.morton3D_invert(idx.cpu().numpy()))
+    for C in (1, 2):
+        grid = rs.uniform(-1, 1, size=(C, 128 ** 3)).astype(np.float32)
+        grid[0, :64] = 0.25  # values equal to the threshold are NOT set (strict >)
+        bits = rm.packbits(cu(grid), 0.25)
+        assert bits.dtype == torch.uint8 and bits.shape[0] == C * 128 ** 3 // 8
+        assert np.array_equal(bits.cpu().numpy(), oracle_cpu.packbits(grid, 0.25))
+        assert np.array_equal(bits.cpu().numpy(), syn.packbits_np(grid, 0.25))
+        # in-place variant reuses the passed buffer (renderer_wtmk.py:530)
+        buf = torch.zeros_like(bits)
+        out = rm.packbits(cu(grid), 0.25, buf)
+        assert out.data_ptr() == buf.data_ptr() and torch.equal(out, bits)
+        if ref_cuda is not None:
+            rb = torch.empty_like(bits)
+            ref_cuda.packbits(cu(grid), bits.shape[0], 0.25, rb)
+            assert torch.equal(rb, bits)
+    # ragged size: N not a multiple of 4 bytes
+    g = rs.uniform(size=(1, 8 * 13)).astype(np.float32)
+    assert np.array_equal(rm.packbits(cu(g), 0.5).cpu().numpy(), syn.packbits_np(g, 0.5))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_march_rays_train_bit_exact(rm, oracle_cpu, ref_cuda, case):
+    rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(case)
+    N = rays_o.shape[0]
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    oxyz, odir, odel, orays, ocnt = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield, C, 128, on, of,
+                                                                noises=noises, dt_gamma=dt_gamma)
+    # C ABI directly so the same noise vector can be injected
+    from nerf_signature_b200 import _lib
+    from nerf_signature_b200.raymarching.raymarching import _scratch
+    P = _lib.ptr
+    M = N * 1024
+    xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+    rays = torch.empty(N, 3, dtype=torch.int32, device="cuda")
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    tn = cu(noises) if noises is not None else None
+    t_o, t_d, t_b, t_n, t_f = cu(rays_o), cu(rays_d), cu(bitfield), cu(on), cu(of)
+    _lib.call("nsig_march_rays_train", P(t_o), P(t_d), P(t_b), bound, dt_gamma, 1024, N, C, 128, M, P(t_n), P(t_f),
+              P(xyzs), P(dirs), P(deltas), P(rays), P(counter), P(tn), P(_scratch(N, "cuda")))
+    torch.cuda.synchronize()
+    cnt = counter.cpu().numpy()
+    assert cnt[0] == ocnt[0] and cnt[1] == N
+    assert cnt[0] > 0
+    r = rays.cpu().numpy()
+    assert np.array_equal(r, orays)  # deterministic ray-order layout == the oracle's sequential order
+    m = int(cnt[0])
+    for got, want in ((xyzs, oxyz), (dirs, odir), (deltas, odel)):
+        assert np.array_equal(got[:m].cpu().numpy().view(np.uint32), want[:m].view(np.uint32))
+    assert float(xyzs[m:].abs().sum()) == 0.0  # rows past the count untouched
+
+    if ref_cuda is not None:  # the real thing, canonical-form comparison (atomic order differs)
+        rx = torch.zeros(M, 3, device="cuda"); rd = torch.zeros(M, 3, device="cuda"); rl = torch.zeros(M, 2, device="cuda")
+        rr = torch.empty(N, 3, dtype=torch.int32, device="cuda")
+        rc = torch.zeros(2, dtype=torch.int32, device="cuda")
+        rn = tn if tn is not None else torch.zeros(N, device="cuda")
+        ref_cuda.march_rays_train(t_o, t_d, t_b, bound, dt_gamma, 1024, N, C, 128, M, t_n, t_f, rx, rd, rl, rr, rc, rn)
+        torch.cuda.synchronize()
+        assert torch.equal(rc, counter)
+        a = canon(xyzs.cpu().numpy(), dirs.cpu().numpy(), deltas.cpu().numpy(), r)
+        b = canon(rx.cpu().numpy(), rd.cpu().numpy(), rl.cpu().numpy(), rr.cpu().numpy())
+        for (ia, ca, xa, da, la), (ib, cb, xb, db, lb) in zip(a, b):
+            assert ia == ib and ca == cb
+            assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
+            assert np.array_equal(da.view(np.uint32), db.view(np.uint32))
+            assert np.array_equal(la.view(np.uint32), lb.view(np.uint32))
+
+
+def test_march_rays_train_api_shapes_and_overflow(rm, oracle_cpu):
+    case = CASES[1]
+    rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(case, 512)
+    t_o, t_d, t_b = cu(rays_o), cu(rays_d), cu(bitfield)
+    nears, fars = rm.near_far_from_aabb(t_o, t_d, cu(aabb), 0.2)
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    xyzs, dirs, deltas, rays = rm.march_rays_train(t_o, t_d, bound, t_b, C, 128, nears, fars, counter, -1, False, 128, True, dt_gamma, 1024)
+    m = int(counter[0])
+    assert xyzs.shape[0] == m + 128 - m % 128 and xyzs.shape[0] % 128 == 0  # raymarching.py:224-229
+    assert dirs.shape == xyzs.shape and deltas.shape == (xyzs.shape[0], 2) and rays.shape == (512, 3)
+    assert float(xyzs[m:].abs().sum()) == 0 and float(deltas[m:].abs().sum()) == 0
+    # mean_count mode: fixed M, rays that do not fit are dropped, tail rows are zero
+    counter2 = torch.zeros(2, dtype=torch.int32, device="cuda")
+    mean_count = m // 2
+    x2, d2, l2, r2 = rm.march_rays_train(t_o, t_d, bound, t_b, C, 128, nears, fars, counter2, mean_count, False, 128, False, dt_gamma, 1024)
+    Mcap = mean_count + 128 - mean_count % 128
+    assert x2.shape[0] == Mcap
+    assert int(counter2[0]) == m  # the counter still counts every ray (raymarching.cu:405)
+    r2 = r2.cpu().numpy()
+    assert np.array_equal(r2, rays.cpu().numpy())
+    kept = r2[(r2[:, 1] + r2[:, 2] <= Mcap) & (r2[:, 2] > 0)]
+    end = int((kept[:, 1] + kept[:, 2]).max())
+    assert torch.equal(x2[:end], xyzs[:end])
+    assert float(x2[end:].abs().sum()) == 0 and float(l2[end:].abs().sum()) == 0
+    # empty input
+    e = torch.zeros(0, 3, device="cuda")
+    n0, f0 = rm.near_far_from_aabb(e, e, cu(aabb), 0.2)
+    assert n0.shape == (0,)
+
+
+def _random_field(M, seed):
+    rs = np.random.RandomState(seed)
+    sigmas = np.exp(rs.normal(0.0, 2.0, size=M)).astype(np.float32)
+    rgbs = rs.uniform(size=(M, 3)).astype(np.float32)
+    return sigmas, rgbs
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[3], CASES[4]], ids=["blender", "360", "360_gamma"])
+def test_composite_train_forward_backward(rm, oracle_cpu, ref_cuda, case):
+    rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(case, 768)
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    oxyz, odir, odel, orays, ocnt = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield, C, 128, on, of,
+                                                                noises=noises, dt_gamma=dt_gamma)
+    m = int(ocnt[0]); M = m + 128 - m % 128
+    sig, rgb = _random_field(M, 5)
+    # make some rays opaque early so that early termination triggers
+    sig[: m // 3] *= 50
+    deltas = odel[:M]
+    for T_thresh in (1e-4, 1e-2):
+        ows, odepth, oimg = oracle_cpu.composite_rays_train_forward(sig, rgb, deltas, orays, T_thresh)
+        ts, tc = cu(sig).requires_grad_(True), cu(rgb).requires_grad_(True)
+        ws, depth, img = rm.composite_rays_train(ts, tc, cu(deltas), cu(orays), T_thresh)
+        for got, want in ((ws, ows), (depth, odepth), (img, oimg)):
+            np.testing.assert_allclose(got.detach().cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+        rs = np.random.RandomState(9)
+        gws = rs.normal(size=ows.shape).astype(np.float32)
+        gimg = rs.normal(size=oimg.shape).astype(np.float32)
+        (ws * cu(gws)).sum().add((img * cu(gimg)).sum()).backward()
+        ogs, ogc = oracle_cpu.composite_rays_train_backward(gws, gimg, sig, rgb, deltas, orays, ows, oimg, T_thresh)
+        scale = np.abs(ogs).max()
+        np.testing.assert_allclose(ts.grad.cpu().numpy(), ogs, rtol=1e-3, atol=1e-5 * scale)
+        np.testing.assert_allclose(tc.grad.cpu().numpy(), ogc, rtol=1e-4, atol=1e-6)
+        # zeros after termination / on padding rows, like the reference's zero-filled buffers
+        assert np.array_equal(ts.grad.cpu().numpy() == 0, ogs == 0)
+        if ref_cuda is not None:
+            N = orays.shape[0]
+            rw = torch.empty(N, device="cuda"); rdp = torch.empty(N, device="cuda"); ri = torch.empty(N, 3, device="cuda")
+            ref_cuda.composite_rays_train_forward(cu(sig), cu(rgb), cu(deltas), cu(orays), M, N, T_thresh, rw, rdp, ri)
+            torch.testing.assert_close(ws.detach(), rw, rtol=2e-5, atol=2e-6)
+            torch.testing.assert_close(img.detach(), ri, rtol=2e-5, atol=2e-6)
+            torch.testing.assert_close(depth.detach(), rdp, rtol=2e-5, atol=2e-6)
+            rgs = torch.zeros(M, device="cuda"); rgc = torch.zeros(M, 3, device="cuda")
+            ref_cuda.composite_rays_train_backward(cu(gws), cu(gimg), cu(sig), cu(rgb), cu(deltas), cu(orays), rw, ri, M, N,
+                                                   T_thresh, rgs, rgc)
+            torch.testing.assert_close(ts.grad, rgs, rtol=1e-3, atol=1e-5 * float(scale))
+            torch.testing.assert_close(tc.grad, rgc, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[4]], ids=["blender", "blender_gamma", "360_gamma"])
+def test_inference_loop_matches_oracle(rm, oracle_cpu, ref_cuda, case):
+    """Drive the reference's alive-ray loop (renderer_wtmk.py:336-367) with both implementations."""
+    rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(case, 600)
+    N = rays_o.shape[0]
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    t_o, t_d, t_b, t_n, t_f = cu(rays_o), cu(rays_d), cu(bitfield), cu(on), cu(of)
+
+    def field(xyz):  # deterministic stand-in for the network
+        s = 20.0 * np.abs(np.sin(7 * xyz[:, 0]) * np.cos(5 * xyz[:, 1])).astype(np.float32)
+        c = (0.5 + 0.5 * np.sin(xyz * 3)).astype(np.float32)
+        return s, c
+
+    # oracle loop
+    ws_o = np.zeros(N, np.float32); dp_o = np.zeros(N, np.float32); im_o = np.zeros((N, 3), np.float32)
+    alive_o = np.arange(N, dtype=np.int32); t_or = on.copy()
+    ws = torch.zeros(N, device="cuda"); dp = torch.zeros(N, device="cuda"); im = torch.zeros(N, 3, device="cuda")
+    alive = torch.arange(N, dtype=torch.int32, device="cuda"); rt = t_n.clone()
+    step = 0
+    while step < 1024:
+        n_alive = alive_o.shape[0]
+        assert alive.shape[0] == n_alive
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        xo, do, lo = oracle_cpu.march_rays(n_alive, n_step, alive_o, t_or, rays_o, rays_d, bound, bitfield, C, 128, on, of,
+                                           align=128, dt_gamma=dt_gamma)
+        xg, dg, lg = rm.march_rays(n_alive, n_step, alive, rt, t_o, t_d, bound, t_b, C, 128, t_n, t_f, 128, False, dt_gamma, 1024)
+        assert np.array_equal(xg.cpu().numpy().view(np.uint32), xo.view(np.uint32))
+        assert np.array_equal(dg.cpu().numpy().view(np.uint32), do.view(np.uint32))
+        assert np.array_equal(lg.cpu().numpy().view(np.uint32), lo.view(np.uint32))
+        if ref_cuda is not None and step < 64:
+            rx = torch.zeros_like(xg); rd = torch.zeros_like(dg); rl = torch.zeros_like(lg)
+            ref_cuda.march_rays(n_alive, n_step, alive, rt, t_o, t_d, bound, dt_gamma, 1024, C, 128, t_b, t_n, t_f, rx, rd, rl,
+                                torch.zeros(n_alive, device="cuda"))
+            assert torch.equal(rx.view(torch.int32), xg.view(torch.int32))
+            assert torch.equal(rl.view(torch.int32), lg.view(torch.int32))
+        s, c = field(xo)
+        oracle_cpu.composite_rays(n_alive, n_step, alive_o, t_or, s, c, lo, ws_o, dp_o, im_o, 1e-4)
+        rm.composite_rays(n_alive, n_step, alive, rt, cu(s), cu(c), lg, ws, dp, im, 1e-4)
+        # kill flags must be identical; when a T<thresh decision flips on rounding the loops would diverge
+        assert np.array_equal(alive.cpu().numpy(), alive_o)
+        alive_o = alive_o[alive_o >= 0]
+        alive = alive[alive >= 0]
+        step += n_step
+    np.testing.assert_allclose(ws.cpu().numpy(), ws_o, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(im.cpu().numpy(), im_o, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dp.cpu().numpy(), dp_o, rtol=1e-4, atol=1e-5)
+
+
+def test_sph_from_ray(rm, oracle_cpu):
+    rays_o, rays_d = syn.blender_rays(1000, seed=2, scale=0.3)
+    c = rm.sph_from_ray(cu(rays_o), cu(rays_d), 4.0)
+    np.testing.assert_allclose(c.cpu().numpy(), oracle_cpu.sph_from_ray(rays_o, rays_d, 4.0), rtol=1e-4, atol=1e-5)
