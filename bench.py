@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ray-batch render/train hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+A "step" is one watermark training step (utils_wtmk_disen.py:1164-1181): fresh random message, watermark
+render pass over message_dim image blocks + content render pass over num_rays rays (both forward and
+backward), HiDDeN decoder, losses, Adam.  metric = rays rendered (and back-propagated) per second, whole job.
+N=1 workload = BASELINE.json configs[1] ("blender_wtmk").  For N>1 (torchrun) every rank runs the same
+per-GPU batch on its own rays and gradients are all-reduced once per step: weak scaling.
+
+`--impl reference` times the oracle port of the reference's pure-PyTorch CPU path (oracle/torch_port.py)
+on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train rays/s (fwd+bwd)"
+UNIT = "rays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="blender_wtmk")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
+    ap.add_argument("--cpu-rays", type=int, default=0, help="override the CPU sample size (rays per pass)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU port (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_run(cfg, steps, warmup, rays_per_pass, num_steps=512):
+    """Time the oracle port of the reference CPU path on a bounded sample: `rays_per_pass` content rays +
+    as many watermark-block rays (message_dim blocks of pH x pW pixels, pH*pW*md ~ rays_per_pass)."""
+    import numpy as np
+    import torch
+    from nerf_signature_b200 import harness
+    from nerf_signature_b200.nerf.hidden_models import get_hidden_decoder_multi_views
+    from oracle import torch_port as tp
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    md = cfg["message_dim"]
+    px = max(1, int(round((rays_per_pass / md) ** 0.5)))
+    sub = dict(cfg)
+    sub["H"], sub["W"] = px * cfg["num_rows"], px * cfg["num_cols"]   # pH = pW = px
+    batch = {k: torch.from_numpy(v) for k, v in harness.make_batch(sub, seed=123, num_rays=rays_per_pass).items()}
+    batch["rays_o"], batch["rays_d"], batch["gt"] = batch["rays_o"][0], batch["rays_d"][0], batch["gt"][0]
+    field = tp.PortField(bound=cfg["bound"], message_dim=md, seed=0)
+    torch.manual_seed(0)
+    decoder = get_hidden_decoder_multi_views(num_bits=1, redundancy=1, num_blocks=8, input_ch=3, channels=64)
+    params = [t for t in field.msg_tables] + list(decoder.parameters())
+    opt = torch.optim.Adam(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    n_rays = rays_per_pass + md * px * px
+    gen = torch.Generator().manual_seed(1)
+    times = []
+    for it in range(warmup + steps):
+        message = torch.randint(0, 2, (md,), generator=gen).float()
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        tp.train_step(field, decoder, batch, message, num_steps=num_steps)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": n_rays * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{rays_per_pass} content + {md}x{px}x{px} watermark-block rays per step, {num_steps} uniform "
+                      f"samples/ray (non-cuda_ray NeRFRenderer.run), {len(times)} timed steps, torch {cores} threads",
+            "ms_per_step": 1e3 * total / len(times), "rays_per_step": n_rays}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nerf_signature_b200 import harness
+    cfg = harness.CONFIGS[args.config]
+    rays = args.cpu_rays or 16
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    # keep the whole run within minutes: ~1.5 s per step at 16+32 rays on 8 cores
+    steps = min(steps, 40)
+    r = cpu_port_run(cfg, steps, warmup, rays)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.config, **{k: cfg[k] for k in ("bound", "message_dim", "num_rays", "dt_gamma")},
+                       "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nerf_signature_b200 has no CPU path "
+                         "(use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nerf_signature_b200 import _build, _lib, harness
+    if rank == 0 and _build.is_stale():
+        _build.build_library()
+    if world > 1:
+        dist.barrier()
+    cfg = dict(harness.CONFIGS[args.config])
+    if args.config.startswith("shard"):
+        cfg["num_rays"] = cfg["num_rays"] // world
+    scene = harness.Scene(cfg, dev, seed=0)
+    md = cfg["message_dim"]
+    n_pool = 4  # distinct host batches cycled through (fresh rays every step)
+    host_batches = [harness.make_batch(cfg, seed=1000 * rank + i) for i in range(n_pool)]
+    pinned = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in host_batches[0].items()}
+    dev_batches = [scene.to_device(b) for b in host_batches]
+    rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
+    h2d_bytes = sum(v.nbytes for v in host_batches[0].values()) + md * 4
+    gen = torch.Generator().manual_seed(7)  # identical message stream on every rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- phase A: device-resident inputs -> `value` --------------------------------------------------
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for i in range(W):
+        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+    spr = scene.samples_per_ray()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    ktimes = _lib.timing_collect()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- phase B: host inputs through the public API, H2D in, loss D2H out -> `e2e` ----------------------
+    for i in range(3):
+        b = scene.to_device(host_batches[i % n_pool], pinned)
+        float(scene.train_step(b, scene.new_message(gen))[0])
+    barrier()
+    e0.record()
+    for i in range(K):
+        b = scene.to_device(host_batches[i % n_pool], pinned)
+        loss, _, _ = scene.train_step(b, scene.new_message(gen))
+        loss_host = float(loss)  # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused field forward) -------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json, copy burst)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    fwd = ktimes.get("nsig_field_forward", {"ms": 0.0, "n": 0})
+    bwd = ktimes.get("nsig_field_backward", {"ms": 0.0, "n": 0})
+    samples_per_step = spr * rays_per_step  # both passes of the last warm-up step have the same ray geometry
+    # SURVEY 8d algorithmic bytes per sample of the field forward: 24 (xyz, dir in) + 1024 (16 levels x 8 corners
+    # x 8 B) + 64 (pre-summed message table gather) + 16 (sigma, rgb out)
+    alg_bytes_per_sample = 24 + 1024 + 64 + 16
+    calls_per_step = max(fwd["n"] / K, 1e-9)
+    avg_ms = fwd["ms"] / max(fwd["n"], 1)
+    samples_per_launch = samples_per_step / calls_per_step
+    achieved = alg_bytes_per_sample * samples_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_field_fwd (nsig_field_forward)", "achieved": achieved, "peak": peak_gbs,
+                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "samples_per_launch": samples_per_launch,
+                "alg_bytes_per_sample": alg_bytes_per_sample,
+                "share_of_step": fwd["ms"] / ms if ms > 0 else None,
+                "field_backward_avg_launch_ms": bwd["ms"] / max(bwd["n"], 1),
+                "field_backward_share_of_step": bwd["ms"] / ms if ms > 0 else None}
+
+    total_rays = rays_per_step * world
+    line = {
+        "metric": METRIC, "value": total_rays * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 MMA operands / f32 accumulate, f32 encoder+march+composite", "data": "synthetic",
+        "config": {"workload": args.config, "bound": cfg["bound"], "scale": cfg["scale"], "dt_gamma": cfg["dt_gamma"],
+                   "message_dim": md, "codebook": f'{cfg["num_rows"]}x{cfg["num_cols"]}',
+                   "content_rays_per_gpu": cfg["num_rays"], "watermark_rays_per_gpu": rays_per_step - cfg["num_rays"],
+                   "rays_per_step_per_gpu": rays_per_step, "mean_samples_per_ray": spr, "occupancy": cfg["occupancy"],
+                   "weights": "random-init (tables U(+-1e-4), Xavier MLPs)", "optimizer": "Adam(fused) + GradScaler",
+                   "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
+                         "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
+                   "parallelism": f"ray-sharded dp{world}"},
+        "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_run(cfg, steps=2, warmup=1, rays_per_pass=args.cpu_rays or 64)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

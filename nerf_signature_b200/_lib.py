@@ -95,11 +95,44 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_timing_names = ()
+_timing_events = []
+
+
+def timing_enable(names):
+    """Bracket every call of the named entry points with CUDA events on the launching stream
+    (bench.py uses this to time the dominant kernel live inside the timed region)."""
+    global _timing_names
+    _timing_names = tuple(names)
+    _timing_events.clear()
+
+
+def timing_collect():
+    """Synchronise and return {name: {"ms": total, "n": calls}}; disables timing."""
+    global _timing_names
+    _timing_names = ()
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _timing_events:
+        d = out.setdefault(name, {"ms": 0.0, "n": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+    _timing_events.clear()
+    return out
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on torch's current stream and check its status."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if name in _timing_names:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        _timing_events.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         if rc == -1:
             raise NsigError(f"{name}: invalid argument (NSIG_EINVAL)")

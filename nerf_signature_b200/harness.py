@@ -1,0 +1,146 @@
+"""Synthetic watermark-training harness: the caller side of the hot path.
+
+The reference's Trainer and datasets are out of scope (host orchestration); this module
+restates only what they feed the hot path with, on synthetic data (no datasets or checkpoints offline):
+  * scene: random-init watermark NeRFNetwork + a deterministic occupancy grid (SURVEY 8d fixtures);
+  * batch: `rays_o_block/rays_d_block [md, pH, pW, 3]` watermark blocks (provider_wtmk.py:481-496 shapes:
+    pH = H // num_rows, pW = W // num_cols of a downscaled frame) and `rays_o/rays_d [1, num_rays, 3]`
+    content rays with ground-truth colours (provider_wtmk.py:527-572);
+  * step: utils_wtmk_disen.py:1164-1181 + 579-646 — fresh random message, two render passes
+    (force_all_rays=True, perturb=False, bg_color=1), HiDDeN decoder, BCE(temp 10) + MSE, backward, Adam.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import synthetic as syn
+from . import parallel
+from . import hash_encoding_wtmk_bit as _hmsg
+
+CONFIGS = {
+    # BASELINE.json configs[1]: Blender shape, bound 1.0, scale 0.8, dt_gamma 0, message_dim 32, 32x32 codebook
+    "blender_wtmk": dict(bound=1.0, scale=0.8, dt_gamma=0.0, message_dim=32, num_rows=32, num_cols=32,
+                         H=400, W=400, num_rays=4096, camera="blender", occupancy="sphere"),
+    # configs[2]: Mip-NeRF-360 shape, bound 2 (CLI default), scale 0.33, dt_gamma 0
+    "360_wtmk": dict(bound=2.0, scale=0.33, dt_gamma=0.0, message_dim=32, num_rows=32, num_cols=32,
+                     H=756, W=1008, num_rays=4096, camera="360", occupancy="sphere"),
+    # configs[4] per-rank shape: message_dim 48, rays sharded across ranks
+    "shard262144_wtmk": dict(bound=1.0, scale=0.8, dt_gamma=0.0, message_dim=48, num_rows=32, num_cols=32,
+                             H=400, W=400, num_rays=262144, camera="blender", occupancy="sphere"),
+}
+
+
+def _pose(cfg, rs):
+    radius = 4.0311 * cfg["scale"] if cfg["camera"] == "blender" else 4.0 * cfg["scale"]
+    return syn.orbit_pose(rs.uniform(math.pi / 3, 2 * math.pi / 3), rs.uniform(0, 2 * math.pi), radius)
+
+
+def _focal(cfg):
+    fov = 0.6911112 if cfg["camera"] == "blender" else 0.9
+    return 0.5 * cfg["W"] / math.tan(0.5 * fov)
+
+
+def make_batch(cfg, seed, num_rays=None, n_blocks=None):
+    """Host (numpy) batch: block rays of `n_blocks` (default message_dim) randomly chosen blocks and
+    `num_rays` random content pixels of one synthetic view, plus random ground-truth colours."""
+    rs = np.random.RandomState(seed)
+    H, W = cfg["H"], cfg["W"]
+    md = cfg["message_dim"] if n_blocks is None else n_blocks
+    num_rays = cfg["num_rays"] if num_rays is None else num_rays
+    pH, pW = H // cfg["num_rows"], W // cfg["num_cols"]
+    focal = _focal(cfg)
+    pose = _pose(cfg, rs)
+    blocks = rs.permutation(cfg["num_rows"] * cfg["num_cols"])[:md]  # provider_wtmk.py:199-204 (seeded randperm)
+    ii, jj = np.meshgrid(np.arange(pH), np.arange(pW), indexing="ij")
+    ids = []
+    for b in blocks:
+        r, c = divmod(int(b), cfg["num_cols"])
+        ids.append(((r * pH + ii) * W + (c * pW + jj)).reshape(-1))
+    ids = np.concatenate(ids)
+    bo, bd = syn.camera_rays(pose, H, W, focal, ids)
+    pose2 = _pose(cfg, rs)
+    co, cd = syn.camera_rays(pose2, H, W, focal, rs.randint(0, H * W, size=num_rays))
+    return {
+        "rays_o_block": bo.reshape(md, pH, pW, 3), "rays_d_block": bd.reshape(md, pH, pW, 3),
+        "rays_o": co.reshape(1, num_rays, 3), "rays_d": cd.reshape(1, num_rays, 3),
+        "gt": rs.uniform(size=(1, num_rays, 3)).astype(np.float32),
+    }
+
+
+def occupancy(cfg, cascade, seed=0):
+    if cfg["occupancy"] == "sphere":
+        return syn.sphere_grid(cascade)
+    return syn.bernoulli_grid(cascade, p=0.5, seed=seed)
+
+
+class Scene:
+    """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
+
+    def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0):
+        from .nerf.network_wtmk_tcnn import NeRFNetwork
+        torch.manual_seed(seed)
+        self.cfg = cfg
+        self.device = device
+        model = NeRFNetwork(bound=cfg["bound"], cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10,
+                            bg_radius=-1, message_dim=cfg["message_dim"], n_views=1)
+        if table_scale != 1.0:
+            with torch.no_grad():
+                for e in list(model.encoder.embeddings) + list(model.msg_encoder.embeddings):
+                    e.weight.mul_(table_scale)
+        grid = occupancy(cfg, model.cascade, seed)
+        model.density_grid.copy_(torch.from_numpy(grid))
+        model.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
+        self.model = model.to(device).train()
+        self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
+        self.fp16 = fp16
+        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
+        self.lambda_w, self.lambda_i = 0.005, 1.0  # README.md:40,45
+        self.opt = dict(dt_gamma=cfg["dt_gamma"], max_steps=1024, T_thresh=1e-4)
+        self.sync = parallel.GradSync()
+        _hmsg.grad_reducer = self.sync.reduce_table_grad if self.sync.enabled else None
+        self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
+
+    def new_message(self, generator=None):
+        """utils_wtmk_disen.py:1165 — a fresh random message every step.  Generated on the host so the
+        bit pattern is known without a device round trip; the device copy is asynchronous."""
+        return torch.randint(0, 2, (self.cfg["message_dim"],), generator=generator).float()
+
+    def to_device(self, batch_np, pinned=None):
+        """numpy batch -> device tensors (through pinned host buffers, asynchronously)."""
+        out = {}
+        for k, v in batch_np.items():
+            t = torch.from_numpy(v)
+            if pinned is not None:
+                pinned[k].copy_(t)
+                t = pinned[k]
+            out[k] = t.to(self.device, non_blocking=True)
+        return out
+
+    def train_step(self, batch, message):
+        """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here)."""
+        model = self.model
+        self.optimizer.zero_grad(set_to_none=True)
+        msg_dev = message.to(self.device, non_blocking=True) if not message.is_cuda else message
+        message_for_render = message  # host bits known -> no .item() round trip inside the encoder
+        out_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message_for_render, staged=False, bg_color=1,
+                             perturb=False, force_all_rays=True, **self.opt)
+        pred = torch.clamp(out_w["image"], min=0, max=1)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
+            decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
+        out_c = model.render(batch["rays_o"], batch["rays_d"], message_for_render, staged=False, bg_color=1,
+                             perturb=False, force_all_rays=True, **self.opt)
+        lossi = F.mse_loss(out_c["image"], batch["gt"], reduction="none").mean()
+        lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
+        loss = self.lambda_w * lossw + self.lambda_i * lossi
+        self.scaler.scale(loss).backward()
+        self.sync.reduce_params(self._decoder_params)
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+        return loss, lossi, lossw
+
+    def samples_per_ray(self):
+        """Measured mean samples/ray of the most recent render call (reads the march counter)."""
+        c = self.model.step_counter[(self.model.local_step - 1) % 16].tolist()
+        return c[0] / max(c[1], 1)

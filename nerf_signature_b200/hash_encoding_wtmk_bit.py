@@ -19,6 +19,10 @@ from .hash_encoding import _hash_encode, level_resolutions
 
 _P = _lib.ptr
 
+# Optional callable applied to dL/dS before it fans out to the selected tables; the data-parallel
+# harness installs parallel.GradSync.reduce_table_grad here (one 4 MiB all-reduce instead of message_dim).
+grad_reducer = None
+
 
 def message_bits(message):
     """Host copy of the bits as a tuple of ints (one D2H transfer; the reference does one per bit)."""
@@ -45,6 +49,8 @@ class _msg_table_sum(Function):
     @staticmethod
     def backward(ctx, grad_S):
         grads = [None] * ctx.n
+        if grad_reducer is not None:
+            grad_S = grad_reducer(grad_S)
         for i, b in enumerate(ctx.bits):
             if ctx.needs_input_grad[3 + 2 * i + b]:
                 grads[2 * i + b] = grad_S

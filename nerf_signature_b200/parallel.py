@@ -1,0 +1,90 @@
+"""Ray-sharded data parallelism (new functionality: the reference has no multi-GPU hot path,
+SURVEY.md 2.4 / 8e).  One process per GPU, torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+Rays are independent through march -> field -> composite, parameters are replicated, so the only
+exchange is the gradient reduction once per step:
+  * the message-table gradient: every selected table's gradient equals dL/dS, so ONE
+    [2^19, 2] fp32 tensor (4 MiB) is all-reduced before it fans out to the message_dim selected tables
+    (hook called from hash_encoding_wtmk_bit._msg_table_sum.backward) instead of message_dim tensors;
+  * all remaining trainable parameters (HiDDeN decoder, ~262 k values; base tables + MLPs in clean
+    mode) as one flat bucket.
+For a watermark batch sharded across ranks the rendered block pixels are all-gathered before the
+decoder (its BatchNorm uses batch statistics over the blocks): `all_gather_pixels`.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous slice [lo, hi) of n units owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradSync:
+    """Averages gradients across ranks once per step."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.enabled = world()[1] > 1
+
+    # --- message-table path: called inside autograd with dL/dS -------------------------------------
+    def reduce_table_grad(self, grad_S):
+        if not self.enabled:
+            return grad_S
+        g = grad_S.contiguous()
+        # stream-ordered (no host wait): autograd consumes g on the compute stream right after this call
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        g.div_(world()[1])
+        return g
+
+    # --- everything else: one flat bucket after backward ---------------------------------------------
+    def reduce_params(self, params):
+        """All-reduce (mean) the .grad of `params` through a single flat buffer."""
+        ws = world()[1]
+        if not self.enabled:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(ws)
+        o = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[o:o + n].view_as(g))
+            o += n
+
+
+def all_gather_pixels(local_pixels, counts, group=None):
+    """Concatenate per-rank [n_r, 3] pixel blocks (n_r = counts[r]) into the full [sum, 3] tensor on every
+    rank, differentiably: the backward pass hands each rank the gradient slice of its own pixels."""
+    return _AllGatherPixels.apply(local_pixels, tuple(int(c) for c in counts), group)
+
+
+class _AllGatherPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, counts, group):
+        rank, ws = world()
+        ctx.counts, ctx.rank = counts, rank
+        if ws == 1:
+            return x.clone()
+        mx = max(counts)
+        pad = torch.zeros(mx, *x.shape[1:], dtype=x.dtype, device=x.device)
+        pad[:x.shape[0]] = x
+        out = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(out, pad, group=group)
+        return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        lo = sum(ctx.counts[:ctx.rank])
+        return g[lo:lo + ctx.counts[ctx.rank]].contiguous(), None, None

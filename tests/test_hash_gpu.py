@@ -32,7 +32,7 @@ def test_base_encoder_golden(golden_hash, tag):
     x = torch.from_numpy(g[f"base_{tag}_x"]).cuda()
     slots = enc.hashed_indices(x).cpu().numpy()
     assert np.array_equal(slots, g[f"base_{tag}_slots"])
-    feat = enc(x).cpu().numpy()
+    feat = enc(x).detach().cpu().numpy()
     assert np.array_equal(feat.view(np.uint32), g[f"base_{tag}_feat"].view(np.uint32))
 
 
@@ -62,7 +62,7 @@ def test_base_encoder_large_vs_oracle(oracle_cpu):
     want, wslots = oracle_cpu.hash_encode_forward(x, tabs, enc.resolutions, 19, want_slots=True)
     xt = torch.from_numpy(x).cuda()
     assert np.array_equal(enc.hashed_indices(xt).cpu().numpy(), wslots)
-    assert np.array_equal(enc(xt).cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(enc(xt).detach().cpu().numpy().view(np.uint32), want.view(np.uint32))
     # empty batch
     assert enc(torch.zeros(0, 3, device="cuda")).shape == (0, 32)
 
@@ -85,7 +85,7 @@ def test_msg_encoder_golden(golden_hash, tag):
     scale = np.abs(ref).max()
     pre = enc(x, msg)                      # pre-summed form (product path)
     per = enc.forward_perbit(x, msg)       # reference-form evaluation order
-    np.testing.assert_allclose(per.cpu().numpy(), ref, rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(per.detach().cpu().numpy(), ref, rtol=0, atol=2e-6 * scale)
     np.testing.assert_allclose(pre.detach().cpu().numpy(), ref, rtol=0, atol=1e-5 * scale)
     if tag == "small":
         pre.backward(torch.from_numpy(g["msg_small_gout"]).cuda())
