@@ -231,7 +231,15 @@ def test_composite_train_forward_backward(rm, oracle_cpu, ref_cuda, case):
         np.testing.assert_allclose(ts.grad.cpu().numpy(), ogs, rtol=1e-3, atol=1e-5 * scale)
         np.testing.assert_allclose(tc.grad.cpu().numpy(), ogc, rtol=1e-4, atol=1e-6)
         # zeros after termination / on padding rows, like the reference's zero-filled buffers
-        assert np.array_equal(ts.grad.cpu().numpy() == 0, ogs == 0)
+        # (exact zeros there; elsewhere a value the sequential oracle rounds to exactly 0 may come out as
+        # rounding noise of the warp-scan order, so the patterns may only differ where both are negligible)
+        got_gs = ts.grad.cpu().numpy()
+        differs = (got_gs == 0) != (ogs == 0)
+        assert np.all(np.abs(got_gs[differs]) <= 1e-6 * scale) and np.all(np.abs(ogs[differs]) <= 1e-6 * scale)
+        tail = np.ones(M, bool)
+        for rid, off, cnt in orays:
+            tail[off:off + cnt] = False
+        assert np.all(got_gs[tail] == 0) and np.all(tc.grad.cpu().numpy()[tail] == 0)
         if ref_cuda is not None:
             N = orays.shape[0]
             rw = torch.empty(N, device="cuda"); rdp = torch.empty(N, device="cuda"); ri = torch.empty(N, 3, device="cuda")
