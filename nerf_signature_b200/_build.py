@@ -44,7 +44,7 @@ def build_library(force=False, verbose=False):
             print(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [_nvcc(), "-shared", "-cudart", "shared", "-o", LIB] + objs
+    cmd = [_nvcc(), "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 

@@ -1,0 +1,108 @@
+"""CPU tests (-m "not gpu") of the drop-in boundary: the C-ABI library builds for sm_100a, loads without a GPU,
+exports exactly what include/nsig.h declares, validates arguments before touching CUDA, and the Python
+layer refuses to run without CUDA (no CPU fallback, no route through oracle/)."""
+import ast
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nsig.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nsig_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from nerf_signature_b200 import _build, _lib
+    _build.build_library()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = lib.load()
+    decl = declared_symbols()
+    assert len(decl) >= 21
+    for name in decl:
+        assert hasattr(handle, name), f"{name} declared in include/nsig.h but not exported"
+    # and the binding table covers the header (nothing declared is unreachable from Python)
+    assert sorted(lib.EXPORTED_SYMBOLS) == decl
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and "nsig_" in l}
+    assert exported == set(decl), exported ^ set(decl)  # C linkage, no stray mangled nsig entry points
+
+
+def test_library_is_sm100a_only_and_has_no_torch_dependency(lib):
+    assert lib.version().startswith("nsig_b200") and "sm_100a" in lib.version()
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+    needed = subprocess.run(["readelf", "-d", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in needed and "c10" not in needed and "python" not in needed
+
+
+def test_argument_validation_happens_before_any_cuda_call(lib):
+    h = lib.load()
+    V = ctypes.c_void_p
+    # empty inputs are a no-op success
+    assert h.nsig_near_far_from_aabb(None, None, None, 0, 0.2, None, None, None) == 0
+    assert h.nsig_packbits(None, 0, 0.5, None, None) == 0
+    assert h.nsig_hash_encode_forward(None, 0, None, None, 16, 19, None, None, None) == 0
+    # null pointers / impossible shapes are NSIG_EINVAL (-1), not a crash
+    assert h.nsig_near_far_from_aabb(None, None, None, 4, 0.2, None, None, None) == -1
+    assert h.nsig_morton3D(None, 8, None, None) == -1
+    assert h.nsig_composite_rays_train_forward(None, None, None, None, 8, 8, 1e-4, None, None, None, None) == -1
+    dummy = (ctypes.c_float * 8)()
+    p = ctypes.cast(dummy, V)
+    tabs = (V * 16)(*[p] * 16)
+    res = (ctypes.c_float * 16)(*[16.0] * 16)
+    assert h.nsig_hash_encode_forward(p, 1, tabs, res, 17, 19, p, None, None) == -1   # > NSIG_MAX_LEVELS
+    assert h.nsig_hash_encode_forward(p, 1, tabs, res, 16, 31, p, None, None) == -1   # log2_T out of range
+    assert h.nsig_march_rays_train(p, p, p, 1.0, 0.0, 1024, 4, 0, 128, 64, p, p, p, p, p, p, p, None, p, None) == -1  # C=0
+    assert h.nsig_march_rays_train_scratch_bytes(1000) == 8000
+
+
+def test_python_layer_has_no_cpu_path(lib):
+    from nerf_signature_b200.hash_encoding import HashEmbedder
+    enc = HashEmbedder(bounding_box=(0, 1), n_levels=16, log2_hashmap_size=10, base_resolution=16, finest_resolution=2048)
+    with pytest.raises(lib.NsigError):
+        enc(torch.rand(4, 3))  # CPU tensor: refuse, never fall back
+    with pytest.raises(lib.NsigError):
+        lib.ptr(torch.zeros(3))
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from nerf_signature_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libnsig_b200.so"))
+    with pytest.raises(_lib.NsigError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under nerf_signature_b200/ may import or reference it."""
+    pkg = os.path.join(ROOT, "nerf_signature_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    mods = [node.module or ""]
+                for m in mods:
+                    assert not (m == "oracle" or m.startswith("oracle.")), f"{f} imports {m}"
+    for dirpath, _, files in os.walk(os.path.join(pkg, "csrc")):
+        for f in files:
+            assert "oracle" not in open(os.path.join(dirpath, f)).read(), f

@@ -1,0 +1,93 @@
+"""CPU tests (-m "not gpu") of the host-side mirror of the reference interface: module structure,
+state-dict keys, freezing policy, level resolutions, synthetic batch shapes.  No kernels run."""
+import inspect
+
+import numpy as np
+import torch
+
+
+def test_raymarching_module_has_the_reference_callables_and_signatures():
+    from nerf_signature_b200 import raymarching as rm
+    # reference raymarching/raymarching.py:22,55,85,108,132,164,241,300,354
+    want = {
+        "_near_far_from_aabb": ["ctx", "rays_o", "rays_d", "aabb", "min_near"],
+        "_sph_from_ray": ["ctx", "rays_o", "rays_d", "radius"],
+        "_morton3D": ["ctx", "coords"],
+        "_morton3D_invert": ["ctx", "indices"],
+        "_packbits": ["ctx", "grid", "thresh", "bitfield"],
+        "_march_rays_train": ["ctx", "rays_o", "rays_d", "bound", "density_bitfield", "C", "H", "nears", "fars", "step_counter",
+                              "mean_count", "perturb", "align", "force_all_rays", "dt_gamma", "max_steps"],
+        "_composite_rays_train": ["ctx", "sigmas", "rgbs", "deltas", "rays", "T_thresh"],
+        "_march_rays": ["ctx", "n_alive", "n_step", "rays_alive", "rays_t", "rays_o", "rays_d", "bound", "density_bitfield", "C",
+                        "H", "near", "far", "align", "perturb", "dt_gamma", "max_steps"],
+        "_composite_rays": ["ctx", "n_alive", "n_step", "rays_alive", "rays_t", "sigmas", "rgbs", "deltas", "weights_sum", "depth",
+                            "image", "T_thresh"],
+    }
+    mod = rm.raymarching
+    for cls, params in want.items():
+        fwd = getattr(mod, cls).forward
+        fwd = inspect.unwrap(fwd)
+        assert list(inspect.signature(fwd).parameters) == params, cls
+        assert callable(getattr(rm, cls[1:]))
+    d = inspect.signature(inspect.unwrap(mod._march_rays_train.forward)).parameters
+    assert (d["mean_count"].default, d["align"].default, d["max_steps"].default, d["dt_gamma"].default) == (-1, -1, 1024, 0)
+    assert inspect.signature(inspect.unwrap(mod._composite_rays.forward)).parameters["T_thresh"].default == 1e-2
+    assert inspect.signature(inspect.unwrap(mod._composite_rays_train.forward)).parameters["T_thresh"].default == 1e-4
+
+
+def test_watermark_network_state_dict_and_freezing_policy():
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+    net = NeRFNetwork(bound=2, cuda_ray=True, message_dim=4)
+    keys = set(net.state_dict().keys())
+    for i in range(16):
+        assert f"encoder.embeddings.{i}.weight" in keys
+    for i in range(8):
+        assert f"msg_encoder.embeddings.{i}.weight" in keys
+    for k in ("sigma_net.params", "color_net.params", "density_grid", "density_bitfield", "step_counter", "aabb_train",
+              "aabb_infer"):
+        assert k in keys, k
+    assert any(k.startswith("msg_decoder.") for k in keys)
+    assert net.cascade == 2 and net.density_bitfield.numel() == 2 * 128 ** 3 // 8 and net.density_grid.shape == (2, 128 ** 3)
+    assert net.sigma_net.params.numel() == 3072 and net.color_net.params.numel() == 7168
+    # network_wtmk_tcnn.py:90-95: base encoder + both MLPs frozen, message tables + decoder trainable
+    assert not any(p.requires_grad for p in net.encoder.parameters())
+    assert not net.sigma_net.params.requires_grad and not net.color_net.params.requires_grad
+    assert all(p.requires_grad for p in net.msg_encoder.parameters())
+    assert all(p.requires_grad for p in net.msg_decoder.parameters())
+    groups = net.get_params(1e-2)
+    assert len(groups) == 2 and all(g["lr"] == 1e-2 for g in groups)
+    assert NeRFNetwork(bound=1, cuda_ray=True, message_dim=4, finetune_decoder=True).get_params(1e-3).__len__() == 1
+    # tables initialised U(-1e-4, 1e-4) (hash_encoding.py:65-66)
+    w = net.encoder.embeddings[3].weight
+    assert w.shape == (2 ** 19, 2) and float(w.abs().max()) <= 1e-4
+
+
+def test_clean_network_trains_everything():
+    from nerf_signature_b200.nerf.network_hash import NeRFNetwork
+    net = NeRFNetwork(bound=1, cuda_ray=True)
+    assert all(p.requires_grad for p in net.parameters())
+    assert len(net.get_params(1e-2)) >= 3
+
+
+def test_encoder_resolutions_follow_the_reference_expression():
+    from nerf_signature_b200.hash_encoding import HashEmbedder
+    from nerf_signature_b200.hash_encoding_wtmk_bit import HashEmbedder as MsgEmbedder, message_bits
+    enc = HashEmbedder(bounding_box=(0, 1), n_levels=16, log2_hashmap_size=8, base_resolution=16, finest_resolution=2048)
+    assert enc.resolutions == [16, 22, 30, 42, 58, 80, 111, 153, 212, 294, 406, 561, 776, 1072, 1482, 2047]
+    m = MsgEmbedder(bounding_box=(0, 1), n_levels=8, log2_hashmap_size=8, base_resolution=2048, finest_resolution=2048,
+                    message_dim=4)
+    assert m.resolution == 2048.0 and len(m.tables()) == 8
+    assert message_bits(torch.tensor([1.0, 0.0, 1.0, 1.0])) == (1, 0, 1, 1)
+
+
+def test_synthetic_batch_shapes_match_the_reference_provider():
+    from nerf_signature_b200 import harness
+    cfg = harness.CONFIGS["blender_wtmk"]
+    b = harness.make_batch(cfg, seed=0)
+    # provider_wtmk.py:481-496: [message_dim, pH, pW, 3] blocks of a 400x400 frame cut 32x32; 4096 content rays
+    assert b["rays_o_block"].shape == (32, 12, 12, 3) and b["rays_d_block"].shape == (32, 12, 12, 3)
+    assert b["rays_o"].shape == (1, 4096, 3) and b["gt"].shape == (1, 4096, 3)
+    np.testing.assert_allclose(np.linalg.norm(b["rays_d"], axis=-1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(np.linalg.norm(b["rays_o"], axis=-1), 4.0311 * 0.8, atol=1e-4)
+    b2 = harness.make_batch(cfg, seed=0)
+    assert all(np.array_equal(b[k], b2[k]) for k in b)  # seeded

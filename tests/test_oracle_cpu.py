@@ -1,0 +1,175 @@
+"""CPU tests (-m "not gpu"): the oracle is only trusted once it reproduces what the REFERENCE produced.
+
+  * oracle/hash_oracle.c and oracle/torch_port.py against tests/golden/hash_golden.npz — outputs of the
+    reference's own hash_encoding.py / hash_encoding_wtmk_bit.py modules (tests/golden/make_golden_hash.py);
+  * oracle/raymarch_oracle.c against tests/golden/raymarch_golden.npz — outputs of the UNMODIFIED reference
+    CUDA extension run on a B200 (tests/golden/make_golden_raymarch.py).
+Integer outputs and every float the march emits: bit-exact.  Composite: 2e-5 (the device uses the
+ex2.approx-based __expf, the C oracle expf).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from make_golden_hash import make_tables
+import make_golden_raymarch as mgr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# hash encoders
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_c_hash_oracle_matches_reference_module(golden_hash, oracle_cpu, tag):
+    g = golden_hash
+    log2_T = int(g[f"base_{tag}_log2T"])
+    tabs = make_tables(int(g[f"base_{tag}_seed"]), 16, log2_T)
+    feat, slots = oracle_cpu.hash_encode_forward(g[f"base_{tag}_x"], tabs, g[f"base_{tag}_res"], log2_T, want_slots=True)
+    assert np.array_equal(slots, g[f"base_{tag}_slots"])                       # hash slots: bit-exact
+    assert np.array_equal(bits(feat), bits(g[f"base_{tag}_feat"]))             # features: bit-exact
+
+
+def test_level_resolutions_are_the_reference_fp32_values(golden_hash):
+    # floor(16 * b**i) in torch fp32 ends at 2047, not 2048
+    want = [16, 22, 30, 42, 58, 80, 111, 153, 212, 294, 406, 561, 776, 1072, 1482, 2047]
+    assert golden_hash["base_full_res"].tolist() == [float(w) for w in want]
+    from oracle import torch_port as tp
+    assert tp.level_resolutions(16, 2048, 16) == [float(w) for w in want]
+    assert tp.level_resolutions(2048, 2048, 64) == [2048.0] * 64
+
+
+def test_c_hash_oracle_backward_matches_reference_autograd(golden_hash, oracle_cpu):
+    g = golden_hash
+    grads = oracle_cpu.hash_encode_backward(g["base_small_x"], g["base_small_gout"], g["base_small_res"], 16,
+                                            int(g["base_small_log2T"]))
+    ref = g["base_small_gtab"]
+    got = np.stack(grads)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    assert np.array_equal(got == 0, ref == 0)
+
+
+@pytest.mark.parametrize("tag", ["small", "md32", "md48"])
+def test_c_msg_oracle_matches_reference_module(golden_hash, oracle_cpu, tag):
+    g = golden_hash
+    log2_T, md = int(g[f"msg_{tag}_log2T"]), int(g[f"msg_{tag}_md"])
+    tabs = make_tables(int(g[f"msg_{tag}_seed"]), 2 * md, log2_T)
+    feat = oracle_cpu.msg_encode_forward(g[f"msg_{tag}_x"], tabs, g[f"msg_{tag}_message"], 2048.0, log2_T)
+    want = g[f"msg_{tag}_feat"]
+    # the reference sums the per-bit results with torch.sum (pairwise order); the oracle sums in bit order
+    np.testing.assert_allclose(feat, want, rtol=1e-5, atol=1e-6 * np.abs(want).max())
+
+
+def test_c_msg_oracle_backward_matches_reference_autograd(golden_hash, oracle_cpu):
+    g = golden_hash
+    md, log2_T = int(g["msg_small_md"]), int(g["msg_small_log2T"])
+    G = oracle_cpu.msg_encode_backward(g["msg_small_x"], g["msg_small_gout"], 2048.0, log2_T)
+    ref = g["msg_small_gtab"]  # [2*md, T, 2]: selected tables carry the gradient, unselected none (zeros)
+    msg = g["msg_small_message"].astype(int)
+    for i in range(md):
+        sel, unsel = ref[2 * i + msg[i]], ref[2 * i + 1 - msg[i]]
+        np.testing.assert_allclose(G, sel, rtol=1e-5, atol=1e-6 * np.abs(sel).max())  # every selected == dS
+        assert not unsel.any()
+
+
+def test_torch_port_matches_reference_modules(golden_hash):
+    from oracle import torch_port as tp
+    g = golden_hash
+    tabs = [torch.from_numpy(t) for t in make_tables(int(g["base_small_seed"]), 16, int(g["base_small_log2T"]))]
+    feat = tp.hash_embed(torch.from_numpy(g["base_small_x"]), tabs, g["base_small_res"].tolist(), int(g["base_small_log2T"]))
+    assert np.array_equal(bits(feat.numpy()), bits(g["base_small_feat"]))
+    md, log2_T = int(g["msg_small_md"]), int(g["msg_small_log2T"])
+    mt = [torch.from_numpy(t) for t in make_tables(int(g["msg_small_seed"]), 2 * md, log2_T)]
+    mf = tp.msg_embed(torch.from_numpy(g["msg_small_x"]), mt, torch.from_numpy(g["msg_small_message"]), 2048.0, log2_T)
+    assert np.array_equal(bits(mf.numpy()), bits(g["msg_small_feat"]))
+    sh = tp.sh_degree4(torch.from_numpy(g["sh_dirs"]))
+    np.testing.assert_allclose(sh.numpy(), g["sh_out"], rtol=1e-6, atol=1e-7)
+
+
+def test_sh_restatement_matches_reference_shencoder(golden_hash):
+    from oracle import field_oracle as fo
+    np.testing.assert_allclose(fo.sh4(torch.from_numpy(golden_hash["sh_dirs"])).numpy(), golden_hash["sh_out"],
+                               rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# raymarching
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="session")
+def golden_rm():
+    path = os.path.join(ROOT, "tests", "golden", "raymarch_golden.npz")
+    if not os.path.exists(path):
+        pytest.fail("tests/golden/raymarch_golden.npz is missing: regenerate it on a GPU box with "
+                    "tests/golden/make_golden_raymarch.py")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("case", mgr.CASES, ids=[c[0] for c in mgr.CASES])
+def test_c_raymarch_oracle_matches_reference_cuda(golden_rm, oracle_cpu, case):
+    g, name = golden_rm, case[0]
+    assert json.loads(str(g[f"{name}_params"])) == list(case)
+    _, cam, N, seed, bound, C, kind, dt_gamma, perturb = case
+    rays_o, rays_d, bitfield, aabb, noises = mgr.case_inputs(case)
+    nears, fars = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    assert np.array_equal(bits(nears), bits(g[f"{name}_nears"])) and np.array_equal(bits(fars), bits(g[f"{name}_fars"]))
+    xyzs, dirs, deltas, rays, counter = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield, C, 128, nears, fars,
+                                                                    noises=noises, dt_gamma=dt_gamma)
+    assert counter.tolist() == [int(g[f"{name}_total"]), N]
+    assert np.array_equal(rays[:, 0], np.arange(N))                            # the oracle's own order is ray order
+    assert np.array_equal(rays[:, 2], g[f"{name}_counts"])                     # per-ray sample counts: bit-exact
+    m = int(counter[0])
+    for got, key in ((xyzs, "xyzs"), (dirs, "dirs"), (deltas, "deltas")):
+        assert np.array_equal(bits(got[:m]), bits(g[f"{name}_{key}"])), key    # every emitted float: bit-exact
+
+    sig, rgb = mgr.seeded_field(m, seed + 11)
+    ws, depth, image = oracle_cpu.composite_rays_train_forward(sig, rgb, deltas[:m], rays, 1e-4)
+    np.testing.assert_allclose(ws, g[f"{name}_ws"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(depth, g[f"{name}_depth"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(image, g[f"{name}_image"], rtol=2e-5, atol=2e-6)
+    rs = np.random.RandomState(seed + 12)
+    gws = rs.normal(size=N).astype(np.float32); gim = rs.normal(size=(N, 3)).astype(np.float32)
+    gs, gc = oracle_cpu.composite_rays_train_backward(gws, gim, sig, rgb, deltas[:m], rays, ws, image, 1e-4)
+    scale = np.abs(g[f"{name}_gsig"]).max()
+    np.testing.assert_allclose(gs, g[f"{name}_gsig"], rtol=1e-3, atol=1e-5 * scale)
+    np.testing.assert_allclose(gc, g[f"{name}_grgb"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", mgr.CASES, ids=[c[0] for c in mgr.CASES])
+def test_c_inference_oracle_matches_reference_cuda_loop(golden_rm, oracle_cpu, case):
+    g, name = golden_rm, case[0]
+    _, cam, N, seed, bound, C, kind, dt_gamma, perturb = case
+    rays_o, rays_d, bitfield, aabb, _ = mgr.case_inputs(case)
+    nears, fars = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    ws = np.zeros(N, np.float32); dp = np.zeros(N, np.float32); im = np.zeros((N, 3), np.float32)
+    alive = np.arange(N, dtype=np.int32); rt = nears.copy()
+    step = iters = 0
+    while step < 1024:
+        n_alive = alive.shape[0]
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        x, d, l = oracle_cpu.march_rays(n_alive, n_step, alive, rt, rays_o, rays_d, bound, bitfield, C, 128, nears, fars,
+                                        align=128, dt_gamma=dt_gamma)
+        s, c = mgr.closed_form_field(x)
+        oracle_cpu.composite_rays(n_alive, n_step, alive, rt, s, c, l, ws, dp, im, 1e-4)
+        alive = alive[alive >= 0]
+        step += n_step; iters += 1
+    assert iters == int(g[f"{name}_inf_iters"])   # same alive-ray schedule as the reference loop
+    np.testing.assert_allclose(ws, g[f"{name}_inf_ws"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(im, g[f"{name}_inf_image"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dp, g[f"{name}_inf_depth"], rtol=1e-4, atol=1e-4)
+
+
+def test_c_morton_packbits_match_reference_cuda(golden_rm, oracle_cpu):
+    g = golden_rm
+    assert np.array_equal(oracle_cpu.morton3D(g["morton_coords"]), g["morton_idx"])
+    assert np.array_equal(oracle_cpu.morton3D_invert(g["morton_idx"]), g["morton_back"])
+    assert np.array_equal(g["morton_back"], g["morton_coords"])
+    assert np.array_equal(oracle_cpu.packbits(g["packbits_grid"], 0.25), g["packbits_bits"])

@@ -1,0 +1,96 @@
+"""CPU tests (-m "not gpu") of the ray-sharding host logic with a real 2-process gloo group:
+shard ranges, the flat-bucket gradient all-reduce, the message-table gradient hook and the differentiable
+pixel all-gather that keeps the HiDDeN decoder's BatchNorm statistics global."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nerf_signature_b200 import parallel
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 4096, 262144, 4608 + 5):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)
+        sync = parallel.GradSync()
+        assert sync.enabled
+        # ---- flat bucket over ragged parameter shapes, some without grads ----
+        params = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (2, 2, 2), (4,))]
+        local = []
+        for i, p in enumerate(params):
+            if i == 3:
+                continue  # no grad on any rank: skipped
+            p.grad = torch.randn_like(p)
+            local.append(p.grad.clone())
+        sync.reduce_params(params)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [g.tolist() for g in local])
+        for i, p in enumerate(params[:3]):
+            want = sum(torch.tensor(gathered[r][i]) for r in range(world)) / world
+            assert torch.allclose(p.grad, want, atol=1e-6)
+        assert params[3].grad is None
+        # ---- message-table gradient hook: mean over ranks of dL/dS ----
+        g = torch.full((16, 2), float(rank + 1))
+        out = sync.reduce_table_grad(g)
+        assert torch.allclose(out, torch.full((16, 2), sum(range(1, world + 1)) / world))
+        # ---- pixel all-gather with ragged counts, gradient returns the local slice ----
+        counts = [5, 3][:world]
+        x = (torch.arange(counts[rank] * 3, dtype=torch.float32).view(-1, 3) + 100 * rank).requires_grad_(True)
+        full = parallel.all_gather_pixels(x, counts)
+        assert full.shape == (sum(counts), 3)
+        lo = sum(counts[:rank])
+        assert torch.equal(full[lo:lo + counts[rank]], x.detach())
+        other = 1 - rank
+        olo = sum(counts[:other])
+        assert float(full[olo, 0]) == 100.0 * other
+        w = torch.arange(sum(counts) * 3, dtype=torch.float32).view(-1, 3)
+        (full * w).sum().backward()
+        assert torch.equal(x.grad, w[lo:lo + counts[rank]])
+        # ---- equivalence: sharded mean-loss gradients == single-process gradients ----
+        torch.manual_seed(7)
+        W = torch.nn.Parameter(torch.randn(3, 4))
+        rays = torch.randn(10, 4)
+        lo, hi = parallel.shard_range(10, rank, world)
+        loss = ((rays[lo:hi] @ W.t()) ** 2).sum() / 10 * world   # local mean scaled so that the rank-mean is global
+        loss.backward()
+        sync.reduce_params([W])
+        W2 = torch.nn.Parameter(W.detach().clone())
+        ((rays @ W2.t()) ** 2).sum().div(10).backward()
+        assert torch.allclose(W.grad, W2.grad, atol=1e-5)
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_gloo_world_size_2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
