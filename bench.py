@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="blender_wtmk")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
+    ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph-captured one")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused = optim.WatermarkAdam; torch = torch.optim.Adam over get_params (implies --no-graph)")
     ap.add_argument("--cpu-rays", type=int, default=0, help="override the CPU sample size (rays per pass)")
     return ap.parse_args()
 
@@ -45,29 +48,75 @@ def parse():
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line), through NVML
+    from a background thread every 5 ms (nvidia-smi -lms starts too slowly for a timed region of ~0.1 s);
+    falls back to the nvidia-smi query loop when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                return self.index
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self._visible_index()), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            masks = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [s[0] for s in self.samples]
+            reasons = sorted(k for k, m in masks.items() if any(s[1] & m for s in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": reasons, "source": "nvml, 5 ms period, during the timed regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -186,11 +235,13 @@ def run_ours(args):
     cfg = dict(harness.CONFIGS[args.config])
     if args.config.startswith("shard"):
         cfg["num_rays"] = cfg["num_rays"] // world
-    scene = harness.Scene(cfg, dev, seed=0)
+    use_graph = (not args.no_graph) and args.optimizer == "fused"
+    scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph)
     md = cfg["message_dim"]
     n_pool = 4  # distinct host batches cycled through (fresh rays every step)
     host_batches = [harness.make_batch(cfg, seed=1000 * rank + i) for i in range(n_pool)]
     pinned = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in host_batches[0].items()}
+    pinned_msg = torch.empty(md, dtype=torch.float32).pin_memory()
     dev_batches = [scene.to_device(b) for b in host_batches]
     rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
     h2d_bytes = sum(v.nbytes for v in host_batches[0].values()) + md * 4
@@ -203,14 +254,15 @@ def run_ours(args):
 
     # ---- phase A: device-resident inputs -> `value` --------------------------------------------------
     W, K = max(args.warmup, 3), max(args.steps, 1)
+    _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])  # external events when captured
     for i in range(W):
         scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
-    spr = scene.samples_per_ray()
+    if not use_graph:
+        _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])  # drop the warm-up events
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -218,24 +270,44 @@ def run_ours(args):
         scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
     e1.record()
     barrier()
-    launches = _lib.launch_count - launches0
-    ktimes = _lib.timing_collect()
+    launches = (scene.launches_per_step * K) if use_graph else (_lib.launch_count - launches0)
+    ktimes = _lib.timing_read()
+    n_samples_step, _ = scene.samples_per_step()
+    spr = n_samples_step / rays_per_step
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    if use_graph:
+        # events inside a graph are re-recorded by every replay: the read above is the LAST timed step; average a
+        # few more synchronised replays of the same graph for a steadier per-launch figure
+        acc = {}
+        for i in range(8):
+            scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+            for name, d in _lib.timing_read().items():
+                a = acc.setdefault(name, {"ms": 0.0, "n": 0})
+                a["ms"] += d["ms"]; a["n"] += d["n"]
+        for name, d in ktimes.items():
+            acc[name]["ms"] += d["ms"]; acc[name]["n"] += d["n"]
+        ktimes_avg, steps_timed = acc, 9
+    else:
+        ktimes_avg, steps_timed = ktimes, K
 
     # ---- phase B: host inputs through the public API, H2D in, loss D2H out -> `e2e` ----------------------
+    def host_step(i):
+        for k, v in host_batches[i % n_pool].items():
+            pinned[k].copy_(torch.from_numpy(v))
+        pinned_msg.copy_(scene.new_message(gen))
+        loss, _, _ = scene.train_step(pinned, pinned_msg)   # H2D of the batch + message from pinned memory
+        return float(loss)                                   # D2H read of the step's result
+
     for i in range(3):
-        b = scene.to_device(host_batches[i % n_pool], pinned)
-        float(scene.train_step(b, scene.new_message(gen))[0])
+        host_step(i)
     barrier()
     e0.record()
     for i in range(K):
-        b = scene.to_device(host_batches[i % n_pool], pinned)
-        loss, _, _ = scene.train_step(b, scene.new_message(gen))
-        loss_host = float(loss)  # D2H read of the step's result
+        loss_host = host_step(i)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -244,6 +316,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+    _lib.timing_collect()
 
     if rank != 0:
         if world > 1:
@@ -258,23 +331,31 @@ def run_ours(args):
         pass
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json, copy burst)") if "hbm_gbs" in peaks \
         else (6650.0, "fallback (B200_PROFILING.md)")
-    fwd = ktimes.get("nsig_field_forward", {"ms": 0.0, "n": 0})
-    bwd = ktimes.get("nsig_field_backward", {"ms": 0.0, "n": 0})
-    samples_per_step = spr * rays_per_step  # both passes of the last warm-up step have the same ray geometry
+    fwd = ktimes_avg.get("nsig_field_forward", {"ms": 0.0, "n": 0})
+    bwd = ktimes_avg.get("nsig_field_backward", {"ms": 0.0, "n": 0})
+    samples_per_step = n_samples_step  # both render passes, read from the march counters
     # SURVEY 8d algorithmic bytes per sample of the field forward: 24 (xyz, dir in) + 1024 (16 levels x 8 corners
     # x 8 B) + 64 (pre-summed message table gather) + 16 (sigma, rgb out)
     alg_bytes_per_sample = 24 + 1024 + 64 + 16
-    calls_per_step = max(fwd["n"] / K, 1e-9)
+    calls_per_step = max(fwd["n"] / steps_timed, 1e-9)
     avg_ms = fwd["ms"] / max(fwd["n"], 1)
     samples_per_launch = samples_per_step / calls_per_step
     achieved = alg_bytes_per_sample * samples_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    step_ms = ms / K
+    traffic = None
+    try:  # ncu dram__bytes_read+write per launch of this kernel, from the committed capture of this round
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["k_field_fwd_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_field_fwd (nsig_field_forward)", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "samples_per_launch": samples_per_launch,
                 "alg_bytes_per_sample": alg_bytes_per_sample,
-                "share_of_step": fwd["ms"] / ms if ms > 0 else None,
+                "share_of_step": (fwd["ms"] / steps_timed) / step_ms if step_ms > 0 else None,
                 "field_backward_avg_launch_ms": bwd["ms"] / max(bwd["n"], 1),
-                "field_backward_share_of_step": bwd["ms"] / ms if ms > 0 else None}
+                "field_backward_share_of_step": (bwd["ms"] / steps_timed) / step_ms if step_ms > 0 else None,
+                "timed": "CUDA events around the launches on the launching stream" +
+                         (" (external event nodes inside the captured step graph; mean of 9 replays)" if use_graph else "")}
 
     total_rays = rays_per_step * world
     line = {
@@ -285,7 +366,10 @@ def run_ours(args):
                    "message_dim": md, "codebook": f'{cfg["num_rows"]}x{cfg["num_cols"]}',
                    "content_rays_per_gpu": cfg["num_rays"], "watermark_rays_per_gpu": rays_per_step - cfg["num_rays"],
                    "rays_per_step_per_gpu": rays_per_step, "mean_samples_per_ray": spr, "occupancy": cfg["occupancy"],
-                   "weights": "random-init (tables U(+-1e-4), Xavier MLPs)", "optimizer": "Adam(fused) + GradScaler",
+                   "weights": "random-init (tables U(+-1e-4), Xavier MLPs)",
+                   "optimizer": ("WatermarkAdam (fused message-table Adam + torch fused Adam for the decoder)"
+                                 if args.optimizer == "fused" else "torch.optim.Adam(fused)") + " + GradScaler",
+                   "step": "one CUDA graph replay per step" if use_graph else "eager",
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
                    "parallelism": f"ray-sharded dp{world}"},

@@ -212,6 +212,25 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
                         float* grad_feat, float* grad_sigma_w, float* grad_color_w,
                         nsig_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* optimizer step of the message tables — nerf/utils_wtmk_disen.py:1175-1181   */
+/* ------------------------------------------------------------------------- */
+
+/* torch.optim.Adam (betas, eps, no weight decay, no amsgrad) over the parameters
+ * network_wtmk_tcnn.py:179-188 hands it, restricted to the message tables: the message_dim tables
+ * embeddings[2i + bit_i] selected by `message` (device float 0/1) are updated with the one gradient
+ * G = dL/dS ([2^log2_T,2] fp32) they all share; unselected tables are untouched, exactly
+ * like parameters whose .grad is None.
+ *   ptr_table: DEVICE array uint64[3][n_tables] = addresses of (param, exp_avg, exp_avg_sq) per table
+ *   steps    : device float[n_tables], per-table step counts (incremented for the selected tables)
+ *   coef     : device float[n_tables][2] scratch (bias-correction scalars)
+ *   grad_scale / found_inf: optional device scalars with torch.amp.GradScaler's meaning (G is divided
+ *   by *grad_scale; the whole step is skipped when *found_inf != 0). */
+int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
+                       const float* message, const float* G, float* steps, float* coef,
+                       const float* grad_scale, const float* found_inf, float lr, float beta1,
+                       float beta2, float eps, uint32_t log2_T, nsig_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

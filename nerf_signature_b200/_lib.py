@@ -40,6 +40,7 @@ _SIGNATURES = {
                             _vp], 1),
     "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
+    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp], 2),
     "nsig_field_backward": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp, _vp,
                              _vp, _vp], 1),
 }
@@ -101,22 +102,36 @@ _timing_events = []
 
 def timing_enable(names):
     """Bracket every call of the named entry points with CUDA events on the launching stream
-    (bench.py uses this to time the dominant kernel live inside the timed region)."""
+    (bench.py uses this to time the dominant kernel live inside the timed region).  Calls made while the
+    stream is being captured into a CUDA graph record EXTERNAL events (event-record nodes), which are
+    re-recorded by every replay: read them with timing_read() after a replay has finished."""
     global _timing_names
     _timing_names = tuple(names)
     _timing_events.clear()
 
 
-def timing_collect():
-    """Synchronise and return {name: {"ms": total, "n": calls}}; disables timing."""
-    global _timing_names
-    _timing_names = ()
+def timing_reset():
+    """Forget the event pairs recorded so far (keeps timing enabled)."""
+    _timing_events.clear()
+
+
+def timing_read():
+    """Synchronise and return {name: {"ms": total, "n": calls}} over the recorded event pairs (for graph
+    replays: the most recent replay).  Keeps the events."""
     torch.cuda.synchronize()
     out = {}
     for name, e0, e1 in _timing_events:
         d = out.setdefault(name, {"ms": 0.0, "n": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["n"] += 1
+    return out
+
+
+def timing_collect():
+    """timing_read(), then disable timing and drop the events."""
+    global _timing_names
+    out = timing_read()
+    _timing_names = ()
     _timing_events.clear()
     return out
 
@@ -126,7 +141,9 @@ def call(name, *args):
     global launch_count
     lib = load()
     if name in _timing_names:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         rc = getattr(lib, name)(*args, stream())
         e1.record()

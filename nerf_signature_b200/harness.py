@@ -78,8 +78,13 @@ def occupancy(cfg, cascade, seed=0):
 class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
-    def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0):
+    def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False):
+        """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
+        "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
+        graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
+        in one CUDA graph on first use; needs optimizer="fused"."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
+        from .optim import WatermarkAdam
         torch.manual_seed(seed)
         self.cfg = cfg
         self.device = device
@@ -93,7 +98,14 @@ class Scene:
         model.density_grid.copy_(torch.from_numpy(grid))
         model.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
         self.model = model.to(device).train()
-        self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
+        if graph and optimizer != "fused":
+            raise ValueError("graph capture needs the fused optimizer (the set of tables with a gradient changes "
+                             "with every message under torch.optim.Adam)")
+        self.fused = optimizer == "fused"
+        if self.fused:
+            self.optimizer = WatermarkAdam(self.model, lr=lr, betas=(0.9, 0.99), eps=1e-15, capturable=graph)
+        else:
+            self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
         self.fp16 = fp16
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.lambda_w, self.lambda_i = 0.005, 1.0  # README.md:40,45
@@ -101,6 +113,10 @@ class Scene:
         self.sync = parallel.GradSync()
         _hmsg.grad_reducer = self.sync.reduce_table_grad if self.sync.enabled else None
         self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
+        self.use_graph = graph
+        self._graph = None
+        self._static = None
+        self.launches_per_step = None
 
     def new_message(self, generator=None):
         """utils_wtmk_disen.py:1165 — a fresh random message every step.  Generated on the host so the
@@ -118,18 +134,22 @@ class Scene:
             out[k] = t.to(self.device, non_blocking=True)
         return out
 
-    def train_step(self, batch, message):
-        """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here)."""
+    def _step_impl(self, batch, message):
+        """utils_wtmk_disen.py:1164-1181 + 579-646; `message` is a host tensor (torch-Adam path: the bits
+        select which tables receive a gradient) or a device tensor (fused path: nothing on the host depends
+        on the bits)."""
         model = self.model
         self.optimizer.zero_grad(set_to_none=True)
         msg_dev = message.to(self.device, non_blocking=True) if not message.is_cuda else message
-        message_for_render = message  # host bits known -> no .item() round trip inside the encoder
-        out_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message_for_render, staged=False, bg_color=1,
+        if self.fused:
+            self.optimizer.set_message(msg_dev)
+            message = msg_dev
+        out_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
                              perturb=False, force_all_rays=True, **self.opt)
         pred = torch.clamp(out_w["image"], min=0, max=1)
         with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
             decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
-        out_c = model.render(batch["rays_o"], batch["rays_d"], message_for_render, staged=False, bg_color=1,
+        out_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
                              perturb=False, force_all_rays=True, **self.opt)
         lossi = F.mse_loss(out_c["image"], batch["gt"], reduction="none").mean()
         lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
@@ -140,7 +160,48 @@ class Scene:
         self.scaler.update()
         return loss, lossi, lossw
 
+    def _capture(self, batch, message):
+        """Warm up on a side stream, then record one step into a CUDA graph with static input buffers."""
+        from . import _lib
+        self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in batch.items()}
+        self._static["message"] = torch.empty(self.cfg["message_dim"], dtype=torch.float32, device=self.device)
+        for k, v in batch.items():
+            self._static[k].copy_(v)
+        self._static["message"].copy_(message)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._step_impl(self._static, self._static["message"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        _lib.timing_reset()  # keep only the (external) events recorded inside the graph
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._step_impl(self._static, self._static["message"])
+        self.launches_per_step = _lib.launch_count - n0
+
+    def train_step(self, batch, message):
+        """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here)."""
+        if not self.use_graph:
+            batch = {k: (v if v.is_cuda else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
+            return self._step_impl(batch, message)
+        if self._graph is None:
+            self._capture(batch, message)
+        for k, v in batch.items():
+            self._static[k].copy_(v, non_blocking=True)
+        self._static["message"].copy_(message, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def samples_per_step(self):
+        """Measured (samples, rays) of the two most recent render calls = one training step (reads the march
+        counters the kernels left on the device)."""
+        ls = self.model.local_step
+        rows = self.model.step_counter[[(ls - 2) % 16, (ls - 1) % 16]].tolist()
+        return sum(r[0] for r in rows), sum(r[1] for r in rows)
+
     def samples_per_ray(self):
-        """Measured mean samples/ray of the most recent render call (reads the march counter)."""
-        c = self.model.step_counter[(self.model.local_step - 1) % 16].tolist()
-        return c[0] / max(c[1], 1)
+        s, r = self.samples_per_step()
+        return s / max(r, 1)

@@ -57,6 +57,31 @@ class _msg_table_sum(Function):
         return (None, None, None) + tuple(grads)
 
 
+class _msg_table_sum_sink(Function):
+    """S = sum_i tables[2i + bit_i] with the bits read on the device, for the fused optimizer path
+    (optim.WatermarkAdam): backward deposits dL/dS into the persistent buffer `sink` instead of
+    materialising message_dim identical table gradients, so nothing here depends on host-side knowledge of
+    the message — the whole training step can be captured in a CUDA graph."""
+
+    @staticmethod
+    def forward(ctx, message, log2_T, sink, *tables):
+        md = len(tables) // 2
+        msg = message.to(device=tables[0].device, dtype=torch.float32).contiguous()
+        S = torch.empty_like(tables[0])
+        tabs = [t.contiguous() for t in tables]
+        _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S))
+        ctx.sink = sink
+        ctx.n = len(tables)
+        return S
+
+    @staticmethod
+    def backward(ctx, grad_S):
+        if grad_reducer is not None:
+            grad_S = grad_reducer(grad_S)
+        ctx.sink.copy_(grad_S)
+        return (None, None, None) + (None,) * ctx.n
+
+
 class HashEmbedder(nn.Module):
     def __init__(self, bounding_box, n_levels=16, n_features_per_level=2,
                  log2_hashmap_size=19, base_resolution=16, finest_resolution=512, message_dim=16):
@@ -85,12 +110,18 @@ class HashEmbedder(nn.Module):
                 "the pre-summed form needs one resolution for every bit (base_resolution == finest_resolution, "
                 "as in nerf/network_wtmk_tcnn.py:43-44)")
         self.resolution = res[0]
+        # set by optim.WatermarkAdam: persistent [T,2] buffer that receives dL/dS (see _msg_table_sum_sink)
+        self.grad_sink = None
 
     def tables(self):
         return [e.weight for e in self.embeddings[:2 * self.message_dim]]
 
     def summed_table(self, message, bits=None):
         """S [T,2] (differentiable w.r.t. the selected tables)."""
+        if self.grad_sink is not None and torch.is_grad_enabled():
+            if message.shape[0] != self.message_dim:
+                raise ValueError(f"message has {message.shape[0]} bits, encoder was built for {self.message_dim}")
+            return _msg_table_sum_sink.apply(message, self.log2_hashmap_size, self.grad_sink, *self.tables())
         if bits is None:
             bits = message_bits(message)
         if len(bits) != self.message_dim:

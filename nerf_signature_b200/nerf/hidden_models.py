@@ -15,16 +15,27 @@ _MEAN = (0.485, 0.456, 0.406)
 _STD = (0.229, 0.224, 0.225)
 
 
+_CONST = {}
+
+
+def _mean_std(x):
+    """Device-resident normalisation constants, built once per (device, dtype): creating them from Python
+    lists on every call is a host-to-device copy per step and cannot be captured in a CUDA graph."""
+    key = (x.device, x.dtype)
+    if key not in _CONST:
+        _CONST[key] = (torch.tensor(_MEAN, dtype=x.dtype, device=x.device).view(-1, 1, 1),
+                       torch.tensor(_STD, dtype=x.dtype, device=x.device).view(-1, 1, 1))
+    return _CONST[key]
+
+
 def normalize_img(x):
     """(x - mean) / std over the channel dim of a [..., 3, H, W] tensor (torchvision Normalize)."""
-    mean = torch.tensor(_MEAN, dtype=x.dtype, device=x.device).view(-1, 1, 1)
-    std = torch.tensor(_STD, dtype=x.dtype, device=x.device).view(-1, 1, 1)
+    mean, std = _mean_std(x)
     return (x - mean) / std
 
 
 def unnormalize_img(x):
-    mean = torch.tensor(_MEAN, dtype=x.dtype, device=x.device).view(-1, 1, 1)
-    std = torch.tensor(_STD, dtype=x.dtype, device=x.device).view(-1, 1, 1)
+    mean, std = _mean_std(x)
     return x * std + mean
 
 

@@ -254,7 +254,10 @@ class NeRFRenderer(nn.Module):
             # sigmas already include density_scale (folded into the fused kernel, reference L294)
             sigmas, rgbs = self.field(xyzs, dirs, message, count=counter)
 
-            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            # worst-case sized buffers cannot overflow, so every live row is owned by a ray: skip the gradient zero-fill
+            composite = raymarching.raymarching.composite_rays_train_live if xyzs.shape[0] == N * max_steps \
+                else raymarching.composite_rays_train
+            weights_sum, depth, image = composite(sigmas, rgbs, deltas, rays, T_thresh)
             image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
             depth = torch.clamp(depth - nears, min=0) / (fars - nears)
             image = image.view(*prefix, 3)

@@ -1,0 +1,101 @@
+"""Optimizer for watermark training: torch.optim.Adam semantics over `NeRFNetwork.get_params(lr)`
+(nerf/network_wtmk_tcnn.py:179-188, nerf/utils_wtmk_disen.py:1175-1181), with the message tables updated
+by one fused kernel (csrc/optim.cu) from the single gradient G = dL/dS they all share.
+
+With plain torch.optim.Adam (which stays fully supported — the encoder then fans G out to the selected
+tables' .grad exactly like the reference's autograd does) a step costs message_dim 4 MiB gradient copies,
+an unscale pass and a 7-stream multi-tensor Adam, and the set of parameters that have a gradient changes
+with every message, which rules out CUDA-graph capture.  WatermarkAdam keeps G in one persistent buffer,
+lets the kernel pick the tables from the device-side message, and is capture-safe; it implements the
+`_step_supports_amp_scaling` contract of torch.amp.GradScaler (grad_scale / found_inf tensors), so
+`scaler.step(optimizer)` / `scaler.update()` work unchanged, inf checks included.
+
+Everything that is not a message table (the HiDDeN decoder) is delegated to a fused torch.optim.Adam.
+"""
+import torch
+
+from . import _lib
+
+_P = _lib.ptr
+
+
+class WatermarkAdam(torch.optim.Optimizer):
+    _step_supports_amp_scaling = True
+
+    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False):
+        enc = model.msg_encoder
+        tables = enc.tables()
+        dev = tables[0].device
+        if dev.type != "cuda":
+            raise _lib.NsigError("WatermarkAdam needs the model on a CUDA device (no CPU path)")
+        table_ids = {id(t) for t in tables}
+        others = []
+        self._train_tables = not getattr(model, "finetune_decoder", False)
+        for group in model.get_params(lr):
+            ps = [p for p in group["params"] if id(p) not in table_ids]
+            if ps:
+                others.append({"params": ps, "lr": group["lr"]})
+        # G = dL/dS lives here; the proxy parameter only exists so that GradScaler's inf check
+        # (_check_inf_per_device walks param_groups) sees G like any other gradient.
+        self.G = torch.zeros_like(tables[0])
+        self._proxy = torch.nn.Parameter(torch.empty_like(tables[0]), requires_grad=True)
+        self._proxy.grad = self.G
+        groups = list(others)
+        if self._train_tables:
+            groups.append({"params": [self._proxy], "lr": lr, "msg_tables": True})
+        super().__init__(groups, dict(lr=lr, betas=betas, eps=eps))
+        self.inner = torch.optim.Adam(others, lr=lr, betas=betas, eps=eps, fused=True, capturable=capturable) \
+            if others else None
+        self.enc = enc
+        self._model = model
+        self.tables = tables
+        self.message = None  # device float [md]; set by the training step before backward
+        if self._train_tables:
+            enc.grad_sink = self.G
+            n = len(tables)
+            self.exp_avg = [torch.zeros_like(t) for t in tables]
+            self.exp_avg_sq = [torch.zeros_like(t) for t in tables]
+            self.steps = torch.zeros(n, dtype=torch.float32, device=dev)
+            self._coef = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+            ptrs = [[t.data_ptr() for t in tables], [t.data_ptr() for t in self.exp_avg],
+                    [t.data_ptr() for t in self.exp_avg_sq]]
+            self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+            self._ptr_key = tuple(ptrs[0])
+
+    def set_message(self, message_dev):
+        self.message = message_dev
+
+    def zero_grad(self, set_to_none=True):
+        if self.inner is not None:
+            self.inner.zero_grad(set_to_none=set_to_none)
+        # G is overwritten (copy_) by every backward; the proxy keeps pointing at it
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("closures are not supported")
+        grad_scale = getattr(self, "grad_scale", None)
+        found_inf = getattr(self, "found_inf", None)
+        if self.inner is not None:
+            for g_out, g_in in zip(self.param_groups, self.inner.param_groups):
+                g_in["lr"] = g_out["lr"]  # lr schedulers act on the outer groups
+            self.inner.grad_scale, self.inner.found_inf = grad_scale, found_inf
+            try:
+                self.inner.step()
+            finally:
+                del self.inner.grad_scale, self.inner.found_inf
+        if self._train_tables:
+            if self.message is None:
+                raise RuntimeError("WatermarkAdam.set_message(message) must be called before step()")
+            if tuple(t.data_ptr() for t in self.tables) != self._ptr_key:
+                raise RuntimeError("message tables were re-allocated after the optimizer was built")
+            group = self.param_groups[-1]
+            beta1, beta2 = group["betas"]
+            md = self.enc.message_dim
+            _lib.call("nsig_msg_adam_step", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(self.G),
+                      _P(self.steps), _P(self._coef), _P(grad_scale), _P(found_inf), float(group["lr"]), float(beta1),
+                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size)
+            # the kernel writes the tables through raw pointers (no autograd version bump): drop the model's
+            # cached S so the next forward re-sums the updated tables
+            self._model._S_cache = None
+        return None

@@ -202,6 +202,7 @@ class _composite_rays_train(Function):
 
         ctx.save_for_backward(sigmas, rgbs, deltas, rays, weights_sum, depth, image)
         ctx.dims = [M, N, T_thresh]
+        ctx.zero_fill = True
 
         return weights_sum, depth, image
 
@@ -215,8 +216,11 @@ class _composite_rays_train(Function):
         sigmas, rgbs, deltas, rays, weights_sum, depth, image = ctx.saved_tensors
         M, N, T_thresh = ctx.dims
 
-        grad_sigmas = torch.zeros_like(sigmas)
-        grad_rgbs = torch.zeros_like(rgbs)
+        # rows owned by no ray (alignment padding, dropped rays) must read as zero (raymarching.py:283-284);
+        # the kernel itself writes every row of every kept ray, zeros after early termination
+        alloc = torch.zeros_like if ctx.zero_fill else torch.empty_like
+        grad_sigmas = alloc(sigmas)
+        grad_rgbs = alloc(rgbs)
 
         _lib.call("nsig_composite_rays_train_backward", _P(grad_weights_sum), _P(grad_image), _P(sigmas), _P(rgbs),
                   _P(deltas), _P(rays), _P(weights_sum), _P(image), M, N, float(T_thresh), _P(grad_sigmas), _P(grad_rgbs))
@@ -224,6 +228,21 @@ class _composite_rays_train(Function):
         return grad_sigmas, grad_rgbs, None, None, None
 
 composite_rays_train = _composite_rays_train.apply
+
+
+class _composite_rays_train_live(_composite_rays_train):
+    """composite_rays_train for callers that only ever consume the sample rows owned by rays (the
+    renderer's sync-free path sizes its buffers for the worst case, N*max_steps rows, and every consumer
+    stops at the live count): identical kernels, but the gradient buffers are not zero-filled."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=torch.float32)
+    def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+        out = _composite_rays_train.forward.__wrapped__(ctx, sigmas, rgbs, deltas, rays, T_thresh)
+        ctx.zero_fill = False
+        return out
+
+composite_rays_train_live = _composite_rays_train_live.apply
 
 # ----------------------------------------
 # infer functions
