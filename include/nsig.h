@@ -199,6 +199,22 @@ int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* 
 int nsig_color_forward(const float* dirs, const void* geo_feat, uint32_t M, const void* color_w,
                        float* rgbs, nsig_stream_t stream);
 
+/* Fused frame renderer = the whole inference branch of NeRFRenderer.run_cuda (nerf/renderer_wtmk.py:323-372:
+ * near_far_from_aabb + the host loop over march_rays -> forward(x,d,message) -> composite_rays with alive-ray
+ * compaction) for N rays in one persistent kernel; a warp owns a ray until it terminates (T < T_thresh) or
+ * leaves the box.  Field arguments as in nsig_field_forward.  Outputs are the loop's accumulators before the
+ * background blend (renderer_wtmk.py:369-370 stay in the caller): weights_sum[N], depth[N] = sum w*t,
+ * image[N,3]; nears/fars[N] optional.  work_counter: device uint32, MUST be zero on entry (dynamic ray
+ * scheduling).  sample_count (optional): device uint32, incremented by the number of samples evaluated.
+ * noises (optional) [N]: start-offset noise for perturb=True (renderer_wtmk.py:353). */
+int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near,
+                     float bound, const uint8_t* grid, uint32_t C, uint32_t H, float dt_gamma,
+                     uint32_t max_steps, float T_thresh, const float* noises, const float* const* tables,
+                     const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
+                     const void* sigma_w, const void* color_w, float density_scale, uint32_t* work_counter,
+                     float* weights_sum, float* depth, float* image, float* nears, float* fars,
+                     uint32_t* sample_count, nsig_stream_t stream);
+
 /* Fused field backward (watermark mode: MLP dgrad only):
  * given dL/dsigma[M], dL/drgb[M,3] and the saved feat[M,32], recompute the MLP
  * activations, back-propagate to the encoder output and scatter-add the gradient of

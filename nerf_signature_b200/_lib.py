@@ -40,6 +40,8 @@ _SIGNATURES = {
                             _vp], 1),
     "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
+    "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
+                          _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp], 2),
     "nsig_field_backward": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp, _vp,
                              _vp, _vp], 1),

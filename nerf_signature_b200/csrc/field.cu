@@ -19,6 +19,7 @@
 // reference's own MLP arithmetic is unpinned); encoder arithmetic is the exact
 // fp32 restatement in hash_common.cuh.
 #include "hash_common.cuh"
+#include "march_common.cuh"
 
 namespace nsig {
 
@@ -211,19 +212,10 @@ __device__ __forceinline__ uint32_t frag_row(uint32_t row0, int mt, int h, int g
 
 // Encode the rows of this thread: A fragments of the sigma net's first layer.
 // fa[mt][ks][2*hk + h]: level = 8*ks + 4*hk + tig, row half h.
+// xn[mt][h][a]: the rows' positions already normalised to the unit box.
 template <int MT>
-__device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
-                                            uint32_t row0, int g, int tig) {
-    float xn[MT][2][3];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
-                xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
-        }
+__device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const FieldParams& p,
+                                                 const float (&xn)[MT][2][3], int g, int tig) {
     float2 f[MT][2][4];  // [mt][h][j]: level tig + 4j
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -278,6 +270,22 @@ __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const Fiel
 #pragma unroll
             for (int j = 0; j < 4; ++j)  // level tig+4j -> k-step j>>1, half-k j&1
                 fa[mt][j >> 1][2 * (j & 1) + h] = pack_h2(f[mt][h][j].x, f[mt][h][j].y);
+}
+
+template <int MT>
+__device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
+                                            uint32_t row0, int g, int tig) {
+    float xn[MT][2][3];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
+                xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
+        }
+    encode_positions<MT>(fa, p, xn, g, tig);
 }
 
 // A fragments of the colour net's first k-step: SH(d) columns {2tig,2tig+1,2tig+8,2tig+9}
@@ -488,6 +496,224 @@ k_color_fwd(const float* __restrict__ dirs, const __half* __restrict__ geo, uint
                 }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused frame renderer: the inference branch of NeRFRenderer.run_cuda (renderer_wtmk.py:323-372) as ONE
+// persistent kernel.  The reference drives march_rays -> network -> composite_rays -> alive-ray compaction
+// from the host, up to ~10^3 iterations per 4096-ray chunk with a device-to-host sync each.
+// Here a warp owns a ray from start to finish: it marches the occupancy grid 32 lattice points at a time
+// (march_window, bit-exact lattice), stages occupied samples in shared memory, evaluates the field on 32
+// samples at once with the same tensor-core path as k_field_fwd (hash gather -> A fragments -> MLPs),
+// composites them with warp scans and stops at the reference's termination rule (T < T_thresh before a
+// sample, renderer_wtmk.py:361 -> raymarching.cu:868-883) or when the ray leaves the box.  No sample ever
+// touches HBM; rays are handed out through an atomic counter so long and short rays balance.
+//
+// Per-ray results equal the reference loop's up to fp32 rounding: the reference accumulates the march
+// parameter through composite_rays' `t += deltas[1]` between chunks, this kernel keeps the exact lattice.
+// ---------------------------------------------------------------------------------------
+struct RenderParams {
+    FieldParams f;  // tables, S, MLP weights, bound, density_scale (xyzs/dirs/M unused)
+    const float* rays_o;
+    const float* rays_d;
+    uint32_t N;
+    const uint8_t* grid;
+    float dt_gamma;
+    uint32_t max_steps, C, H;
+    const float* aabb;
+    float min_near, T_thresh;
+    const float* noises;      // optional [N] (perturb)
+    uint32_t* work_counter;   // zero-initialised by the caller
+    float* weights_sum;       // [N]
+    float* depth;             // [N]   sum w * t (not normalised)
+    float* image;             // [N,3] (no background)
+    float* nears;             // optional [N]
+    float* fars;              // optional [N]
+    uint32_t* sample_count;   // optional: total samples evaluated (atomicAdd)
+};
+
+constexpr int kRenderWarps = 4;
+constexpr int kStageSlots = 64;
+// per-warp staging (floats): xyz[64][3] + dt[64] + dreal[64] + sigma[32] + rgb[32][3]
+constexpr int kStageFloats = kStageSlots * 5 + 32 * 4;
+constexpr int kFwdHalfsPad = (kFwdHalfs + 7) / 8 * 8;
+
+__global__ void __launch_bounds__(kRenderWarps * 32)
+k_render_rays(const RenderParams p) {
+    constexpr int MT = 2;
+    extern __shared__ __align__(16) __half sm[];
+    stage_forward_weights(sm, p.f.sigma_w, p.f.color_w, true);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    float* st_xyz = reinterpret_cast<float*>(sm + kFwdHalfsPad) + warp * kStageFloats;
+    float* st_dt = st_xyz + kStageSlots * 3;
+    float* st_dr = st_dt + kStageSlots;
+    float* st_sig = st_dr + kStageSlots;
+    float* st_rgb = st_sig + 32;
+    const MarchCfg c = make_cfg(p.f.bound_add, p.dt_gamma, p.max_steps, p.C, p.H);
+    const uint32_t lt_mask = lanemask_lt();
+    uint32_t evaluated = 0;
+
+    for (;;) {
+        uint32_t n = 0;
+        if (lane == 0) n = atomicAdd(p.work_counter, 1u);
+        n = __shfl_sync(NSIG_FULL_MASK, n, 0);
+        if (n >= p.N) break;
+        const RayConst r = load_ray(p.rays_o, p.rays_d, n);
+        float near, far;
+        near_far_one(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, p.aabb, p.min_near, near, far);
+        if (lane == 0) {
+            if (p.nears) p.nears[n] = near;
+            if (p.fars) p.fars[n] = far;
+        }
+        // the colour net's SH inputs depend on the ray only: build its first k-step once
+        uint32_t sh_lo, sh_hi;
+        {
+            float o[16];
+            sh4(r.dx, r.dy, r.dz, o);
+            float lo0 = o[0], lo1 = o[1], hi0 = o[8], hi1 = o[9];
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (tig == t) { lo0 = o[2 * t]; lo1 = o[2 * t + 1]; hi0 = o[2 * t + 8]; hi1 = o[2 * t + 9]; }
+            sh_lo = pack_h2(lo0, lo1);
+            sh_hi = pack_h2(hi0, hi1);
+        }
+        const float t0 = perturbed_start(near, p.noises ? p.noises[n] : 0.0f, c);
+        MarchState ms{t0, -INFINITY, t0};
+        float T = 1.0f, t_acc = near;  // composite_rays starts its t from rays_t = nears (renderer_wtmk.py:345)
+        float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_w = 0.f, acc_d = 0.f;
+        uint32_t total = 0, nbuf = 0;
+        for (;;) {
+            // ---- march until 32 samples are staged or the ray ends ----
+            while (nbuf < 32 && ms.t < far && total + nbuf < p.max_steps) {
+                const Window w = march_window(ms, r, c, p.grid, far, lane, lt_mask);
+                if ((w.emitted >> lane) & 1u) {
+                    const uint32_t slot = nbuf + __popc(w.emitted & lt_mask);
+                    st_xyz[slot * 3] = w.p.x; st_xyz[slot * 3 + 1] = w.p.y; st_xyz[slot * 3 + 2] = w.p.z;
+                    st_dt[slot] = w.p.dt;
+                    st_dr[slot] = w.delta_real;
+                }
+                nbuf += (uint32_t)__popc(w.emitted);
+            }
+            __syncwarp();
+            const uint32_t nb = min(min(nbuf, 32u), p.max_steps - total);
+            if (nb == 0) break;
+            // ---- field on rows [0, nb) ----
+            {
+                float xn[MT][2][3];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t row = min((uint32_t)(mt * 16 + h * 8 + g), nb - 1);
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            xn[mt][h][a] = __fmul_rn(__fadd_rn(st_xyz[row * 3 + a], p.f.bound_add), p.f.bound_mul);
+                    }
+                uint32_t fa[MT][2][4];
+                encode_positions<MT>(fa, p.f, xn, g, tig);
+                uint32_t h1[MT][4][4];
+                {
+                    float cc[MT][8][4];
+                    layer<MT, 2, 8>(cc, fa, sm + oWs0, kS32, g, tig);
+                    relu_to_a<MT, 8>(h1, cc);
+                }
+                float so[MT][2][4];
+                layer<MT, 4, 2>(so, h1, sm + oWs1, kS64, g, tig);
+                if (tig == 3) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            st_sig[mt * 16 + h * 8 + g] = __fmul_rn(p.f.density_scale, expf(so[mt][1][2 * h + 1]));
+                }
+                uint32_t ca[MT][2][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    ca[mt][0][0] = sh_lo; ca[mt][0][1] = sh_lo; ca[mt][0][2] = sh_hi; ca[mt][0][3] = sh_hi;
+                }
+                geo_to_a<MT>(ca, so, tig);
+                uint32_t h2[MT][4][4];
+                {
+                    float cc[MT][8][4];
+                    layer<MT, 2, 8>(cc, ca, sm + oWc0, kS32, g, tig);
+                    relu_to_a<MT, 8>(h1, cc);
+                    layer<MT, 4, 8>(cc, h1, sm + oWc1, kS64, g, tig);
+                    relu_to_a<MT, 8>(h2, cc);
+                }
+                float co[MT][1][4];
+                layer<MT, 4, 1>(co, h2, sm + oWc2, kS64, g, tig);
+                if (tig < 2) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int row = mt * 16 + h * 8 + g;
+                            const float s0 = 1.0f / (1.0f + expf(-co[mt][0][2 * h]));
+                            if (tig == 0) {
+                                st_rgb[row * 3] = s0;
+                                st_rgb[row * 3 + 1] = 1.0f / (1.0f + expf(-co[mt][0][2 * h + 1]));
+                            } else {
+                                st_rgb[row * 3 + 2] = s0;
+                            }
+                        }
+                }
+            }
+            __syncwarp();
+            // ---- composite (raymarching.cu:850-890): lane k owns sample k ----
+            bool terminated;
+            {
+                const bool valid = (uint32_t)lane < nb;
+                const float sigma = valid ? st_sig[lane] : 0.f;
+                const float dt = valid ? st_dt[lane] : 0.f;
+                const float dr = valid ? st_dr[lane] : 0.f;
+                const float alpha = 1.0f - __expf(-sigma * dt);
+                const float one_m = valid ? (1.0f - alpha) : 1.0f;
+                const float Tincl = T * warp_scan_mul(one_m, lane);
+                float Tbefore = __shfl_up_sync(NSIG_FULL_MASK, Tincl, 1);
+                if (lane == 0) Tbefore = T;
+                const float tcum = t_acc + warp_scan_add(dr, lane);
+                // the reference accumulates a sample, then stops if the transmittance BEFORE it was below T_thresh
+                const uint32_t dead = __ballot_sync(NSIG_FULL_MASK, valid && (Tbefore < p.T_thresh));
+                const int stop = dead ? (__ffs(dead) - 1) : 32;
+                if (valid && lane <= stop) {
+                    const float w = alpha * Tbefore;
+                    acc_r += w * st_rgb[lane * 3]; acc_g += w * st_rgb[lane * 3 + 1]; acc_b += w * st_rgb[lane * 3 + 2];
+                    acc_d += w * tcum;
+                    acc_w += w;
+                }
+                terminated = dead != 0;
+                T = __shfl_sync(NSIG_FULL_MASK, Tincl, 31);
+                t_acc = __shfl_sync(NSIG_FULL_MASK, tcum, 31);
+            }
+            total += nb;
+            evaluated += nb;
+            if (terminated) break;
+            // ---- keep the samples that did not fit into this batch ----
+            const uint32_t left = nbuf - nb;
+            float kx = 0.f, ky = 0.f, kz = 0.f, kdt = 0.f, kdr = 0.f;
+            if ((uint32_t)lane < left) {
+                const uint32_t src = nb + lane;
+                kx = st_xyz[src * 3]; ky = st_xyz[src * 3 + 1]; kz = st_xyz[src * 3 + 2];
+                kdt = st_dt[src]; kdr = st_dr[src];
+            }
+            __syncwarp();
+            if ((uint32_t)lane < left) {
+                st_xyz[lane * 3] = kx; st_xyz[lane * 3 + 1] = ky; st_xyz[lane * 3 + 2] = kz;
+                st_dt[lane] = kdt; st_dr[lane] = kdr;
+            }
+            nbuf = left;
+            __syncwarp();
+        }
+        acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
+        acc_w = warp_sum(acc_w); acc_d = warp_sum(acc_d);
+        if (lane == 0) {
+            p.weights_sum[n] = acc_w;
+            p.depth[n] = acc_d;
+            p.image[(size_t)n * 3] = acc_r; p.image[(size_t)n * 3 + 1] = acc_g; p.image[(size_t)n * 3 + 2] = acc_b;
+        }
+    }
+    if (p.sample_count && lane == 0 && evaluated) atomicAdd(p.sample_count, evaluated);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -790,6 +1016,36 @@ int nsig_color_forward(const float* dirs, const void* geo_feat, uint32_t M, cons
     const size_t smem = kFwdHalfs * sizeof(__half);
     k_color_fwd<<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
         dirs, reinterpret_cast<const __half*>(geo_feat), M, reinterpret_cast<const __half*>(color_w), rgbs);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near,
+                     float bound, const uint8_t* grid, uint32_t C, uint32_t H, float dt_gamma, uint32_t max_steps,
+                     float T_thresh, const float* noises, const float* const* tables, const float* resolutions,
+                     uint32_t log2_T, const float* S, float msg_resolution, const void* sigma_w, const void* color_w,
+                     float density_scale, uint32_t* work_counter, float* weights_sum, float* depth, float* image,
+                     float* nears, float* fars, uint32_t* sample_count, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!rays_o || !rays_d || !aabb || !grid || !color_w || !work_counter || !weights_sum || !depth || !image)
+        return NSIG_EINVAL;
+    if (C == 0 || C > 31 || H == 0 || H > 1024 || max_steps == 0) return NSIG_EINVAL;
+    RenderParams p;
+    const int rc = fill_field_params(p.f, rays_o /*unused*/, rays_d, 0, bound, tables, resolutions, log2_T, S,
+                                     msg_resolution, sigma_w, color_w, nullptr, density_scale);
+    if (rc) return rc;
+    p.rays_o = rays_o; p.rays_d = rays_d; p.N = N; p.grid = grid; p.dt_gamma = dt_gamma;
+    p.max_steps = max_steps; p.C = C; p.H = H; p.aabb = aabb; p.min_near = min_near; p.T_thresh = T_thresh;
+    p.noises = noises; p.work_counter = work_counter; p.weights_sum = weights_sum; p.depth = depth; p.image = image;
+    p.nears = nears; p.fars = fars; p.sample_count = sample_count;
+    const size_t smem = kFwdHalfsPad * sizeof(__half) + (size_t)kRenderWarps * kStageFloats * sizeof(float);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t want = div_up(N, kRenderWarps);
+    int per_sm = 3;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_rays, kRenderWarps * 32, smem);
+    const uint32_t cap = (uint32_t)sms * (uint32_t)(per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
+    k_render_rays<<<want < cap ? want : cap, kRenderWarps * 32, smem, (cudaStream_t)stream>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -193,3 +193,29 @@ def color_forward(dirs, geo_feat, color_mlp):
     rgbs = torch.empty(M, 3, dtype=torch.float32, device=dirs.device)
     _lib.call("nsig_color_forward", _P(dirs), _P(geo), M, _P(color_mlp.half_weights()), _P(rgbs))
     return rgbs
+
+
+@torch.no_grad()
+def render_rays(rays_o, rays_d, aabb, min_near, bitfield, cascade, grid_size, dt_gamma, max_steps, T_thresh, noises,
+                S, cfg, sigma_mlp, color_mlp, tables):
+    """Whole-frame inference in one persistent kernel (nsig_render_rays): returns the accumulators of the
+    reference's alive-ray loop — weights_sum [N], depth [N] (sum w*t), image [N,3] without background —
+    plus nears/fars [N] and a device counter holding the number of samples evaluated."""
+    rays_o = rays_o.contiguous().float()
+    rays_d = rays_d.contiguous().float()
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
+    depth = torch.empty(N, dtype=torch.float32, device=dev)
+    image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    nears = torch.empty(N, dtype=torch.float32, device=dev)
+    fars = torch.empty(N, dtype=torch.float32, device=dev)
+    counters = torch.zeros(2, dtype=torch.int32, device=dev)  # [work counter, samples evaluated]
+    tabs = [t.contiguous() for t in tables]
+    Sc = S.contiguous() if S is not None else None
+    _lib.call("nsig_render_rays", _P(rays_o), _P(rays_d), N, _P(aabb.contiguous()), float(min_near), cfg.bound,
+              _P(bitfield.contiguous()), int(cascade), int(grid_size), float(dt_gamma), int(max_steps), float(T_thresh),
+              _P(noises), _lib.pointer_array(tabs), _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc),
+              cfg.msg_resolution, _P(sigma_mlp.half_weights()), _P(color_mlp.half_weights()), cfg.density_scale,
+              _P(counters[0:1]), _P(weights_sum), _P(depth), _P(image), _P(nears), _P(fars), _P(counters[1:2]))
+    return weights_sum, depth, image, nears, fars, counters[1]

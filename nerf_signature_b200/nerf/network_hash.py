@@ -47,6 +47,9 @@ class NeRFNetwork(NeRFRenderer):
         return field_forward(xyzs, dirs, None, count, self._cfg(self.density_scale), self.sigma_net,
                              self.color_net, self.encoder.tables())
 
+    def field_args(self, message=None):
+        return (None, self._cfg(self.density_scale), self.sigma_net, self.color_net, self.encoder.tables())
+
     def forward(self, x, d):
         return field_forward(x, d, None, None, self._cfg(1.0), self.sigma_net, self.color_net,
                              self.encoder.tables())

@@ -96,6 +96,12 @@ class NeRFNetwork(NeRFRenderer):
         return field_forward(xyzs, dirs, self._summed_table(message), count, self._cfg(self.density_scale),
                              self.sigma_net, self.color_net, self.encoder.tables())
 
+    def field_args(self, message):
+        """renderer hook for the fused frame renderer: (S, cfg, sigma_mlp, color_mlp, base tables)."""
+        S = self._summed_table(message)
+        return (S.detach() if S is not None else None, self._cfg(self.density_scale), self.sigma_net, self.color_net,
+                self.encoder.tables())
+
     # ---- reference API -------------------------------------------------------------------------
     def forward(self, x, d, message=None):
         # x: [N, 3] in [-bound, bound]; d: [N, 3] normalised.  Returns sigma [N] fp32, color [N,3] fp32.

@@ -1,0 +1,97 @@
+"""-m gpu: the fused frame renderer (nsig_render_rays, one persistent kernel) against the reference-shaped
+alive-ray loop (march_rays -> forward -> composite_rays with compaction, renderer_wtmk.py:323-372) that
+tests/test_raymarching_gpu.py pins to the oracle kernel by kernel.  Tolerance 1e-3 (north_star), observed ~1e-5:
+the loop re-derives the march parameter through composite_rays' `t += deltas[1]`, the fused kernel keeps the
+exact lattice; both use fp16 MMA operands with fp32 accumulation."""
+import numpy as np
+import pytest
+import torch
+
+from nerf_signature_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(bound, md, table_scale=300.0, seed=0, sigma_gain=0.0):
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+    torch.manual_seed(seed)
+    net = NeRFNetwork(bound=bound, cuda_ray=True, message_dim=md)
+    with torch.no_grad():
+        for e in list(net.encoder.embeddings) + list(net.msg_encoder.embeddings):
+            e.weight.mul_(table_scale)
+        if sigma_gain:
+            # bias the density logit upwards (through the weights of the sigma output row) so that rays terminate early
+            net.sigma_net.params[2048:2048 + 64] += sigma_gain
+    net = net.cuda().eval()
+    grid = syn.sphere_grid(net.cascade)
+    net.density_grid.copy_(torch.from_numpy(grid))
+    net.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
+    return net
+
+
+@pytest.mark.parametrize("bound,rays_fn,dt_gamma,sigma_gain", [(1.0, syn.blender_rays, 0.0, 0.0),
+                                                               (1.0, syn.blender_rays, 0.0, 0.6),
+                                                               (2.0, syn.rays_360, 1.0 / 128, 0.3)])
+def test_fused_renderer_matches_reference_loop(bound, rays_fn, dt_gamma, sigma_gain):
+    md = 8
+    net = _net(bound, md, sigma_gain=sigma_gain)
+    rays_o, rays_d = rays_fn(1500, seed=11)
+    ro, rd = torch.from_numpy(rays_o)[None].cuda(), torch.from_numpy(rays_d)[None].cuda()
+    msg = torch.from_numpy(np.random.RandomState(2).randint(0, 2, size=md).astype(np.float32)).cuda()
+    kw = dict(staged=False, bg_color=1, perturb=False, dt_gamma=dt_gamma, max_steps=1024, T_thresh=1e-4)
+    with torch.no_grad():
+        net.fused_inference = True
+        a = net.render(ro, rd, msg, **kw)
+        n_samples = int(net.last_render_samples)
+        net.fused_inference = False
+        b = net.render(ro, rd, msg, **kw)
+    assert n_samples > 1500
+    img_a, img_b = a["image"].cpu().numpy(), b["image"].cpu().numpy()
+    assert np.abs(img_b - 1.0).max() > 0.05        # the scene is actually visible (not all background)
+    np.testing.assert_allclose(img_a, img_b, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(a["depth"].cpu().numpy(), b["depth"].cpu().numpy(), rtol=1e-3, atol=2e-4)
+    # staged rendering in chunks gives the same frame
+    with torch.no_grad():
+        net.fused_inference = True
+        c = net.render(ro, rd, msg, staged=True, max_ray_batch=400, bg_color=1, perturb=False, dt_gamma=dt_gamma,
+                       max_steps=1024, T_thresh=1e-4)
+    np.testing.assert_allclose(c["image"].cpu().numpy(), img_a, rtol=1e-6, atol=1e-7)
+
+
+def test_fused_renderer_early_termination_saves_samples():
+    md = 4
+    rays_o, rays_d = syn.blender_rays(2000, seed=5)
+    ro, rd = torch.from_numpy(rays_o)[None].cuda(), torch.from_numpy(rays_d)[None].cuda()
+    msg = torch.zeros(md).cuda()
+    counts = []
+    for gain in (0.0, 12.0):
+        net = _net(1.0, md, sigma_gain=gain)
+        with torch.no_grad():
+            net.render(ro, rd, msg, staged=False, bg_color=1, perturb=False, T_thresh=1e-2)
+        counts.append(int(net.last_render_samples))
+    assert counts[1] < 0.7 * counts[0], counts
+
+
+def test_fused_renderer_clean_model_and_edge_cases():
+    from nerf_signature_b200.nerf.network_hash import NeRFNetwork
+    torch.manual_seed(0)
+    net = NeRFNetwork(bound=1, cuda_ray=True).cuda().eval()
+    grid = syn.sphere_grid(1)
+    net.density_grid.copy_(torch.from_numpy(grid))
+    net.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
+    rays_o, rays_d = syn.blender_rays(300, seed=1)
+    rays_o[:5] = np.array([5, 5, 5], np.float32)      # rays that miss the box
+    rays_d[:5] = np.array([0, 0, 1], np.float32)
+    ro, rd = torch.from_numpy(rays_o)[None].cuda(), torch.from_numpy(rays_d)[None].cuda()
+    with torch.no_grad():
+        a = net.render(ro, rd, staged=False, bg_color=1, perturb=False)
+        net.fused_inference = False
+        b = net.render(ro, rd, staged=False, bg_color=1, perturb=False)
+    np.testing.assert_allclose(a["image"].cpu().numpy(), b["image"].cpu().numpy(), rtol=1e-3, atol=1e-4)
+    assert torch.all(a["image"][0, :5] == 1.0)        # pure background
+    # empty grid: every ray is background, zero samples
+    net.density_bitfield.zero_()
+    net.fused_inference = True
+    with torch.no_grad():
+        e = net.render(ro, rd, staged=False, bg_color=1, perturb=False)
+    assert torch.all(e["image"] == 1.0) and int(net.last_render_samples) == 0
