@@ -44,6 +44,9 @@ constexpr int kBwdHalfs = oWs0T + 32 * kS64;
 
 constexpr int kFieldWarps = 4;
 constexpr int kFieldThreads = kFieldWarps * 32;
+#ifndef NSIG_FWD_MINB
+#define NSIG_FWD_MINB 4  // resident CTAs per SM the forward kernel is compiled for (register cap 65536/(128*MINB))
+#endif
 
 struct FieldParams {
     const float* xyzs;
@@ -51,9 +54,9 @@ struct FieldParams {
     uint32_t M;
     float bound_add;   // bound
     float bound_mul;   // fl(1 / (2*bound)): torch divides by a scalar as x * (1/s) on CUDA
-    TablePtrs base;    // 16 levels
-    const float2* S;   // pre-summed message table or null
-    float msg_grid_size;
+    FusedTablePtrs base;  // 16 levels
+    const float2* S;      // pre-summed message table or null
+    LevelGeom msg_geom;
     uint32_t mask;
     const __half* sigma_w;
     const __half* color_w;
@@ -221,13 +224,13 @@ __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const
     for (int j = 0; j < 4; ++j) {
         const int level = tig + 4 * j;
         const float2* tab = p.base.t[level];
-        const float gs = p.base.grid_size[level];
+        const LevelGeom L = p.base.geom[level];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const Voxel v = locate(xn[mt][h][0], xn[mt][h][1], xn[mt][h][2], gs);
-                f[mt][h][j] = encode_level(tab, v, p.mask);
+                const Voxel v = locate_fused(xn[mt][h][0], xn[mt][h][1], xn[mt][h][2], L);
+                f[mt][h][j] = encode_level_fused(tab, v, p.mask);
             }
     }
     if (p.S != nullptr) {
@@ -244,8 +247,8 @@ __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const
                 for (int h = 0; h < 2; ++h)
                     if (mt * 2 + h == sel) { sx = xn[mt][h][0]; sy = xn[mt][h][1]; sz = xn[mt][h][2]; }
             if (sel < MT * 2) {
-                const Voxel v = locate(sx, sy, sz, p.msg_grid_size);
-                mine = encode_level(p.S, v, p.mask);
+                const Voxel v = locate_fused(sx, sy, sz, p.msg_geom);
+                mine = encode_level_fused(p.S, v, p.mask);
             }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -325,7 +328,7 @@ __device__ __forceinline__ void geo_to_a(uint32_t (&ca)[MT][2][4], const float (
 // forward
 // ---------------------------------------------------------------------------------------
 template <bool COLOR>
-__global__ void __launch_bounds__(kFieldThreads)
+__global__ void __launch_bounds__(kFieldThreads, NSIG_FWD_MINB)
 k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__ rgbs, __half* __restrict__ feat_out,
             __half* __restrict__ geo_out) {
     constexpr int MT = 2;
@@ -952,10 +955,10 @@ static int fill_field_params(FieldParams& p, const float* xyzs, const float* dir
     for (int l = 0; l < NSIG_MAX_LEVELS; ++l) {
         if (!tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
         p.base.t[l] = reinterpret_cast<const float2*>(tables[l]);
-        p.base.grid_size[l] = 1.0f / resolutions[l];
+        p.base.geom[l] = make_level_geom(resolutions[l]);
     }
     p.S = reinterpret_cast<const float2*>(S);
-    p.msg_grid_size = (msg_resolution > 0.0f) ? 1.0f / msg_resolution : 0.0f;
+    p.msg_geom = make_level_geom((msg_resolution > 0.0f) ? msg_resolution : 1.0f);
     if (S && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
     p.mask = (1u << log2_T) - 1u;
     p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
@@ -965,7 +968,13 @@ static int fill_field_params(FieldParams& p, const float* xyzs, const float* dir
     return 0;
 }
 
-static int field_grid(uint32_t M, uint32_t rows_per_cta, int ctas_per_sm) {
+// persistent grid: exactly one resident wave (occupancy queried from the runtime), tiles handed out grid-stride
+template <typename K>
+static int field_grid(K kernel, size_t smem, uint32_t M, uint32_t rows_per_cta) {
+    int ctas_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kFieldThreads, smem) != cudaSuccess ||
+        ctas_per_sm < 1)
+        ctas_per_sm = 1;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t tiles = div_up(M, rows_per_cta);
@@ -986,7 +995,7 @@ int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float b
                                      sigma_w, color_w, M_dev, density_scale);
     if (rc) return rc;
     const size_t smem = kFwdHalfs * sizeof(__half);
-    k_field_fwd<true><<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+    k_field_fwd<true><<<field_grid(k_field_fwd<true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, (cudaStream_t)stream>>>(
         p, sigmas, rgbs, reinterpret_cast<__half*>(feat_out), nullptr);
     NSIG_LAUNCH_CHECK();
     return 0;
@@ -1003,7 +1012,7 @@ int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* 
                                      sigma_w, nullptr, nullptr, density_scale);
     if (rc) return rc;
     const size_t smem = kFwdHalfs * sizeof(__half);
-    k_field_fwd<false><<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+    k_field_fwd<false><<<field_grid(k_field_fwd<false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, (cudaStream_t)stream>>>(
         p, sigmas, nullptr, nullptr, reinterpret_cast<__half*>(geo_feat));
     NSIG_LAUNCH_CHECK();
     return 0;
@@ -1014,7 +1023,7 @@ int nsig_color_forward(const float* dirs, const void* geo_feat, uint32_t M, cons
     if (M == 0) return 0;
     if (!dirs || !geo_feat || !color_w || !rgbs) return NSIG_EINVAL;
     const size_t smem = kFwdHalfs * sizeof(__half);
-    k_color_fwd<<<field_grid(M, kFieldWarps * 32, 4), kFieldThreads, smem, (cudaStream_t)stream>>>(
+    k_color_fwd<<<field_grid(k_color_fwd, smem, M, kFieldWarps * 32), kFieldThreads, smem, (cudaStream_t)stream>>>(
         dirs, reinterpret_cast<const __half*>(geo_feat), M, reinterpret_cast<const __half*>(color_w), rgbs);
     NSIG_LAUNCH_CHECK();
     return 0;
@@ -1078,7 +1087,8 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
         cudaFuncSetAttribute(k_field_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    const int grid = field_grid(M, kFieldWarps * 16, 4);
+    const int grid = grad_feat ? field_grid(k_field_bwd<true>, smem, M, kFieldWarps * 16)
+                               : field_grid(k_field_bwd<false>, smem, M, kFieldWarps * 16);
     if (grad_feat)
         k_field_bwd<true><<<grid, kFieldThreads, smem, (cudaStream_t)stream>>>(p);
     else

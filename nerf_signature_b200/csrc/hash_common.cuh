@@ -94,4 +94,87 @@ struct TablePtrs {
     float grid_size[NSIG_MAX_LEVELS];  // fl(1/resolution)
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Cheaper per-level geometry for the FUSED kernels (field.cu), whose features are rounded to fp16 MMA
+// operands anyway.  Integer slots stay bit-exact, interpolation weights may differ from the reference's
+// fp32 value in the last ulp:
+//   * index: fl32(x / g) is obtained as fl32(fl64(x) * fl64(1/g)).  This is the SAME float for every input:
+//     the double product is within 2^-52 (relative) of x/g, while x/g is either exactly representable
+//     (g a power of two) or at relative distance >= 2^-49 from every fp32 rounding midpoint (a midpoint m has
+//     25 significant bits with the last one set; m*g == x would need m*g to fit in 24 bits, impossible for a g
+//     whose mantissa is not 1).  One DMUL + one conversion instead of an IEEE division (~10 instructions with
+//     a guarded slow path); checked exhaustively around every cell boundary in tests/test_hash_gpu.py.
+//   * weight: (x - vmin) * fl(1/g) instead of (x - vmin) / (vmax - vmin)  (relative difference <= 2e-7).
+//   * trilinear interpolation with FMA contraction (a*(1-w) + b*w -> fma(b, w, a*(1-w))).
+// ---------------------------------------------------------------------------------------------------
+struct LevelGeom {
+    double rgd;    // 1.0 / (double)gs
+    float gs;      // fl(1/resolution)   (hash_encoding.py:37)
+    float inv_gs;  // fl(1/gs)
+};
+
+__host__ inline LevelGeom make_level_geom(float resolution) {
+    LevelGeom L;
+    L.gs = 1.0f / resolution;
+    L.rgd = 1.0 / (double)L.gs;
+    L.inv_gs = (float)L.rgd;
+    return L;
+}
+
+__device__ __forceinline__ void locate_axis_fused(float x, const LevelGeom& L, uint32_t& idx, float& w) {
+    const float xc = fminf(fmaxf(x, 0.0f), 1.0f);
+    const float q = __double2float_rn(__dmul_rn((double)xc, L.rgd));  // == __fdiv_rn(xc, L.gs), see above
+    const float fi = floorf(q);
+    idx = (uint32_t)(int)fi;
+    w = __fmul_rn(__fsub_rn(x, __fmul_rn(fi, L.gs)), L.inv_gs);
+}
+
+__device__ __forceinline__ Voxel locate_fused(float x, float y, float z, const LevelGeom& L) {
+#ifdef NSIG_EXACT_GEOM  // A/B switch for profiling: the reference-order arithmetic of the stand-alone encoder
+    return locate(x, y, z, L.gs);
+#endif
+    Voxel v;
+    uint32_t ix, iy, iz;
+    locate_axis_fused(x, L, ix, v.wx);
+    locate_axis_fused(y, L, iy, v.wy);
+    locate_axis_fused(z, L, iz, v.wz);
+    v.hx0 = ix;            v.hx1 = ix + 1u;
+    v.hy0 = iy * kPrimeY;  v.hy1 = v.hy0 + kPrimeY;
+    v.hz0 = iz * kPrimeZ;  v.hz1 = v.hz0 + kPrimeZ;
+    return v;
+}
+
+__device__ __forceinline__ float lerp_fma(float a, float b, float w, float omw) { return fmaf(b, w, a * omw); }
+
+__device__ __forceinline__ float2 trilerp_fma(const float2 e[8], const Voxel& v) {
+    const float ox = 1.0f - v.wx, oy = 1.0f - v.wy, oz = 1.0f - v.wz;
+    float2 r;
+    {
+        const float c00 = lerp_fma(e[0].x, e[4].x, v.wx, ox), c01 = lerp_fma(e[1].x, e[5].x, v.wx, ox);
+        const float c10 = lerp_fma(e[2].x, e[6].x, v.wx, ox), c11 = lerp_fma(e[3].x, e[7].x, v.wx, ox);
+        r.x = lerp_fma(lerp_fma(c00, c10, v.wy, oy), lerp_fma(c01, c11, v.wy, oy), v.wz, oz);
+    }
+    {
+        const float c00 = lerp_fma(e[0].y, e[4].y, v.wx, ox), c01 = lerp_fma(e[1].y, e[5].y, v.wx, ox);
+        const float c10 = lerp_fma(e[2].y, e[6].y, v.wx, ox), c11 = lerp_fma(e[3].y, e[7].y, v.wx, ox);
+        r.y = lerp_fma(lerp_fma(c00, c10, v.wy, oy), lerp_fma(c01, c11, v.wy, oy), v.wz, oz);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float2 encode_level_fused(const float2* __restrict__ table, const Voxel& v, uint32_t mask) {
+    float2 e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = __ldg(table + corner_slot(v, k, mask));
+#ifdef NSIG_EXACT_GEOM
+    return trilerp(e, v);
+#endif
+    return trilerp_fma(e, v);
+}
+
+struct FusedTablePtrs {
+    const float2* t[NSIG_MAX_LEVELS];
+    LevelGeom geom[NSIG_MAX_LEVELS];
+};
+
 }  // namespace nsig
