@@ -319,8 +319,7 @@ def run_ours(args):
     _lib.timing_collect()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- roofline of the dominant kernel (fused field forward) -------------------------------------------
@@ -380,8 +379,16 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_run(cfg, steps=2, warmup=1, rays_per_pass=args.cpu_rays or 64)
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroy_process_group() can block on communicators that were captured
+    into the step's CUDA graph; every rank has already passed the final barrier, so a hard exit is safe."""
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -102,17 +102,22 @@ class Scene:
             raise ValueError("graph capture needs the fused optimizer (the set of tables with a gradient changes "
                              "with every message under torch.optim.Adam)")
         self.fused = optimizer == "fused"
+        self.sync = parallel.GradSync()
+        self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
+        self.flat_sync = self.fused and self.sync.enabled
         if self.fused:
-            self.optimizer = WatermarkAdam(self.model, lr=lr, betas=(0.9, 0.99), eps=1e-15, capturable=graph)
+            gbuf = None
+            if self.flat_sync:  # one flat bucket [dL/dS | decoder grads] -> one all-reduce per step
+                gbuf = self.sync.make_flat_buffer(self.model.msg_encoder.tables()[0].numel(), self._decoder_params, device)
+            self.optimizer = WatermarkAdam(self.model, lr=lr, betas=(0.9, 0.99), eps=1e-15, capturable=graph,
+                                           grad_buffer=gbuf)
         else:
             self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
         self.fp16 = fp16
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.lambda_w, self.lambda_i = 0.005, 1.0  # README.md:40,45
         self.opt = dict(dt_gamma=cfg["dt_gamma"], max_steps=1024, T_thresh=1e-4)
-        self.sync = parallel.GradSync()
-        _hmsg.grad_reducer = self.sync.reduce_table_grad if self.sync.enabled else None
-        self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
+        _hmsg.grad_reducer = self.sync.reduce_table_grad if (self.sync.enabled and not self.flat_sync) else None
         self.use_graph = graph
         self._graph = None
         self._static = None
@@ -139,7 +144,10 @@ class Scene:
         select which tables receive a gradient) or a device tensor (fused path: nothing on the host depends
         on the bits)."""
         model = self.model
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.flat_sync:
+            self.sync.zero_flat()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         msg_dev = message.to(self.device, non_blocking=True) if not message.is_cuda else message
         if self.fused:
             self.optimizer.set_message(msg_dev)
@@ -155,7 +163,10 @@ class Scene:
         lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
         loss = self.lambda_w * lossw + self.lambda_i * lossi
         self.scaler.scale(loss).backward()
-        self.sync.reduce_params(self._decoder_params)
+        if self.flat_sync:
+            self.sync.reduce_flat()
+        else:
+            self.sync.reduce_params(self._decoder_params)
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss, lossi, lossw

@@ -22,7 +22,9 @@ _P = _lib.ptr
 class WatermarkAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
 
-    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False):
+    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False, grad_buffer=None):
+        """grad_buffer: optional pre-allocated [T*2] fp32 storage for G (the data-parallel harness passes a slice
+        of its flat all-reduce bucket)."""
         enc = model.msg_encoder
         tables = enc.tables()
         dev = tables[0].device
@@ -37,7 +39,7 @@ class WatermarkAdam(torch.optim.Optimizer):
                 others.append({"params": ps, "lr": group["lr"]})
         # G = dL/dS lives here; the proxy parameter only exists so that GradScaler's inf check
         # (_check_inf_per_device walks param_groups) sees G like any other gradient.
-        self.G = torch.zeros_like(tables[0])
+        self.G = torch.zeros_like(tables[0]) if grad_buffer is None else grad_buffer.view_as(tables[0])
         self._proxy = torch.nn.Parameter(torch.empty_like(tables[0]), requires_grad=True)
         self._proxy.grad = self.G
         groups = list(others)

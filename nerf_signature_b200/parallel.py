@@ -45,6 +45,32 @@ class GradSync:
         g.div_(world()[1])
         return g
 
+    # --- fused path: ONE all-reduce per step over a persistent flat gradient buffer -------------------
+    def make_flat_buffer(self, table_numel, params, device):
+        """Allocate [dL/dS | every other trainable gradient] as one fp32 buffer and point each parameter's .grad
+        at its slice, so backward accumulates straight into the bucket and a single NCCL all-reduce (AVG)
+        per step synchronises everything (no per-tensor copies, no separate division)."""
+        n = table_numel + sum(p.numel() for p in params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.table_numel = table_numel
+        o = table_numel
+        for p in params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        return self.flat[:table_numel]
+
+    def zero_flat(self):
+        self.flat[self.table_numel:].zero_()  # dL/dS is overwritten (copy_) by backward, the rest accumulates
+
+    def reduce_flat(self):
+        if not self.enabled:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo (CPU tests) has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(world()[1])
+
     # --- everything else: one flat bucket after backward ---------------------------------------------
     def reduce_params(self, params):
         """All-reduce (mean) the .grad of `params` through a single flat buffer."""

@@ -94,3 +94,42 @@ def test_gloo_world_size_2():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def _flat_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(rank)
+        sync = parallel.GradSync()
+        params = [torch.nn.Parameter(torch.randn(s)) for s in ((4, 3), (5,), (2, 2))]
+        G = sync.make_flat_buffer(8, params, torch.device("cpu"))
+        assert G.numel() == 8 and sync.flat.numel() == 8 + 12 + 5 + 4
+        # gradients accumulate straight into the bucket (.grad are views of it)
+        G.copy_(torch.full((8,), float(rank + 1)))
+        loss = sum((p * (rank + 1)).sum() for p in params)
+        loss.backward()
+        assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in params)
+        # gloo has no AVG: emulate it the way reduce_flat does on NCCL (SUM then divide) to check the layout
+        dist.all_reduce(sync.flat, op=dist.ReduceOp.SUM)
+        sync.flat.div_(world)
+        mean = sum(range(1, world + 1)) / world
+        assert torch.allclose(G, torch.full((8,), mean))
+        for p in params:
+            assert torch.allclose(p.grad, torch.full_like(p, mean))
+        sync.zero_flat()
+        assert torch.allclose(G, torch.full((8,), mean)) and all(float(p.grad.abs().sum()) == 0 for p in params)
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_flat_gradient_bucket_gloo_world_size_2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_flat_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
