@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="blender_wtmk")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
+    ap.add_argument("--no-render", action="store_true", help="skip the full-frame inference leg")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph-captured one")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = optim.WatermarkAdam; torch = torch.optim.Adam over get_params (implies --no-graph)")
@@ -318,6 +319,21 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     _lib.timing_collect()
 
+    # ---- full-frame inference (second half of BASELINE's metric): the 10 test views sharded over the ranks ------
+    render = {}
+    if not args.no_render:
+        n_views = 10
+        mine = [v for v in range(n_views) if v % world == rank] or [rank % n_views]
+        for name in ("blender_800x800", "llff_1008x756"):
+            fms, fsamples = harness.time_frames(name, dev, mine)
+            t = torch.tensor([fms], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms_max = float(t.item())
+            render[name] = {"ms_per_frame": fms_max, "views": n_views, "frames_per_s_all_gpus": world * 1e3 / fms_max,
+                            "samples_per_frame": fsamples,
+                            "path": "NeRFRenderer.render(eval) -> nsig_render_rays (one persistent kernel per frame)"}
+
     if rank != 0:
         _finish(world)
         return
@@ -374,7 +390,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded dp{world}"},
         "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_run(cfg, steps=2, warmup=1, rays_per_pass=args.cpu_rays or 64)

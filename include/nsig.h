@@ -220,7 +220,11 @@ int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const
  * activations, back-propagate to the encoder output and scatter-add the gradient of
  * channels 30,31 into G ([2^log2_T,2] fp32 = gradient of the pre-summed table S,
  * caller zero-fills).  grad_feat (optional) [M,32] fp32 receives the full encoder-output
- * gradient (needed for base-table training in clean mode). */
+ * gradient (needed for base-table training in clean mode).
+ * grad_sigma_w / grad_color_w (optional, both or neither): fp32 [NSIG_SIGMA_PARAMS] / [NSIG_COLOR_PARAMS]
+ * gradients of the MLP weights in the layout of sigma_w / color_w (clean-model training,
+ * network_hash.py:154-161), ACCUMULATED into the buffers (caller zero-fills): tensor-core contraction over the
+ * rows of each 16-sample tile, fp32 accumulation per CTA in shared memory, one global atomic per weight and CTA. */
 int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float bound,
                         const void* feat, const float* grad_sigmas, const float* grad_rgbs,
                         const void* sigma_w, const void* color_w, float density_scale,

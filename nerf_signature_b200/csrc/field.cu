@@ -41,6 +41,7 @@ constexpr int oWc0T = oWc1T + 64 * kS64;   // [16][64] inputs 16..31 (geo part)
 constexpr int oWs1T = oWc0T + 16 * kS64;   // [64][16] outputs permuted like oWs1
 constexpr int oWs0T = oWs1T + 64 * kS16;   // [32][64]
 constexpr int kBwdHalfs = oWs0T + 32 * kS64;
+constexpr int kBwdHalfsPad = (kBwdHalfs + 7) / 8 * 8;
 
 constexpr int kFieldWarps = 4;
 constexpr int kFieldThreads = kFieldWarps * 32;
@@ -738,6 +739,8 @@ struct FieldBwdParams {
     float* grad_feat;  // [M,32] fp32 full encoder-output gradient (may be null)
     const int32_t* M_dev;
     float density_scale;
+    float* grad_sigma_w;  // [3072] fp32 weight gradients (accumulated; WGRAD only)
+    float* grad_color_w;  // [7168]
 };
 
 // power-of-two scale that brings |v| into [0.5, 1): keeps the fp16 gradient chain in range
@@ -749,7 +752,77 @@ __device__ __forceinline__ float pow2_scale(float vmax) {
     return scalbnf(1.0f, -e);
 }
 
-template <bool FULL_GRAD>
+// ---- weight gradients (clean-model training, nerf/network_hash.py:154-161 trains both MLPs) --------------
+// dW[out][in] = sum over rows of dOut[row][out] * In[row][in]: the contraction runs over the row index, which is
+// the M index of BOTH operands as the forward/dgrad passes hold them (A-fragment layout).  movmatrix transposes
+// the 8x8 blocks in registers, which turns an A fragment of dOut into the A fragment of dOut^T and an A fragment of
+// In into the B fragment [k = row][n = in]; one m16n8k16 MMA per (16 outs x 8 ins) block then contracts the tile's
+// 16 rows.  Products are accumulated per CTA in shared memory (fp32) and flushed once with global atomics.
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
+    uint32_t r;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// rescale a packed fp16 pair by a power of two (exact until underflow)
+__device__ __forceinline__ uint32_t scale_h2(uint32_t v, float ratio) {
+    __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(ratio));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// X: layer input  [16 rows x 16*KS_IN],  A-fragment layout (reg 2*hk + h: rows h*8+g, cols ks*16 + hk*8 + 2tig..)
+// Y: output grad  [16 rows x 16*KS_OUT], same layout, rows pre-scaled to the tile's common power-of-two scale
+// acc: shared fp32 [out][in] (row-major, leading dimension 16*KS_IN); ROT: output row r accumulates into param row
+// (r + ROT) & 15 (the sigma net's second matrix is staged with its rows rotated by one).
+template <int KS_IN, int KS_OUT, int ROT = 0>
+__device__ __forceinline__ void wgrad_tile(float* __restrict__ acc, const uint32_t (&X)[KS_IN][4],
+                                           const uint32_t (&Y)[KS_OUT][4], float inv_tile, int g, int tig) {
+    constexpr int LD = 16 * KS_IN;
+    uint32_t XT[KS_IN][4];
+#pragma unroll
+    for (int ks = 0; ks < KS_IN; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) XT[ks][r] = movmatrix_trans(X[ks][r]);
+#pragma unroll
+    for (int mo = 0; mo < KS_OUT; ++mo) {
+        uint32_t a[4];
+        a[0] = movmatrix_trans(Y[mo][0]);  // (outs 0-7,  rows 0-7)
+        a[1] = movmatrix_trans(Y[mo][2]);  // (outs 8-15, rows 0-7)
+        a[2] = movmatrix_trans(Y[mo][1]);  // (outs 0-7,  rows 8-15)
+        a[3] = movmatrix_trans(Y[mo][3]);  // (outs 8-15, rows 8-15)
+#pragma unroll
+        for (int ni = 0; ni < 2 * KS_IN; ++ni) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(c, a, XT[ni >> 1][2 * (ni & 1)], XT[ni >> 1][2 * (ni & 1) + 1]);
+            const int col = ni * 8 + 2 * tig;
+            int r0 = mo * 16 + g, r1 = r0 + 8;
+            if (ROT) { r0 = (r0 & ~15) | ((r0 + ROT) & 15); r1 = (r1 & ~15) | ((r1 + ROT) & 15); }
+            atomicAdd(acc + r0 * LD + col, c[0] * inv_tile);
+            atomicAdd(acc + r0 * LD + col + 1, c[1] * inv_tile);
+            atomicAdd(acc + r1 * LD + col, c[2] * inv_tile);
+            atomicAdd(acc + r1 * LD + col + 1, c[3] * inv_tile);
+        }
+    }
+}
+
+// fragments of a gradient tile brought from per-row scales to the tile's common scale
+template <int KS>
+__device__ __forceinline__ void to_tile_scale(uint32_t (&dst)[KS][4], const uint32_t (&src)[KS][4], float ratio0,
+                                              float ratio1) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        dst[ks][0] = scale_h2(src[ks][0], ratio0);
+        dst[ks][1] = scale_h2(src[ks][1], ratio1);
+        dst[ks][2] = scale_h2(src[ks][2], ratio0);
+        dst[ks][3] = scale_h2(src[ks][3], ratio1);
+    }
+}
+
+// offsets of the five matrices inside the flat fp32 accumulators (= the FusedMLP `params` layout)
+constexpr int aWs0 = 0, aWs1 = 2048, aWc0 = 3072, aWc1 = 3072 + 2048, aWc2 = 3072 + 2048 + 4096;
+constexpr int kWgradFloats = NSIG_SIGMA_PARAMS + NSIG_COLOR_PARAMS;
+
+template <bool FULL_GRAD, bool WGRAD>
 __global__ void __launch_bounds__(kFieldThreads)
 k_field_bwd(const FieldBwdParams p) {
     constexpr int MT = 1;
@@ -759,6 +832,9 @@ k_field_bwd(const FieldBwdParams p) {
     if (M == 0) return;
     stage_forward_weights(sm, p.sigma_w, p.color_w, true);
     stage_backward_weights(sm, p.sigma_w, p.color_w);
+    float* wacc = reinterpret_cast<float*>(sm + kBwdHalfsPad);
+    if (WGRAD)
+        for (int i = threadIdx.x; i < kWgradFloats; i += blockDim.x) wacc[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
     const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
@@ -810,14 +886,13 @@ k_field_bwd(const FieldBwdParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) fa[mt][j >> 1][2 * (j & 1) + h] = __ldg(src + tig + 4 * j);
             }
-        uint32_t h1s[MT][4][4], h1c[MT][4][4], h2c[MT][4][4];
+        uint32_t h1s[MT][4][4], h1c[MT][4][4], h2c[MT][4][4], ca[MT][2][4];
         float so[MT][2][4], co[MT][1][4];
         {
             float c[MT][8][4];
             layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
             relu_to_a<MT, 8>(h1s, c);
             layer<MT, 4, 2>(so, h1s, sm + oWs1, kS64, g, tig);
-            uint32_t ca[MT][2][4];
             sh_rows<MT>(ca, dirs_, M_, row0, g, tig);
             geo_to_a<MT>(ca, so, tig);
             layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
@@ -827,7 +902,7 @@ k_field_bwd(const FieldBwdParams p) {
             layer<MT, 4, 1>(co, h2c, sm + oWc2, kS64, g, tig);
         }
         // ---- output-activation gradients, normalised per row by a power of two ----
-        float d_rgb[MT][2][2], d_logit[MT][2], inv_scale[MT][2];
+        float d_rgb[MT][2][2], d_logit[MT][2], inv_scale[MT][2], row_sc[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -843,9 +918,23 @@ k_field_bwd(const FieldBwdParams p) {
                 vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 1));
                 vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 2));
                 const float sc = pow2_scale(vmax);
+                row_sc[mt][h] = (vmax > 0.0f && isfinite(vmax)) ? sc : INFINITY;  // rows without gradient do not set the tile scale
                 inv_scale[mt][h] = 1.0f / sc;
                 d_rgb[mt][h][0] *= sc; d_rgb[mt][h][1] *= sc; d_logit[mt][h] *= sc;
             }
+        // common power-of-two scale of the tile's rows (weight gradients contract over rows)
+        float wr0 = 0.f, wr1 = 0.f, inv_tile = 0.f;
+        if (WGRAD) {
+            float s_tile = fminf(row_sc[0][0], row_sc[0][1]);
+            s_tile = fminf(s_tile, __shfl_xor_sync(NSIG_FULL_MASK, s_tile, 4));
+            s_tile = fminf(s_tile, __shfl_xor_sync(NSIG_FULL_MASK, s_tile, 8));
+            s_tile = fminf(s_tile, __shfl_xor_sync(NSIG_FULL_MASK, s_tile, 16));
+            if (isfinite(s_tile)) {
+                inv_tile = 1.0f / s_tile;
+                wr0 = isfinite(row_sc[0][0]) ? s_tile / row_sc[0][0] : 0.f;
+                wr1 = isfinite(row_sc[0][1]) ? s_tile / row_sc[0][1] : 0.f;
+            }
+        }
         // ---- colour net dgrad ----
         uint32_t da[MT][1][4];
 #pragma unroll
@@ -858,10 +947,25 @@ k_field_bwd(const FieldBwdParams p) {
         float dgeo[MT][2][4];
         {
             float c[MT][8][4];
+            if (WGRAD) {   // dWc2 = d out^T x h2
+                uint32_t y[1][4];
+                to_tile_scale<1>(y, da[0], wr0, wr1);
+                wgrad_tile<4, 1>(wacc + aWc2, h2c[0], y, inv_tile, g, tig);
+            }
             layer<MT, 1, 8>(c, da, sm + oWc2T, kS16, g, tig);        // d h2 = d out x W2
             grad_to_a<MT, 8>(dh, c, h2c);
+            if (WGRAD) {   // dWc1 = d z2^T x h1
+                uint32_t y[4][4];
+                to_tile_scale<4>(y, dh[0], wr0, wr1);
+                wgrad_tile<4, 4>(wacc + aWc1, h1c[0], y, inv_tile, g, tig);
+            }
             layer<MT, 4, 8>(c, dh, sm + oWc1T, kS64, g, tig);        // d h1 = d h2 x W1
             grad_to_a<MT, 8>(dh, c, h1c);
+            if (WGRAD) {   // dWc0 = d z1^T x [SH, geo]
+                uint32_t y[4][4];
+                to_tile_scale<4>(y, dh[0], wr0, wr1);
+                wgrad_tile<2, 4>(wacc + aWc0, ca[0], y, inv_tile, g, tig);
+            }
             layer<MT, 4, 2>(dgeo, dh, sm + oWc0T, kS64, g, tig);     // d geo = (d h1 x W0)[:, 16:32]
         }
         // ---- sigma net dgrad: d out' = [d geo0..14, d logit] ----
@@ -874,8 +978,18 @@ k_field_bwd(const FieldBwdParams p) {
         }
         {
             float c[MT][8][4];
+            if (WGRAD) {   // dWs1 = d out'^T x h1s (staged rows are rotated by one: out' row r is param row (r+1)%16)
+                uint32_t y[1][4];
+                to_tile_scale<1>(y, da[0], wr0, wr1);
+                wgrad_tile<4, 1, 1>(wacc + aWs1, h1s[0], y, inv_tile, g, tig);
+            }
             layer<MT, 1, 8>(c, da, sm + oWs1T, kS16, g, tig);        // d h1s = d out' x W1'
             grad_to_a<MT, 8>(dh, c, h1s);
+            if (WGRAD) {   // dWs0 = d z1s^T x feat
+                uint32_t y[4][4];
+                to_tile_scale<4>(y, dh[0], wr0, wr1);
+                wgrad_tile<2, 4>(wacc + aWs0, fa[0], y, inv_tile, g, tig);
+            }
         }
         float gmsg[MT][2][2];  // d feature 30,31 (valid on tig == 3)
         if (FULL_GRAD) {
@@ -933,6 +1047,13 @@ k_field_bwd(const FieldBwdParams p) {
                         red_add_v2(p.G + (size_t)corner_slot(v, k, p.mask) * 2, corner_grad(v, k, gx), corner_grad(v, k, gy));
                 }
             }
+        }
+    }
+    if (WGRAD) {  // one global atomic per weight and CTA
+        __syncthreads();
+        for (int i = threadIdx.x; i < kWgradFloats; i += blockDim.x) {
+            const float v = wacc[i];
+            if (v != 0.0f) atomicAdd((i < NSIG_SIGMA_PARAMS ? p.grad_sigma_w + i : p.grad_color_w + (i - NSIG_SIGMA_PARAMS)), v);
         }
     }
 }
@@ -1066,7 +1187,7 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
                         nsig_stream_t stream) {
     if (M == 0) return 0;
     if (!xyzs || !dirs || !feat || !grad_sigmas || !grad_rgbs || !sigma_w || !color_w) return NSIG_EINVAL;
-    if (grad_sigma_w || grad_color_w) return NSIG_EINVAL;  // weight gradients: see nsig_mlp_wgrad
+    if ((grad_sigma_w == nullptr) != (grad_color_w == nullptr)) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
     if (G && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
     FieldBwdParams p;
@@ -1080,19 +1201,25 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
     p.mask = (1u << log2_T) - 1u;
     p.G = G; p.grad_feat = grad_feat;
     p.M_dev = M_dev; p.density_scale = density_scale;
-    const size_t smem = kBwdHalfs * sizeof(__half);
+    p.grad_sigma_w = grad_sigma_w; p.grad_color_w = grad_color_w;
+    const bool wgrad = grad_sigma_w != nullptr;
+    const size_t smem = kBwdHalfsPad * sizeof(__half) + (wgrad ? kWgradFloats * sizeof(float) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_field_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_field_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int big = (int)(kBwdHalfsPad * sizeof(__half) + kWgradFloats * sizeof(float));
+        cudaFuncSetAttribute(k_field_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_field_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_field_bwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         attr_set = true;
     }
-    const int grid = grad_feat ? field_grid(k_field_bwd<true>, smem, M, kFieldWarps * 16)
-                               : field_grid(k_field_bwd<false>, smem, M, kFieldWarps * 16);
-    if (grad_feat)
-        k_field_bwd<true><<<grid, kFieldThreads, smem, (cudaStream_t)stream>>>(p);
-    else
-        k_field_bwd<false><<<grid, kFieldThreads, smem, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (wgrad) {  // weight gradients imply the full feature gradient path (clean-model training)
+        k_field_bwd<true, true><<<field_grid(k_field_bwd<true, true>, smem, M, kFieldWarps * 16), kFieldThreads, smem, st>>>(p);
+    } else if (grad_feat) {
+        k_field_bwd<true, false><<<field_grid(k_field_bwd<true, false>, smem, M, kFieldWarps * 16), kFieldThreads, smem, st>>>(p);
+    } else {
+        k_field_bwd<false, false><<<field_grid(k_field_bwd<false, false>, smem, M, kFieldWarps * 16), kFieldThreads, smem, st>>>(p);
+    }
     NSIG_LAUNCH_CHECK();
     return 0;
 }

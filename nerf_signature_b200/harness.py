@@ -25,7 +25,7 @@ CONFIGS = {
                          H=400, W=400, num_rays=4096, camera="blender", occupancy="sphere"),
     # configs[2]: Mip-NeRF-360 shape, bound 2 (CLI default), scale 0.33, dt_gamma 0
     "360_wtmk": dict(bound=2.0, scale=0.33, dt_gamma=0.0, message_dim=32, num_rows=32, num_cols=32,
-                     H=756, W=1008, num_rays=4096, camera="360", occupancy="sphere"),
+                     H=756, W=1008, num_rays=4096, camera="360", occupancy="sphere", grid_update_every=16),
     # configs[4] per-rank shape: message_dim 48, rays sharded across ranks
     "shard262144_wtmk": dict(bound=1.0, scale=0.8, dt_gamma=0.0, message_dim=48, num_rows=32, num_cols=32,
                              H=400, W=400, num_rays=262144, camera="blender", occupancy="sphere"),
@@ -119,6 +119,7 @@ class Scene:
         self.opt = dict(dt_gamma=cfg["dt_gamma"], max_steps=1024, T_thresh=1e-4)
         _hmsg.grad_reducer = self.sync.reduce_table_grad if (self.sync.enabled and not self.flat_sync) else None
         self.use_graph = graph
+        self.iteration = 0
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -192,9 +193,21 @@ class Scene:
         with torch.cuda.graph(self._graph):
             self._static_out = self._step_impl(self._static, self._static["message"])
         self.launches_per_step = _lib.launch_count - n0
+        ls = self.model.local_step
+        self._graph_rows = [(ls - 2) % 16, (ls - 1) % 16]  # the march counters baked into the graph
 
     def train_step(self, batch, message):
-        """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here)."""
+        """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here).  Configs with
+        `grid_update_every` also run NeRFRenderer.update_extra_state every that many iterations (the clean trainer's
+        cadence, nerf/utils.py:855-857; BASELINE configs[2] asks for it in watermark training too)."""
+        out = self._train_step(batch, message)
+        self.iteration += 1
+        every = self.cfg.get("grid_update_every", 0)
+        if every and self.iteration % every == 0:
+            self.model.update_extra_state(message.to(self.device) if not message.is_cuda else message)
+        return out
+
+    def _train_step(self, batch, message):
         if not self.use_graph:
             batch = {k: (v if v.is_cuda else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
             return self._step_impl(batch, message)
@@ -206,13 +219,69 @@ class Scene:
         self._graph.replay()
         return self._static_out
 
+    def _counter_rows(self):
+        if self.use_graph and getattr(self, "_graph_rows", None) is not None:
+            return self._graph_rows
+        ls = self.model.local_step
+        return [(ls - 2) % 16, (ls - 1) % 16]
+
     def samples_per_step(self):
         """Measured (samples, rays) of the two most recent render calls = one training step (reads the march
         counters the kernels left on the device)."""
-        ls = self.model.local_step
-        rows = self.model.step_counter[[(ls - 2) % 16, (ls - 1) % 16]].tolist()
+        rows = self.model.step_counter[self._counter_rows()].tolist()
         return sum(r[0] for r in rows), sum(r[1] for r in rows)
 
     def samples_per_ray(self):
         s, r = self.samples_per_step()
         return s / max(r, 1)
+
+
+# -------------------------------------------------------------------------------------------------------
+# full-frame inference (BASELINE configs[3]): 800x800 Blender / 1008x756 LLFF-shaped test views
+# -------------------------------------------------------------------------------------------------------
+FRAME_CONFIGS = {
+    "blender_800x800": dict(H=800, W=800, bound=1.0, fov=0.6911112, radius=4.0311 * 0.8),
+    "llff_1008x756": dict(H=756, W=1008, bound=2.0, fov=0.9, radius=4.0 * 0.33),
+}
+
+
+def frame_rays(fc, view):
+    """All H*W rays of synthetic test view `view` (host numpy)."""
+    rs = np.random.RandomState(9000 + view)
+    focal = 0.5 * fc["W"] / math.tan(0.5 * fc["fov"])
+    pose = syn.orbit_pose(rs.uniform(math.pi / 3, 2 * math.pi / 3), rs.uniform(0, 2 * math.pi), fc["radius"])
+    return syn.camera_rays(pose, fc["H"], fc["W"], focal, np.arange(fc["H"] * fc["W"]))
+
+
+def time_frames(name, device, views, message_dim=32, seed=0, fused=True, staged=False):
+    """Render `views` (list of view ids) of frame config `name` through NeRFRenderer.render in eval mode
+    (main_nerf_wtmk.py --test path: renderer_wtmk.py:541-574 -> run_cuda inference branch) with a random-init
+    watermark network and the sphere occupancy fixture.  Returns (ms per frame, samples per frame)."""
+    from .nerf.network_wtmk_tcnn import NeRFNetwork
+    fc = FRAME_CONFIGS[name]
+    torch.manual_seed(seed)
+    net = NeRFNetwork(bound=fc["bound"], cuda_ray=True, message_dim=message_dim).to(device).eval()
+    grid = syn.sphere_grid(net.cascade)
+    net.density_grid.copy_(torch.from_numpy(grid))
+    net.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
+    net.fused_inference = fused
+    msg = torch.randint(0, 2, (message_dim,)).float().to(device)
+    frames = []
+    for v in views:
+        o, d = frame_rays(fc, v)
+        frames.append((torch.from_numpy(o)[None].to(device), torch.from_numpy(d)[None].to(device)))
+    kw = dict(staged=staged, bg_color=1, perturb=False, dt_gamma=0.0, max_steps=1024)
+    counts = []
+    with torch.no_grad():
+        net.render(*frames[0], msg, **kw)  # warm-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in frames:
+            net.render(*f, msg, **kw)
+            if fused and not staged:
+                counts.append(net.last_render_samples)
+        e1.record()
+        torch.cuda.synchronize()
+    samples = float(sum(int(c) for c in counts)) / max(len(counts), 1) if counts else None
+    return e0.elapsed_time(e1) / len(frames), samples

@@ -96,13 +96,15 @@ class FieldConfig:
 class _field_forward(Function):
     """(sigmas [M], rgbs [M,3]) = field(xyzs, dirs; S, base tables, MLP weights).
 
-    Differentiable w.r.t. S (the pre-summed message table) and, for the clean model, the base tables.
-    MLP weight gradients are not produced here (frozen in watermark training).
-    `count` is an optional device int32 holding the live row count (the march counter).
+    Differentiable w.r.t. S (the pre-summed message table), the base tables and both MLPs' flat weight vectors
+    (clean-model training; in watermark training everything but S is frozen, SURVEY F13, and the backward
+    kernel then runs its dgrad-only variant).  `count` is an optional device int32 holding the live row count
+    (the march counter).
     """
+    N_FIXED = 9  # inputs before *tables
 
     @staticmethod
-    def forward(ctx, xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, *tables):
+    def forward(ctx, xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, sigma_params, color_params, *tables):
         xyzs = xyzs.contiguous().float()
         dirs = dirs.contiguous().float()
         M = xyzs.shape[0]
@@ -110,13 +112,9 @@ class _field_forward(Function):
         sigmas = torch.empty(M, dtype=torch.float32, device=dev)
         rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
         need_S = S is not None and ctx.needs_input_grad[2]
-        need_tab = any(ctx.needs_input_grad[7:])
-        if torch.is_grad_enabled() and (sigma_mlp.params.requires_grad or color_mlp.params.requires_grad):
-            raise NotImplementedError(
-                "MLP weight gradients (clean-model training, main_nerf.py) are not implemented in this round: "
-                "freeze sigma_net/color_net (as watermark training does, network_wtmk_tcnn.py:90-95) or run under "
-                "torch.no_grad()")
-        save = need_S or need_tab
+        need_w = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
+        need_tab = any(ctx.needs_input_grad[_field_forward.N_FIXED:])
+        save = need_S or need_tab or need_w
         feat = torch.empty(M, 32, dtype=torch.float16, device=dev) if save else None
         tabs = [t.contiguous() for t in tables]
         sw, cw = sigma_mlp.half_weights(), color_mlp.half_weights()
@@ -130,12 +128,13 @@ class _field_forward(Function):
             ctx.count = count
             ctx.S_shape = tuple(S.shape) if S is not None else None
             ctx.tab_shapes = [tuple(t.shape) for t in tables]
+        ctx.n_tables = len(tables)
         ctx.has_graph = save
         return sigmas, rgbs
 
     @staticmethod
     def backward(ctx, grad_sigmas, grad_rgbs):
-        n_in = 7 + len(getattr(ctx, "tab_shapes", []))
+        n_in = _field_forward.N_FIXED + ctx.n_tables
         if not ctx.has_graph:
             return (None,) * n_in
         xyzs, dirs, feat, sw, cw = ctx.saved_tensors
@@ -145,26 +144,31 @@ class _field_forward(Function):
         grad_sigmas = grad_sigmas.contiguous().float()
         grad_rgbs = grad_rgbs.contiguous().float()
         need_S = ctx.S_shape is not None and ctx.needs_input_grad[2]
-        need_tab = ctx.needs_input_grad[7:]
+        need_w = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
+        need_tab = ctx.needs_input_grad[_field_forward.N_FIXED:]
         G = torch.zeros(ctx.S_shape, dtype=torch.float32, device=dev) if need_S else None
         # rows past the live count are not written by the kernel: start from zeros in that case
         alloc = torch.zeros if ctx.count is not None else torch.empty
         grad_feat = alloc(M, 32, dtype=torch.float32, device=dev) if any(need_tab) else None
+        gsw = torch.zeros(sw.numel(), dtype=torch.float32, device=dev) if need_w else None
+        gcw = torch.zeros(cw.numel(), dtype=torch.float32, device=dev) if need_w else None
         _lib.call("nsig_field_backward", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
                   _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G),
-                  _P(grad_feat), None, None)
-        tab_grads = [None] * len(ctx.tab_shapes)
+                  _P(grad_feat), _P(gsw), _P(gcw))
+        tab_grads = [None] * ctx.n_tables
         if any(need_tab):
             xn = (xyzs + cfg.bound) * (1.0 / (2.0 * cfg.bound))  # network_wtmk_tcnn.py:101
             gt = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.tab_shapes]
             _lib.call("nsig_hash_encode_backward", _P(xn.contiguous()), _P(grad_feat.contiguous()), M,
                       _lib.pointer_array(gt), _lib.float_array(cfg.resolutions), len(gt), cfg.log2_T)
             tab_grads = [g if n else None for g, n in zip(gt, need_tab)]
-        return (None, None, G, None, None, None, None) + tuple(tab_grads)
+        return (None, None, G, None, None, None, None,
+                gsw if ctx.needs_input_grad[7] else None, gcw if ctx.needs_input_grad[8] else None) + tuple(tab_grads)
 
 
 def field_forward(xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, tables):
-    return _field_forward.apply(xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, *tables)
+    return _field_forward.apply(xyzs, dirs, S, count, cfg, sigma_mlp, color_mlp, sigma_mlp.params, color_mlp.params,
+                                *tables)
 
 
 @torch.no_grad()
