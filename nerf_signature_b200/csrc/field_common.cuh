@@ -1,0 +1,353 @@
+// field_common.cuh — pieces shared by the fused field kernels (field.cu) and the occupancy-grid sweep
+// (grid.cu): shared-memory weight layout, m16n8k16 layer helpers, fragment-layout hash encoding, SH4,
+// the FieldParams block and its host-side validation.
+#pragma once
+#include "hash_common.cuh"
+#include "march_common.cuh"
+
+namespace nsig {
+
+// ---- shared-memory weight layout (halfs); row strides padded by 8 halfs: conflict-free B loads
+constexpr int kS32 = 40;  // stride of a [*,32] matrix
+constexpr int kS64 = 72;  // stride of a [*,64] matrix
+constexpr int kS16 = 24;  // stride of a [*,16] matrix
+// forward copies, [out][in]
+constexpr int oWs0 = 0;                    // [64][32]
+constexpr int oWs1 = oWs0 + 64 * kS32;     // [16][64] rows permuted: r' <- (r'+1)%16
+constexpr int oWc0 = oWs1 + 16 * kS64;     // [64][32] (input column 31 zeroed)
+constexpr int oWc1 = oWc0 + 64 * kS32;     // [64][64]
+constexpr int oWc2 = oWc1 + 64 * kS64;     // [8][64]  (outputs 0..7; 3..7 are padding)
+constexpr int kFwdHalfs = oWc2 + 8 * kS64;
+// transposed copies for dgrad, [in][out]
+constexpr int oWc2T = kFwdHalfs;           // [64][16] (outputs >= 3 zeroed)
+constexpr int oWc1T = oWc2T + 64 * kS16;   // [64][64]
+constexpr int oWc0T = oWc1T + 64 * kS64;   // [16][64] inputs 16..31 (geo part)
+constexpr int oWs1T = oWc0T + 16 * kS64;   // [64][16] outputs permuted like oWs1
+constexpr int oWs0T = oWs1T + 64 * kS16;   // [32][64]
+constexpr int kBwdHalfs = oWs0T + 32 * kS64;
+constexpr int kBwdHalfsPad = (kBwdHalfs + 7) / 8 * 8;
+
+constexpr int kFieldWarps = 4;
+constexpr int kFieldThreads = kFieldWarps * 32;
+#ifndef NSIG_FWD_MINB
+#define NSIG_FWD_MINB 4  // resident CTAs per SM the forward kernel is compiled for (register cap 65536/(128*MINB))
+#endif
+
+struct FieldParams {
+    const float* xyzs;
+    const float* dirs;
+    uint32_t M;
+    float bound_add;   // bound
+    float bound_mul;   // fl(1 / (2*bound)): torch divides by a scalar as x * (1/s) on CUDA
+    FusedTablePtrs base;  // 16 levels
+    const float2* S;      // pre-summed message table or null
+    LevelGeom msg_geom;
+    uint32_t mask;
+    const __half* sigma_w;
+    const __half* color_w;
+    const int32_t* M_dev;  // optional device-side sample count (march counter): M = min(M, *M_dev)
+    float density_scale;   // sigma = density_scale * exp(logit)  (renderer_wtmk.py:294)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+    return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C[MT][NT] (+)= A[MT][KS] x W^T, W in shared memory as [n][k] with `stride` halfs per row.
+// NT0 = first n-tile computed (lets the caller skip unused output columns).
+template <int MT, int KS, int NT, int NT0 = 0>
+__device__ __forceinline__ void layer(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KS][4],
+                                      const __half* __restrict__ W, int stride, int g, int tig) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.f; }
+        const __half* wrow = W + ((NT0 + nt) * 8 + g) * stride + 2 * tig;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + ks * 16);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma16816(c[mt][nt], a[mt][ks], b0, b1);
+        }
+    }
+}
+
+// accumulators of a 16 x (NT*8) layer output -> A fragments of the next layer (ReLU, fp16)
+template <int MT, int NT>
+__device__ __forceinline__ void relu_to_a(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            a[mt][ks][0] = pack_relu_h2(c[mt][2 * ks][0], c[mt][2 * ks][1]);
+            a[mt][ks][1] = pack_relu_h2(c[mt][2 * ks][2], c[mt][2 * ks][3]);
+            a[mt][ks][2] = pack_relu_h2(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1]);
+            a[mt][ks][3] = pack_relu_h2(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3]);
+        }
+}
+
+// gradient accumulators -> A fragments, masked by the forward activation (ReLU'(h) = h > 0)
+__device__ __forceinline__ uint32_t pack_masked(float a, float b, uint32_t act) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&act);
+    const __half2 m = __hgt2(h, __float2half2_rn(0.0f));  // 1.0 where h > 0
+    __half2 v = __hmul2(__floats2half2_rn(a, b), m);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int MT, int NT>
+__device__ __forceinline__ void grad_to_a(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4],
+                                          const uint32_t (&act)[MT][NT / 2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            a[mt][ks][0] = pack_masked(c[mt][2 * ks][0], c[mt][2 * ks][1], act[mt][ks][0]);
+            a[mt][ks][1] = pack_masked(c[mt][2 * ks][2], c[mt][2 * ks][3], act[mt][ks][1]);
+            a[mt][ks][2] = pack_masked(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1], act[mt][ks][2]);
+            a[mt][ks][3] = pack_masked(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3], act[mt][ks][3]);
+        }
+}
+
+// ---- weight staging ---------------------------------------------------------------------
+__device__ __forceinline__ void stage_forward_weights(__half* sm, const __half* __restrict__ sw,
+                                                      const __half* __restrict__ cw, bool color) {
+    const __half zero = __float2half(0.0f);
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int r = i >> 5, c = i & 31;
+        sm[oWs0 + r * kS32 + c] = sw[i];
+        if (color) sm[oWc0 + r * kS32 + c] = (c == 31) ? zero : cw[i];
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        const int r = i >> 6, c = i & 63;  // smem row r holds param row (r+1)%16: [geo0..14, logit]
+        sm[oWs1 + r * kS64 + c] = sw[2048 + ((r + 1) & 15) * 64 + c];
+    }
+    if (color) {
+        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+            const int r = i >> 6, c = i & 63;
+            sm[oWc1 + r * kS64 + c] = cw[2048 + i];
+        }
+        for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) {
+            const int r = i >> 6, c = i & 63;
+            sm[oWc2 + r * kS64 + c] = cw[2048 + 4096 + i];
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_backward_weights(__half* sm, const __half* __restrict__ sw,
+                                                       const __half* __restrict__ cw) {
+    const __half zero = __float2half(0.0f);
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+        const int n = i >> 4, k = i & 15;  // n = hidden (in) index, k = output index
+        sm[oWc2T + n * kS16 + k] = (k < 3) ? cw[2048 + 4096 + k * 64 + n] : zero;
+        sm[oWs1T + n * kS16 + k] = sw[2048 + ((k + 1) & 15) * 64 + n];
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        sm[oWc1T + n * kS64 + k] = cw[2048 + k * 64 + n];
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;  // n = colour-net input 16+n (geo part; input 31 is padding)
+        sm[oWc0T + n * kS64 + k] = (n == 15) ? zero : cw[k * 32 + 16 + n];
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        sm[oWs0T + n * kS64 + k] = sw[k * 32 + n];
+    }
+}
+
+// ---- SH degree 4 at v = ((d+1)/2)*2-1 (network_wtmk_tcnn.py:114 + tcnn's [0,1] convention);
+//      formulas of hash_encoding.py:162-193 -----------------------------------------------------
+__device__ __forceinline__ void sh4(float dx, float dy, float dz, float (&o)[16]) {
+    const float x = __fmaf_rn(__fmul_rn(__fadd_rn(dx, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float y = __fmaf_rn(__fmul_rn(__fadd_rn(dy, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float z = __fmaf_rn(__fmul_rn(__fadd_rn(dz, 1.0f), 0.5f), 2.0f, -1.0f);
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.4886025119029199f * y;
+    o[2] = 0.4886025119029199f * z;
+    o[3] = -0.4886025119029199f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.5462742152960396f * (xx - yy);
+    o[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
+    o[10] = 2.890611442640554f * xy * z;
+    o[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
+    o[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    o[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
+    o[14] = 1.445305721320277f * z * (xx - yy);
+    o[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+
+// row index helpers: a warp owns rows [row0, row0 + 16*MT); thread (g,tig) owns rows
+// row0 + mt*16 + h*8 + g for mt < MT, h in {0,1}; fragment register index is 2*half_k + h.
+template <int MT>
+__device__ __forceinline__ uint32_t frag_row(uint32_t row0, int mt, int h, int g) {
+    return row0 + mt * 16 + h * 8 + g;
+}
+
+// Encode the rows of this thread: A fragments of the sigma net's first layer.
+// fa[mt][ks][2*hk + h]: level = 8*ks + 4*hk + tig, row half h.
+// xn[mt][h][a]: the rows' positions already normalised to the unit box.
+template <int MT>
+__device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const FieldParams& p,
+                                                 const float (&xn)[MT][2][3], int g, int tig) {
+    float2 f[MT][2][4];  // [mt][h][j]: level tig + 4j
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int level = tig + 4 * j;
+        const float2* tab = p.base.t[level];
+        const LevelGeom L = p.base.geom[level];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const Voxel v = locate_fused(xn[mt][h][0], xn[mt][h][1], xn[mt][h][2], L);
+                f[mt][h][j] = encode_level_fused(tab, v, p.mask);
+            }
+    }
+    if (p.S != nullptr) {
+        // message feature (hash_encoding_wtmk_bit.py, pre-summed form): quad thread `tig` evaluates row
+        // (mt = tig>>1, h = tig&1) of each 2-tile group, thread tig==3 (owner of channels 30,31) collects.
+#pragma unroll
+        for (int q = 0; q < (MT * 2 + 3) / 4; ++q) {
+            const int sel = q * 4 + tig;  // which (mt,h) this thread evaluates
+            float2 mine = make_float2(0.f, 0.f);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (mt * 2 + h == sel) { sx = xn[mt][h][0]; sy = xn[mt][h][1]; sz = xn[mt][h][2]; }
+            if (sel < MT * 2) {
+                const Voxel v = locate_fused(sx, sy, sz, p.msg_geom);
+                mine = encode_level_fused(p.S, v, p.mask);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int src = mt * 2 + h - q * 4;  // quad lane that evaluated this row
+                    if (src >= 0 && src < 4) {
+                        const float mx = __shfl_sync(NSIG_FULL_MASK, mine.x, (g << 2) | src);
+                        const float my = __shfl_sync(NSIG_FULL_MASK, mine.y, (g << 2) | src);
+                        if (tig == 3) {  // x_feature[:, -2:] += msg_feature (network_wtmk_tcnn.py:106)
+                            f[mt][h][3].x = __fadd_rn(f[mt][h][3].x, mx);
+                            f[mt][h][3].y = __fadd_rn(f[mt][h][3].y, my);
+                        }
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // level tig+4j -> k-step j>>1, half-k j&1
+                fa[mt][j >> 1][2 * (j & 1) + h] = pack_h2(f[mt][h][j].x, f[mt][h][j].y);
+}
+
+template <int MT>
+__device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
+                                            uint32_t row0, int g, int tig) {
+    float xn[MT][2][3];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
+                xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
+        }
+    encode_positions<MT>(fa, p, xn, g, tig);
+}
+
+// A fragments of the colour net's first k-step: SH(d) columns {2tig,2tig+1,2tig+8,2tig+9}
+template <int MT>
+__device__ __forceinline__ void sh_rows(uint32_t (&ca)[MT][2][4], const float* __restrict__ dirs, uint32_t M,
+                                        uint32_t row0, int g, int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
+            float o[16];
+            sh4(__ldg(dirs + (size_t)r * 3), __ldg(dirs + (size_t)r * 3 + 1), __ldg(dirs + (size_t)r * 3 + 2), o);
+            float lo0 = o[0], lo1 = o[1], hi0 = o[8], hi1 = o[9];
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (tig == t) { lo0 = o[2 * t]; lo1 = o[2 * t + 1]; hi0 = o[2 * t + 8]; hi1 = o[2 * t + 9]; }
+            ca[mt][0][h] = pack_h2(lo0, lo1);
+            ca[mt][0][2 + h] = pack_h2(hi0, hi1);
+        }
+}
+
+// geo features (sigma net outputs in the permuted order [geo0..14, logit]) -> colour k-step 1;
+// column 15 (the logit; the colour net's padded input 31) is cleared.
+template <int MT>
+__device__ __forceinline__ void geo_to_a(uint32_t (&ca)[MT][2][4], const float (&so)[MT][2][4], int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        ca[mt][1][0] = pack_h2(so[mt][0][0], so[mt][0][1]);
+        ca[mt][1][1] = pack_h2(so[mt][0][2], so[mt][0][3]);
+        ca[mt][1][2] = pack_h2(so[mt][1][0], (tig == 3) ? 0.0f : so[mt][1][1]);
+        ca[mt][1][3] = pack_h2(so[mt][1][2], (tig == 3) ? 0.0f : so[mt][1][3]);
+    }
+}
+}  // namespace nsig
+
+static inline int fill_field_params(nsig::FieldParams& p, const float* xyzs, const float* dirs, uint32_t M, float bound,
+                             const float* const* tables, const float* resolutions, uint32_t log2_T,
+                             const float* S, float msg_resolution, const void* sigma_w, const void* color_w,
+                             const int32_t* M_dev, float density_scale) {
+    if (!xyzs || !tables || !resolutions || !sigma_w) return NSIG_EINVAL;
+    if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
+    p.xyzs = xyzs;
+    p.dirs = dirs;
+    p.M = M;
+    p.bound_add = bound;
+    p.bound_mul = 1.0f / (2.0f * bound);
+    for (int l = 0; l < NSIG_MAX_LEVELS; ++l) {
+        if (!tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
+        p.base.t[l] = reinterpret_cast<const float2*>(tables[l]);
+        p.base.geom[l] = nsig::make_level_geom(resolutions[l]);
+    }
+    p.S = reinterpret_cast<const float2*>(S);
+    p.msg_geom = nsig::make_level_geom((msg_resolution > 0.0f) ? msg_resolution : 1.0f);
+    if (S && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
+    p.mask = (1u << log2_T) - 1u;
+    p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
+    p.color_w = reinterpret_cast<const __half*>(color_w);
+    p.M_dev = M_dev;
+    p.density_scale = density_scale;
+    return 0;
+}
+
+// persistent grid: exactly one resident wave (occupancy queried from the runtime), tiles handed out grid-stride
+template <typename K>
+static inline int field_grid(K kernel, size_t smem, uint32_t M, uint32_t rows_per_cta) {
+    int ctas_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, nsig::kFieldThreads, smem) != cudaSuccess ||
+        ctas_per_sm < 1)
+        ctas_per_sm = 1;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t tiles = nsig::div_up(M, rows_per_cta);
+    const uint32_t cap = (uint32_t)(sms * ctas_per_sm);
+    return (int)(tiles < cap ? tiles : cap);
+}
+
