@@ -157,6 +157,15 @@ int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* cons
                                    float resolution, uint32_t log2_T, float* out,
                                    nsig_stream_t stream);
 
+/* half2 shadow copies of n_levels base tables for the fused kernels (BASELINE north_star kernel 2: "vectorised
+ * half2 loads"): tables_h2[l][i] = fp16(tables[l][i] * 2^k_l) with 2^k_l the power of two that puts the level's
+ * largest magnitude in [2^14, 2^15); inv_scale[l] = 2^-k_l (device float[n_levels]).  absmax_scratch: device
+ * uint32[n_levels].  Both pointer arrays are HOST arrays of device pointers.  The base tables are frozen in
+ * watermark training (network_wtmk_tcnn.py:90-95), so this runs once; clean training refreshes it per step. */
+int nsig_tables_to_half2(const float* const* tables, uint32_t n_levels, uint32_t log2_T,
+                         void* const* tables_h2, float* inv_scale, uint32_t* absmax_scratch,
+                         nsig_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* field network — nerf/network_wtmk_tcnn.py:97-124, nerf/network_hash.py:77-110 */
 /* ------------------------------------------------------------------------- */
@@ -180,19 +189,25 @@ int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* cons
  *          kernel processes min(M, *M_dev) rows, so no host sync is needed to size the launch
  * outputs: sigmas[M] fp32, rgbs[M,3] fp32 (sigmoid applied)
  *          feat_out (optional) [M,32] fp16: encoder output incl. message feature, saved for
- *          the backward pass. */
+ *          the backward pass.
+ *   tables_h2 / h2_inv_scale (optional, both or neither): half2 shadow copies of the 16 base tables and their
+ *          device float[16] de-scaling factors, as nsig_tables_to_half2 writes them.  When given, the kernel
+ *          gathers those (one 32-bit load per corner) instead of the fp32 tables; hash slots are unchanged, the
+ *          features carry one extra fp16 rounding (<= 2^-11 of the largest corner value), within the path's 1e-3. */
 int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float bound,
                        const float* const* tables, const float* resolutions, uint32_t log2_T,
                        const float* S, float msg_resolution, const void* sigma_w,
                        const void* color_w, float density_scale, const int32_t* M_dev,
-                       float* sigmas, float* rgbs, void* feat_out, nsig_stream_t stream);
+                       float* sigmas, float* rgbs, void* feat_out, const void* const* tables_h2,
+                       const float* h2_inv_scale, nsig_stream_t stream);
 
 /* Density-only variant: NeRFNetwork.density (network_wtmk_tcnn.py:126-143);
  * geo_feat (optional) [M,15] fp16. */
 int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* const* tables,
                        const float* resolutions, uint32_t log2_T, const float* S,
                        float msg_resolution, const void* sigma_w, float density_scale,
-                       float* sigmas, void* geo_feat, nsig_stream_t stream);
+                       float* sigmas, void* geo_feat, const void* const* tables_h2,
+                       const float* h2_inv_scale, nsig_stream_t stream);
 
 /* Colour branch only: NeRFNetwork.color (network_wtmk_tcnn.py:146-176): SH4(dirs) ++ geo_feat
  * ([M,15] fp16 from nsig_field_density) -> colour MLP -> sigmoid -> rgbs[M,3] fp32. */
@@ -213,7 +228,8 @@ int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const
                      const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
                      const void* sigma_w, const void* color_w, float density_scale, uint32_t* work_counter,
                      float* weights_sum, float* depth, float* image, float* nears, float* fars,
-                     uint32_t* sample_count, nsig_stream_t stream);
+                     uint32_t* sample_count, const void* const* tables_h2, const float* h2_inv_scale,
+                     nsig_stream_t stream);
 
 /* Fused field backward (watermark mode: MLP dgrad only):
  * given dL/dsigma[M], dL/drgb[M,3] and the saved feat[M,32], recompute the MLP
@@ -231,6 +247,63 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
                         const int32_t* M_dev, float msg_resolution, uint32_t log2_T, float* G,
                         float* grad_feat, float* grad_sigma_w, float* grad_color_w,
                         nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* occupancy grid — nerf/renderer_wtmk.py:380-538; ray generation — nerf/utils_wtmk_disen.py:59-143 */
+/* ------------------------------------------------------------------------- */
+
+/* The density sweep of NeRFRenderer.update_extra_state (renderer_wtmk.py:456-514) in one launch for all
+ * cascades: cell -> centre + jitter -> NeRFNetwork.density -> sigma * density_scale.
+ *   cells == NULL (full update, n must be H^3): every cell of every cascade once, in Morton order, and
+ *          the EMA density_grid = max(density_grid * decay, sigma) where both are >= 0 (renderer_wtmk.py:521-523)
+ *          is applied in place; *sum (optional, device double) += sum of max(density_grid, 0).
+ *   cells != NULL ([C, n] Morton indices, e.g. from nsig_grid_sample_cells): partial update; sigma is
+ *          recorded with an atomic max in tmp_grid ([C, H^3], caller fills with -1; where the reference's
+ *          index_put keeps an arbitrary one of duplicate draws, this keeps the largest) and
+ *          nsig_grid_finalize applies the EMA.
+ *   noise (optional) [C, n, 3] in [0,1): the torch.rand_like values of renderer_wtmk.py:479,505; NULL = an
+ *          in-kernel Philox4x32-10 stream keyed by `seed` (the reference's stream is torch's global
+ *          generator, which no other implementation can reproduce).
+ * Field arguments as in nsig_field_density.  bound is a double because the reference evaluates
+ * bound - bound/H in python floats before rounding to fp32. */
+int nsig_grid_sweep(float* density_grid, float* tmp_grid, const int32_t* cells, uint32_t n,
+                    const float* noise, uint64_t seed, uint32_t C, uint32_t H, double bound, float decay,
+                    const float* const* tables, const float* resolutions, uint32_t log2_T,
+                    const float* S, float msg_resolution, const void* sigma_w, float density_scale,
+                    double* sum, const void* const* tables_h2, const float* h2_inv_scale,
+                    nsig_stream_t stream);
+
+/* EMA + mean of the partial update (renderer_wtmk.py:521-524) over all n_cells = C*H^3 cells:
+ * density_grid = max(density_grid * decay, tmp_grid) where both >= 0; *sum += sum of max(density_grid, 0). */
+int nsig_grid_finalize(float* density_grid, const float* tmp_grid, uint32_t n_cells, float decay,
+                       double* sum, nsig_stream_t stream);
+
+/* packbits (raymarching.cu:268-289) with the threshold of renderer_wtmk.py:524-530 computed on the device:
+ * mean_density = *sum / n_cells, thresh = min(mean_density, density_thresh).  stats (optional, device
+ * float[2]) receives (mean_density, thresh).  n_bytes = n_cells / 8. */
+int nsig_grid_pack(const float* density_grid, uint32_t n_bytes, const double* sum, uint32_t n_cells,
+                   float density_thresh, uint8_t* bitfield, float* stats, nsig_stream_t stream);
+
+/* Cell selection of the partial update (renderer_wtmk.py:489-501) without torch.nonzero's host sync:
+ * cells[c, 0:n_uniform) = morton3D(randint(0, H, 3)); cells[c, n_uniform:) = uniformly drawn members of
+ * {i : density_grid[c, i] > 0} (ordered compaction, then a random pick).  cells: int32 [C, n_uniform+n_occupied]. */
+size_t nsig_grid_sample_cells_scratch_bytes(uint32_t C, uint32_t H);
+int nsig_grid_sample_cells(const float* density_grid, uint32_t C, uint32_t H, uint32_t n_uniform,
+                           uint32_t n_occupied, uint64_t seed, int32_t* cells, void* scratch,
+                           nsig_stream_t stream);
+
+/* NeRFRenderer.mark_untrained_grid (renderer_wtmk.py:380-442): density_grid[c, i] = -1 for every cell whose
+ * centre no camera sees (z > 0, |x| < cx/fx * z + 2*half, |y| < cy/fy * z + 2*half).  poses: [B,4,4] cam2world. */
+int nsig_mark_untrained_grid(const float* poses, uint32_t B, float fx, float fy, float cx, float cy,
+                             uint32_t C, uint32_t H, double bound, float* density_grid,
+                             nsig_stream_t stream);
+
+/* get_rays (utils_wtmk_disen.py:59-143): rays_o/rays_d [B,N,3] of pixels inds[b*inds_batch_stride + n]
+ * (int64 pixel ids h*W + w; inds_batch_stride = 0 shares one index list over the batch, as the reference's
+ * expand does; inds == NULL means all H*W pixels, N = H*W).  poses: [B,4,4] cam2world. */
+int nsig_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H,
+                  uint32_t W, const int64_t* inds, int64_t inds_batch_stride, uint32_t N,
+                  float* rays_o, float* rays_d, nsig_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* optimizer step of the message tables — nerf/utils_wtmk_disen.py:1175-1181   */

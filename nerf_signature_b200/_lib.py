@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libnsig_b200.so")
 
 _c = ctypes
 _vp, _u32, _f32, _sz = _c.c_void_p, _c.c_uint32, _c.c_float, _c.c_size_t
+_u64, _i64, _f64 = _c.c_uint64, _c.c_int64, _c.c_double
 
 # name -> (argtypes, number of kernel launches one call performs)
 _SIGNATURES = {
@@ -37,17 +38,26 @@ _SIGNATURES = {
     "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _vp], 1),
     "nsig_msg_encode_forward_perbit": ([_vp, _u32, _vp, _u32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp,
-                            _vp], 1),
-    "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp], 1),
+                            _vp, _vp, _vp], 1),
+    "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp], 1),
+    "nsig_tables_to_half2": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp], 2),
+    "nsig_grid_sweep": ([_vp, _vp, _vp, _u32, _vp, _u64, _u32, _u32, _f64, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32,
+                         _vp, _vp, _vp, _vp], 1),
+    "nsig_grid_finalize": ([_vp, _vp, _u32, _f32, _vp, _vp], 1),
+    "nsig_grid_pack": ([_vp, _u32, _vp, _u32, _f32, _vp, _vp, _vp], 1),
+    "nsig_grid_sample_cells": ([_vp, _u32, _u32, _u32, _u32, _u64, _vp, _vp, _vp], 4),
+    "nsig_mark_untrained_grid": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f64, _vp, _vp], 1),
+    "nsig_get_rays": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _i64, _u32, _vp, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
-                          _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
+                          _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp], 2),
     "nsig_field_backward": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp, _vp,
                              _vp, _vp], 1),
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes",
+                                                "nsig_grid_sample_cells_scratch_bytes"])
 
 _lib = None
 _lock = threading.Lock()
@@ -79,6 +89,8 @@ def load():
         lib.nsig_version.argtypes = []
         lib.nsig_march_rays_train_scratch_bytes.restype = _sz
         lib.nsig_march_rays_train_scratch_bytes.argtypes = [_u32]
+        lib.nsig_grid_sample_cells_scratch_bytes.restype = _sz
+        lib.nsig_grid_sample_cells_scratch_bytes.argtypes = [_u32, _u32]
         _lib = lib
     return _lib
 

@@ -26,7 +26,7 @@ namespace nsig {
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
-template <bool COLOR>
+template <bool COLOR, bool H2>
 __global__ void __launch_bounds__(kFieldThreads, NSIG_FWD_MINB)
 k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__ rgbs, __half* __restrict__ feat_out,
             __half* __restrict__ geo_out) {
@@ -44,7 +44,7 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
         const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
         if (row0 >= M) continue;
         uint32_t fa[MT][2][4];
-        encode_rows<MT>(fa, p, M, row0, g, tig);
+        encode_rows<MT, H2>(fa, p, M, row0, g, tig);
         if (feat_out) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -240,6 +240,7 @@ constexpr int kStageSlots = 64;
 constexpr int kStageFloats = kStageSlots * 5 + 32 * 4;
 constexpr int kFwdHalfsPad = (kFwdHalfs + 7) / 8 * 8;
 
+template <bool H2>
 __global__ void __launch_bounds__(kRenderWarps * 32)
 k_render_rays(const RenderParams p) {
     constexpr int MT = 2;
@@ -313,7 +314,7 @@ k_render_rays(const RenderParams p) {
                             xn[mt][h][a] = __fmul_rn(__fadd_rn(st_xyz[row * 3 + a], p.f.bound_add), p.f.bound_mul);
                     }
                 uint32_t fa[MT][2][4];
-                encode_positions<MT>(fa, p.f, xn, g, tig);
+                encode_positions<MT, H2>(fa, p.f, xn, g, tig);
                 uint32_t h1[MT][4][4];
                 {
                     float cc[MT][8][4];
@@ -765,16 +766,23 @@ extern "C" {
 int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float bound, const float* const* tables,
                        const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
                        const void* sigma_w, const void* color_w, float density_scale, const int32_t* M_dev,
-                       float* sigmas, float* rgbs, void* feat_out, nsig_stream_t stream) {
+                       float* sigmas, float* rgbs, void* feat_out, const void* const* tables_h2,
+                       const float* h2_inv_scale, nsig_stream_t stream) {
     if (M == 0) return 0;
     if (!dirs || !color_w || !sigmas || !rgbs) return NSIG_EINVAL;
     FieldParams p;
     const int rc = fill_field_params(p, xyzs, dirs, M, bound, tables, resolutions, log2_T, S, msg_resolution,
-                                     sigma_w, color_w, M_dev, density_scale);
+                                     sigma_w, color_w, M_dev, density_scale, tables_h2, h2_inv_scale);
     if (rc) return rc;
     const size_t smem = kFwdHalfs * sizeof(__half);
-    k_field_fwd<true><<<field_grid(k_field_fwd<true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, (cudaStream_t)stream>>>(
-        p, sigmas, rgbs, reinterpret_cast<__half*>(feat_out), nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    __half* feat = reinterpret_cast<__half*>(feat_out);
+    if (tables_h2)
+        k_field_fwd<true, true><<<field_grid(k_field_fwd<true, true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
+            p, sigmas, rgbs, feat, nullptr);
+    else
+        k_field_fwd<true, false><<<field_grid(k_field_fwd<true, false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
+            p, sigmas, rgbs, feat, nullptr);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -782,16 +790,22 @@ int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float b
 int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* const* tables,
                        const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
                        const void* sigma_w, float density_scale, float* sigmas, void* geo_feat,
-                       nsig_stream_t stream) {
+                       const void* const* tables_h2, const float* h2_inv_scale, nsig_stream_t stream) {
     if (M == 0) return 0;
     if (!sigmas) return NSIG_EINVAL;
     FieldParams p;
     const int rc = fill_field_params(p, xyzs, nullptr, M, bound, tables, resolutions, log2_T, S, msg_resolution,
-                                     sigma_w, nullptr, nullptr, density_scale);
+                                     sigma_w, nullptr, nullptr, density_scale, tables_h2, h2_inv_scale);
     if (rc) return rc;
     const size_t smem = kFwdHalfs * sizeof(__half);
-    k_field_fwd<false><<<field_grid(k_field_fwd<false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, (cudaStream_t)stream>>>(
-        p, sigmas, nullptr, nullptr, reinterpret_cast<__half*>(geo_feat));
+    cudaStream_t st = (cudaStream_t)stream;
+    __half* geo = reinterpret_cast<__half*>(geo_feat);
+    if (tables_h2)
+        k_field_fwd<false, true><<<field_grid(k_field_fwd<false, true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
+            p, sigmas, nullptr, nullptr, geo);
+    else
+        k_field_fwd<false, false><<<field_grid(k_field_fwd<false, false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
+            p, sigmas, nullptr, nullptr, geo);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -812,14 +826,15 @@ int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const
                      float T_thresh, const float* noises, const float* const* tables, const float* resolutions,
                      uint32_t log2_T, const float* S, float msg_resolution, const void* sigma_w, const void* color_w,
                      float density_scale, uint32_t* work_counter, float* weights_sum, float* depth, float* image,
-                     float* nears, float* fars, uint32_t* sample_count, nsig_stream_t stream) {
+                     float* nears, float* fars, uint32_t* sample_count, const void* const* tables_h2,
+                     const float* h2_inv_scale, nsig_stream_t stream) {
     if (N == 0) return 0;
     if (!rays_o || !rays_d || !aabb || !grid || !color_w || !work_counter || !weights_sum || !depth || !image)
         return NSIG_EINVAL;
     if (C == 0 || C > 31 || H == 0 || H > 1024 || max_steps == 0) return NSIG_EINVAL;
     RenderParams p;
     const int rc = fill_field_params(p.f, rays_o /*unused*/, rays_d, 0, bound, tables, resolutions, log2_T, S,
-                                     msg_resolution, sigma_w, color_w, nullptr, density_scale);
+                                     msg_resolution, sigma_w, color_w, nullptr, density_scale, tables_h2, h2_inv_scale);
     if (rc) return rc;
     p.rays_o = rays_o; p.rays_d = rays_d; p.N = N; p.grid = grid; p.dt_gamma = dt_gamma;
     p.max_steps = max_steps; p.C = C; p.H = H; p.aabb = aabb; p.min_near = min_near; p.T_thresh = T_thresh;
@@ -830,9 +845,12 @@ int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t want = div_up(N, kRenderWarps);
     int per_sm = 3;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_rays, kRenderWarps * 32, smem);
+    if (tables_h2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_rays<true>, kRenderWarps * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_rays<false>, kRenderWarps * 32, smem);
     const uint32_t cap = (uint32_t)sms * (uint32_t)(per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
-    k_render_rays<<<want < cap ? want : cap, kRenderWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    const uint32_t blocks = want < cap ? want : cap;
+    if (tables_h2) k_render_rays<true><<<blocks, kRenderWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    else k_render_rays<false><<<blocks, kRenderWarps * 32, smem, (cudaStream_t)stream>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -201,7 +201,8 @@ __device__ __forceinline__ uint32_t frag_row(uint32_t row0, int mt, int h, int g
 // Encode the rows of this thread: A fragments of the sigma net's first layer.
 // fa[mt][ks][2*hk + h]: level = 8*ks + 4*hk + tig, row half h.
 // xn[mt][h][a]: the rows' positions already normalised to the unit box.
-template <int MT>
+// H2: gather the half2 shadow tables (p.base.th / inv_scale) instead of the fp32 ones.
+template <int MT, bool H2 = false>
 __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const FieldParams& p,
                                                  const float (&xn)[MT][2][3], int g, int tig) {
     float2 f[MT][2][4];  // [mt][h][j]: level tig + 4j
@@ -209,13 +210,15 @@ __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const
     for (int j = 0; j < 4; ++j) {
         const int level = tig + 4 * j;
         const float2* tab = p.base.t[level];
+        const __half2* tabh = p.base.th[level];
+        const float inv_scale = H2 ? __ldg(p.base.inv_scale + level) : 1.0f;
         const LevelGeom L = p.base.geom[level];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const Voxel v = locate_fused(xn[mt][h][0], xn[mt][h][1], xn[mt][h][2], L);
-                f[mt][h][j] = encode_level_fused(tab, v, p.mask);
+                f[mt][h][j] = H2 ? encode_level_fused_h2(tabh, v, p.mask, inv_scale) : encode_level_fused(tab, v, p.mask);
             }
     }
     if (p.S != nullptr) {
@@ -260,7 +263,7 @@ __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const
                 fa[mt][j >> 1][2 * (j & 1) + h] = pack_h2(f[mt][h][j].x, f[mt][h][j].y);
 }
 
-template <int MT>
+template <int MT, bool H2 = false>
 __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
                                             uint32_t row0, int g, int tig) {
     float xn[MT][2][3];
@@ -273,7 +276,7 @@ __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const Fiel
             for (int a = 0; a < 3; ++a)  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
                 xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
         }
-    encode_positions<MT>(fa, p, xn, g, tig);
+    encode_positions<MT, H2>(fa, p, xn, g, tig);
 }
 
 // A fragments of the colour net's first k-step: SH(d) columns {2tig,2tig+1,2tig+8,2tig+9}
@@ -313,8 +316,10 @@ __device__ __forceinline__ void geo_to_a(uint32_t (&ca)[MT][2][4], const float (
 static inline int fill_field_params(nsig::FieldParams& p, const float* xyzs, const float* dirs, uint32_t M, float bound,
                              const float* const* tables, const float* resolutions, uint32_t log2_T,
                              const float* S, float msg_resolution, const void* sigma_w, const void* color_w,
-                             const int32_t* M_dev, float density_scale) {
+                             const int32_t* M_dev, float density_scale, const void* const* tables_h2 = nullptr,
+                             const float* h2_inv_scale = nullptr) {
     if (!xyzs || !tables || !resolutions || !sigma_w) return NSIG_EINVAL;
+    if ((tables_h2 == nullptr) != (h2_inv_scale == nullptr)) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
     p.xyzs = xyzs;
     p.dirs = dirs;
@@ -325,7 +330,10 @@ static inline int fill_field_params(nsig::FieldParams& p, const float* xyzs, con
         if (!tables[l] || !(resolutions[l] > 0.0f)) return NSIG_EINVAL;
         p.base.t[l] = reinterpret_cast<const float2*>(tables[l]);
         p.base.geom[l] = nsig::make_level_geom(resolutions[l]);
+        p.base.th[l] = tables_h2 ? reinterpret_cast<const __half2*>(tables_h2[l]) : nullptr;
+        if (tables_h2 && !tables_h2[l]) return NSIG_EINVAL;
     }
+    p.base.inv_scale = h2_inv_scale;
     p.S = reinterpret_cast<const float2*>(S);
     p.msg_geom = nsig::make_level_geom((msg_resolution > 0.0f) ? msg_resolution : 1.0f);
     if (S && !(msg_resolution > 0.0f)) return NSIG_EINVAL;

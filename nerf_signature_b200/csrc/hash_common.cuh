@@ -162,6 +162,9 @@ __device__ __forceinline__ float2 trilerp_fma(const float2 e[8], const Voxel& v)
     return r;
 }
 
+// (An x-pair merged variant - one 128-bit load for both x-neighbours when the lower x index is even - was measured
+// SLOWER, 0.168 vs 0.137 ms per 555k samples: the L1 data pipe returns 32 lanes x 4 B per wavefront, so wider
+// per-lane loads cost proportionally more wavefronts.  profiles/r01_field_kernels_v1.txt.)
 __device__ __forceinline__ float2 encode_level_fused(const float2* __restrict__ table, const Voxel& v, uint32_t mask) {
     float2 e[8];
 #pragma unroll
@@ -172,9 +175,29 @@ __device__ __forceinline__ float2 encode_level_fused(const float2* __restrict__ 
     return trilerp_fma(e, v);
 }
 
+// half2 shadow tables (north_star kernel 2: "vectorised half2 loads"): entry = (f0, f1) * scale_l rounded to fp16,
+// scale_l a power of two chosen per level so the largest magnitude sits just below 2^15 (no fp16 subnormals for
+// U(+-1e-4) initialisations, no overflow for trained tables).  One 32-bit load per corner: the L1 data pipe moves
+// 32 lanes x 4 B per wavefront, so this halves the wavefronts of the gather against the fp32 (8 B per lane) tables.
+// Interpolation stays fp32; the result is multiplied by 1/scale_l (exact).  Absolute error per feature
+// <= 2^-11 * max|corner|, the same size as the fp16 rounding the MMA operands get anyway.
+__device__ __forceinline__ float2 encode_level_fused_h2(const __half2* __restrict__ table, const Voxel& v, uint32_t mask,
+                                                        float inv_scale) {
+    float2 e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(table) + corner_slot(v, k, mask));
+        e[k] = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+    }
+    const float2 r = trilerp_fma(e, v);
+    return make_float2(r.x * inv_scale, r.y * inv_scale);
+}
+
 struct FusedTablePtrs {
     const float2* t[NSIG_MAX_LEVELS];
     LevelGeom geom[NSIG_MAX_LEVELS];
+    const __half2* th[NSIG_MAX_LEVELS];  // half2 shadow tables (all null: fp32 tables are gathered)
+    const float* inv_scale;              // device float[NSIG_MAX_LEVELS] = 1 / scale_l
 };
 
 }  // namespace nsig

@@ -110,6 +110,45 @@ k_msg_table_sum(MsgTablePtrs tp, uint32_t message_dim, const float* __restrict__
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// ---- half2 shadow tables for the fused kernels (hash_common.cuh: encode_level_fused_h2) ----------------------------
+struct ShadowPtrs {
+    const float* src[NSIG_MAX_LEVELS];
+    __half2* dst[NSIG_MAX_LEVELS];
+};
+
+// pass 1: per-level max |v| (as the bit pattern of a non-negative float, so an integer atomicMax orders it)
+__global__ void __launch_bounds__(256)
+k_shadow_absmax(ShadowPtrs tp, uint32_t n_vec4, uint32_t* __restrict__ absmax_bits) {
+    const uint32_t level = blockIdx.y;
+    const float4* src = reinterpret_cast<const float4*>(tp.src[level]);
+    float m = 0.f;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n_vec4; i += gridDim.x * 256u) {
+        const float4 v = ld_stream4(src + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(NSIG_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(absmax_bits + level, __float_as_uint(m));
+}
+
+// pass 2: dst = fp16(src * 2^k), k chosen so that max|v| * 2^k lies in [2^14, 2^15); inv_scale[level] = 2^-k
+__global__ void __launch_bounds__(256)
+k_shadow_convert(ShadowPtrs tp, uint32_t n_vec4, const uint32_t* __restrict__ absmax_bits, float* __restrict__ inv_scale) {
+    const uint32_t level = blockIdx.y;
+    const float m = __uint_as_float(absmax_bits[level]);
+    int e = 0;
+    float scale = 1.0f;
+    if (m > 0.f) { frexpf(m, &e); scale = scalbnf(1.0f, max(-100, min(100, 15 - e))); }  // m = f * 2^e, f in [0.5, 1)
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[level] = 1.0f / scale;
+    const float4* src = reinterpret_cast<const float4*>(tp.src[level]);
+    uint2* dst = reinterpret_cast<uint2*>(tp.dst[level]);
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n_vec4; i += gridDim.x * 256u) {
+        const float4 v = ld_stream4(src + i);
+        const __half2 a = __floats2half2_rn(v.x * scale, v.y * scale), b = __floats2half2_rn(v.z * scale, v.w * scale);
+        dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+}
+
 // reference-form message encoder: per bit gather + trilerp, summed in bit order
 __global__ void __launch_bounds__(256)
 k_msg_encode_perbit(const float* __restrict__ x, uint32_t B, MsgTablePtrs tp, uint32_t message_dim,
@@ -208,6 +247,29 @@ int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* cons
     }
     k_msg_encode_perbit<<<div_up(B, 256), 256, 0, (cudaStream_t)stream>>>(
         x, B, tp, message_dim, message, 1.0f / resolution, (1u << log2_T) - 1u, out);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_tables_to_half2(const float* const* tables, uint32_t n_levels, uint32_t log2_T, void* const* tables_h2,
+                         float* inv_scale, uint32_t* absmax_scratch, nsig_stream_t stream) {
+    if (n_levels == 0) return 0;
+    if (!tables || !tables_h2 || !inv_scale || !absmax_scratch) return NSIG_EINVAL;
+    if (n_levels > NSIG_MAX_LEVELS || log2_T < 1 || log2_T > 30) return NSIG_EINVAL;
+    ShadowPtrs tp;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        if (!tables[l] || !tables_h2[l] || (((uintptr_t)tables[l]) & 15) || (((uintptr_t)tables_h2[l]) & 7)) return NSIG_EINVAL;
+        tp.src[l] = tables[l];
+        tp.dst[l] = reinterpret_cast<__half2*>(tables_h2[l]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(absmax_scratch, 0, n_levels * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    const uint32_t n_vec4 = (1u << log2_T) / 2;  // T entries x 2 floats / 4
+    const dim3 grid(min(div_up(n_vec4, 256u), 148u * 2u), n_levels);
+    k_shadow_absmax<<<grid, 256, 0, st>>>(tp, n_vec4, absmax_scratch);
+    NSIG_LAUNCH_CHECK();
+    k_shadow_convert<<<grid, 256, 0, st>>>(tp, n_vec4, absmax_scratch, inv_scale);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

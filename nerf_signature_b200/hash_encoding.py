@@ -51,6 +51,13 @@ class _hash_encode(Function):
         return (None, None, None) + tuple(g if n else None for g, n in zip(grads, need))
 
 
+class HalfTables:
+    """half2 shadow tables + their per-level de-scaling factors (device float[16])."""
+
+    def __init__(self, tables, inv_scale, scratch):
+        self.tables, self.inv_scale, self.scratch = tables, inv_scale, scratch
+
+
 class HashEmbedder(nn.Module):
     def __init__(self, bounding_box, n_levels=16, n_features_per_level=2,
                  log2_hashmap_size=19, base_resolution=16, finest_resolution=512):
@@ -77,9 +84,31 @@ class HashEmbedder(nn.Module):
         for i in range(n_levels):
             nn.init.uniform_(self.embeddings[i].weight, a=-0.0001, b=0.0001)
         self.resolutions = level_resolutions(self.base_resolution, self.b, n_levels)
+        self._shadow = None      # HalfTables for the fused kernels (not part of the state dict)
+        self._shadow_key = None
 
     def tables(self):
         return [e.weight for e in self.embeddings]
+
+    @torch.no_grad()
+    def half_tables(self):
+        """half2 shadow copies of the level tables for the fused field kernels (nsig_tables_to_half2): one 32-bit
+        gather per corner instead of 64.  Rebuilt whenever a table's storage or version changes (once in watermark
+        training, where the base encoder is frozen; every optimizer step in clean training, ~96 MB of traffic)."""
+        tabs = self.tables()
+        key = tuple((t.data_ptr(), t._version) for t in tabs)
+        if self._shadow is not None and self._shadow_key == key:
+            return self._shadow
+        dev = tabs[0].device
+        if self._shadow is None or self._shadow.inv_scale.device != dev:
+            self._shadow = HalfTables([torch.empty(t.shape[0], 2, dtype=torch.float16, device=dev) for t in tabs],
+                                      torch.ones(16, dtype=torch.float32, device=dev),
+                                      torch.zeros(16, dtype=torch.int32, device=dev))
+        sh = self._shadow
+        _lib.call("nsig_tables_to_half2", _lib.pointer_array([t.contiguous() for t in tabs]), len(tabs),
+                  self.log2_hashmap_size, _lib.pointer_array(sh.tables), _P(sh.inv_scale), _P(sh.scratch))
+        self._shadow_key = key
+        return sh
 
     def forward(self, x):
         # x: B x 3 in the unit box

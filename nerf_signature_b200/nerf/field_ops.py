@@ -85,12 +85,20 @@ class SHEncoding(nn.Module):
 class FieldConfig:
     """Everything the field kernels need besides tensors."""
 
-    def __init__(self, bound, resolutions, log2_T, msg_resolution, density_scale=1.0):
+    def __init__(self, bound, resolutions, log2_T, msg_resolution, density_scale=1.0, shadow=None):
+        self.shadow = shadow  # hash_encoding.HalfTables or None (gather the fp32 tables)
         self.bound = float(bound)
         self.resolutions = list(resolutions)
         self.log2_T = int(log2_T)
         self.msg_resolution = float(msg_resolution)
         self.density_scale = float(density_scale)
+
+
+def _shadow_args(cfg):
+    """(tables_h2, h2_inv_scale) arguments of the fused entry points."""
+    if cfg.shadow is None:
+        return None, None
+    return _lib.pointer_array(cfg.shadow.tables), _P(cfg.shadow.inv_scale)
 
 
 class _field_forward(Function):
@@ -121,7 +129,7 @@ class _field_forward(Function):
         Sc = S.contiguous() if S is not None else None
         _lib.call("nsig_field_forward", _P(xyzs), _P(dirs), M, cfg.bound, _lib.pointer_array(tabs),
                   _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc), cfg.msg_resolution, _P(sw), _P(cw),
-                  cfg.density_scale, _P(count), _P(sigmas), _P(rgbs), _P(feat))
+                  cfg.density_scale, _P(count), _P(sigmas), _P(rgbs), _P(feat), *_shadow_args(cfg))
         if save:
             ctx.save_for_backward(xyzs, dirs, feat, sw, cw)
             ctx.cfg = cfg
@@ -184,7 +192,7 @@ def field_density(xyzs, S, cfg, sigma_mlp, tables, want_geo=True):
     Sc = S.contiguous() if S is not None else None
     _lib.call("nsig_field_density", _P(xyzs), M, cfg.bound, _lib.pointer_array(tabs), _lib.float_array(cfg.resolutions),
               cfg.log2_T, _P(Sc), cfg.msg_resolution, _P(sigma_mlp.half_weights()), cfg.density_scale, _P(sigmas),
-              _P(geo))
+              _P(geo), *_shadow_args(cfg))
     return sigmas, geo
 
 
@@ -221,5 +229,39 @@ def render_rays(rays_o, rays_d, aabb, min_near, bitfield, cascade, grid_size, dt
               _P(bitfield.contiguous()), int(cascade), int(grid_size), float(dt_gamma), int(max_steps), float(T_thresh),
               _P(noises), _lib.pointer_array(tabs), _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc),
               cfg.msg_resolution, _P(sigma_mlp.half_weights()), _P(color_mlp.half_weights()), cfg.density_scale,
-              _P(counters[0:1]), _P(weights_sum), _P(depth), _P(image), _P(nears), _P(fars), _P(counters[1:2]))
+              _P(counters[0:1]), _P(weights_sum), _P(depth), _P(image), _P(nears), _P(fars), _P(counters[1:2]),
+              *_shadow_args(cfg))
     return weights_sum, depth, image, nears, fars, counters[1]
+
+
+@torch.no_grad()
+def grid_update(density_grid, bitfield, full, decay, density_thresh, C, H, bound, seed, S, cfg, sigma_mlp, tables,
+                cells=None, noise=None):
+    """Host side of NeRFRenderer.update_extra_state (csrc/grid.cu): density sweep + EMA + packbits, in place on
+    `density_grid` [C,H^3] and `bitfield`.  Returns a device float[2] = (mean_density, threshold used)."""
+    dev = density_grid.device
+    H3 = H ** 3
+    sums = torch.zeros(1, dtype=torch.float64, device=dev)
+    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    tabs = [t.contiguous() for t in tables]
+    Sc = S.contiguous() if S is not None else None
+    field = (_lib.pointer_array(tabs), _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc), cfg.msg_resolution,
+             _P(sigma_mlp.half_weights()), cfg.density_scale)
+    if noise is not None:
+        noise = noise.contiguous().float()
+    if full:
+        _lib.call("nsig_grid_sweep", _P(density_grid), None, None, H3, _P(noise), seed, C, H, bound, decay, *field,
+                  _P(sums), *_shadow_args(cfg))
+    else:
+        if cells is None:
+            n = H3 // 4
+            cells = torch.empty(C, 2 * n, dtype=torch.int32, device=dev)
+            scratch = torch.empty(_lib.load().nsig_grid_sample_cells_scratch_bytes(C, H), dtype=torch.uint8, device=dev)
+            _lib.call("nsig_grid_sample_cells", _P(density_grid), C, H, n, n, seed ^ 0x5DEECE66D, _P(cells), _P(scratch))
+        cells = cells.contiguous().to(torch.int32)
+        tmp = torch.full_like(density_grid, -1.0)
+        _lib.call("nsig_grid_sweep", _P(density_grid), _P(tmp), _P(cells), cells.shape[1], _P(noise), seed, C, H, bound,
+                  decay, *field, None, *_shadow_args(cfg))
+        _lib.call("nsig_grid_finalize", _P(density_grid), _P(tmp), C * H3, decay, _P(sums))
+    _lib.call("nsig_grid_pack", _P(density_grid), C * H3 // 8, _P(sums), C * H3, density_thresh, _P(bitfield), _P(stats))
+    return stats

@@ -41,7 +41,9 @@ class NeRFNetwork(NeRFRenderer):
                                   n_hidden_layers=num_layers_color - 1, seed=1338)
 
     def _cfg(self, density_scale=1.0):
-        return FieldConfig(self.bound, self.encoder.resolutions, self.encoder.log2_hashmap_size, 0.0, density_scale)
+        shadow = self.encoder.half_tables() if self.half2_tables else None
+        return FieldConfig(self.bound, self.encoder.resolutions, self.encoder.log2_hashmap_size, 0.0, density_scale,
+                           shadow)
 
     def field(self, xyzs, dirs, message=None, count=None):
         return field_forward(xyzs, dirs, None, count, self._cfg(self.density_scale), self.sigma_net,

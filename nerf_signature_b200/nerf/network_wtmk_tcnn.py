@@ -73,8 +73,9 @@ class NeRFNetwork(NeRFRenderer):
 
     # ---- helpers -----------------------------------------------------------------------------
     def _cfg(self, density_scale=1.0):
+        shadow = self.encoder.half_tables() if self.half2_tables else None
         return FieldConfig(self.bound, self.encoder.resolutions, self.encoder.log2_hashmap_size,
-                           self.msg_encoder.resolution, density_scale)
+                           self.msg_encoder.resolution, density_scale, shadow)
 
     def _summed_table(self, message):
         """S for this message; cached across the two render passes of a training step (keyed on the

@@ -13,9 +13,11 @@ What changed underneath (B200-first):
   * the network evaluation is ONE fused kernel (csrc/field.cu) instead of ~400 torch kernels.
   * run_cuda (inference branch) keeps the reference's alive-ray compaction loop semantics but compacts
     on the device and reads the alive count back once per iteration.
-  * update_extra_state evaluates the density of all 128^3 cells of a cascade in one fused launch.
+  * update_extra_state is one fused sweep (cell -> jitter -> encode -> sigma MLP -> EMA) + packbits with a
+    device-side threshold; mark_untrained_grid is one launch (csrc/grid.cu).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -80,6 +82,14 @@ class NeRFRenderer(nn.Module):
         aabb_infer = aabb_train.clone()
         self.register_buffer('aabb_train', aabb_train)
         self.register_buffer('aabb_infer', aabb_infer)
+
+        self._pending_stats = None
+        self._last_stats = None
+        self._mean_density = 0
+        self._mean_count = 0
+        # gather half2 shadow copies of the (frozen) base tables in the fused kernels (hash_encoding.half_tables);
+        # NSIG_FP32_TABLES=1 keeps the fp32 gathers (A/B switch)
+        self.half2_tables = os.environ.get("NSIG_FP32_TABLES", "0") != "1"
 
         self.cuda_ray = cuda_ray
         if cuda_ray:
@@ -324,110 +334,77 @@ class NeRFRenderer(nn.Module):
         """(density_scale * sigma, rgb) of the samples; implemented by the network subclasses."""
         raise NotImplementedError()
 
+    # ------------------------------------------------------------------------------------------
+    # occupancy grid (reference renderer_wtmk.py:380-538) — fused kernels of csrc/grid.cu
+    # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        # poses: [B, 4, 4] cam2world, intrinsic: (fx, fy, cx, cy)   (reference renderer_wtmk.py:380-442)
+        """density_grid = -1 for every cell no training camera sees (reference renderer_wtmk.py:380-442: 8 blocks
+        of 64^3 cells x cascades x pose chunks of `S`, ~10 torch kernels each).  One launch here: a thread owns a
+        cell and walks all B poses from shared memory.  poses: [B,4,4] cam2world; intrinsic: (fx, fy, cx, cy)."""
         if not self.cuda_ray:
             return
-
-        if isinstance(poses, np.ndarray):
-            poses = torch.from_numpy(poses)
-
-        B = poses.shape[0]
-        fx, fy, cx, cy = intrinsic
         dev = self.density_bitfield.device
-
-        X = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        Y = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        Z = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-
-        count = torch.zeros_like(self.density_grid)
-        poses = poses.to(count.device)
-
-        for xs in X:
-            for ys in Y:
-                for zs in Z:
-                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    world_xyzs = (2 * coords.float() / (self.grid_size - 1) - 1).unsqueeze(0)
-
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        half_grid_size = bound / self.grid_size
-                        cas_world_xyzs = world_xyzs * (bound - half_grid_size)
-
-                        head = 0
-                        while head < B:
-                            tail = min(head + S, B)
-                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
-                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]
-                            mask_z = cam_xyzs[:, :, 2] > 0
-                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < cx / fx * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < cy / fy * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            mask = (mask_z & mask_x & mask_y).sum(0).reshape(-1)
-                            count[cas, indices] += mask
-                            head += S
-
-        self.density_grid[count == 0] = -1
+        poses = torch.as_tensor(poses, dtype=torch.float32).to(dev).contiguous()
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        _lib.call("nsig_mark_untrained_grid", _P(poses), poses.shape[0], fx, fy, cx, cy, int(self.cascade),
+                  int(self.grid_size), float(self.bound), _P(self.density_grid))
 
     @torch.no_grad()
-    def update_extra_state(self, message=None, decay=0.95, S=128):
-        # reference renderer_wtmk.py:445-538
+    def update_extra_state(self, message=None, decay=0.95, S=128, cells=None, noise=None):
+        """Occupancy EMA + bitfield + mean_count (reference renderer_wtmk.py:445-538).
+
+        Full update (first 16 calls): every cell of every cascade, jittered, through density() and the EMA in ONE
+        kernel; partial update: H^3/4 uniform + H^3/4 occupied cells per cascade, selected on the device.  The
+        threshold min(mean_density, density_thresh) is taken from a device-side sum, so nothing here waits for
+        the GPU: `mean_density` / `mean_count` are fetched lazily when somebody reads them.
+        `cells` ([C,n] int32 Morton indices) and `noise` ([C,n,3] in [0,1)) override the random draws
+        (parity tests feed the reference's draws); `S` is accepted for signature compatibility."""
         if not self.cuda_ray:
             return
-
-        tmp_grid = - torch.ones_like(self.density_grid)
-        dev = self.density_bitfield.device
-        H = self.grid_size
-
-        if self.iter_density < 16:
-            # full update: every cell of every cascade, one fused density launch per cascade
-            ar = torch.arange(H, dtype=torch.int32, device=dev)
-            xx, yy, zz = custom_meshgrid(ar, ar, ar)
-            coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-            indices = raymarching.morton3D(coords).long()
-            xyzs = 2 * coords.float() / (H - 1) - 1
-            for cas in range(self.cascade):
-                bound = min(2 ** cas, self.bound)
-                half_grid_size = bound / H
-                cas_xyzs = xyzs * (bound - half_grid_size)
-                cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
-                sigmas = self.density(cas_xyzs, message)['sigma'].reshape(-1).detach()
-                sigmas *= self.density_scale
-                tmp_grid[cas, indices] = sigmas
-        else:
-            N = H ** 3 // 4
-            for cas in range(self.cascade):
-                coords = torch.randint(0, H, (N, 3), device=dev)
-                indices = raymarching.morton3D(coords).long()
-                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
-                occ_indices = occ_indices[rand_mask]
-                occ_coords = raymarching.morton3D_invert(occ_indices)
-                indices = torch.cat([indices, occ_indices], dim=0)
-                coords = torch.cat([coords, occ_coords], dim=0)
-                xyzs = 2 * coords.float() / (H - 1) - 1
-                bound = min(2 ** cas, self.bound)
-                half_grid_size = bound / H
-                cas_xyzs = xyzs * (bound - half_grid_size)
-                cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
-                sigmas = self.density(cas_xyzs, message)['sigma'].reshape(-1).detach()
-                sigmas *= self.density_scale
-                tmp_grid[cas, indices] = sigmas
-
-        valid_mask = (self.density_grid >= 0) & (tmp_grid >= 0)
-        self.density_grid[valid_mask] = torch.maximum(self.density_grid[valid_mask] * decay, tmp_grid[valid_mask])
-        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        from .field_ops import grid_update
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # host generator: follows torch.manual_seed, no device sync
+        full = self.iter_density < 16 and cells is None
+        Smsg, cfg, sigma_mlp, _, tables = self.field_args(message)
+        stats = grid_update(self.density_grid, self.density_bitfield, full, float(decay), float(self.density_thresh),
+                            int(self.cascade), int(self.grid_size), float(self.bound), seed, Smsg, cfg, sigma_mlp,
+                            tables, cells=cells, noise=noise)
         self.iter_density += 1
-
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
-
         total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        count_sum = self.step_counter[:total_step, 0].sum() if total_step > 0 else None
+        self._pending_stats = (stats, count_sum, total_step)
+        self._last_stats = stats  # device float[2]: (mean_density, threshold used for the bitfield)
         self.local_step = 0
+
+    def _resolve_stats(self):
+        """Bring the last update_extra_state's (mean_density, mean_count) to the host (renderer_wtmk.py:524,534)."""
+        pend, self._pending_stats = self._pending_stats, None
+        if pend is None:
+            return
+        stats, count_sum, total_step = pend
+        self._mean_density = float(stats[0].item())
+        if count_sum is not None:
+            self._mean_count = int(count_sum.item() / total_step)
+
+    @property
+    def mean_density(self):
+        self._resolve_stats()
+        return self._mean_density
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._resolve_stats()
+        self._mean_density = v
+
+    @property
+    def mean_count(self):
+        self._resolve_stats()
+        return self._mean_count
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._resolve_stats()
+        self._mean_count = v
 
     def render(self, rays_o, rays_d, message=None, staged=False, max_ray_batch=4096, **kwargs):
         # rays_o, rays_d: [B, N, 3]  (reference renderer_wtmk.py:541-574)
