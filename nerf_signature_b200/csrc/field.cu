@@ -38,12 +38,14 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
     stage_forward_weights(sm, p.sigma_w, p.color_w, COLOR);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    [[maybe_unused]] uint32_t* feat_s = reinterpret_cast<uint32_t*>(sm + kFwdHalfsPad) + warp * kFeatWords;
     const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
     const uint32_t n_tiles = div_up(M, rows_per_cta);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
         if (row0 >= M) continue;
         uint32_t fa[MT][2][4];
+#ifndef NSIG_GATHER_V2
         encode_rows<MT, H2>(fa, p, M, row0, g, tig);
         if (feat_out) {
 #pragma unroll
@@ -58,6 +60,24 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
                     }
                 }
         }
+#else
+        {
+            const float* xr = p.xyzs + (size_t)min(row0 + lane, M - 1) * 3;  // x = (x + bound) / (2*bound)  (network_wtmk_tcnn.py:101)
+            const float px = __fmul_rn(__fadd_rn(__ldg(xr), p.bound_add), p.bound_mul);
+            const float py = __fmul_rn(__fadd_rn(__ldg(xr + 1), p.bound_add), p.bound_mul);
+            const float pz = __fmul_rn(__fadd_rn(__ldg(xr + 2), p.bound_add), p.bound_mul);
+            gather_tile<H2>(fa, p, px, py, pz, feat_s, lane);
+        }
+        if (feat_out) {  // the tile is row-major in shared memory: 64 contiguous bytes per row, 16 B per lane
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int chunk = i * 32 + lane, row = chunk >> 2, part = chunk & 3;
+                if (row0 + row < M)
+                    *reinterpret_cast<uint4*>(feat_out + (size_t)(row0 + row) * 32 + part * 8) =
+                        *reinterpret_cast<const uint4*>(feat_s + row * kFeatStride + part * 4);
+            }
+        }
+#endif
         // sigma net: 32 -> 64 (ReLU) -> 16
         uint32_t h1[MT][4][4];
         {
@@ -238,7 +258,6 @@ constexpr int kRenderWarps = 4;
 constexpr int kStageSlots = 64;
 // per-warp staging (floats): xyz[64][3] + dt[64] + dreal[64] + sigma[32] + rgb[32][3]
 constexpr int kStageFloats = kStageSlots * 5 + 32 * 4;
-constexpr int kFwdHalfsPad = (kFwdHalfs + 7) / 8 * 8;
 
 template <bool H2>
 __global__ void __launch_bounds__(kRenderWarps * 32)
@@ -253,6 +272,8 @@ k_render_rays(const RenderParams p) {
     float* st_dr = st_dt + kStageSlots;
     float* st_sig = st_dr + kStageSlots;
     float* st_rgb = st_sig + 32;
+    [[maybe_unused]] uint32_t* feat_s = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(sm + kFwdHalfsPad) + kRenderWarps * kStageFloats) +
+                       warp * kFeatWords;
     const MarchCfg c = make_cfg(p.f.bound_add, p.dt_gamma, p.max_steps, p.C, p.H);
     const uint32_t lt_mask = lanemask_lt();
     uint32_t evaluated = 0;
@@ -303,6 +324,8 @@ k_render_rays(const RenderParams p) {
             if (nb == 0) break;
             // ---- field on rows [0, nb) ----
             {
+                uint32_t fa[MT][2][4];
+#ifndef NSIG_GATHER_V2
                 float xn[MT][2][3];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
@@ -313,8 +336,16 @@ k_render_rays(const RenderParams p) {
                         for (int a = 0; a < 3; ++a)
                             xn[mt][h][a] = __fmul_rn(__fadd_rn(st_xyz[row * 3 + a], p.f.bound_add), p.f.bound_mul);
                     }
-                uint32_t fa[MT][2][4];
                 encode_positions<MT, H2>(fa, p.f, xn, g, tig);
+#else
+                {
+                    const uint32_t row = min((uint32_t)lane, nb - 1);
+                    const float px = __fmul_rn(__fadd_rn(st_xyz[row * 3], p.f.bound_add), p.f.bound_mul);
+                    const float py = __fmul_rn(__fadd_rn(st_xyz[row * 3 + 1], p.f.bound_add), p.f.bound_mul);
+                    const float pz = __fmul_rn(__fadd_rn(st_xyz[row * 3 + 2], p.f.bound_add), p.f.bound_mul);
+                    gather_tile<H2>(fa, p.f, px, py, pz, feat_s, lane);
+                }
+#endif
                 uint32_t h1[MT][4][4];
                 {
                     float cc[MT][8][4];
@@ -774,7 +805,7 @@ int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float b
     const int rc = fill_field_params(p, xyzs, dirs, M, bound, tables, resolutions, log2_T, S, msg_resolution,
                                      sigma_w, color_w, M_dev, density_scale, tables_h2, h2_inv_scale);
     if (rc) return rc;
-    const size_t smem = kFwdHalfs * sizeof(__half);
+    const size_t smem = kFieldFwdSmem;
     cudaStream_t st = (cudaStream_t)stream;
     __half* feat = reinterpret_cast<__half*>(feat_out);
     if (tables_h2)
@@ -797,7 +828,7 @@ int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* 
     const int rc = fill_field_params(p, xyzs, nullptr, M, bound, tables, resolutions, log2_T, S, msg_resolution,
                                      sigma_w, nullptr, nullptr, density_scale, tables_h2, h2_inv_scale);
     if (rc) return rc;
-    const size_t smem = kFwdHalfs * sizeof(__half);
+    const size_t smem = kFieldFwdSmem;
     cudaStream_t st = (cudaStream_t)stream;
     __half* geo = reinterpret_cast<__half*>(geo_feat);
     if (tables_h2)
@@ -840,7 +871,7 @@ int nsig_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const
     p.max_steps = max_steps; p.C = C; p.H = H; p.aabb = aabb; p.min_near = min_near; p.T_thresh = T_thresh;
     p.noises = noises; p.work_counter = work_counter; p.weights_sum = weights_sum; p.depth = depth; p.image = image;
     p.nears = nears; p.fars = fars; p.sample_count = sample_count;
-    const size_t smem = kFwdHalfsPad * sizeof(__half) + (size_t)kRenderWarps * kStageFloats * sizeof(float);
+    const size_t smem = kFwdHalfsPad * sizeof(__half) + (size_t)kRenderWarps * (kStageFloats * sizeof(float) + kFeatWordsAlloc * 4);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t want = div_up(N, kRenderWarps);

@@ -18,6 +18,7 @@ constexpr int oWc0 = oWs1 + 16 * kS64;     // [64][32] (input column 31 zeroed)
 constexpr int oWc1 = oWc0 + 64 * kS32;     // [64][64]
 constexpr int oWc2 = oWc1 + 64 * kS64;     // [8][64]  (outputs 0..7; 3..7 are padding)
 constexpr int kFwdHalfs = oWc2 + 8 * kS64;
+constexpr int kFwdHalfsPad = (kFwdHalfs + 7) / 8 * 8;  // 16-byte aligned end of the forward weights
 // transposed copies for dgrad, [in][out]
 constexpr int oWc2T = kFwdHalfs;           // [64][16] (outputs >= 3 zeroed)
 constexpr int oWc1T = oWc2T + 64 * kS16;   // [64][64]
@@ -277,6 +278,123 @@ __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const Fiel
                 xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
         }
     encode_positions<MT, H2>(fa, p, xn, g, tig);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-cooperative gather (v2).  ncu shows the v1 gather above bound by the L1 tag stage: one 128-byte line
+// per cycle and SM, 87 % busy (profiles/r01_field_kernels_v1.txt: 31.0 M tag requests in 241.8 k cycles x 148 SMs),
+// so the lever is the number of DISTINCT LINES per load instruction, not bytes.  Here a load instruction covers
+// 16 consecutive rows x the two x-neighbours of one (y,z) corner pair of ONE level:
+//   * the hash is x ^ y*P1 ^ z*P2, so for an even x index the two x-neighbours are adjacent table entries - the
+//     lane pair (xbit = 0,1) then hits the same line: ~6 instead of 8 lines per row and level;
+//   * 16 rows of a ray (instead of 8 rows x 4 levels) share voxels - hence lines - on the coarse levels.
+// Each lane accumulates its 4 weighted corners, one xor-shuffle adds the x-neighbour, the even lane writes the
+// feature (fp16 pair) into a per-warp shared-memory tile [32 rows][16 levels] and ldmatrix turns the tile into the
+// m16n8k16 A fragments.  Interpolation is a plain weighted sum of the 8 corners (association differs from the
+// reference's x,y,z lerp order by fp32 rounding only; the result is rounded to fp16 for the MMA anyway).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFeatStride = 20;                    // 32-bit words per row of the feature tile (64 B + 16 B pad)
+constexpr int kFeatWords = 32 * kFeatStride;       // per warp
+// dynamic shared memory of the 4-warp field kernels: forward weights + one feature tile per warp
+#ifdef NSIG_GATHER_V2
+constexpr int kFeatWordsAlloc = kFeatWords;
+#else
+constexpr int kFeatWordsAlloc = 0;                 // the default (v1) gather goes straight to fragments
+#endif
+constexpr size_t kFieldFwdSmem = kFwdHalfsPad * sizeof(__half) + (size_t)kFieldWarps * kFeatWordsAlloc * sizeof(uint32_t);
+
+template <bool H2>
+__device__ __forceinline__ float2 gather_half_voxel(const FieldParams& p, int level, float x, float y, float z,
+                                                    int xbit) {
+    const LevelGeom L = p.base.geom[level];
+    uint32_t ix, iy, iz;
+    float wx, wy, wz;
+    locate_axis_fused(x, L, ix, wx);
+    locate_axis_fused(y, L, iy, wy);
+    locate_axis_fused(z, L, iz, wz);
+    const uint32_t hx = ix + (uint32_t)xbit;
+    const float fx = xbit ? wx : 1.0f - wx;
+    const uint32_t hy0 = iy * kPrimeY, hy1 = hy0 + kPrimeY, hz0 = iz * kPrimeZ, hz1 = hz0 + kPrimeZ;
+    const float fy0 = fx * (1.0f - wy), fy1 = fx * wy, oz = 1.0f - wz;
+    const uint32_t s00 = (hx ^ hy0 ^ hz0) & p.mask, s01 = (hx ^ hy0 ^ hz1) & p.mask;
+    const uint32_t s10 = (hx ^ hy1 ^ hz0) & p.mask, s11 = (hx ^ hy1 ^ hz1) & p.mask;
+    float2 e00, e01, e10, e11;
+    if (H2) {
+        const uint32_t* t = reinterpret_cast<const uint32_t*>(p.base.th[level]);
+        const uint32_t r00 = __ldg(t + s00), r01 = __ldg(t + s01), r10 = __ldg(t + s10), r11 = __ldg(t + s11);
+        e00 = __half22float2(*reinterpret_cast<const __half2*>(&r00));
+        e01 = __half22float2(*reinterpret_cast<const __half2*>(&r01));
+        e10 = __half22float2(*reinterpret_cast<const __half2*>(&r10));
+        e11 = __half22float2(*reinterpret_cast<const __half2*>(&r11));
+    } else {
+        const float2* t = p.base.t[level];
+        e00 = __ldg(t + s00); e01 = __ldg(t + s01); e10 = __ldg(t + s10); e11 = __ldg(t + s11);
+    }
+    const float w00 = fy0 * oz, w01 = fy0 * wz, w10 = fy1 * oz, w11 = fy1 * wz;
+    float2 a;
+    a.x = fmaf(w11, e11.x, fmaf(w10, e10.x, fmaf(w01, e01.x, w00 * e00.x)));
+    a.y = fmaf(w11, e11.y, fmaf(w10, e10.y, fmaf(w01, e01.y, w00 * e00.y)));
+    if (H2) { const float inv = __ldg(p.base.inv_scale + level); a.x *= inv; a.y *= inv; }
+    return a;
+}
+
+// message feature of one row half (pre-summed table S, fp32): same lane-pair scheme
+__device__ __forceinline__ float2 gather_half_voxel_msg(const FieldParams& p, float x, float y, float z, int xbit) {
+    uint32_t ix, iy, iz;
+    float wx, wy, wz;
+    locate_axis_fused(x, p.msg_geom, ix, wx);
+    locate_axis_fused(y, p.msg_geom, iy, wy);
+    locate_axis_fused(z, p.msg_geom, iz, wz);
+    const uint32_t hx = ix + (uint32_t)xbit;
+    const float fx = xbit ? wx : 1.0f - wx;
+    const uint32_t hy0 = iy * kPrimeY, hy1 = hy0 + kPrimeY, hz0 = iz * kPrimeZ, hz1 = hz0 + kPrimeZ;
+    const float fy0 = fx * (1.0f - wy), fy1 = fx * wy, oz = 1.0f - wz;
+    const float2 e00 = __ldg(p.S + ((hx ^ hy0 ^ hz0) & p.mask)), e01 = __ldg(p.S + ((hx ^ hy0 ^ hz1) & p.mask));
+    const float2 e10 = __ldg(p.S + ((hx ^ hy1 ^ hz0) & p.mask)), e11 = __ldg(p.S + ((hx ^ hy1 ^ hz1) & p.mask));
+    const float w00 = fy0 * oz, w01 = fy0 * wz, w10 = fy1 * oz, w11 = fy1 * wz;
+    float2 a;
+    a.x = fmaf(w11, e11.x, fmaf(w10, e10.x, fmaf(w01, e01.x, w00 * e00.x)));
+    a.y = fmaf(w11, e11.y, fmaf(w10, e10.y, fmaf(w01, e01.y, w00 * e00.y)));
+    return a;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const uint32_t* smem_row) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// (px,py,pz): normalised position of tile row `lane`.  feat_s: this warp's [32][kFeatStride] tile.
+// On return fa holds the A fragments of both 16-row tiles and feat_s the fp16 features (row-major, 16 half2 per row).
+template <bool H2>
+__device__ __forceinline__ void gather_tile(uint32_t (&fa)[2][2][4], const FieldParams& p, float px, float py, float pz,
+                                            uint32_t* __restrict__ feat_s, int lane) {
+    const int xbit = lane & 1, r16 = lane >> 1;
+    __syncwarp();  // the previous tile's readers are done with feat_s
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+        const int row = grp * 16 + r16;
+        const float x = __shfl_sync(NSIG_FULL_MASK, px, row), y = __shfl_sync(NSIG_FULL_MASK, py, row),
+                    z = __shfl_sync(NSIG_FULL_MASK, pz, row);
+#pragma unroll 4
+        for (int level = 0; level < NSIG_MAX_LEVELS; ++level) {
+            float2 a = gather_half_voxel<H2>(p, level, x, y, z, xbit);
+            if (level == NSIG_MAX_LEVELS - 1 && p.S != nullptr) {  // x_feature[:, -2:] += msg_feature (network_wtmk_tcnn.py:106)
+                const float2 m = gather_half_voxel_msg(p, x, y, z, xbit);
+                a.x += m.x; a.y += m.y;
+            }
+            a.x += __shfl_xor_sync(NSIG_FULL_MASK, a.x, 1);
+            a.y += __shfl_xor_sync(NSIG_FULL_MASK, a.y, 1);
+            if (xbit == 0) feat_s[row * kFeatStride + level] = pack_h2(a.x, a.y);
+        }
+    }
+    __syncwarp();
+    // A fragment of tile mt, k-step ks: lanes 0-15 address rows 0-15 at halfs [16ks, 16ks+8), lanes 16-31 the next 8
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            ldmatrix_x4(fa[mt][ks], feat_s + (mt * 16 + (lane & 15)) * kFeatStride + ks * 8 + (lane >> 4) * 4);
 }
 
 // A fragments of the colour net's first k-step: SH(d) columns {2tig,2tig+1,2tig+8,2tig+9}

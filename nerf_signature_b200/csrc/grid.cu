@@ -67,6 +67,7 @@ k_grid_sweep(const SweepParams p) {
     stage_forward_weights(sm, p.f.sigma_w, nullptr, false);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    [[maybe_unused]] uint32_t* feat_s = reinterpret_cast<uint32_t*>(sm + kFwdHalfsPad) + warp * kFeatWords;
     const uint32_t H3 = p.H * p.H * p.H;
     const uint32_t tiles_per_cas = div_up(p.n, 32u);
     const uint32_t total = p.C * tiles_per_cas;
@@ -77,32 +78,50 @@ k_grid_sweep(const SweepParams p) {
         const double bound_c = fmin(ldexp(1.0, (int)cas), p.bound);   // min(2 ** cas, self.bound)
         const double half_d = bound_c / (double)p.H;
         const float scale = (float)(bound_c - half_d), half = (float)half_d;
-        float xn[MT][2][3];
-        uint32_t cell[MT][2];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t i = min(i0 + mt * 16 + h * 8 + g, p.n - 1);
-                const uint32_t idx = p.cells ? (uint32_t)p.cells[(size_t)cas * p.n + i] : i;
-                cell[mt][h] = idx;
-                float u[3];
-                if (p.noise) {
-                    const float* nz = p.noise + ((size_t)cas * p.n + i) * 3;
-                    u[0] = __ldg(nz); u[1] = __ldg(nz + 1); u[2] = __ldg(nz + 2);
-                } else {
-                    const uint4 r = philox4x32_10(make_uint4(i, cas, 0x6e736967u, 0u), make_uint2(p.seed_lo, p.seed_hi));
-                    u[0] = u01(r.x); u[1] = u01(r.y); u[2] = u01(r.z);
-                }
-                const uint32_t c3[3] = {morton3D_invert(idx), morton3D_invert(idx >> 1), morton3D_invert(idx >> 2)};
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float x = cell_axis(c3[a], u[a], r_hm1, scale, half);
-                    xn[mt][h][a] = __fmul_rn(__fadd_rn(x, p.f.bound_add), p.f.bound_mul);  // network_wtmk_tcnn.py:129
-                }
+        // position of cell i of this cascade (centre + jitter), normalised to the unit box
+        auto cell_pos = [&](uint32_t i, uint32_t& idx, float (&pn)[3]) {
+            idx = p.cells ? (uint32_t)p.cells[(size_t)cas * p.n + i] : i;
+            float u[3];
+            if (p.noise) {
+                const float* nz = p.noise + ((size_t)cas * p.n + i) * 3;
+                u[0] = __ldg(nz); u[1] = __ldg(nz + 1); u[2] = __ldg(nz + 2);
+            } else {
+                const uint4 r = philox4x32_10(make_uint4(i, cas, 0x6e736967u, 0u), make_uint2(p.seed_lo, p.seed_hi));
+                u[0] = u01(r.x); u[1] = u01(r.y); u[2] = u01(r.z);
             }
+            const uint32_t c3[3] = {morton3D_invert(idx), morton3D_invert(idx >> 1), morton3D_invert(idx >> 2)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = cell_axis(c3[a], u[a], r_hm1, scale, half);
+                pn[a] = __fmul_rn(__fadd_rn(x, p.f.bound_add), p.f.bound_mul);  // network_wtmk_tcnn.py:129
+            }
+        };
         uint32_t fa[MT][2][4];
-        encode_positions<MT, H2>(fa, p.f, xn, g, tig);
+        uint32_t cell[MT][2];  // cells of the rows whose sigma this thread ends up holding
+#ifndef NSIG_GATHER_V2
+        {
+            float xn[MT][2][3];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) cell_pos(min(i0 + mt * 16 + h * 8 + g, p.n - 1), cell[mt][h], xn[mt][h]);
+            encode_positions<MT, H2>(fa, p.f, xn, g, tig);
+        }
+#else
+        {   // lane r owns cell i0 + r of the tile: position -> warp-cooperative gather
+            uint32_t idx;
+            float pn[3];
+            cell_pos(min(i0 + (uint32_t)lane, p.n - 1), idx, pn);
+            gather_tile<H2>(fa, p.f, pn[0], pn[1], pn[2], feat_s, lane);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t i = min(i0 + mt * 16 + h * 8 + g, p.n - 1);
+                    cell[mt][h] = p.cells ? (uint32_t)p.cells[(size_t)cas * p.n + i] : i;
+                }
+        }
+#endif
         uint32_t h1[MT][4][4];
         {
             float c[MT][8][4];
@@ -401,7 +420,7 @@ int nsig_grid_sweep(float* density_grid, float* tmp_grid, const int32_t* cells, 
     if (rc) return rc;
     p.grid = density_grid; p.tmp = tmp_grid; p.cells = cells; p.noise = noise; p.n = n; p.C = C; p.H = H;
     p.bound = bound; p.decay = decay; p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.sum = sum;
-    const size_t smem = kFwdHalfs * sizeof(__half);
+    const size_t smem = kFieldFwdSmem;
     const uint32_t tiles = C * div_up(n, 32u);
     if (tables_h2)
         k_grid_sweep<true><<<field_grid(k_grid_sweep<true>, smem, tiles * 32u, kFieldWarps * 32), kFieldThreads, smem,
