@@ -240,7 +240,8 @@ def run_ours(args):
     scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph)
     md = cfg["message_dim"]
     n_pool = 4  # distinct host batches cycled through (fresh rays every step)
-    host_batches = [harness.make_batch(cfg, seed=1000 * rank + i) for i in range(n_pool)]
+    seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
+    host_batches = [harness.make_batch(cfg, seed=1000 * seed_rank + i) for i in range(n_pool)]
     pinned = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in host_batches[0].items()}
     pinned_msg = torch.empty(md, dtype=torch.float32).pin_memory()
     dev_batches = [scene.to_device(b) for b in host_batches]
@@ -260,10 +261,10 @@ def run_ours(args):
         scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
     if not use_graph:
         _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])  # drop the warm-up events
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # NVML start-up (tens of ms, rank 0 only) BEFORE the barrier: ranks enter the timed region together
+    barrier()
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -387,7 +388,7 @@ def run_ours(args):
                    "step": "one CUDA graph replay per step" if use_graph else "eager",
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
-                   "parallelism": f"ray-sharded dp{world}"},
+                   "parallelism": f"ray-sharded dp{world}", "exchange": scene.sync.exchange},
         "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,

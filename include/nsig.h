@@ -306,6 +306,22 @@ int nsig_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, 
                   float* rays_o, float* rays_d, nsig_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
+/* gradient exchange of the ray-sharded training path (no reference precedent) */
+/* ------------------------------------------------------------------------- */
+
+/* In-place all-reduce (MEAN) of a float bucket that lives in peer-mapped ("symmetric") memory on every rank of
+ * one NVLink/NVSwitch node, as one kernel: entry barrier, two-shot reduce (rank r reduces and broadcasts slice r),
+ * exit barrier.  bufs / flags: HOST arrays of `world` device pointers - every rank's bucket and flag buffer as
+ * mapped into THIS process (bufs[rank] is the local bucket).  flags[r]: uint32[nsig_allreduce_grid() * world],
+ * zero-initialised once; the barriers reset them.  multicast: NVSwitch multicast address of the bucket (the
+ * reduction then happens in the switch: multimem.ld_reduce / multimem.st) or NULL (plain P2P loads and stores).
+ * n: bucket length in floats, a multiple of 4.  Every rank must call it with the same n and the same launch
+ * order; stream-ordered, CUDA-graph capturable. */
+uint32_t nsig_allreduce_grid(void);
+int nsig_allreduce_mean_inplace(void* const* bufs, void* const* flags, void* multicast, uint32_t n,
+                                uint32_t rank, uint32_t world, nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
 /* optimizer step of the message tables — nerf/utils_wtmk_disen.py:1175-1181   */
 /* ------------------------------------------------------------------------- */
 

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "nsig_grid_sample_cells": ([_vp, _u32, _u32, _u32, _u32, _u64, _vp, _vp, _vp], 4),
     "nsig_mark_untrained_grid": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f64, _vp, _vp], 1),
     "nsig_get_rays": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _i64, _u32, _vp, _vp, _vp], 1),
+    "nsig_allreduce_mean_inplace": ([_vp, _vp, _vp, _u32, _u32, _u32, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
@@ -57,7 +58,7 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes",
-                                                "nsig_grid_sample_cells_scratch_bytes"])
+                                                "nsig_grid_sample_cells_scratch_bytes", "nsig_allreduce_grid"])
 
 _lib = None
 _lock = threading.Lock()
@@ -91,6 +92,8 @@ def load():
         lib.nsig_march_rays_train_scratch_bytes.argtypes = [_u32]
         lib.nsig_grid_sample_cells_scratch_bytes.restype = _sz
         lib.nsig_grid_sample_cells_scratch_bytes.argtypes = [_u32, _u32]
+        lib.nsig_allreduce_grid.restype = _u32
+        lib.nsig_allreduce_grid.argtypes = []
         _lib = lib
     return _lib
 

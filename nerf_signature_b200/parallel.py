@@ -11,6 +11,9 @@ exchange is the gradient reduction once per step:
 For a watermark batch sharded across ranks the rendered block pixels are all-gathered before the
 decoder (its BatchNorm uses batch statistics over the blocks): `all_gather_pixels`.
 """
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -28,12 +31,49 @@ def shard_range(n, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class SymmetricBucket:
+    """A flat fp32 gradient bucket in peer-mapped (symmetric) memory with its one-kernel mean all-reduce
+    (csrc/collective.cu: nsig_allreduce_mean_inplace - NVSwitch multicast when the fabric offers it, plain P2P
+    otherwise).  Raises when symmetric memory cannot be set up; the caller then stays on NCCL."""
+
+    def __init__(self, n, device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        rank, ws = world()
+        group = group if group is not None else dist.group.WORLD
+        self.n = (n + 4 * ws - 1) // (4 * ws) * (4 * ws)
+        self.buf = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group=group)
+        grid = int(_lib.load().nsig_allreduce_grid())
+        self.flags = symm_mem.empty(grid * ws, dtype=torch.int32, device=device)
+        self.fhdl = symm_mem.rendezvous(self.flags, group=group)
+        self.buf.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # nobody raises a flag before every flag buffer is zero
+        self._bufs = (ctypes.c_void_p * ws)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self._flags = (ctypes.c_void_p * ws)(*[int(p) for p in self.fhdl.buffer_ptrs])
+        mc = int(self.hdl.multicast_ptr) if getattr(self.hdl, "has_multicast_support", False) else 0
+        if os.environ.get("NSIG_AR_NO_MULTICAST") == "1":
+            mc = 0
+        self.multicast = mc
+        self.rank, self.world = rank, ws
+
+    def all_reduce_mean(self):
+        from . import _lib
+        _lib.call("nsig_allreduce_mean_inplace", self._bufs, self._flags, self.multicast or None, self.n, self.rank,
+                  self.world)
+
+
 class GradSync:
     """Averages gradients across ranks once per step."""
 
     def __init__(self, group=None):
         self.group = group
         self.enabled = world()[1] > 1
+        self.bucket = None        # SymmetricBucket when the one-kernel exchange is in use
+        self.exchange = "none" if not self.enabled else "nccl"
 
     # --- message-table path: called inside autograd with dL/dS -------------------------------------
     def reduce_table_grad(self, grad_S):
@@ -51,7 +91,20 @@ class GradSync:
         at its slice, so backward accumulates straight into the bucket and a single NCCL all-reduce (AVG)
         per step synchronises everything (no per-tensor copies, no separate division)."""
         n = table_numel + sum(p.numel() for p in params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.flat = None
+        if (self.enabled and dist.get_backend(self.group) == "nccl" and torch.device(device).type == "cuda"
+                and os.environ.get("NSIG_AR_NCCL") != "1"):
+            try:  # peer-memory bucket; NCCL remains the exchange when the platform refuses symmetric memory
+                self.bucket = SymmetricBucket(n, device, self.group)
+                self.flat = self.bucket.buf[:n]
+                self.exchange = "nvls-multicast kernel" if self.bucket.multicast else "p2p kernel"
+            except Exception as e:  # noqa: BLE001
+                self.bucket = None
+                if world()[0] == 0:
+                    print(f"[nsig] symmetric-memory bucket unavailable ({type(e).__name__}: {str(e)[:120]}); "
+                          "gradient exchange stays on NCCL", file=sys.stderr, flush=True)
+        if self.flat is None:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=device)
         self.table_numel = table_numel
         o = table_numel
         for p in params:
@@ -63,9 +116,11 @@ class GradSync:
         self.flat[self.table_numel:].zero_()  # dL/dS is overwritten (copy_) by backward, the rest accumulates
 
     def reduce_flat(self):
-        if not self.enabled:
+        if not self.enabled or os.environ.get("NSIG_DIAG_SKIP_REDUCE") == "1":  # diagnosis only: wrong gradients
             return
-        if dist.get_backend(self.group) == "nccl":
+        if self.bucket is not None:
+            self.bucket.all_reduce_mean()
+        elif dist.get_backend(self.group) == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         else:  # gloo (CPU tests) has no AVG
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
