@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph-captured one")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = optim.WatermarkAdam; torch = torch.optim.Adam over get_params (implies --no-graph)")
+    ap.add_argument("--split-render", action="store_true",
+                    help="two render calls per step (block rays, then content rays) like the reference trainer, instead "
+                         "of one call over their concatenation")
     ap.add_argument("--cpu-rays", type=int, default=0, help="override the CPU sample size (rays per pass)")
     return ap.parse_args()
 
@@ -237,7 +240,8 @@ def run_ours(args):
     if args.config.startswith("shard"):
         cfg["num_rays"] = cfg["num_rays"] // world
     use_graph = (not args.no_graph) and args.optimizer == "fused"
-    scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph)
+    scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph,
+                          merged_render=not args.split_render)
     md = cfg["message_dim"]
     n_pool = 4  # distinct host batches cycled through (fresh rays every step)
     seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
@@ -385,7 +389,9 @@ def run_ours(args):
                    "weights": "random-init (tables U(+-1e-4), Xavier MLPs)",
                    "optimizer": ("WatermarkAdam (fused message-table Adam + torch fused Adam for the decoder)"
                                  if args.optimizer == "fused" else "torch.optim.Adam(fused)") + " + GradScaler",
-                   "step": "one CUDA graph replay per step" if use_graph else "eager",
+                   "step": ("one CUDA graph replay per step" if use_graph else "eager") +
+                           ("; both render passes in one call over [block rays | content rays]" if not args.split_render
+                            else "; two render calls (block rays, content rays)"),
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
                    "parallelism": f"ray-sharded dp{world}", "exchange": scene.sync.exchange},

@@ -78,7 +78,8 @@ def occupancy(cfg, cascade, seed=0):
 class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
-    def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False):
+    def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
+                 merged_render=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -119,6 +120,7 @@ class Scene:
         self.opt = dict(dt_gamma=cfg["dt_gamma"], max_steps=1024, T_thresh=1e-4)
         _hmsg.grad_reducer = self.sync.reduce_table_grad if (self.sync.enabled and not self.flat_sync) else None
         self.use_graph = graph
+        self.merged_render = merged_render  # one render call over [block rays | content rays] instead of two
         self.iteration = 0
         self._graph = None
         self._static = None
@@ -153,14 +155,25 @@ class Scene:
         if self.fused:
             self.optimizer.set_message(msg_dev)
             message = msg_dev
-        out_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
-                             perturb=False, force_all_rays=True, **self.opt)
-        pred = torch.clamp(out_w["image"], min=0, max=1)
+        if self.merged_render:
+            # the two render passes of the reference step (utils_wtmk_disen.py:592,641) see the same network and the
+            # same message and rays are independent: one launch chain over [block rays | content rays]
+            ob, db = batch["rays_o_block"], batch["rays_d_block"]
+            nb = ob.numel() // 3
+            out = model.render(torch.cat([ob.reshape(1, nb, 3), batch["rays_o"]], dim=1),
+                               torch.cat([db.reshape(1, nb, 3), batch["rays_d"]], dim=1), message, staged=False,
+                               bg_color=1, perturb=False, force_all_rays=True, **self.opt)
+            image_w, image_c = out["image"][0, :nb].reshape(ob.shape), out["image"][:, nb:]
+        else:
+            image_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
+                                   perturb=False, force_all_rays=True, **self.opt)["image"]
+        pred = torch.clamp(image_w, min=0, max=1)
         with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
             decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
-        out_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
-                             perturb=False, force_all_rays=True, **self.opt)
-        lossi = F.mse_loss(out_c["image"], batch["gt"], reduction="none").mean()
+        if not self.merged_render:
+            image_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
+                                   perturb=False, force_all_rays=True, **self.opt)["image"]
+        lossi = F.mse_loss(image_c, batch["gt"], reduction="none").mean()
         lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
         loss = self.lambda_w * lossw + self.lambda_i * lossi
         self.scaler.scale(loss).backward()
@@ -194,7 +207,8 @@ class Scene:
             self._static_out = self._step_impl(self._static, self._static["message"])
         self.launches_per_step = _lib.launch_count - n0
         ls = self.model.local_step
-        self._graph_rows = [(ls - 2) % 16, (ls - 1) % 16]  # the march counters baked into the graph
+        n_calls = 1 if self.merged_render else 2
+        self._graph_rows = [(ls - k) % 16 for k in range(n_calls, 0, -1)]  # the march counters baked into the graph
 
     def train_step(self, batch, message):
         """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here).  Configs with
@@ -223,7 +237,7 @@ class Scene:
         if self.use_graph and getattr(self, "_graph_rows", None) is not None:
             return self._graph_rows
         ls = self.model.local_step
-        return [(ls - 2) % 16, (ls - 1) % 16]
+        return [(ls - k) % 16 for k in range(1 if self.merged_render else 2, 0, -1)]
 
     def samples_per_step(self):
         """Measured (samples, rays) of the two most recent render calls = one training step (reads the march

@@ -95,3 +95,19 @@ def test_graph_step_matches_eager_step():
     for x, y in zip(_msg_tables(e), _msg_tables(g)):
         _close_frac(x, y, rtol=1e-3, atol=1e-5)
     assert g.launches_per_step and g.launches_per_step > 10
+
+
+def test_merged_render_matches_two_render_calls():
+    """One render call over [block rays | content rays] (harness merged_render) is the same step as the reference's
+    two calls: rays are independent, only the scatter order of dL/dS changes."""
+    a, b = _scene(optimizer="fused"), _scene(optimizer="fused", merged_render=True)
+    batches = _batches(a, 2)
+    gen = torch.Generator().manual_seed(6)
+    for i in range(4):
+        m = a.new_message(gen)
+        la = [float(x) for x in a.train_step(batches[i % 2], m)]
+        lb = [float(x) for x in b.train_step(batches[i % 2], m)]
+        np.testing.assert_allclose(lb, la, rtol=1e-4, atol=1e-6)
+    assert a.samples_per_step() == b.samples_per_step()
+    for x, y in zip(_msg_tables(a), _msg_tables(b)):
+        _close_frac(x, y, rtol=1e-3, atol=1e-5)
