@@ -179,10 +179,28 @@ __device__ __forceinline__ Window march_window(MarchState& s, const RayConst& r,
     // lattice: t_{k+1} = t_k + dt(t_k), sequential fp32 adds exactly like the reference
     float my_t = s.t, tc = s.t;
     if (c.dt_gamma == 0.0f) {  // dt(t) == dt_min for every finite t: skip the clamp chain
+        // Closed form of the sequential adds.  While t stays inside one binade every t_k is a multiple of
+        // u = ulp(t) and fl(t_k + dt) = t_k + step with the SAME step = fl(t_0 + dt) - t_0 (dt rounded to a multiple of
+        // u), unless dt sits exactly half-way between two multiples (then round-to-even alternates with t_k's parity).
+        // So t_k = t_0 + k*step, exactly representable, one FMA per lane instead of a 32-deep dependent chain.  The
+        // serial chain remains for windows that cross a power of two, for the tie case and for non-normal t.
+        const float t1 = __fadd_rn(s.t, c.dt_min);
+        const float step = __fsub_rn(t1, s.t);                      // exact (both multiples of u, within 2x of each other)
+        const float hi = __fmaf_rn(32.0f, step, s.t);               // t_32 if the closed form holds
+        const uint32_t b0 = __float_as_uint(s.t), bh = __float_as_uint(hi);
+        const float u = __uint_as_float((b0 & 0x7f800000u) - (23u << 23));          // ulp of the binade of t_0
+        const float resid = __fsub_rn(c.dt_min, step);              // exact: |resid| <= u/2, a multiple of ulp(dt)
+        const bool closed = (b0 >> 23) == (bh >> 23) && (b0 >> 23) > 24u && (b0 >> 23) < 255u &&
+                            fabsf(resid) != __fmul_rn(0.5f, u) && t1 > s.t;
+        if (closed) {
+            my_t = __fmaf_rn((float)lane, step, s.t);
+            tc = hi;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if (k == lane) my_t = tc;
-            tc = __fadd_rn(tc, c.dt_min);
+            for (int k = 0; k < 32; ++k) {
+                if (k == lane) my_t = tc;
+                tc = __fadd_rn(tc, c.dt_min);
+            }
         }
     } else {
 #pragma unroll

@@ -19,9 +19,13 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__registers_p
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 cols = []
-idx = int(sys.argv[1]) if sys.argv[1].isdigit() else 0
+idxs = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0]
 files = [a for a in sys.argv[1:] if not a.isdigit()]
-for f in files:
+if len(files) == 1 and len(idxs) > 1:
+    files = files * len(idxs)
+else:
+    idxs = idxs * len(files) if len(idxs) == 1 else idxs
+for f, idx in zip(files, idxs):
     out = subprocess.run(["ncu", "-i", f, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, r = rows[0], rows[2 + idx]
