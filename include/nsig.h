@@ -306,6 +306,28 @@ int nsig_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, 
                   float* rays_o, float* rays_d, nsig_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
+/* HiDDeN message decoder — nerf/hidden_models.py:16-35, 104-137 */
+/* ------------------------------------------------------------------------- */
+
+/* HiddenDecoder_multi_views(num_blocks, num_bits, input_ch=3, channels=64, redundancy) applied to
+ * normalize_img(image): forward and backward as a chain of tensor-core kernels (csrc/decoder.cu) with the
+ * rounding points of torch.autocast(float16).  image: [B,H,W,3] fp32 (the rendered blocks, already clamped to
+ * [0,1]; the ImageNet normalisation of hidden_models.normalize_img is applied inside).
+ * params: HOST array of 4*(num_blocks+1)+2 device pointers (fp32): per ConvBNRelu block conv.weight [cout,cin,3,3],
+ * conv.bias, bn.weight, bn.bias (the last block has num_bits*redundancy <= 8 outputs), then linear.weight,
+ * linear.bias.  workspace: nsig_decoder_workspace_bytes() bytes, kept between forward and backward.
+ * forward writes logits [B, num_bits] fp32 (HiddenDecoder_multi_views.forward's return value).
+ * backward takes dlogits [B, num_bits] fp32, ACCUMULATES every parameter gradient into grads (same order and
+ * shapes as params, fp32) and writes dimage [B,H,W,3] fp32 (optional). */
+size_t nsig_decoder_workspace_bytes(uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks);
+int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
+                         uint32_t num_bits, uint32_t redundancy, const float* const* params, void* workspace,
+                         float* logits, nsig_stream_t stream);
+int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
+                          uint32_t num_bits, uint32_t redundancy, const float* const* params,
+                          float* const* grads, void* workspace, float* dimage, nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
 /* gradient exchange of the ray-sharded training path (no reference precedent) */
 /* ------------------------------------------------------------------------- */
 

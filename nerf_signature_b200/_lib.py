@@ -49,6 +49,8 @@ _SIGNATURES = {
     "nsig_mark_untrained_grid": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f64, _vp, _vp], 1),
     "nsig_get_rays": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _i64, _u32, _vp, _vp, _vp], 1),
     "nsig_allreduce_mean_inplace": ([_vp, _vp, _vp, _u32, _u32, _u32, _vp], 1),
+    "nsig_decoder_forward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp], 1),
+    "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
@@ -58,7 +60,8 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes",
-                                                "nsig_grid_sample_cells_scratch_bytes", "nsig_allreduce_grid"])
+                                                "nsig_grid_sample_cells_scratch_bytes", "nsig_allreduce_grid",
+                                                "nsig_decoder_workspace_bytes"])
 
 _lib = None
 _lock = threading.Lock()
@@ -92,6 +95,8 @@ def load():
         lib.nsig_march_rays_train_scratch_bytes.argtypes = [_u32]
         lib.nsig_grid_sample_cells_scratch_bytes.restype = _sz
         lib.nsig_grid_sample_cells_scratch_bytes.argtypes = [_u32, _u32]
+        lib.nsig_decoder_workspace_bytes.restype = _sz
+        lib.nsig_decoder_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32]
         lib.nsig_allreduce_grid.restype = _u32
         lib.nsig_allreduce_grid.argtypes = []
         _lib = lib

@@ -79,7 +79,7 @@ class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
-                 merged_render=False):
+                 merged_render=False, fused_decoder=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -98,6 +98,11 @@ class Scene:
         grid = occupancy(cfg, model.cascade, seed)
         model.density_grid.copy_(torch.from_numpy(grid))
         model.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
+        if not (fused_decoder and fp16):
+            # plain-module decoder: NHWC weights.  Its input `pred.permute(0, 3, 1, 2)` of an [md, pH, pW, 3] image is
+            # already a channels_last view and cuDNN's tensor-core kernels are NHWC; with NCHW weights every conv is
+            # wrapped in layout-conversion kernels (-4 % step time).  Shapes and state-dict keys are unaffected.
+            model.msg_decoder = model.msg_decoder.to(memory_format=torch.channels_last)
         self.model = model.to(device).train()
         if graph and optimizer != "fused":
             raise ValueError("graph capture needs the fused optimizer (the set of tables with a gradient changes "
@@ -121,6 +126,7 @@ class Scene:
         _hmsg.grad_reducer = self.sync.reduce_table_grad if (self.sync.enabled and not self.flat_sync) else None
         self.use_graph = graph
         self.merged_render = merged_render  # one render call over [block rays | content rays] instead of two
+        self.fused_decoder = fused_decoder and fp16  # the kernels implement the float16-autocast arithmetic
         self.iteration = 0
         self._graph = None
         self._static = None
@@ -168,8 +174,11 @@ class Scene:
             image_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
                                    perturb=False, force_all_rays=True, **self.opt)["image"]
         pred = torch.clamp(image_w, min=0, max=1)
-        with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
-            decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
+        if self.fused_decoder:   # normalisation + HiDDeN decoder forward/backward as tensor-core kernels (csrc/decoder.cu)
+            decoded = model.decode_blocks(pred)
+        else:                    # utils_wtmk_disen.py:592-595 verbatim: the plain module under autocast
+            with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
+                decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
         if not self.merged_render:
             image_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
                                    perturb=False, force_all_rays=True, **self.opt)["image"]

@@ -134,6 +134,12 @@ class NeRFNetwork(NeRFRenderer):
             rgbs = h
         return rgbs
 
+    def decode_blocks(self, image):
+        """msg_decoder(normalization(image.permute(0, 3, 1, 2))) for rendered blocks `image` [B,H,W,3] in [0,1], with
+        float16-autocast arithmetic (utils_wtmk_disen.py:592-595), through the fused decoder kernels."""
+        from .decoder_ops import decode
+        return decode(self.msg_decoder, image)
+
     def get_params(self, lr):
         if self.finetune_decoder:
             params = [

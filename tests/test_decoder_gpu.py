@@ -1,0 +1,93 @@
+"""-m gpu parity of the fused HiDDeN decoder kernels (csrc/decoder.cu) against the plain PyTorch module
+(nerf/hidden_models.py: HiddenDecoder_multi_views under float16 autocast, exactly as the training step calls it) and
+against the same module in fp32.  Tolerances: both the autocast module and the kernels round activations and
+activation gradients to fp16 at the same points but sum in different orders, so each is compared with the fp32
+result and they must be equally close: logits 3e-3 absolute, gradients 3e-2 relative L2."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _decoder(seed, num_bits=1, redundancy=1):
+    from nerf_signature_b200.nerf.hidden_models import get_hidden_decoder_multi_views
+    torch.manual_seed(seed)
+    dec = get_hidden_decoder_multi_views(num_bits=num_bits, redundancy=redundancy, num_blocks=8, input_ch=3, channels=64)
+    with torch.no_grad():   # non-trivial BatchNorm affine parameters and biases
+        for m in dec.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    return dec.cuda()
+
+
+def _run_module(dec, image, gout, autocast):
+    from nerf_signature_b200.nerf.hidden_models import normalize_img
+    dec.zero_grad(set_to_none=True)
+    image = image.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+        out = dec(normalize_img(image.permute(0, 3, 1, 2)))
+    (out.float() * gout).sum().backward()
+    return out.float().detach(), image.grad.detach(), [p.grad.detach().clone() for p in dec.parameters()]
+
+
+def _run_fused(dec, image, gout):
+    from nerf_signature_b200.nerf import decoder_ops
+    dec.zero_grad(set_to_none=True)
+    image = image.clone().requires_grad_(True)
+    out = decoder_ops.decode(dec, image)
+    (out * gout).sum().backward()
+    return out.detach(), image.grad.detach(), [p.grad.detach().clone() for p in dec.parameters()]
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("B,H,W,bits,red", [(32, 12, 12, 1, 1), (8, 23, 31, 1, 1), (3, 5, 7, 1, 1), (5, 9, 16, 2, 3)])
+def test_fused_decoder_matches_module(B, H, W, bits, red):
+    from nerf_signature_b200.nerf import decoder_ops
+    dec = _decoder(0, bits, red)
+    assert decoder_ops.decoder_params(dec) is not None
+    g = torch.Generator(device="cuda").manual_seed(1)
+    image = torch.rand(B, H, W, 3, device="cuda", generator=g)
+    gout = torch.randn(B, bits, device="cuda", generator=g) * 64.0     # GradScaler-sized upstream gradient
+    o32, di32, gp32 = _run_module(dec, image, gout, autocast=False)
+    o16, di16, gp16 = _run_module(dec, image, gout, autocast=True)
+    of, dif, gpf = _run_fused(dec, image, gout)
+    assert of.shape == o32.shape == (B, bits)
+    scale = float(o32.abs().max()) + 1e-6
+    err_f, err_16 = float((of - o32).abs().max()), float((o16 - o32).abs().max())
+    assert err_f <= max(3e-3 * max(scale, 1.0), 2.0 * err_16), (err_f, err_16)
+    assert _rel(dif, di32) <= max(3e-2, 2.0 * _rel(di16, di32)), (_rel(dif, di32), _rel(di16, di32))
+    names = [n for n, _ in dec.named_parameters()]
+    for n, a, b16, b32 in zip(names, gpf, gp16, gp32):
+        if n.endswith("layers.0.bias"):
+            # conv bias under BatchNorm: the true gradient is 0, what remains is rounding noise - compare magnitudes only
+            assert float(a.abs().max()) <= 10 * float(b16.abs().max()) + 1e-2 * float(gp32[0].abs().max()), n
+            continue
+        assert a.shape == b32.shape
+        assert _rel(a, b32) <= max(3e-2, 2.0 * _rel(b16, b32)), (n, _rel(a, b32), _rel(b16, b32))
+
+
+def test_fused_decoder_accumulates_into_existing_grads_and_skips_frozen():
+    from nerf_signature_b200.nerf import decoder_ops
+    dec = _decoder(2)
+    image = torch.rand(4, 12, 12, 3, device="cuda")
+    gout = torch.ones(4, 1, device="cuda")
+    _, _, g1 = _run_fused(dec, image, gout)
+    out = decoder_ops.decode(dec, image)            # second backward without zeroing: gradients add up
+    (out * gout).sum().backward()
+    for (n, p), a in zip(dec.named_parameters(), g1):
+        if n.endswith("layers.0.bias"):
+            continue                                  # conv bias under BatchNorm: pure rounding noise (true gradient 0)
+        torch.testing.assert_close(p.grad, 2 * a, rtol=1e-3, atol=1e-6 + 1e-2 * float(a.abs().max()))  # fp32 atomics: order noise
+    dec.zero_grad(set_to_none=True)
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    img = image.clone().requires_grad_(True)
+    decoder_ops.decode(dec, img).sum().backward()    # frozen decoder: only the image gradient
+    assert img.grad is not None and all(p.grad is None for p in dec.parameters())

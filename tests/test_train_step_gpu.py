@@ -111,3 +111,16 @@ def test_merged_render_matches_two_render_calls():
     assert a.samples_per_step() == b.samples_per_step()
     for x, y in zip(_msg_tables(a), _msg_tables(b)):
         _close_frac(x, y, rtol=1e-3, atol=1e-5)
+
+
+def test_fused_decoder_step_matches_module_step():
+    """The training step with the fused decoder kernels against the step with the plain PyTorch decoder: same losses
+    on the first steps (both use float16-autocast arithmetic; they differ by summation order only)."""
+    a, b = _scene(optimizer="fused"), _scene(optimizer="fused", fused_decoder=True)
+    batches = _batches(a, 2)
+    gen = torch.Generator().manual_seed(8)
+    for i in range(3):
+        m = a.new_message(gen)
+        la = [float(x) for x in a.train_step(batches[i % 2], m)]
+        lb = [float(x) for x in b.train_step(batches[i % 2], m)]
+        np.testing.assert_allclose(lb, la, rtol=5e-3 if i else 2e-3, atol=1e-5)
