@@ -145,81 +145,102 @@ __device__ __forceinline__ void stage_tile(__half* tile, const __half* __restric
 }
 
 struct ConvParams {
-    const __half* src;     // [B,H,W,CIN]   activation (IN_RAW), z of the producing layer (IN_BNGELU) or da (IN_DZ)
+    const __half* src;     // [B,H,W,SCH]   activation (IN_RAW), z of the producing layer (IN_BNGELU) or da (IN_DZ)
     const __half* src2;    // z (IN_DZ)
     BnSrc bn;              // BatchNorm state of the input transform
     const __half* w;       // [COUT][9][CIN] fp16 (already rotated/transposed for data gradients)
     const float* bias;     // [COUT] or null
     __half* dst;           // [B,H,W,COUT]
+    __half* act_out;       // optional [B,H,W,SCH]: the transformed input (a_{l-1} forward, dz_l backward) is written
+                           // here once, by the CTA that owns the rows, for the weight-gradient kernel
     double* out_sums;      // [2][COUT] or null: += sum / sum of squares of the (fp16-rounded) outputs
     int B, H, W, R;        // R = image rows per CTA
     int cout_valid;        // outputs >= cout_valid are written as zero (channel padding)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// 3x3 / pad 1 convolution as an implicit GEMM.  grid = (ceil(H/R), B).
+// 3x3 / pad 1 convolution as an implicit GEMM.  grid = (ceil(H/R), B), R*W <= 64 pixels per CTA preferred.
+// A warp owns one n-tile (8 output channels) and up to 4 m-tiles (64 pixels): each weight fragment is loaded once per
+// k-step straight from global memory (the 74 KB of a layer's weights stay in L1/L2; staging them through shared
+// memory cost more than the math) and reused for every m-tile; A fragments come from the staged input tile.
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int SCH, int COUT, int MODE>
 __global__ void __launch_bounds__(kDecThreads)
 k_dec_conv(const ConvParams p) {
-    constexpr int STRIDE = CIN + 8, WSTRIDE = 9 * CIN + 8, NT = COUT / 8, KS = CIN / 16;
+    constexpr int STRIDE = CIN + 8, NT = COUT / 8, KS = CIN / 16, MB = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* wsm = reinterpret_cast<__half*>(smem_raw);                       // [COUT][WSTRIDE]
-    __half* tile = wsm + COUT * WSTRIDE;                                     // [(R+2)*(W+2)][STRIDE]
+    __half* tile = reinterpret_cast<__half*>(smem_raw);                      // [(R+2)*(W+2)][STRIDE]
     BnCoef* coef = reinterpret_cast<BnCoef*>(tile + (size_t)(p.R + 2) * (p.W + 2) * STRIDE);
     const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
 
     if (MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
+        __syncthreads();
     }
-    for (int i = threadIdx.x; i < COUT * (9 * CIN / 8); i += blockDim.x) {
-        const int row = i / (9 * CIN / 8), ck = i - row * (9 * CIN / 8);
-        *reinterpret_cast<uint4*>(wsm + row * WSTRIDE + ck * 8) = *reinterpret_cast<const uint4*>(p.w + (size_t)row * 9 * CIN + ck * 8);
-    }
-    __syncthreads();
     stage_tile<CIN, SCH, MODE>(tile, p.src, p.src2, coef, b, r0, R, p.H, p.W);
     __syncthreads();
 
-    const int P = R * p.W, TW = p.W + 2, m_tiles = (P + 15) / 16;
-    for (int item = warp; item < m_tiles * NT; item += kDecWarps) {
-        const int mt = item / NT, nt = item - mt * NT;
-        // this lane's A row for ldmatrix: pixel mt*16 + (lane & 15), clamped; centre tap position in the tile
-        const int pa = min(mt * 16 + (lane & 15), P - 1);
-        const int ra = pa / p.W, wa = pa - ra * p.W;
-        const __half* arow = tile + ((size_t)(ra + 1) * TW + (wa + 1)) * STRIDE + (lane >> 4) * 8;
-        const __half* wrow = wsm + (nt * 8 + g) * WSTRIDE + 2 * tig;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const int P = R * p.W, TW = p.W + 2, m_tiles = (P + 15) / 16, m_groups = (m_tiles + MB - 1) / MB;
+    if (p.act_out) {  // materialise the centre rows of the transformed tile
+        constexpr int CK = SCH / 8;
+        for (int i = threadIdx.x; i < P * CK; i += blockDim.x) {
+            const int pix = i / CK, ck = i - pix * CK, rr = pix / p.W, ww = pix - rr * p.W;
+            *reinterpret_cast<uint4*>(p.act_out + (((size_t)b * p.H + r0 + rr) * p.W + ww) * SCH + ck * 8) =
+                *reinterpret_cast<const uint4*>(tile + ((size_t)(rr + 1) * TW + (ww + 1)) * STRIDE + ck * 8);
+        }
+    }
+    for (int item = warp; item < m_groups * NT; item += kDecWarps) {
+        const int mg = item / NT, nt = item - mg * NT;
+        const __half* arow[MB];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {  // this lane's A row of m-tile mg*MB+m: pixel clamped to the strip
+            const int pa = min((mg * MB + m) * 16 + (lane & 15), P - 1);
+            const int ra = pa / p.W, wa = pa - ra * p.W;
+            arow[m] = tile + ((size_t)(ra + 1) * TW + (wa + 1)) * STRIDE + (lane >> 4) * 8;
+        }
+        const int mcount = min(MB, m_tiles - mg * MB);
+        const __half* wrow = p.w + (size_t)(nt * 8 + g) * (9 * CIN) + 2 * tig;
+        float c[MB][4];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) { c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f; }
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const int dy = t / 3 - 1, dx = t % 3 - 1;
-            const __half* at = arow + (dy * TW + dx) * STRIDE;
+            const int off = ((t / 3 - 1) * TW + (t % 3 - 1)) * STRIDE;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                uint32_t a[4];
-                ldsm_x4(a, at + ks * 16);
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16 + 8);
-                mma_16816(c, a, b0, b1);
+                const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16));
+                const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16 + 8));
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                    if (m < mcount) {
+                        uint32_t a[4];
+                        ldsm_x4(a, arow[m] + off + ks * 16);
+                        mma_16816(c[m], a, b0, b1);
+                    }
+                }
             }
         }
-        // epilogue: rows g, g+8 of the m-tile; columns nt*8 + 2tig, +1
+        // epilogue: rows g, g+8 of each m-tile; columns nt*8 + 2tig, +1
         const int col = nt * 8 + 2 * tig;
         const float bias0 = (p.bias && col < p.cout_valid) ? p.bias[col] : 0.f;
         const float bias1 = (p.bias && col + 1 < p.cout_valid) ? p.bias[col + 1] : 0.f;
         float l1[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int pp = mt * 16 + h * 8 + g;
-            if (pp < P) {
-                const int rr = pp / p.W, ww = pp - rr * p.W;
-                __half o0 = f2h(c[2 * h] + bias0), o1 = f2h(c[2 * h + 1] + bias1);
-                if (col >= p.cout_valid) o0 = f2h(0.f);
-                if (col + 1 >= p.cout_valid) o1 = f2h(0.f);
-                const __half2 o = __halves2half2(o0, o1);
-                *reinterpret_cast<__half2*>(p.dst + (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col) = o;
-                const float f0 = h2f(o0), f1 = h2f(o1);
-                l1[0] += f0; l1[1] += f1; l2[0] += f0 * f0; l2[1] += f1 * f1;
+        for (int m = 0; m < MB; ++m) {
+            if (m >= mcount) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pp = (mg * MB + m) * 16 + h * 8 + g;
+                if (pp < P) {
+                    const int rr = pp / p.W, ww = pp - rr * p.W;
+                    __half o0 = f2h(c[m][2 * h] + bias0), o1 = f2h(c[m][2 * h + 1] + bias1);
+                    if (col >= p.cout_valid) o0 = f2h(0.f);
+                    if (col + 1 >= p.cout_valid) o1 = f2h(0.f);
+                    *reinterpret_cast<__half2*>(p.dst + (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col) = __halves2half2(o0, o1);
+                    const float f0 = h2f(o0), f1 = h2f(o1);
+                    l1[0] += f0; l1[1] += f1; l2[0] += f0 * f0; l2[1] += f1 * f1;
+                }
             }
         }
         if (p.out_sums) {
@@ -269,8 +290,16 @@ k_dec_bwd_stats(const __half* __restrict__ da, const __half* __restrict__ z, BnS
             a2[k] += dy * ((zf - c.mean) * c.rstd);
         }
     }
+    // lanes l, l+CK, l+2CK, ... of a warp hold the same channels: fold them before touching shared memory
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&red[0][slot * 8 + k], a1[k]); atomicAdd(&red[1][slot * 8 + k], a2[k]); }
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int o = 16; o >= CK; o >>= 1) { a1[k] += __shfl_xor_sync(NSIG_FULL_MASK, a1[k], o); a2[k] += __shfl_xor_sync(NSIG_FULL_MASK, a2[k], o); }
+    }
+    if ((threadIdx.x & 31) < CK) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { atomicAdd(&red[0][slot * 8 + k], a1[k]); atomicAdd(&red[1][slot * 8 + k], a2[k]); }
+    }
     __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
         atomicAdd(bsums + ch, (double)red[0][ch]);
@@ -279,94 +308,93 @@ k_dec_bwd_stats(const __half* __restrict__ da, const __half* __restrict__ z, BnS
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// weight gradient of one conv layer: dW[co][tap][ci] += sum_pixels dz[p][co] * a[p + tap][ci];  db[co] += sum dz.
-// grid = (ceil(H/R), B); dW fp32 [COUT_REAL][CIN_REAL][3][3] (torch layout), accumulated with atomics.
+// weight gradient of one conv layer: dW[co][ci][tap] += sum_pixels dz[p][co] * a[p + tap][ci];  db[co] += sum dz.
+// grid = (9 taps, G image groups).  A CTA owns ONE tap and keeps its [COUT x CIN] partial in registers while it walks
+// over its images strip by strip (a and dz are the tensors materialised by the forward / data-gradient convs, so
+// staging is a plain shifted copy), then adds it to dW with one atomic per element: 9*G*COUT*CIN atomics per layer
+// instead of one full dW per strip.  Both MMA operands are transposed 8x8 blocks (ldmatrix.trans): the contraction
+// runs over pixels, which is the row index of both tiles.
 // ---------------------------------------------------------------------------------------------------------------
 struct WgradParams {
-    const __half* a_src;   // input of the layer: x0 (IN_RAW) or z of the previous layer (IN_BNGELU)   [B,H,W,CIN]
-    BnSrc a_bn;
-    const __half* da;      // gradient wrt this layer's activation                                       [B,H,W,COUT]
-    const __half* z;       // this layer's conv output
-    BnSrc bn;              // this layer's BatchNorm state (incl. backward sums)
+    const __half* a;       // input activation of the layer [B,H,W,CIN] (x0 or the materialised a_{l-1})
+    const __half* dz;      // gradient wrt the conv output  [B,H,W,DCH] (materialised by the data-gradient conv)
     float* dW;             // [cout_real][cin_real][3][3]
     float* db;             // [cout_real]
     int B, H, W, R, cin_real, cout_real;
 };
 
-// COUT = output channels padded to the MMA's M granularity (16); DCH = channels per pixel of da / z in memory.
-template <int CIN, int COUT, int DCH, int AMODE>
+template <int CIN, int COUT, int DCH>
 __global__ void __launch_bounds__(kDecThreads)
 k_dec_wgrad(const WgradParams p) {
-    constexpr int ASTR = CIN + 8, DSTR = COUT + 8, MT = COUT / 16, NT = CIN / 8;
+    constexpr int ASTR = CIN + 8, DSTR = COUT + 8, MT = COUT / 16, NT = CIN / 8, ITEMS = MT * NT;
+    constexpr int PER_WARP = (ITEMS + kDecWarps - 1) / kDecWarps;          // 4 (64x64), 1 (64x16 or 16x64)
+    constexpr int NT_PER = PER_WARP;                                        // a warp's items share one m-tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* atile = reinterpret_cast<__half*>(smem_raw);                         // [(R+2)*(W+2)][ASTR]
-    const int TW = p.W + 2;
-    const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0);
-    const int P = R * p.W, Ppad = (P + 15) / 16 * 16;
-    __half* dtile = atile + (size_t)(p.R + 2) * TW * ASTR;                       // [Ppad_max][DSTR]
-    const int Ppad_max = (p.R * p.W + 15) / 16 * 16;
-    BnCoef* coef_a = reinterpret_cast<BnCoef*>(dtile + (size_t)Ppad_max * DSTR);
-    BnCoef* coef_d = coef_a + CIN;
+    const int Pmax = (p.R * p.W + 15) / 16 * 16;
+    __half* atile = reinterpret_cast<__half*>(smem_raw);                    // [Pmax][ASTR]  a shifted by this CTA's tap
+    __half* dtile = atile + (size_t)Pmax * ASTR;                            // [Pmax][DSTR]
+    const int t = blockIdx.x, dy = t / 3 - 1, dx = t % 3 - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
-
-    if (AMODE == IN_BNGELU)
-        for (int ch = threadIdx.x; ch < CIN; ch += blockDim.x) coef_a[ch] = bn_coef(p.a_bn, ch, false);
-    for (int ch = threadIdx.x; ch < DCH; ch += blockDim.x) coef_d[ch] = bn_coef(p.bn, ch, true);
-    __syncthreads();
-    stage_tile<CIN, CIN, AMODE>(atile, p.a_src, nullptr, coef_a, b, r0, R, p.H, p.W);
-    // dz tile: rows = pixels of the strip (no halo), zero rows up to a multiple of 16
-    for (int i = threadIdx.x; i < Ppad * (COUT / 8); i += blockDim.x) {
-        const int pix = i / (COUT / 8), ck = i - pix * (COUT / 8);
-        uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (pix < P && ck * 8 < DCH) {
-            const int rr = pix / p.W, ww = pix - rr * p.W;
-            const size_t off = (((size_t)b * p.H + r0 + rr) * p.W + ww) * DCH + ck * 8;
-            const uint4 v = *reinterpret_cast<const uint4*>(p.da + off);
-            const uint4 v2 = *reinterpret_cast<const uint4*>(p.z + off);
-            const __half* hd = reinterpret_cast<const __half*>(&v);
-            const __half* hz = reinterpret_cast<const __half*>(&v2);
-            __half* ho = reinterpret_cast<__half*>(&out);
+    const int item0 = warp * PER_WARP;                                      // items [item0, item0 + PER_WARP): (mt, nt..)
+    const int mt = item0 / NT, nt0 = item0 - mt * NT;
+    const bool active = item0 < ITEMS;
+    float c[PER_WARP][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ho[k] = (ck * 8 + k < p.cout_real) ? dz_from(hd[k], hz[k], coef_d[ck * 8 + k]) : f2h(0.f);
-        }
-        *reinterpret_cast<uint4*>(dtile + (size_t)pix * DSTR + ck * 8) = out;
-    }
-    __syncthreads();
+    for (int j = 0; j < PER_WARP; ++j) { c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f; }
+    float dbias = 0.f;
 
-    // bias gradient: column sums of the dz tile
-    for (int co = threadIdx.x; co < p.cout_real; co += blockDim.x) {
-        float s = 0.f;
-        for (int pix = 0; pix < P; ++pix) s += h2f(dtile[(size_t)pix * DSTR + co]);
-        atomicAdd(p.db + co, s);
-    }
-
-    // items: (tap, m-tile of 16 couts, n-tile of 8 cins)
-    for (int item = warp; item < 9 * MT * NT; item += kDecWarps) {
-        const int t = item / (MT * NT), rem = item - t * (MT * NT), mt = rem / NT, nt = rem - mt * NT;
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k0 = 0; k0 < Ppad; k0 += 16) {
-            // A = dz^T: matrices (m 0-7,k 0-7), (m 8-15,k 0-7), (m 0-7,k 8-15), (m 8-15,k 8-15) = transposed 8x8 blocks of
-            // dtile rows (pixels) k0 + (lane&7) + 8*(lane>>4), columns mt*16 + 8*((lane>>3)&1)
-            uint32_t a[4];
-            ldsm_x4_trans(a, dtile + (size_t)(k0 + (lane & 7) + ((lane >> 4) << 3)) * DSTR + mt * 16 + (((lane >> 3) & 1) << 3));
-            // B[k = pixel][n = ci]: transposed 8x8 blocks of the shifted a rows; lanes 0-7 -> k0..k0+7, lanes 8-15 -> k0+8..
-            const int pk = min(k0 + (lane & 15), P - 1);     // rows >= P multiply zero dz rows
-            const int rk = pk / p.W, wk = pk - rk * p.W;
-            uint32_t bb[2];
-            ldsm_x2_trans(bb, atile + ((size_t)(rk + 1 + dy) * TW + (wk + 1 + dx)) * ASTR + nt * 8);
-            mma_16816(c, a, bb[0], bb[1]);
-        }
-        // c[0],c[1]: (co = mt*16+g, ci = nt*8+2tig, +1); c[2],c[3]: co + 8
+    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
+        for (int r0 = 0; r0 < p.H; r0 += p.R) {
+            const int R = min(p.R, p.H - r0), P = R * p.W, Ppad = (P + 15) / 16 * 16;
+            __syncthreads();
+            for (int i = threadIdx.x; i < Ppad * (CIN / 8); i += blockDim.x) {
+                const int pix = i / (CIN / 8), ck = i - pix * (CIN / 8);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (pix < P) {
+                    const int rr = r0 + pix / p.W + dy, ww = pix % p.W + dx;
+                    if (rr >= 0 && rr < p.H && ww >= 0 && ww < p.W)
+                        v = *reinterpret_cast<const uint4*>(p.a + (((size_t)b * p.H + rr) * p.W + ww) * CIN + ck * 8);
+                }
+                *reinterpret_cast<uint4*>(atile + (size_t)pix * ASTR + ck * 8) = v;
+            }
+            for (int i = threadIdx.x; i < Ppad * (COUT / 8); i += blockDim.x) {
+                const int pix = i / (COUT / 8), ck = i - pix * (COUT / 8);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (pix < P && ck * 8 < DCH)
+                    v = *reinterpret_cast<const uint4*>(p.dz + (((size_t)b * p.H + r0 + pix / p.W) * p.W + pix % p.W) * DCH + ck * 8);
+                *reinterpret_cast<uint4*>(dtile + (size_t)pix * DSTR + ck * 8) = v;
+            }
+            __syncthreads();
+            if (t == 4 && threadIdx.x < p.cout_real) {  // bias gradient: column sums of dz (centre-tap CTAs only)
+                for (int pix = 0; pix < P; ++pix) dbias += h2f(dtile[(size_t)pix * DSTR + threadIdx.x]);
+            }
+            if (active) {
+                for (int k0 = 0; k0 < Ppad; k0 += 16) {
+                    uint32_t a[4];
+                    ldsm_x4_trans(a, dtile + (size_t)(k0 + (lane & 7) + ((lane >> 4) << 3)) * DSTR + mt * 16 + (((lane >> 3) & 1) << 3));
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int co = mt * 16 + h * 8 + g;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int ci = nt * 8 + 2 * tig + e;
-                if (co < p.cout_real && ci < p.cin_real) atomicAdd(p.dW + ((size_t)co * p.cin_real + ci) * 9 + t, c[2 * h + e]);
+                    for (int j = 0; j < NT_PER; ++j) {
+                        uint32_t bb[2];
+                        ldsm_x2_trans(bb, atile + (size_t)(k0 + (lane & 15)) * ASTR + (nt0 + j) * 8);
+                        mma_16816(c[j], a, bb[0], bb[1]);
+                    }
+                }
             }
         }
+    }
+    if (t == 4 && threadIdx.x < p.cout_real) atomicAdd(p.db + threadIdx.x, dbias);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < NT_PER; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int co = mt * 16 + h * 8 + g;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ci = (nt0 + j) * 8 + 2 * tig + e;
+                    if (co < p.cout_real && ci < p.cin_real) atomicAdd(p.dW + ((size_t)co * p.cin_real + ci) * 9 + t, c[j][2 * h + e]);
+                }
+            }
     }
 }
 
@@ -374,9 +402,17 @@ k_dec_wgrad(const WgradParams p) {
 // parameter preparation: fp16 conv weights in [COUT_PAD][9][CIN_PAD] (forward) and the rotated / transposed copy
 // [CIN_PAD][9][COUT_PAD] with tap 8-t (data gradient), from torch's fp32 [cout][cin][3][3].
 // ---------------------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const float* w[17]; __half* wf[17]; __half* wr[17];
+    int cout[17], cin[17], cout_pad[17], cin_pad[17];
+};
 __global__ void __launch_bounds__(256)
-k_dec_prep_weights(const float* __restrict__ w, int cout, int cin, int cout_pad, int cin_pad, __half* __restrict__ wf,
-                   __half* __restrict__ wr) {
+k_dec_prep_weights(const PrepParams q) {
+    const int l = blockIdx.y;
+    const float* __restrict__ w = q.w[l];
+    const int cout = q.cout[l], cin = q.cin[l], cout_pad = q.cout_pad[l], cin_pad = q.cin_pad[l];
+    __half* __restrict__ wf = q.wf[l];
+    __half* __restrict__ wr = q.wr[l];
     const int n = cout_pad * 9 * cin_pad;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         {   // forward layout: i = (co, t, ci)
@@ -483,10 +519,14 @@ k_dec_head_bwd(const HeadParams p) {
     }
 }
 
+struct BnGradParams { const double* bsums[17]; float* dgamma[17]; float* dbeta[17]; int c_pad[17], c_real[17]; };
 __global__ void __launch_bounds__(64)
-k_dec_bn_grads(const double* __restrict__ bsums, int C_pad, int c_real, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int ch = threadIdx.x;
-    if (ch < c_real) { atomicAdd(dbeta + ch, (float)bsums[ch]); atomicAdd(dgamma + ch, (float)bsums[C_pad + ch]); }
+k_dec_bn_grads(const BnGradParams q) {   // dbeta = sum dy, dgamma = sum dy*yhat: the backward statistics themselves
+    const int l = blockIdx.x, ch = threadIdx.x;
+    if (ch < q.c_real[l]) {
+        atomicAdd(q.dbeta[l] + ch, (float)q.bsums[l][ch]);
+        atomicAdd(q.dgamma[l] + ch, (float)q.bsums[l][q.c_pad[l] + ch]);
+    }
 }
 
 }  // namespace nsig
@@ -501,9 +541,9 @@ namespace {
 constexpr int kMaxLayers = 16;
 
 struct DecLayout {
-    int B, H, W, L;            // L = number of 64-channel conv blocks (num_blocks); layer L+1 is the nb-channel block
+    int B, H, W, L;            // L = number of 64-channel conv blocks (num_blocks); block L is the nb-channel one
     size_t n_pix;
-    size_t off_x0, off_z[kMaxLayers + 1], off_da[2], off_da9, off_dx0, off_pooled;
+    size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz, off_da9, off_dx0, off_pooled;
     size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_sums[kMaxLayers + 1], off_bsums[kMaxLayers + 1];
     size_t off_sums_begin, sums_bytes, total;
 };
@@ -518,7 +558,9 @@ DecLayout make_layout(int B, int H, int W, int L) {
     d.off_x0 = o; o = align_up(o + d.n_pix * 16 * 2);
     for (int l = 0; l < L; ++l) { d.off_z[l] = o; o = align_up(o + d.n_pix * 64 * 2); }
     d.off_z[L] = o; o = align_up(o + d.n_pix * 8 * 2);
+    for (int l = 0; l < L; ++l) { d.off_a[l] = o; o = align_up(o + d.n_pix * 64 * 2); }   // a_l = GELU(BN(z_l)), l < L
     for (int k = 0; k < 2; ++k) { d.off_da[k] = o; o = align_up(o + d.n_pix * 64 * 2); }
+    d.off_dz = o; o = align_up(o + d.n_pix * 64 * 2);
     d.off_da9 = o; o = align_up(o + d.n_pix * 8 * 2);
     d.off_dx0 = o; o = align_up(o + d.n_pix * 16 * 2);
     d.off_pooled = o; o = align_up(o + (size_t)B * 8 * 2);
@@ -537,24 +579,27 @@ DecLayout make_layout(int B, int H, int W, int L) {
     return d;
 }
 
-int pick_rows(int B, int H, int W, int cin, int cout, bool wgrad) {
-    // rows per CTA: enough strips to fill the 148 SMs (conv), few strips for the weight gradient (every CTA adds a full
-    // dW with atomics), and staged tiles below ~96 KB next to the 75 KB of weights (conv) / the dz tile (wgrad)
-    const int strips = wgrad ? 2 : (148 + B - 1) / B;
+// image rows per conv CTA: at most 64 pixels (4 m-tiles per warp pass), at least ~148 CTAs when the batch allows it
+int conv_rows(int B, int H, int W) {
+    int R = 64 / W > 0 ? 64 / W : 1;
+    const int strips = (148 + B - 1) / B;
     const int want = (H + strips - 1) / strips > 0 ? (H + strips - 1) / strips : 1;
-    for (int R = want; R >= 1; --R) {
-        size_t bytes = (size_t)(R + 2) * (W + 2) * (cin + 8) * 2;
-        if (wgrad) bytes += (size_t)((R * W + 15) / 16 * 16) * (cout + 8) * 2;
-        if (bytes <= 96 * 1024) return R < H ? R : H;
-    }
-    return 0;
+    if (want < R) R = want;
+    return R < H ? R : H;
+}
+// image rows per weight-gradient step: as many pixels as fit next to each other in ~160 KB of shared memory
+int wgrad_rows(int H, int W, int cin, int cout) {
+    const size_t per_pix = (size_t)(cin + 8 + cout + 8) * 2;
+    int R = (int)((160 * 1024) / (per_pix * (size_t)W));
+    if (R < 1) return 0;
+    return R < H ? R : H;
 }
 
 template <int CIN, int SCH, int COUT, int MODE>
 int launch_conv(ConvParams p, cudaStream_t st) {
-    p.R = pick_rows(p.B, p.H, p.W, CIN, COUT, false);
-    if (p.R <= 0) return NSIG_EINVAL;
-    const size_t smem = (size_t)COUT * (9 * CIN + 8) * 2 + (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + CIN * sizeof(BnCoef);
+    p.R = conv_rows(p.B, p.H, p.W);
+    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + CIN * sizeof(BnCoef);
+    if (smem > 200 * 1024) return NSIG_EINVAL;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_conv<CIN, SCH, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
     k_dec_conv<CIN, SCH, COUT, MODE><<<dim3((p.H + p.R - 1) / p.R, p.B), kDecThreads, smem, st>>>(p);
@@ -562,15 +607,15 @@ int launch_conv(ConvParams p, cudaStream_t st) {
     return 0;
 }
 
-template <int CIN, int COUT, int DCH, int AMODE>
+template <int CIN, int COUT, int DCH>
 int launch_wgrad(WgradParams p, cudaStream_t st) {
-    p.R = pick_rows(p.B, p.H, p.W, CIN, COUT, true);
+    p.R = wgrad_rows(p.H, p.W, CIN, COUT);
     if (p.R <= 0) return NSIG_EINVAL;
-    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + (size_t)((p.R * p.W + 15) / 16 * 16) * (COUT + 8) * 2 +
-                        (CIN + COUT) * sizeof(BnCoef);
+    const size_t smem = (size_t)((p.R * p.W + 15) / 16 * 16) * (CIN + 8 + COUT + 8) * 2;
     static bool set = false;
-    if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    k_dec_wgrad<CIN, COUT, DCH, AMODE><<<dim3((p.H + p.R - 1) / p.R, p.B), kDecThreads, smem, st>>>(p);
+    if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    const int G = p.B < 16 ? p.B : 16;
+    k_dec_wgrad<CIN, COUT, DCH><<<dim3(9, G), kDecThreads, smem, st>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -600,11 +645,13 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
     auto D64 = [&](size_t off) { return reinterpret_cast<double*>(ws + off); };
     cudaError_t e = cudaMemsetAsync(ws + d.off_sums_begin, 0, d.sums_bytes, st);
     if (e != cudaSuccess) return (int)e;
+    PrepParams q{};
     for (int l = 0; l <= L; ++l) {
-        const int cin = l == 0 ? 3 : 64, cout = l == L ? nb : 64, cin_p = l == 0 ? 16 : 64, cout_p = l == L ? 16 : 64;
-        k_dec_prep_weights<<<32, 256, 0, st>>>(params[4 * l], cout, cin, cout_p, cin_p, H16(d.off_wf[l]), H16(d.off_wr[l]));
-        NSIG_LAUNCH_CHECK();
+        q.w[l] = params[4 * l]; q.wf[l] = H16(d.off_wf[l]); q.wr[l] = H16(d.off_wr[l]);
+        q.cin[l] = l == 0 ? 3 : 64; q.cout[l] = l == L ? nb : 64; q.cin_pad[l] = l == 0 ? 16 : 64; q.cout_pad[l] = l == L ? 16 : 64;
     }
+    k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, st>>>(q);
+    NSIG_LAUNCH_CHECK();
     k_dec_prep_input<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(image, (int)d.n_pix, H16(d.off_x0));
     NSIG_LAUNCH_CHECK();
     const float inv_n = 1.0f / (float)d.n_pix;
@@ -619,6 +666,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
             rc = launch_conv<16, 16, 64, IN_RAW>(p, st);
         } else {
             p.src = H16(d.off_z[l - 1]);
+            p.act_out = H16(d.off_a[l - 1]);   // a_{l-1}, kept for the weight gradient of this layer
             p.bn = BnSrc{D64(d.off_sums[l - 1]), nullptr, params[4 * (l - 1) + 2], params[4 * (l - 1) + 3], inv_n, 64, 64};
             rc = l == L ? launch_conv<64, 64, 8, IN_BNGELU>(p, st) : launch_conv<64, 64, 64, IN_BNGELU>(p, st);
         }
@@ -658,45 +706,42 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
     NSIG_LAUNCH_CHECK();
 
     const __half* da = H16(d.off_da9);
+    const int stat_blocks = n_pix / 64 < 64 ? (n_pix / 64 > 0 ? n_pix / 64 : 1) : 64;
     for (int l = L; l >= 0; --l) {
-        const int stat_blocks = 148;
         BnSrc bn{D64(d.off_sums[l]), D64(d.off_bsums[l]), params[4 * l + 2], params[4 * l + 3], inv_n, l == L ? 8 : 64, l == L ? nb : 64};
         // (1) backward statistics = dbeta, dgamma
         if (l == L) k_dec_bwd_stats<8><<<stat_blocks, kDecThreads, 0, st>>>(da, H16(d.off_z[l]), bn, D64(d.off_bsums[l]), n_pix);
         else k_dec_bwd_stats<64><<<stat_blocks, kDecThreads, 0, st>>>(da, H16(d.off_z[l]), bn, D64(d.off_bsums[l]), n_pix);
         NSIG_LAUNCH_CHECK();
-        // (2) weight / bias gradient
-        WgradParams w{};
-        w.da = da; w.z = H16(d.off_z[l]); w.bn = bn; w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
-        w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
+        // (2) data gradient da_{l-1} = conv(dz_l, rotated weights); the staged dz_l is written out for (3)
+        ConvParams p{};
+        p.B = (int)B; p.H = (int)H; p.W = (int)W;
+        p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = H16(d.off_wr[l]); p.act_out = H16(d.off_dz);
+        __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
+        p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
         int rc;
-        if (l == 0) {
-            w.a_src = H16(d.off_x0);
-            rc = launch_wgrad<16, 64, 64, IN_RAW>(w, st);
-        } else {
-            w.a_src = H16(d.off_z[l - 1]);
-            w.a_bn = BnSrc{D64(d.off_sums[l - 1]), nullptr, params[4 * (l - 1) + 2], params[4 * (l - 1) + 3], inv_n, 64, 64};
-            rc = l == L ? launch_wgrad<64, 16, 8, IN_BNGELU>(w, st) : launch_wgrad<64, 64, 64, IN_BNGELU>(w, st);
-        }
+        if (l == L) rc = launch_conv<16, 8, 64, IN_DZ>(p, st);
+        else if (l == 0) rc = launch_conv<64, 64, 16, IN_DZ>(p, st);
+        else rc = launch_conv<64, 64, 64, IN_DZ>(p, st);
         if (rc) return rc;
-        // (3) data gradient: da_{l-1} = conv(dz_l, rotated weights)
-        if (l > 0 || dimage) {
-            ConvParams p{};
-            p.B = (int)B; p.H = (int)H; p.W = (int)W;
-            p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = H16(d.off_wr[l]); p.bias = nullptr; p.out_sums = nullptr;
-            __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
-            p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
-            if (l == L) rc = launch_conv<16, 8, 64, IN_DZ>(p, st);
-            else if (l == 0) rc = launch_conv<64, 64, 16, IN_DZ>(p, st);
-            else rc = launch_conv<64, 64, 64, IN_DZ>(p, st);
-            if (rc) return rc;
-            da = out;
-        }
+        // (3) weight / bias gradient from the materialised a_{l-1} and dz_l
+        WgradParams w{};
+        w.dz = H16(d.off_dz); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
+        w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
+        w.a = l == 0 ? H16(d.off_x0) : H16(d.off_a[l - 1]);
+        if (l == 0) rc = launch_wgrad<16, 64, 64>(w, st);
+        else if (l == L) rc = launch_wgrad<64, 16, 8>(w, st);
+        else rc = launch_wgrad<64, 64, 64>(w, st);
+        if (rc) return rc;
+        da = out;
     }
-    for (int l = 0; l <= L; ++l) {   // dbeta = sum dy, dgamma = sum dy*yhat: the backward statistics themselves
-        k_dec_bn_grads<<<1, 64, 0, st>>>(D64(d.off_bsums[l]), l == L ? 8 : 64, l == L ? nb : 64, grads[4 * l + 2], grads[4 * l + 3]);
-        NSIG_LAUNCH_CHECK();
+    BnGradParams q{};
+    for (int l = 0; l <= L; ++l) {
+        q.bsums[l] = D64(d.off_bsums[l]); q.dgamma[l] = grads[4 * l + 2]; q.dbeta[l] = grads[4 * l + 3];
+        q.c_pad[l] = l == L ? 8 : 64; q.c_real[l] = l == L ? nb : 64;
     }
+    k_dec_bn_grads<<<L + 1, 64, 0, st>>>(q);
+    NSIG_LAUNCH_CHECK();
     if (dimage) {
         k_dec_input_grad<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(H16(d.off_dx0), n_pix, dimage);
         NSIG_LAUNCH_CHECK();

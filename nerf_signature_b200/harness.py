@@ -110,7 +110,9 @@ class Scene:
         self.fused = optimizer == "fused"
         self.sync = parallel.GradSync()
         self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
-        self.flat_sync = self.fused and self.sync.enabled
+        # one flat [dL/dS | decoder gradients] buffer whenever the fused optimizer is used: a single fill per step
+        # instead of one zeros/add pair per decoder parameter, and the bucket of the multi-GPU exchange
+        self.flat_sync = self.fused
         if self.fused:
             gbuf = None
             if self.flat_sync:  # one flat bucket [dL/dS | decoder grads] -> one all-reduce per step

@@ -108,7 +108,8 @@ class GradSync:
         self.table_numel = table_numel
         o = table_numel
         for p in params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            # same memory layout as the parameter (e.g. channels_last conv weights): torch's fused Adam insists on it
+            p.grad = self.flat[o:o + p.numel()].as_strided(p.shape, p.stride())
             o += p.numel()
         return self.flat[:table_numel]
 

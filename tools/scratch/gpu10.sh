@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python tools/profile_step.py --out gpurun_out/profile_step4.txt > /dev/null 2>&1; head -40 gpurun_out/profile_step4.txt | cut -c1-150
+timeout 600 python -m pytest tests/test_train_step_gpu.py -x -q 2>&1 | grep -v Warning | tail -40
