@@ -46,6 +46,8 @@ def parse():
                          "of one call over their concatenation")
     ap.add_argument("--torch-decoder", action="store_true",
                     help="run the HiDDeN decoder as the plain PyTorch module under autocast instead of the fused kernels")
+    ap.add_argument("--torch-losses", action="store_true",
+                    help="clamp / MSE / BCE / weighting as plain torch expressions instead of the loss-head kernels")
     ap.add_argument("--cpu-rays", type=int, default=0, help="override the CPU sample size (rays per pass)")
     return ap.parse_args()
 
@@ -243,7 +245,8 @@ def run_ours(args):
         cfg["num_rays"] = cfg["num_rays"] // world
     use_graph = (not args.no_graph) and args.optimizer == "fused"
     scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph,
-                          merged_render=not args.split_render, fused_decoder=not args.torch_decoder)
+                          merged_render=not args.split_render, fused_decoder=not args.torch_decoder,
+                          fused_losses=not args.torch_losses)
     md = cfg["message_dim"]
     n_pool = 4  # distinct host batches cycled through (fresh rays every step)
     seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
@@ -397,6 +400,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
                    "decoder": "fused kernels (csrc/decoder.cu)" if scene.fused_decoder else "plain PyTorch module (autocast)",
+                   "losses": "loss-head kernels (csrc/wtmk_loss.cu)" if scene.fused_losses else "plain torch expressions",
                    "parallelism": f"ray-sharded dp{world}", "exchange": scene.sync.exchange},
         "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

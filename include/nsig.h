@@ -103,6 +103,26 @@ int nsig_composite_rays_train_backward(const float* grad_weights_sum, const floa
                                        float* grad_sigmas, float* grad_rgbs,
                                        nsig_stream_t stream);
 
+/* composite_rays_train_forward plus the epilogue NeRFRenderer.run_cuda applies to its outputs in the training
+ * branch (renderer_wtmk.py:298-303), in the same kernel:
+ *     image_out = image + (1 - weights_sum)[:, None] * bg_color      (scalar bg_color)
+ *     depth_out = clamp(depth - nears, min=0) / (fars - nears)
+ * weights_sum / depth / image still receive the raw composite outputs (the backward needs them).
+ * The backward takes the gradient of image_out (and optionally of weights_sum, NULL = none): the background term
+ * contributes -bg_color * sum_c grad_image_out[c] to d/d weights_sum.  depth carries no gradient, as in the
+ * reference (raymarching.py:275). */
+int nsig_composite_rays_train_blend_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                            const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                            float bg_color, const float* nears, const float* fars,
+                                            float* weights_sum, float* depth, float* image,
+                                            float* image_out, float* depth_out, nsig_stream_t stream);
+int nsig_composite_rays_train_blend_backward(const float* grad_weights_sum, const float* grad_image_out,
+                                             const float* sigmas, const float* rgbs, const float* deltas,
+                                             const int32_t* rays, const float* weights_sum,
+                                             const float* image, uint32_t M, uint32_t N, float T_thresh,
+                                             float bg_color, float* grad_sigmas, float* grad_rgbs,
+                                             nsig_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* inference march / composite — raymarching/src/raymarching.h:17-18          */
 /* ------------------------------------------------------------------------- */
@@ -326,6 +346,29 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
 int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
                           uint32_t num_bits, uint32_t redundancy, const float* const* params,
                           float* const* grads, void* workspace, float* dimage, nsig_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* loss head of the watermark training step — nerf/utils_wtmk_disen.py:592-593, 636-644 */
+/* ------------------------------------------------------------------------- */
+
+/* image: the rendered [block rays | content rays] pixels as n_total floats, the first n_block of which belong to the
+ * watermark blocks.  forward: pred = clamp(image[:n_block], 0, 1) (utils_wtmk_disen.py:593), content = image[n_block:].
+ * backward: grad_image = [grad_pred where 0 <= image <= 1 else 0 | grad_content]; a NULL gradient reads as zeros. */
+int nsig_split_clamp_forward(const float* image, uint32_t n_block, uint32_t n_total, float* pred, float* content,
+                             nsig_stream_t stream);
+int nsig_split_clamp_backward(const float* image, const float* grad_pred, const float* grad_content,
+                              uint32_t n_block, uint32_t n_total, float* grad_image, nsig_stream_t stream);
+
+/* lossi = mean((image - gt)^2) over n floats (utils_wtmk_disen.py:636), lossw = mean BCE-with-logits of
+ * logits[md] * temp against message[md] (utils_wtmk_disen.py:441,641), loss = lambda_w*lossw + lambda_i*lossi (:644).
+ * forward writes out[3] = (loss, lossi, lossw) and the gradients of `loss`: g_image[n], g_logits[md];
+ * backward scales them by the device scalar *grad_out (the incoming gradient of `loss`, e.g. the GradScaler's
+ * scale) into d_image / d_logits.  One CTA, no atomics: deterministic. */
+int nsig_wtmk_loss_forward(const float* image, const float* gt, uint32_t n, const float* logits,
+                           const float* message, uint32_t md, float lambda_w, float lambda_i, float temp,
+                           float* out, float* g_image, float* g_logits, nsig_stream_t stream);
+int nsig_wtmk_loss_backward(const float* g_image, const float* g_logits, uint32_t n, uint32_t md,
+                            const float* grad_out, float* d_image, float* d_logits, nsig_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* gradient exchange of the ray-sharded training path (no reference precedent) */

@@ -32,6 +32,14 @@ _SIGNATURES = {
                                             _vp], 1),
     "nsig_march_rays": ([_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp, _vp], 1),
+    "nsig_composite_rays_train_blend_forward": ([_vp, _vp, _vp, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp], 1),
+    "nsig_composite_rays_train_blend_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _f32,
+                                                  _vp, _vp, _vp], 1),
+    "nsig_split_clamp_forward": ([_vp, _u32, _u32, _vp, _vp, _vp], 1),
+    "nsig_split_clamp_backward": ([_vp, _vp, _vp, _u32, _u32, _vp, _vp], 1),
+    "nsig_wtmk_loss_forward": ([_vp, _vp, _u32, _vp, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp, _vp], 1),
+    "nsig_wtmk_loss_backward": ([_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp], 1),
     "nsig_composite_rays": ([_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_hash_encode_forward": ([_vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp, _vp], 1),
     "nsig_hash_encode_backward": ([_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp], 1),
@@ -49,8 +57,12 @@ _SIGNATURES = {
     "nsig_mark_untrained_grid": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f64, _vp, _vp], 1),
     "nsig_get_rays": ([_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _i64, _u32, _vp, _vp, _vp], 1),
     "nsig_allreduce_mean_inplace": ([_vp, _vp, _vp, _u32, _u32, _u32, _vp], 1),
-    "nsig_decoder_forward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp], 1),
-    "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp], 1),
+    # kernels per call as a function of the arguments (args[4] = num_blocks): weight prep, input prep, num_blocks+1
+    # convs, head / head, last-block statistics, num_blocks+1 data-gradient convs and weight-gradient kernels,
+    # BatchNorm parameter gradients, input gradient
+    "nsig_decoder_forward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp], lambda a: a[4] + 4),
+    "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+                              lambda a: 2 * (a[4] + 1) + 3 + (1 if a[10] is not None else 0)),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
@@ -176,7 +188,27 @@ def call(name, *args):
         if rc == -1:
             raise NsigError(f"{name}: invalid argument (NSIG_EINVAL)")
         raise NsigError(f"{name}: CUDA error {rc}")
-    launch_count += _SIGNATURES[name][1]
+    n = _SIGNATURES[name][1]
+    launch_count += n(args) if callable(n) else n
+
+
+_side_streams = {}
+
+
+def side_stream(device=None, which=0):
+    """A per-device auxiliary torch stream for work that is independent of the main launch chain (the message-table
+    sum next to the march, the decoder's Adam next to the message-table Adam).  Fork with
+    `s.wait_stream(torch.cuda.current_stream())`, join with `torch.cuda.current_stream().wait_stream(s)`; inside a
+    CUDA-graph capture the pair becomes a parallel branch of the graph.  NSIG_NO_SIDE_STREAMS=1 returns None."""
+    if os.environ.get("NSIG_NO_SIDE_STREAMS") == "1":
+        return None
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    key = (dev, which)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def pointer_array(tensors):

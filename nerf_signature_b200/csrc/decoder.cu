@@ -22,6 +22,9 @@
 // shape: 3x3 convs, `channels` = 64, num_bits*redundancy <= 8, BatchNorm eps 1e-3, exact (erf) GELU.
 #include "nsig_common.cuh"
 
+#include <cstdlib>
+#include <mutex>
+
 namespace nsig {
 
 constexpr int kDecThreads = 256;
@@ -154,6 +157,12 @@ struct ConvParams {
     __half* act_out;       // optional [B,H,W,SCH]: the transformed input (a_{l-1} forward, dz_l backward) is written
                            // here once, by the CTA that owns the rows, for the weight-gradient kernel
     double* out_sums;      // [2][COUT] or null: += sum / sum of squares of the (fp16-rounded) outputs
+    // data-gradient convs only: the outputs are da of the PREVIOUS layer; with z_out / bn_out of that layer the epilogue
+    // also accumulates its backward statistics out_bsums[0][c] += sum dy, [1][c] += sum dy*yhat (dy = da*GELU'(BN(z))),
+    // which is everything k_dec_bwd_stats would compute in a separate pass over da and z
+    const __half* z_out;   // [B,H,W,COUT] or null
+    BnSrc bn_out;
+    double* out_bsums;     // [2][COUT] or null
     int B, H, W, R;        // R = image rows per CTA
     int cout_valid;        // outputs >= cout_valid are written as zero (channel padding)
 };
@@ -171,11 +180,15 @@ k_dec_conv(const ConvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* tile = reinterpret_cast<__half*>(smem_raw);                      // [(R+2)*(W+2)][STRIDE]
     BnCoef* coef = reinterpret_cast<BnCoef*>(tile + (size_t)(p.R + 2) * (p.W + 2) * STRIDE);
+    BnCoef* coef_out = coef + CIN;                                           // [COUT], data-gradient convs with out_bsums
     const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
 
     if (MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
+        if (bstats)
+            for (int ch = threadIdx.x; ch < COUT; ch += blockDim.x) coef_out[ch] = bn_coef(p.bn_out, ch, false);
         __syncthreads();
     }
     stage_tile<CIN, SCH, MODE>(tile, p.src, p.src2, coef, b, r0, R, p.H, p.W);
@@ -237,21 +250,37 @@ k_dec_conv(const ConvParams p) {
                     __half o0 = f2h(c[m][2 * h] + bias0), o1 = f2h(c[m][2 * h + 1] + bias1);
                     if (col >= p.cout_valid) o0 = f2h(0.f);
                     if (col + 1 >= p.cout_valid) o1 = f2h(0.f);
-                    *reinterpret_cast<__half2*>(p.dst + (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col) = __halves2half2(o0, o1);
-                    const float f0 = h2f(o0), f1 = h2f(o1);
-                    l1[0] += f0; l1[1] += f1; l2[0] += f0 * f0; l2[1] += f1 * f1;
+                    const size_t oidx = (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col;
+                    *reinterpret_cast<__half2*>(p.dst + oidx) = __halves2half2(o0, o1);
+                    if (bstats) {   // backward statistics of the layer whose da this is (same arithmetic as k_dec_bwd_stats)
+                        const __half2 zz = *reinterpret_cast<const __half2*>(p.z_out + oidx);
+                        const __half zh[2] = {__low2half(zz), __high2half(zz)}, dh[2] = {o0, o1};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const BnCoef& co = coef_out[col + e];
+                            const float zf = h2f(zh[e]);
+                            const __half y = f2h(fmaf(zf, co.scale, co.shift));
+                            const float dy = h2f(f2h(h2f(dh[e]) * gelu_grad_f(h2f(y))));
+                            l1[e] += dy;
+                            l2[e] += dy * ((zf - co.mean) * co.rstd);
+                        }
+                    } else {
+                        const float f0 = h2f(o0), f1 = h2f(o1);
+                        l1[0] += f0; l1[1] += f1; l2[0] += f0 * f0; l2[1] += f1 * f1;
+                    }
                 }
             }
         }
-        if (p.out_sums) {
+        double* const sums_dst = bstats ? p.out_bsums : p.out_sums;
+        if (sums_dst) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 float a1 = l1[e], a2 = l2[e];
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) { a1 += __shfl_xor_sync(NSIG_FULL_MASK, a1, o); a2 += __shfl_xor_sync(NSIG_FULL_MASK, a2, o); }
                 if (g == 0 && col + e < p.cout_valid) {
-                    atomicAdd(p.out_sums + col + e, (double)a1);
-                    atomicAdd(p.out_sums + COUT + col + e, (double)a2);
+                    atomicAdd(sums_dst + col + e, (double)a1);
+                    atomicAdd(sums_dst + COUT + col + e, (double)a2);
                 }
             }
         }
@@ -341,7 +370,8 @@ k_dec_wgrad(const WgradParams p) {
     float c[PER_WARP][4];
 #pragma unroll
     for (int j = 0; j < PER_WARP; ++j) { c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f; }
-    float dbias = 0.f;
+    float dbias = 0.f;   // centre-tap CTAs: thread (co = tid % 64, part = tid / 64) sums every 4th pixel of column co of dz
+    const int bco = threadIdx.x & 63, bpart = threadIdx.x >> 6;
 
     for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
         for (int r0 = 0; r0 < p.H; r0 += p.R) {
@@ -365,8 +395,8 @@ k_dec_wgrad(const WgradParams p) {
                 *reinterpret_cast<uint4*>(dtile + (size_t)pix * DSTR + ck * 8) = v;
             }
             __syncthreads();
-            if (t == 4 && threadIdx.x < p.cout_real) {  // bias gradient: column sums of dz (centre-tap CTAs only)
-                for (int pix = 0; pix < P; ++pix) dbias += h2f(dtile[(size_t)pix * DSTR + threadIdx.x]);
+            if (t == 4 && bco < p.cout_real) {  // bias gradient: column sums of dz (centre-tap CTAs only)
+                for (int pix = bpart; pix < P; pix += kDecThreads / 64) dbias += h2f(dtile[(size_t)pix * DSTR + bco]);
             }
             if (active) {
                 for (int k0 = 0; k0 < Ppad; k0 += 16) {
@@ -382,7 +412,7 @@ k_dec_wgrad(const WgradParams p) {
             }
         }
     }
-    if (t == 4 && threadIdx.x < p.cout_real) atomicAdd(p.db + threadIdx.x, dbias);
+    if (t == 4 && bco < p.cout_real) atomicAdd(p.db + bco, dbias);
     if (active) {
 #pragma unroll
         for (int j = 0; j < NT_PER; ++j)
@@ -543,7 +573,7 @@ constexpr int kMaxLayers = 16;
 struct DecLayout {
     int B, H, W, L;            // L = number of 64-channel conv blocks (num_blocks); block L is the nb-channel one
     size_t n_pix;
-    size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz, off_da9, off_dx0, off_pooled;
+    size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz[kMaxLayers + 1], off_da9, off_dx0, off_pooled;
     size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_sums[kMaxLayers + 1], off_bsums[kMaxLayers + 1];
     size_t off_sums_begin, sums_bytes, total;
 };
@@ -560,7 +590,8 @@ DecLayout make_layout(int B, int H, int W, int L) {
     d.off_z[L] = o; o = align_up(o + d.n_pix * 8 * 2);
     for (int l = 0; l < L; ++l) { d.off_a[l] = o; o = align_up(o + d.n_pix * 64 * 2); }   // a_l = GELU(BN(z_l)), l < L
     for (int k = 0; k < 2; ++k) { d.off_da[k] = o; o = align_up(o + d.n_pix * 64 * 2); }
-    d.off_dz = o; o = align_up(o + d.n_pix * 64 * 2);
+    // dz_l per layer: the weight-gradient kernels run on a side stream while the data-gradient chain goes on
+    for (int l = 0; l <= L; ++l) { d.off_dz[l] = o; o = align_up(o + d.n_pix * (l == L ? 8 : 64) * 2); }
     d.off_da9 = o; o = align_up(o + d.n_pix * 8 * 2);
     d.off_dx0 = o; o = align_up(o + d.n_pix * 16 * 2);
     d.off_pooled = o; o = align_up(o + (size_t)B * 8 * 2);
@@ -598,7 +629,7 @@ int wgrad_rows(int H, int W, int cin, int cout) {
 template <int CIN, int SCH, int COUT, int MODE>
 int launch_conv(ConvParams p, cudaStream_t st) {
     p.R = conv_rows(p.B, p.H, p.W);
-    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + CIN * sizeof(BnCoef);
+    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + (size_t)(CIN + COUT) * sizeof(BnCoef);
     if (smem > 200 * 1024) return NSIG_EINVAL;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_conv<CIN, SCH, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
@@ -614,10 +645,40 @@ int launch_wgrad(WgradParams p, cudaStream_t st) {
     const size_t smem = (size_t)((p.R * p.W + 15) / 16 * 16) * (CIN + 8 + COUT + 8) * 2;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    const int G = p.B < 16 ? p.B : 16;
+    static const int g_max = [] { const char* e = getenv("NSIG_DEC_WGRAD_G"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    const int G = p.B < g_max ? p.B : g_max;   // image groups: 9*G CTAs, each adds its [COUT x CIN] partial with atomics
     k_dec_wgrad<CIN, COUT, DCH><<<dim3(9, G), kDecThreads, smem, st>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
+}
+
+// Side stream of the backward chain.  The data-gradient convs form a dependent chain (layer l needs the statistics of
+// da_l); the weight gradient of layer l only needs a_{l-1} (forward) and dz_l (written by the data-gradient conv of
+// layer l), and nothing downstream of it but the optimizer.  It is launched on a second stream that forks from the
+// caller's stream after that conv and joins it at the end of the call: in a stream capture this becomes a parallel
+// branch of the graph, eagerly the kernels simply overlap (neither chain fills the 148 SMs).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[kMaxLayers + 1] = {};
+    cudaEvent_t join = nullptr;
+    bool ok = false;
+};
+std::mutex g_side_mutex;   // one backward launch chain at a time: the fork/join events are shared per device
+
+SideStream* side_stream_for_current_device() {
+    static SideStream side[64];
+    static const bool disabled = [] { const char* e = getenv("NSIG_DEC_NO_SIDE"); return e && e[0] == '1'; }();
+    int dev = 0;
+    if (disabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = side[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int l = 0; l <= kMaxLayers; ++l)
+            if (cudaEventCreateWithFlags(&s.fork[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
 }
 
 }  // namespace
@@ -705,35 +766,56 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
     k_dec_head_bwd<<<B, 256, 0, st>>>(h);
     NSIG_LAUNCH_CHECK();
 
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream* side = side_stream_for_current_device();
     const __half* da = H16(d.off_da9);
     const int stat_blocks = n_pix / 64 < 64 ? (n_pix / 64 > 0 ? n_pix / 64 : 1) : 64;
     for (int l = L; l >= 0; --l) {
         BnSrc bn{D64(d.off_sums[l]), D64(d.off_bsums[l]), params[4 * l + 2], params[4 * l + 3], inv_n, l == L ? 8 : 64, l == L ? nb : 64};
-        // (1) backward statistics = dbeta, dgamma
-        if (l == L) k_dec_bwd_stats<8><<<stat_blocks, kDecThreads, 0, st>>>(da, H16(d.off_z[l]), bn, D64(d.off_bsums[l]), n_pix);
-        else k_dec_bwd_stats<64><<<stat_blocks, kDecThreads, 0, st>>>(da, H16(d.off_z[l]), bn, D64(d.off_bsums[l]), n_pix);
-        NSIG_LAUNCH_CHECK();
+        // (1) backward statistics = dbeta, dgamma.  Only the last block needs a pass of its own (its da comes from the
+        //     head); for every other layer the data-gradient conv that produced da_l accumulated them in its epilogue.
+        if (l == L) {
+            k_dec_bwd_stats<8><<<stat_blocks, kDecThreads, 0, st>>>(da, H16(d.off_z[l]), bn, D64(d.off_bsums[l]), n_pix);
+            NSIG_LAUNCH_CHECK();
+        }
         // (2) data gradient da_{l-1} = conv(dz_l, rotated weights); the staged dz_l is written out for (3)
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
-        p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = H16(d.off_wr[l]); p.act_out = H16(d.off_dz);
+        p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = H16(d.off_wr[l]); p.act_out = H16(d.off_dz[l]);
         __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
         p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
+        if (l > 0) {   // outputs are da_{l-1}: accumulate layer l-1's backward statistics on the way out
+            p.z_out = H16(d.off_z[l - 1]);
+            p.bn_out = BnSrc{D64(d.off_sums[l - 1]), nullptr, params[4 * (l - 1) + 2], params[4 * (l - 1) + 3], inv_n, 64, 64};
+            p.out_bsums = D64(d.off_bsums[l - 1]);
+        }
         int rc;
         if (l == L) rc = launch_conv<16, 8, 64, IN_DZ>(p, st);
         else if (l == 0) rc = launch_conv<64, 64, 16, IN_DZ>(p, st);
         else rc = launch_conv<64, 64, 64, IN_DZ>(p, st);
         if (rc) return rc;
-        // (3) weight / bias gradient from the materialised a_{l-1} and dz_l
+        // (3) weight / bias gradient from the materialised a_{l-1} and dz_l, on the side stream
+        cudaStream_t wst = st;
+        if (side) {
+            cudaError_t e = cudaEventRecord(side->fork[l], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork[l], 0);
+            if (e != cudaSuccess) return (int)e;
+            wst = side->stream;
+        }
         WgradParams w{};
-        w.dz = H16(d.off_dz); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
+        w.dz = H16(d.off_dz[l]); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
         w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
         w.a = l == 0 ? H16(d.off_x0) : H16(d.off_a[l - 1]);
-        if (l == 0) rc = launch_wgrad<16, 64, 64>(w, st);
-        else if (l == L) rc = launch_wgrad<64, 16, 8>(w, st);
-        else rc = launch_wgrad<64, 64, 64>(w, st);
+        if (l == 0) rc = launch_wgrad<16, 64, 64>(w, wst);
+        else if (l == L) rc = launch_wgrad<64, 16, 8>(w, wst);
+        else rc = launch_wgrad<64, 64, 64>(w, wst);
         if (rc) return rc;
         da = out;
+    }
+    if (side) {
+        cudaError_t e = cudaEventRecord(side->join, side->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
+        if (e != cudaSuccess) return (int)e;
     }
     BnGradParams q{};
     for (int l = 0; l <= L; ++l) {

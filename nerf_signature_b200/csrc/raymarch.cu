@@ -245,12 +245,33 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_ali
 // ---------------------------------------------------------------------------------------
 constexpr int kCompWarps = 8;
 
+// Optional epilogue of run_cuda's training branch (renderer_wtmk.py:298-303), one rounded fp32 op per torch op:
+//   image = image + (1 - weights_sum)[:, None] * bg_color        (scalar bg_color)
+//   depth = clamp(depth - nears, min=0) / (fars - nears)
+struct CompositeBlend {
+    float* image_out;      // [N,3] or null (no epilogue)
+    float* depth_out;      // [N]
+    const float* nears;    // [N]
+    const float* fars;     // [N]
+    float bg;
+};
+
+__device__ __forceinline__ void blend_outputs(const CompositeBlend& bl, uint32_t index, float ws, float d, float r,
+                                              float g, float b) {
+    const float k = __fmul_rn(__fsub_rn(1.0f, ws), bl.bg);
+    bl.image_out[index * 3] = __fadd_rn(r, k);
+    bl.image_out[index * 3 + 1] = __fadd_rn(g, k);
+    bl.image_out[index * 3 + 2] = __fadd_rn(b, k);
+    const float near = bl.nears[index], far = bl.fars[index];
+    bl.depth_out[index] = __fdiv_rn(fmaxf(__fsub_rn(d, near), 0.0f), __fsub_rn(far, near));
+}
+
 
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                       const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M,
                       uint32_t N, float T_thresh, float* __restrict__ weights_sum,
-                      float* __restrict__ depth, float* __restrict__ image) {
+                      float* __restrict__ depth, float* __restrict__ image, CompositeBlend bl) {
     const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5);
     if (n >= N) return;
     const int lane = threadIdx.x & 31;
@@ -260,6 +281,7 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
         if (lane == 0) {
             weights_sum[index] = 0; depth[index] = 0;
             image[index * 3] = 0; image[index * 3 + 1] = 0; image[index * 3 + 2] = 0;
+            if (bl.image_out) blend_outputs(bl, index, 0.f, 0.f, 0.f, 0.f, 0.f);
         }
         return;
     }
@@ -294,6 +316,7 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     if (lane == 0) {
         weights_sum[index] = ws; depth[index] = d;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+        if (bl.image_out) blend_outputs(bl, index, ws, d, r, g, b);
     }
 }
 
@@ -306,15 +329,16 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
                       const float* __restrict__ deltas, const int* __restrict__ rays,
                       const float* __restrict__ weights_sum, const float* __restrict__ image,
                       uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas,
-                      float* __restrict__ grad_rgbs) {
+                      float* __restrict__ grad_rgbs, float blend_bg) {
     const uint32_t n = blockIdx.x * kCompWarps + (threadIdx.x >> 5);
     if (n >= N) return;
     const int lane = threadIdx.x & 31;
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1],
                    num_steps = (uint32_t)rays[n * 3 + 2];
     if (num_steps == 0 || offset + num_steps > M) return;
-    const float gws = grad_weights_sum[index];
     const float gr = grad_image[index * 3], gg = grad_image[index * 3 + 1], gb = grad_image[index * 3 + 2];
+    // with the fused background blend grad_image is the gradient of image + (1 - ws) * bg: d/d ws gains -bg * sum(grad)
+    const float gws = (grad_weights_sum ? grad_weights_sum[index] : 0.0f) - blend_bg * (gr + gg + gb);
     const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
     const float ws_term = gws * (1.0f - weights_sum[index]);
     float T = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f;  // state before the chunk
@@ -494,7 +518,38 @@ int nsig_composite_rays_train_forward(const float* sigmas, const float* rgbs, co
     if (N == 0) return 0;
     if (!sigmas || !rgbs || !deltas || !rays || !weights_sum || !depth || !image) return NSIG_EINVAL;
     k_composite_train_fwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
-        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image, CompositeBlend{});
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_composite_rays_train_blend_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                            const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                            float bg_color, const float* nears, const float* fars,
+                                            float* weights_sum, float* depth, float* image, float* image_out,
+                                            float* depth_out, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!sigmas || !rgbs || !deltas || !rays || !weights_sum || !depth || !image || !nears || !fars || !image_out ||
+        !depth_out)
+        return NSIG_EINVAL;
+    k_composite_train_fwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
+        CompositeBlend{image_out, depth_out, nears, fars, bg_color});
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_composite_rays_train_blend_backward(const float* grad_weights_sum, const float* grad_image_out,
+                                             const float* sigmas, const float* rgbs, const float* deltas,
+                                             const int32_t* rays, const float* weights_sum, const float* image,
+                                             uint32_t M, uint32_t N, float T_thresh, float bg_color,
+                                             float* grad_sigmas, float* grad_rgbs, nsig_stream_t stream) {
+    if (N == 0) return 0;
+    if (!grad_image_out || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image || !grad_sigmas || !grad_rgbs)
+        return NSIG_EINVAL;
+    k_composite_train_bwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        grad_weights_sum, grad_image_out, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh,
+        grad_sigmas, grad_rgbs, bg_color);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -510,7 +565,7 @@ int nsig_composite_rays_train_backward(const float* grad_weights_sum, const floa
         return NSIG_EINVAL;
     k_composite_train_bwd<<<div_up(N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh,
-        grad_sigmas, grad_rgbs);
+        grad_sigmas, grad_rgbs, 0.0f);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

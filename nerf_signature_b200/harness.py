@@ -79,11 +79,13 @@ class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
-                 merged_render=False, fused_decoder=False):
+                 merged_render=False, fused_decoder=False, fused_losses=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
-        in one CUDA graph on first use; needs optimizer="fused"."""
+        in one CUDA graph on first use; needs optimizer="fused".
+        fused_losses: clamp / MSE / BCE / weighting through the loss-head kernels (nerf/loss_ops.py) instead of the
+        plain torch expressions of utils_wtmk_disen.py:593,636-644."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
         from .optim import WatermarkAdam
         torch.manual_seed(seed)
@@ -129,6 +131,7 @@ class Scene:
         self.use_graph = graph
         self.merged_render = merged_render  # one render call over [block rays | content rays] instead of two
         self.fused_decoder = fused_decoder and fp16  # the kernels implement the float16-autocast arithmetic
+        self.fused_losses = fused_losses
         self.iteration = 0
         self._graph = None
         self._static = None
@@ -163,19 +166,31 @@ class Scene:
         if self.fused:
             self.optimizer.set_message(msg_dev)
             message = msg_dev
+        from .nerf.loss_ops import split_clamp, wtmk_loss
+        ob = batch["rays_o_block"]
+        nb = ob.numel() // 3
         if self.merged_render:
             # the two render passes of the reference step (utils_wtmk_disen.py:592,641) see the same network and the
             # same message and rays are independent: one launch chain over [block rays | content rays]
-            ob, db = batch["rays_o_block"], batch["rays_d_block"]
-            nb = ob.numel() // 3
-            out = model.render(torch.cat([ob.reshape(1, nb, 3), batch["rays_o"]], dim=1),
-                               torch.cat([db.reshape(1, nb, 3), batch["rays_d"]], dim=1), message, staged=False,
-                               bg_color=1, perturb=False, force_all_rays=True, **self.opt)
-            image_w, image_c = out["image"][0, :nb].reshape(ob.shape), out["image"][:, nb:]
+            if "rays_o_all" in batch:   # static buffers of the captured step: already concatenated
+                o_all, d_all = batch["rays_o_all"], batch["rays_d_all"]
+            else:
+                o_all = torch.cat([ob.reshape(1, nb, 3), batch["rays_o"]], dim=1)
+                d_all = torch.cat([batch["rays_d_block"].reshape(1, nb, 3), batch["rays_d"]], dim=1)
+            out = model.render(o_all, d_all, message, staged=False, bg_color=1, perturb=False, force_all_rays=True,
+                               **self.opt)
+            if self.fused_losses:
+                pred, image_c = split_clamp(out["image"], nb)
+                pred, image_c = pred.view(ob.shape), image_c.view(batch["rays_o"].shape)
+            else:
+                image_w, image_c = out["image"][0, :nb].reshape(ob.shape), out["image"][:, nb:]
         else:
             image_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
                                    perturb=False, force_all_rays=True, **self.opt)["image"]
-        pred = torch.clamp(image_w, min=0, max=1)
+            if self.fused_losses:
+                pred = split_clamp(image_w, nb)[0].view(ob.shape)
+        if not self.fused_losses:
+            pred = torch.clamp(image_w, min=0, max=1)
         if self.fused_decoder:   # normalisation + HiDDeN decoder forward/backward as tensor-core kernels (csrc/decoder.cu)
             decoded = model.decode_blocks(pred)
         else:                    # utils_wtmk_disen.py:592-595 verbatim: the plain module under autocast
@@ -184,9 +199,12 @@ class Scene:
         if not self.merged_render:
             image_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
                                    perturb=False, force_all_rays=True, **self.opt)["image"]
-        lossi = F.mse_loss(image_c, batch["gt"], reduction="none").mean()
-        lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
-        loss = self.lambda_w * lossw + self.lambda_i * lossi
+        if self.fused_losses:
+            loss, lossi, lossw = wtmk_loss(image_c, batch["gt"], decoded, msg_dev, self.lambda_w, self.lambda_i, 10.0)
+        else:
+            lossi = F.mse_loss(image_c, batch["gt"], reduction="none").mean()
+            lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
+            loss = self.lambda_w * lossw + self.lambda_i * lossi
         self.scaler.scale(loss).backward()
         if self.flat_sync:
             self.sync.reduce_flat()
@@ -201,9 +219,16 @@ class Scene:
         from . import _lib
         self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in batch.items()}
         self._static["message"] = torch.empty(self.cfg["message_dim"], dtype=torch.float32, device=self.device)
-        for k, v in batch.items():
-            self._static[k].copy_(v)
-        self._static["message"].copy_(message)
+        if self.merged_render:
+            # [block rays | content rays] live concatenated in the static buffers; the per-key entries are views of them,
+            # so the input copies of a replay land in place and the captured step needs no torch.cat
+            nb, nc = batch["rays_o_block"].numel() // 3, batch["rays_o"].numel() // 3
+            for a in ("o", "d"):
+                full = torch.empty(1, nb + nc, 3, dtype=torch.float32, device=self.device)
+                self._static[f"rays_{a}_all"] = full
+                self._static[f"rays_{a}_block"] = full[0, :nb].view(batch[f"rays_{a}_block"].shape)
+                self._static[f"rays_{a}"] = full[:, nb:].view(batch[f"rays_{a}"].shape)
+        self._copy_inputs(batch, message)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -220,6 +245,11 @@ class Scene:
         ls = self.model.local_step
         n_calls = 1 if self.merged_render else 2
         self._graph_rows = [(ls - k) % 16 for k in range(n_calls, 0, -1)]  # the march counters baked into the graph
+
+    def _copy_inputs(self, batch, message):
+        for k, v in batch.items():
+            self._static[k].copy_(v, non_blocking=True)
+        self._static["message"].copy_(message, non_blocking=True)
 
     def train_step(self, batch, message):
         """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here).  Configs with
@@ -238,9 +268,7 @@ class Scene:
             return self._step_impl(batch, message)
         if self._graph is None:
             self._capture(batch, message)
-        for k, v in batch.items():
-            self._static[k].copy_(v, non_blocking=True)
-        self._static["message"].copy_(message, non_blocking=True)
+        self._copy_inputs(batch, message)
         self._graph.replay()
         return self._static_out
 

@@ -72,13 +72,17 @@ class _msg_table_sum_sink(Function):
         _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S))
         ctx.sink = sink
         ctx.n = len(tables)
+        # the fused field backward scatter-adds dL/dS straight into `sink` (FieldConfig.S_sink) and returns no gradient
+        # for S: this node then receives None, which must NOT be materialised as zeros and copied over the sink
+        ctx.set_materialize_grads(False)
         return S
 
     @staticmethod
     def backward(ctx, grad_S):
-        if grad_reducer is not None:
-            grad_S = grad_reducer(grad_S)
-        ctx.sink.copy_(grad_S)
+        if grad_S is not None:  # a consumer that returned dL/dS the ordinary way (e.g. the stand-alone encoder)
+            if grad_reducer is not None:
+                grad_S = grad_reducer(grad_S)
+            ctx.sink.add_(grad_S)
         return (None, None, None) + (None,) * ctx.n
 
 

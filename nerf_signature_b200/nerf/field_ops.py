@@ -85,8 +85,11 @@ class SHEncoding(nn.Module):
 class FieldConfig:
     """Everything the field kernels need besides tensors."""
 
-    def __init__(self, bound, resolutions, log2_T, msg_resolution, density_scale=1.0, shadow=None):
+    def __init__(self, bound, resolutions, log2_T, msg_resolution, density_scale=1.0, shadow=None, S_sink=None):
         self.shadow = shadow  # hash_encoding.HalfTables or None (gather the fp32 tables)
+        # persistent [T,2] fp32 buffer that accumulates dL/dS directly (optim.WatermarkAdam's G, zeroed by its
+        # zero_grad): the backward kernel scatter-adds into it and no gradient is returned for S
+        self.S_sink = S_sink
         self.bound = float(bound)
         self.resolutions = list(resolutions)
         self.log2_T = int(log2_T)
@@ -154,7 +157,8 @@ class _field_forward(Function):
         need_S = ctx.S_shape is not None and ctx.needs_input_grad[2]
         need_w = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
         need_tab = ctx.needs_input_grad[_field_forward.N_FIXED:]
-        G = torch.zeros(ctx.S_shape, dtype=torch.float32, device=dev) if need_S else None
+        direct = need_S and cfg.S_sink is not None
+        G = cfg.S_sink if direct else (torch.zeros(ctx.S_shape, dtype=torch.float32, device=dev) if need_S else None)
         # rows past the live count are not written by the kernel: start from zeros in that case
         alloc = torch.zeros if ctx.count is not None else torch.empty
         grad_feat = alloc(M, 32, dtype=torch.float32, device=dev) if any(need_tab) else None
@@ -170,7 +174,7 @@ class _field_forward(Function):
             _lib.call("nsig_hash_encode_backward", _P(xn.contiguous()), _P(grad_feat.contiguous()), M,
                       _lib.pointer_array(gt), _lib.float_array(cfg.resolutions), len(gt), cfg.log2_T)
             tab_grads = [g if n else None for g, n in zip(gt, need_tab)]
-        return (None, None, G, None, None, None, None,
+        return (None, None, None if direct else G, None, None, None, None,
                 gsw if ctx.needs_input_grad[7] else None, gcw if ctx.needs_input_grad[8] else None) + tuple(tab_grads)
 
 

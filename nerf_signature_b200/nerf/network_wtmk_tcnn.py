@@ -7,6 +7,8 @@ decoder trainable; `finetune_decoder` also freezes the message tables), same
 forward / density / color / get_params.  tiny-cuda-nn is replaced by the fused sm_100a kernels in
 csrc/field.cu; the per-bit message encoder runs in its pre-summed form (hash_encoding_wtmk_bit.py).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -15,6 +17,8 @@ from .field_ops import FusedMLP, SHEncoding, FieldConfig, field_forward, field_d
 from .hidden_models import get_hidden_decoder_multi_views, normalize_img
 from ..hash_encoding import HashEmbedder
 from ..hash_encoding_wtmk_bit import HashEmbedder as HashEmbedder_msg, message_bits
+from .. import hash_encoding_wtmk_bit as _hmsg
+from .. import _lib
 
 
 class NeRFNetwork(NeRFRenderer):
@@ -74,8 +78,10 @@ class NeRFNetwork(NeRFRenderer):
     # ---- helpers -----------------------------------------------------------------------------
     def _cfg(self, density_scale=1.0):
         shadow = self.encoder.half_tables() if self.half2_tables else None
+        sink = self.msg_encoder.grad_sink if (torch.is_grad_enabled() and _hmsg.grad_reducer is None
+                                              and os.environ.get("NSIG_NO_DIRECT_SINK") != "1") else None
         return FieldConfig(self.bound, self.encoder.resolutions, self.encoder.log2_hashmap_size,
-                           self.msg_encoder.resolution, density_scale, shadow)
+                           self.msg_encoder.resolution, density_scale, shadow, sink)
 
     def _summed_table(self, message):
         """S for this message; cached across the two render passes of a training step (keyed on the
@@ -92,8 +98,30 @@ class NeRFNetwork(NeRFRenderer):
         self._S_cache = (key, S, message)  # keep `message` alive so id() stays unique
         return S
 
+    def prefetch_summed_table(self, message):
+        """renderer hook, called before the march: start the table sum (message_dim x 4 MiB streamed, independent of the
+        rays) on a side stream so it overlaps the march kernels; `field` joins the stream before the first use of S."""
+        if message is None or not message.is_cuda:
+            return
+        side = _lib.side_stream(message.device)
+        if side is None:
+            return
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            S = self._summed_table(message)
+        S.record_stream(cur)
+        self._S_pending = side
+
+    def _join_prefetch(self):
+        side = getattr(self, "_S_pending", None)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            self._S_pending = None
+
     def field(self, xyzs, dirs, message, count=None):
         """renderer hook: (density_scale * sigma, rgb), fused."""
+        self._join_prefetch()
         return field_forward(xyzs, dirs, self._summed_table(message), count, self._cfg(self.density_scale),
                              self.sigma_net, self.color_net, self.encoder.tables())
 

@@ -106,6 +106,9 @@ class NeRFRenderer(nn.Module):
         # inference branch of run_cuda: one persistent kernel per call (True) or the reference's host-driven
         # march_rays / composite_rays loop (False; kept for parity tests and API fidelity)
         self.fused_inference = True
+        # training branch of run_cuda: fold `image + (1 - weights_sum) * bg_color` and the depth normalisation into the
+        # composite kernels when bg_color is a scalar (NSIG_TORCH_EPILOGUE=1 keeps the element-wise torch ops)
+        self.fused_epilogue = os.environ.get("NSIG_TORCH_EPILOGUE", "0") != "1"
         self.last_render_samples = None
 
     def forward(self, x, d):
@@ -259,6 +262,8 @@ class NeRFRenderer(nn.Module):
         results = {}
 
         if self.training:
+            if message is not None and hasattr(self, "prefetch_summed_table"):
+                self.prefetch_summed_table(message)  # the table sum overlaps the march (side stream)
             counter = self.step_counter[self.local_step % 16]
             counter.zero_()
             self.local_step += 1
@@ -269,11 +274,16 @@ class NeRFRenderer(nn.Module):
             sigmas, rgbs = self.field(xyzs, dirs, message, count=counter)
 
             # worst-case sized buffers cannot overflow, so every live row is owned by a ray: skip the gradient zero-fill
-            composite = raymarching.raymarching.composite_rays_train_live if xyzs.shape[0] == N * max_steps \
-                else raymarching.composite_rays_train
-            weights_sum, depth, image = composite(sigmas, rgbs, deltas, rays, T_thresh)
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-            depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            live = xyzs.shape[0] == N * max_steps
+            if isinstance(bg_color, (int, float)) and self.fused_epilogue:
+                # composite + background blend + depth normalisation in one kernel (same fp32 operations)
+                weights_sum, depth, image = raymarching.raymarching.composite_rays_train_blend(
+                    sigmas, rgbs, deltas, rays, nears, fars, float(bg_color), T_thresh, not live)
+            else:
+                composite = raymarching.raymarching.composite_rays_train_live if live else raymarching.composite_rays_train
+                weights_sum, depth, image = composite(sigmas, rgbs, deltas, rays, T_thresh)
+                image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
             image = image.view(*prefix, 3)
             depth = depth.view(*prefix)
 

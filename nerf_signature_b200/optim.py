@@ -70,7 +70,8 @@ class WatermarkAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         if self.inner is not None:
             self.inner.zero_grad(set_to_none=set_to_none)
-        # G is overwritten (copy_) by every backward; the proxy keeps pointing at it
+        # the field backward ACCUMULATES dL/dS into G (FieldConfig.S_sink); the proxy keeps pointing at it
+        self.G.zero_()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -78,12 +79,20 @@ class WatermarkAdam(torch.optim.Optimizer):
             raise NotImplementedError("closures are not supported")
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
+        side = None
         if self.inner is not None:
             for g_out, g_in in zip(self.param_groups, self.inner.param_groups):
                 g_in["lr"] = g_out["lr"]  # lr schedulers act on the outer groups
             self.inner.grad_scale, self.inner.found_inf = grad_scale, found_inf
+            # the decoder's (tiny, latency-bound) Adam runs next to the HBM-bound message-table Adam
+            side = _lib.side_stream(self.G.device, 1) if self._train_tables else None
             try:
-                self.inner.step()
+                if side is not None:
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        self.inner.step()
+                else:
+                    self.inner.step()
             finally:
                 del self.inner.grad_scale, self.inner.found_inf
         if self._train_tables:
@@ -100,4 +109,6 @@ class WatermarkAdam(torch.optim.Optimizer):
             # the kernel writes the tables through raw pointers (no autograd version bump): drop the model's
             # cached S so the next forward re-sums the updated tables
             self._model._S_cache = None
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         return None

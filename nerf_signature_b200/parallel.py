@@ -114,7 +114,7 @@ class GradSync:
         return self.flat[:table_numel]
 
     def zero_flat(self):
-        self.flat[self.table_numel:].zero_()  # dL/dS is overwritten (copy_) by backward, the rest accumulates
+        self.flat.zero_()  # one fill: dL/dS (scatter-added by the field backward) and the decoder gradients both accumulate
 
     def reduce_flat(self):
         if not self.enabled or os.environ.get("NSIG_DIAG_SKIP_REDUCE") == "1":  # diagnosis only: wrong gradients

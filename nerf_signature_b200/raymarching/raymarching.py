@@ -244,6 +244,59 @@ class _composite_rays_train_live(_composite_rays_train):
 
 composite_rays_train_live = _composite_rays_train_live.apply
 
+
+class _composite_rays_train_blend(Function):
+    """composite_rays_train followed by the epilogue of NeRFRenderer.run_cuda's training branch
+    (renderer_wtmk.py:298-303) in the same kernels:
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color          (scalar bg_color)
+        depth = clamp(depth - nears, min=0) / (fars - nears)
+    Returns (weights_sum, depth, image) with those final values; differentiable in sigmas and rgbs through image and
+    weights_sum (depth carries no gradient, as in the reference's composite backward, raymarching.py:275).
+    Replaces 7 element-wise launches forward and ~6 backward per render call."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=torch.float32)
+    def forward(ctx, sigmas, rgbs, deltas, rays, nears, fars, bg_color, T_thresh=1e-4, zero_fill=True):
+        sigmas = sigmas.contiguous()
+        rgbs = rgbs.contiguous()
+        deltas = deltas.contiguous()
+        rays = rays.contiguous()
+        M = sigmas.shape[0]
+        N = rays.shape[0]
+        dev = sigmas.device
+        weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
+        depth_raw = torch.empty(N, dtype=torch.float32, device=dev)     # raw composite outputs (image_raw is saved)
+        image_raw = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.call("nsig_composite_rays_train_blend_forward", _P(sigmas), _P(rgbs), _P(deltas), _P(rays), M, N,
+                  float(T_thresh), float(bg_color), _P(nears.contiguous()), _P(fars.contiguous()), _P(weights_sum),
+                  _P(depth_raw), _P(image_raw), _P(image), _P(depth))
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, weights_sum, image_raw)
+        ctx.dims = [M, N, float(T_thresh), float(bg_color)]
+        ctx.zero_fill = bool(zero_fill)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(depth)
+        return weights_sum, depth, image
+
+    @staticmethod
+    @custom_bwd
+    def backward(ctx, grad_weights_sum, grad_depth, grad_image):
+        sigmas, rgbs, deltas, rays, weights_sum, image_raw = ctx.saved_tensors
+        M, N, T_thresh, bg_color = ctx.dims
+        if grad_image is None:
+            grad_image = torch.zeros_like(image_raw)
+        grad_image = grad_image.contiguous().view(N, 3)
+        gws = grad_weights_sum.contiguous() if grad_weights_sum is not None else None
+        alloc = torch.zeros_like if ctx.zero_fill else torch.empty_like
+        grad_sigmas = alloc(sigmas)
+        grad_rgbs = alloc(rgbs)
+        _lib.call("nsig_composite_rays_train_blend_backward", _P(gws), _P(grad_image), _P(sigmas), _P(rgbs), _P(deltas),
+                  _P(rays), _P(weights_sum), _P(image_raw), M, N, T_thresh, bg_color, _P(grad_sigmas), _P(grad_rgbs))
+        return grad_sigmas, grad_rgbs, None, None, None, None, None, None, None
+
+composite_rays_train_blend = _composite_rays_train_blend.apply
+
 # ----------------------------------------
 # infer functions
 # ----------------------------------------

@@ -308,3 +308,41 @@ def test_sph_from_ray(rm, oracle_cpu):
     rays_o, rays_d = syn.blender_rays(1000, seed=2, scale=0.3)
     c = rm.sph_from_ray(cu(rays_o), cu(rays_d), 4.0)
     np.testing.assert_allclose(c.cpu().numpy(), oracle_cpu.sph_from_ray(rays_o, rays_d, 4.0), rtol=1e-4, atol=1e-5)
+
+
+def test_composite_train_blend_matches_composite_plus_torch_epilogue(rm, oracle_cpu):
+    """composite_rays_train_blend == composite_rays_train followed by run_cuda's element-wise epilogue
+    (renderer_wtmk.py:298-303): forward values bit-exact, gradients equal (same kernels, the background term folded
+    into d/d weights_sum)."""
+    from nerf_signature_b200.raymarching import raymarching as rmod
+    rays_o, rays_d, bound, C, grid, bitfield, aabb, dt_gamma, noises = make_case(CASES[0], 512)
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    oxyz, odir, odel, orays, ocnt = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield, C, 128, on, of,
+                                                                noises=noises, dt_gamma=dt_gamma)
+    m = int(ocnt[0]); M = m + 128 - m % 128
+    sig, rgb = _random_field(M, 3)
+    sig[: m // 3] *= 50
+    nears, fars = cu(on), cu(of)
+    rs = np.random.RandomState(4)
+    gimg = cu(rs.normal(size=(rays_o.shape[0], 3)).astype(np.float32))
+    gws = cu(rs.normal(size=(rays_o.shape[0],)).astype(np.float32))
+    for bg, use_ws in ((1.0, False), (0.3, True)):
+        res = []
+        for fused in (False, True):
+            ts, tc = cu(sig).requires_grad_(True), cu(rgb).requires_grad_(True)
+            if fused:
+                ws, depth, img = rmod.composite_rays_train_blend(ts, tc, cu(odel[:M]), cu(orays), nears, fars, bg, 1e-4, True)
+            else:
+                ws, depth, img = rm.composite_rays_train(ts, tc, cu(odel[:M]), cu(orays), 1e-4)
+                img = img + (1 - ws).unsqueeze(-1) * bg
+                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            loss = (img * gimg).sum()
+            if use_ws:
+                loss = loss + (ws * gws).sum()
+            loss.backward()
+            res.append([t.detach().cpu().numpy() for t in (ws, depth, img, ts.grad, tc.grad)])
+        for k, (a, b) in enumerate(zip(*res)):
+            if k < 3:   # rays that miss the box have near == far == FLT_MAX-like sentinels: 0/0 depth in both forms
+                assert np.array_equal(a, b, equal_nan=True), (k, np.abs(a - b)[np.isfinite(a - b)].max())
+            else:
+                np.testing.assert_allclose(b, a, rtol=1e-5, atol=1e-6 * np.abs(a).max())

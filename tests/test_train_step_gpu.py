@@ -34,17 +34,23 @@ def _msg_tables(scene):
     return [e.weight.detach().clone() for e in scene.model.msg_encoder.embeddings]
 
 
-def test_fused_adam_matches_torch_adam_with_gradscaler():
+@pytest.mark.parametrize("merged", [True, False])
+def test_fused_adam_matches_torch_adam_with_gradscaler(merged):
     """Same seeds, same messages: WatermarkAdam (one kernel from G) == torch.optim.Adam on the fanned-out
-    per-table gradients, including the untouched unselected tables and the per-table step counts."""
-    a, b = _scene(optimizer="torch"), _scene(optimizer="fused")
+    per-table gradients, including the untouched unselected tables and the per-table step counts.
+    With one render call per step both optimizers see the SAME scatter-added dL/dS, so the losses agree to 1e-5.
+    With the reference's two render calls the torch path sums two separately accumulated gradients (autograd) while the
+    fused path accumulates both passes into one buffer: fp32 rounding differs, and Adam (eps 1e-15) turns a gradient
+    that cancels to rounding noise into a +-lr update of that element - the losses then agree to 1e-3 only."""
+    a, b = _scene(optimizer="torch", merged_render=merged), _scene(optimizer="fused", merged_render=merged)
     batches = _batches(a, 3)
     gen = torch.Generator().manual_seed(3)
     msgs = [a.new_message(gen) for _ in range(6)]
+    tol = 1e-5 if merged else 1e-3
     for i, m in enumerate(msgs):
         la = a.train_step(batches[i % 3], m)
         lb = b.train_step(batches[i % 3], m)
-        assert abs(float(la[0]) - float(lb[0])) <= 1e-5 * abs(float(la[0])) + 1e-7, i
+        assert abs(float(la[0]) - float(lb[0])) <= tol * abs(float(la[0])) + 1e-7, i
     ta, tb = _msg_tables(a), _msg_tables(b)
     for x, y in zip(ta, tb):
         _close_frac(x, y, rtol=2e-4, atol=2e-6)
@@ -124,3 +130,50 @@ def test_fused_decoder_step_matches_module_step():
         la = [float(x) for x in a.train_step(batches[i % 2], m)]
         lb = [float(x) for x in b.train_step(batches[i % 2], m)]
         np.testing.assert_allclose(lb, la, rtol=5e-3 if i else 2e-3, atol=1e-5)
+
+
+def test_fused_loss_head_step_matches_torch_losses():
+    """clamp / MSE / BCE / weighting through the loss-head kernels (nerf/loss_ops.py) against the plain torch
+    expressions of utils_wtmk_disen.py:593,636-644, merged and split render, eager and captured."""
+    for merged in (True, False):
+        a = _scene(optimizer="fused", merged_render=merged)
+        b = _scene(optimizer="fused", merged_render=merged, fused_losses=True)
+        batches = _batches(a, 2)
+        gen = torch.Generator().manual_seed(11)
+        for i in range(4):
+            m = a.new_message(gen)
+            la = [float(x) for x in a.train_step(batches[i % 2], m)]
+            lb = [float(x) for x in b.train_step(batches[i % 2], m)]
+            np.testing.assert_allclose(lb, la, rtol=1e-4, atol=1e-6)
+        for x, y in zip(_msg_tables(a), _msg_tables(b)):
+            _close_frac(x, y, rtol=1e-3, atol=1e-5)
+
+
+def test_loss_ops_against_torch():
+    import torch.nn.functional as F
+    from nerf_signature_b200.nerf.loss_ops import split_clamp, wtmk_loss
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    img = (torch.rand(1, 700, 3, generator=g) * 1.6 - 0.3).to(dev)   # values below 0 and above 1
+    img[0, 5, 1] = 0.0
+    img[0, 6, 2] = 1.0                                                # boundaries pass the gradient (min <= x <= max)
+    gt = torch.rand(1, 400, 3, generator=g).to(dev)
+    logits = torch.randn(7, 1, generator=g).to(dev)
+    msg = torch.randint(0, 2, (7,), generator=g).float().to(dev)
+    wp = torch.randn(300, 3, generator=g).to(dev)
+    outs = []
+    for fused in (False, True):
+        x = img.clone().requires_grad_(True)
+        z = logits.clone().requires_grad_(True)
+        if fused:
+            pred, content = split_clamp(x, 300)
+            loss, lossi, lossw = wtmk_loss(content.view(1, 400, 3), gt, z, msg, 0.005, 1.0, 10.0)
+        else:
+            pred, content = torch.clamp(x[0, :300], min=0, max=1), x[:, 300:]
+            lossi = F.mse_loss(content, gt, reduction="none").mean()
+            lossw = F.binary_cross_entropy_with_logits(z * 10.0, msg.unsqueeze(-1), reduction="mean")
+            loss = 0.005 * lossw + 1.0 * lossi
+        ((loss + (pred * wp).sum()) * 128.0).backward()
+        outs.append([t.detach().cpu().numpy() for t in (loss, lossi, lossw, pred, x.grad, z.grad)])
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(b, a, rtol=2e-6, atol=1e-7)
