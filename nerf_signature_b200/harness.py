@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from . import synthetic as syn
 from . import parallel
 from . import hash_encoding_wtmk_bit as _hmsg
+from . import _lib
 
 CONFIGS = {
     # BASELINE.json configs[1]: Blender shape, bound 1.0, scale 0.8, dt_gamma 0, message_dim 32, 32x32 codebook
@@ -79,13 +80,17 @@ class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
-                 merged_render=False, fused_decoder=False, fused_losses=False):
+                 merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
         in one CUDA graph on first use; needs optimizer="fused".
         fused_losses: clamp / MSE / BCE / weighting through the loss-head kernels (nerf/loss_ops.py) instead of the
-        plain torch expressions of utils_wtmk_disen.py:593,636-644."""
+        plain torch expressions of utils_wtmk_disen.py:593,636-644.
+        overlap_decoder (two render calls, like the reference step): the decoder runs on a side stream.  Its forward
+        and backward are chains of ~10 small latency-bound kernels each that leave most SMs idle; with the watermark
+        blocks rendered first, the content pass (march, field forward, composite - and in the backward pass its field
+        backward) executes next to them.  In the captured step these are parallel branches of one graph."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
         from .optim import WatermarkAdam
         torch.manual_seed(seed)
@@ -132,6 +137,7 @@ class Scene:
         self.merged_render = merged_render  # one render call over [block rays | content rays] instead of two
         self.fused_decoder = fused_decoder and fp16  # the kernels implement the float16-autocast arithmetic
         self.fused_losses = fused_losses
+        self.overlap_decoder = overlap_decoder and not merged_render
         self.iteration = 0
         self._graph = None
         self._static = None
@@ -191,14 +197,23 @@ class Scene:
                 pred = split_clamp(image_w, nb)[0].view(ob.shape)
         if not self.fused_losses:
             pred = torch.clamp(image_w, min=0, max=1)
-        if self.fused_decoder:   # normalisation + HiDDeN decoder forward/backward as tensor-core kernels (csrc/decoder.cu)
-            decoded = model.decode_blocks(pred)
-        else:                    # utils_wtmk_disen.py:592-595 verbatim: the plain module under autocast
-            with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
-                decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
+        side = _lib.side_stream(self.device, 2) if self.overlap_decoder else None
+        main = torch.cuda.current_stream()
+        if side is not None:     # fork: the decoder chain runs next to the content pass below
+            side.wait_stream(main)
+            pred.record_stream(side)
+        with torch.cuda.stream(side if side is not None else main):
+            if self.fused_decoder:   # normalisation + HiDDeN decoder forward/backward as tensor-core kernels (csrc/decoder.cu)
+                decoded = model.decode_blocks(pred)
+            else:                    # utils_wtmk_disen.py:592-595 verbatim: the plain module under autocast
+                with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
+                    decoded = model.msg_decoder(model.normalization(pred.permute(0, 3, 1, 2)))
         if not self.merged_render:
             image_c = model.render(batch["rays_o"], batch["rays_d"], message, staged=False, bg_color=1,
                                    perturb=False, force_all_rays=True, **self.opt)["image"]
+        if side is not None:     # join before the loss reads the logits
+            main.wait_stream(side)
+            decoded.record_stream(main)
         if self.fused_losses:
             loss, lossi, lossw = wtmk_loss(image_c, batch["gt"], decoded, msg_dev, self.lambda_w, self.lambda_i, 10.0)
         else:

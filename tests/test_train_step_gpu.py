@@ -177,3 +177,32 @@ def test_loss_ops_against_torch():
         outs.append([t.detach().cpu().numpy() for t in (loss, lossi, lossw, pred, x.grad, z.grad)])
     for a, b in zip(*outs):
         np.testing.assert_allclose(b, a, rtol=2e-6, atol=1e-7)
+
+
+def test_decoder_on_side_stream_matches_sequential_step():
+    """overlap_decoder only changes WHERE the decoder kernels run (a side stream next to the content pass), eagerly and
+    as parallel branches of the captured graph: same losses, same table updates."""
+    a = _scene(optimizer="fused", fused_decoder=True, fused_losses=True)
+    b = _scene(optimizer="fused", fused_decoder=True, fused_losses=True, overlap_decoder=True)
+    c = _scene(optimizer="fused", fused_decoder=True, fused_losses=True, overlap_decoder=True, graph=True)
+    assert b.overlap_decoder and c.overlap_decoder
+    batches = _batches(a, 2)
+    gen = torch.Generator().manual_seed(12)
+    msgs = [a.new_message(gen) for _ in range(5)]
+    c._capture(batches[0], msgs[0])
+    for _ in range(3):          # the capture warm-up ran 3 eager steps on (batch 0, message 0)
+        a.train_step(batches[0], msgs[0])
+        b.train_step(batches[0], msgs[0])
+    for i, m in enumerate(msgs):
+        la = [float(x) for x in a.train_step(batches[i % 2], m)]
+        lb = [float(x) for x in b.train_step(batches[i % 2], m)]
+        lc = [float(x) for x in c.train_step(batches[i % 2], m)]
+        np.testing.assert_allclose(lb, la, rtol=5e-3 if i else 1e-4, atol=1e-5)
+        np.testing.assert_allclose(lc, la, rtol=5e-3 if i else 1e-4, atol=1e-5)
+    # the content pass's field backward now scatters into dL/dS BEFORE the block pass's (it no longer waits for the
+    # decoder), and the fp16 decoder backward sums with atomics: after 8 Adam steps (eps 1e-15: sign-like updates for
+    # gradients at rounding-noise level) a few percent of the entries may sit one lr apart
+    for x, y in zip(_msg_tables(a), _msg_tables(b)):
+        _close_frac(x, y, rtol=1e-3, atol=1e-5, max_bad=5e-2)
+    for x, y in zip(_msg_tables(a), _msg_tables(c)):
+        _close_frac(x, y, rtol=1e-3, atol=1e-5, max_bad=5e-2)

@@ -25,7 +25,8 @@ def main():
 
     dev = torch.device("cuda:0")
     cfg = dict(harness.CONFIGS[args.config])
-    scene = harness.Scene(cfg, dev, seed=0, merged_render=True, fused_decoder=os.environ.get("NSIG_TORCH_DECODER") != "1",
+    mode = os.environ.get("NSIG_RENDER_MODE", "merged")
+    scene = harness.Scene(cfg, dev, seed=0, merged_render=mode == "merged", overlap_decoder=mode == "overlap", fused_decoder=os.environ.get("NSIG_TORCH_DECODER") != "1",
                           fused_losses=os.environ.get("NSIG_TORCH_LOSSES") != "1")
     batches = [scene.to_device(harness.make_batch(cfg, seed=i)) for i in range(2)]
     gen = torch.Generator().manual_seed(7)
