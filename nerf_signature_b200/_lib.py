@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsig_b200.so")
+LIB_PATH = os.environ.get("NSIG_LIB") or os.path.join(_HERE, "libnsig_b200.so")  # NSIG_LIB: A/B builds (tools only)
 
 _c = ctypes
 _vp, _u32, _f32, _sz = _c.c_void_p, _c.c_uint32, _c.c_float, _c.c_size_t
