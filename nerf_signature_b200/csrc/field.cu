@@ -571,7 +571,48 @@ k_field_bwd(const FieldBwdParams p) {
     const uint32_t n_tiles = div_up(M, rows_per_cta);
     const float* dirs_ = p.dirs;
     const uint32_t M_ = M;
+    // Inputs of a tile (per thread): incoming gradients, saved features (A fragments), view directions of its rows and
+    // the position of the row it scatters.  They are loaded one tile AHEAD: the loads of tile i+1 are issued before the
+    // MLP work of tile i, so their L2/HBM latency (30 % of the warp time in ncu's source view of the non-prefetching
+    // version, profiles/r01_experiments_v5.txt) is covered by ~300 tensor-core instructions instead of being waited for.
+    struct TileIn {
+        float gs[MT][2], gc[MT][2][2], dv[MT][2][3], sx[(MT * 2 + 3) / 4][3];
+        uint32_t fa[MT][2][4];
+    };
+    auto load_tile = [&](uint32_t tile, TileIn& t) {
+        const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                t.gs[mt][h] = 0.f; t.gc[mt][h][0] = t.gc[mt][h][1] = 0.f;
+                if (r < M) {
+                    if (tig == 3) t.gs[mt][h] = __ldg(p.grad_sigmas + r);
+                    if (tig == 0) { t.gc[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3); t.gc[mt][h][1] = __ldg(p.grad_rgbs + (size_t)r * 3 + 1); }
+                    if (tig == 1) t.gc[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3 + 2);
+                }
+                const uint32_t rc = min(r, M - 1);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.feat + (size_t)rc * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t.fa[mt][j >> 1][2 * (j & 1) + h] = __ldg(src + tig + 4 * j);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) t.dv[mt][h][a] = __ldg(dirs_ + (size_t)rc * 3 + a);
+            }
+        // the row whose 8 corners this thread scatters: quad thread `tig` takes row (mt,h) = 4q + tig
+#pragma unroll
+        for (int q = 0; q < (MT * 2 + 3) / 4; ++q) {
+            const int sel = q * 4 + tig;
+            const uint32_t r = row0 + (sel >> 1) * 16 + (sel & 1) * 8 + g;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) t.sx[q][a] = (sel < MT * 2 && r < M) ? __ldg(p.xyzs + (size_t)r * 3 + a) : 0.f;
+        }
+    };
+    TileIn nxt;
+    if (blockIdx.x < n_tiles) load_tile(blockIdx.x, nxt);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileIn cur = nxt;
+        if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);
         const uint32_t row0 = tile * rows_per_cta + warp * 16 * MT;
         if (row0 >= M) continue;
         // incoming gradients of this thread's rows; skip the tile when the whole warp has none
@@ -581,13 +622,7 @@ k_field_bwd(const FieldBwdParams p) {
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint32_t r = frag_row<MT>(row0, mt, h, g);
-                gs_in[mt][h] = 0.f; gc_in[mt][h][0] = gc_in[mt][h][1] = 0.f;
-                if (r < M) {
-                    if (tig == 3) gs_in[mt][h] = __ldg(p.grad_sigmas + r);
-                    if (tig == 0) { gc_in[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3); gc_in[mt][h][1] = __ldg(p.grad_rgbs + (size_t)r * 3 + 1); }
-                    if (tig == 1) gc_in[mt][h][0] = __ldg(p.grad_rgbs + (size_t)r * 3 + 2);
-                }
+                gs_in[mt][h] = cur.gs[mt][h]; gc_in[mt][h][0] = cur.gc[mt][h][0]; gc_in[mt][h][1] = cur.gc[mt][h][1];
                 any |= (gs_in[mt][h] != 0.f) | (gc_in[mt][h][0] != 0.f) | (gc_in[mt][h][1] != 0.f);
             }
         if (!__any_sync(NSIG_FULL_MASK, any)) {
@@ -610,12 +645,9 @@ k_field_bwd(const FieldBwdParams p) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t r = min(frag_row<MT>(row0, mt, h, g), M - 1);
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.feat + (size_t)r * 32);
+            for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fa[mt][j >> 1][2 * (j & 1) + h] = __ldg(src + tig + 4 * j);
-            }
+                for (int e = 0; e < 4; ++e) fa[mt][ks][e] = cur.fa[mt][ks][e];
         uint32_t h1s[MT][4][4], h1c[MT][4][4], h2c[MT][4][4], ca[MT][2][4];
         float so[MT][2][4], co[MT][1][4];
         {
@@ -623,7 +655,7 @@ k_field_bwd(const FieldBwdParams p) {
             layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
             relu_to_a<MT, 8>(h1s, c);
             layer<MT, 4, 2>(so, h1s, sm + oWs1, kS64, g, tig);
-            sh_rows<MT>(ca, dirs_, M_, row0, g, tig);
+            sh_rows_vals<MT>(ca, cur.dv, tig);
             geo_to_a<MT>(ca, so, tig);
             layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
             relu_to_a<MT, 8>(h1c, c);
@@ -770,7 +802,7 @@ k_field_bwd(const FieldBwdParams p) {
                     float xn[3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
-                        xn[a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)myrow * 3 + a), p.bound_add), p.bound_mul);
+                        xn[a] = __fmul_rn(__fadd_rn(cur.sx[q][a], p.bound_add), p.bound_mul);   // prefetched position of myrow
                     const Voxel v = locate(xn[0], xn[1], xn[2], p.msg_grid_size);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
@@ -894,6 +926,7 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
     if (M == 0) return 0;
     if (!xyzs || !dirs || !feat || !grad_sigmas || !grad_rgbs || !sigma_w || !color_w) return NSIG_EINVAL;
     if ((grad_sigma_w == nullptr) != (grad_color_w == nullptr)) return NSIG_EINVAL;
+    if ((((uintptr_t)sigma_w) | ((uintptr_t)color_w)) & 15) return NSIG_EINVAL;   // 16-byte weight staging
     if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
     if (G && !(msg_resolution > 0.0f)) return NSIG_EINVAL;
     FieldBwdParams p;

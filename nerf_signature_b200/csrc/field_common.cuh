@@ -121,49 +121,76 @@ __device__ __forceinline__ void grad_to_a(uint32_t (&a)[MT][NT / 2][4], const fl
 }
 
 // ---- weight staging ---------------------------------------------------------------------
+// Each CTA copies the (frozen) MLP weights into its padded shared-memory layout once.  The copies move 16 bytes
+// (8 halfs) per load: the 2-byte-per-thread version spent ~7 % of the backward kernel's warp time here (ncu source view,
+// profiles/r01_experiments_v5.txt).  Row lengths (32 / 64 halfs) and padded strides (80 / 144 / 48 bytes) are multiples
+// of 16 bytes, so a chunk never straddles a row; the flat fp16 parameter vectors must be 16-byte aligned (the entry
+// points return NSIG_EINVAL otherwise; torch allocations are 256-byte aligned).
+__device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void sts16(__half* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint4 zero_last_half(uint4 v) { v.w &= 0x0000ffffu; return v; }   // halfs 0..6 kept, half 7 = 0
+
 __device__ __forceinline__ void stage_forward_weights(__half* sm, const __half* __restrict__ sw,
                                                       const __half* __restrict__ cw, bool color) {
-    const __half zero = __float2half(0.0f);
-    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
-        const int r = i >> 5, c = i & 31;
-        sm[oWs0 + r * kS32 + c] = sw[i];
-        if (color) sm[oWc0 + r * kS32 + c] = (c == 31) ? zero : cw[i];
+    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {          // [64][32]: 4 chunks per row
+        const int r = i >> 2, c = (i & 3) * 8;
+        sts16(sm + oWs0 + r * kS32 + c, ldg16(sw + r * 32 + c));
+        if (color) {                                                    // input column 31 is padding: zeroed
+            const uint4 v = ldg16(cw + r * 32 + c);
+            sts16(sm + oWc0 + r * kS32 + c, c == 24 ? zero_last_half(v) : v);
+        }
     }
-    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-        const int r = i >> 6, c = i & 63;  // smem row r holds param row (r+1)%16: [geo0..14, logit]
-        sm[oWs1 + r * kS64 + c] = sw[2048 + ((r + 1) & 15) * 64 + c];
+    for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {          // [16][64]: smem row r holds param row (r+1)%16
+        const int r = i >> 3, c = (i & 7) * 8;                          //           = [geo0..14, logit]
+        sts16(sm + oWs1 + r * kS64 + c, ldg16(sw + 2048 + ((r + 1) & 15) * 64 + c));
     }
     if (color) {
-        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-            const int r = i >> 6, c = i & 63;
-            sm[oWc1 + r * kS64 + c] = cw[2048 + i];
+        for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+            const int r = i >> 3, c = (i & 7) * 8;
+            sts16(sm + oWc1 + r * kS64 + c, ldg16(cw + 2048 + r * 64 + c));
         }
-        for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) {
-            const int r = i >> 6, c = i & 63;
-            sm[oWc2 + r * kS64 + c] = cw[2048 + 4096 + i];
+        for (int i = threadIdx.x; i < 8 * 8; i += blockDim.x) {
+            const int r = i >> 3, c = (i & 7) * 8;
+            sts16(sm + oWc2 + r * kS64 + c, ldg16(cw + 2048 + 4096 + r * 64 + c));
         }
     }
+}
+
+// transposed copies for the data gradients: 8 consecutive source elements (one 16-byte load) go to 8 consecutive
+// shared-memory ROWS of one column
+__device__ __forceinline__ void scatter8(__half* dst, int stride, uint4 v) {
+    const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j * stride] = h[j];
 }
 
 __device__ __forceinline__ void stage_backward_weights(__half* sm, const __half* __restrict__ sw,
                                                        const __half* __restrict__ cw) {
     const __half zero = __float2half(0.0f);
-    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
-        const int n = i >> 4, k = i & 15;  // n = hidden (in) index, k = output index
-        sm[oWc2T + n * kS16 + k] = (k < 3) ? cw[2048 + 4096 + k * 64 + n] : zero;
-        sm[oWs1T + n * kS16 + k] = sw[2048 + ((k + 1) & 15) * 64 + n];
+    // oWc2T [64][16]: column k < 3 = colour output k (source row k of [16][64]), other columns zero
+    // oWs1T [64][16]: column k = permuted sigma output k (source row (k+1)%16 of [16][64])
+    for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {
+        const int k = i >> 3, n = (i & 7) * 8;                          // source row k, columns n..n+7
+        if (k < 3) scatter8(sm + oWc2T + n * kS16 + k, kS16, ldg16(cw + 2048 + 4096 + k * 64 + n));
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm[oWc2T + (n + j) * kS16 + k] = zero;
+        }
+        scatter8(sm + oWs1T + n * kS16 + k, kS16, ldg16(sw + 2048 + ((k + 1) & 15) * 64 + n));
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-        const int n = i >> 6, k = i & 63;
-        sm[oWc1T + n * kS64 + k] = cw[2048 + k * 64 + n];
+    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {          // oWc1T[n][k] = Wc1[k][n]
+        const int k = i >> 3, n = (i & 7) * 8;
+        scatter8(sm + oWc1T + n * kS64 + k, kS64, ldg16(cw + 2048 + k * 64 + n));
     }
-    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-        const int n = i >> 6, k = i & 63;  // n = colour-net input 16+n (geo part; input 31 is padding)
-        sm[oWc0T + n * kS64 + k] = (n == 15) ? zero : cw[k * 32 + 16 + n];
+    for (int i = threadIdx.x; i < 64 * 2; i += blockDim.x) {          // oWc0T[n][k] = Wc0[k][16 + n], n < 16 (n == 15: padding)
+        const int k = i >> 1, n = (i & 1) * 8;
+        uint4 v = ldg16(cw + k * 32 + 16 + n);
+        if (n == 8) v = zero_last_half(v);
+        scatter8(sm + oWc0T + n * kS64 + k, kS64, v);
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
-        const int n = i >> 6, k = i & 63;
-        sm[oWs0T + n * kS64 + k] = sw[k * 32 + n];
+    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {          // oWs0T[n][k] = Ws0[k][n], n < 32
+        const int k = i >> 2, n = (i & 3) * 8;
+        scatter8(sm + oWs0T + n * kS64 + k, kS64, ldg16(sw + k * 32 + n));
     }
 }
 
@@ -417,6 +444,24 @@ __device__ __forceinline__ void sh_rows(uint32_t (&ca)[MT][2][4], const float* _
         }
 }
 
+// same, from directions already in registers (dv[mt][h] = direction of row (mt,h))
+template <int MT>
+__device__ __forceinline__ void sh_rows_vals(uint32_t (&ca)[MT][2][4], const float (&dv)[MT][2][3], int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float o[16];
+            sh4(dv[mt][h][0], dv[mt][h][1], dv[mt][h][2], o);
+            float lo0 = o[0], lo1 = o[1], hi0 = o[8], hi1 = o[9];
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (tig == t) { lo0 = o[2 * t]; lo1 = o[2 * t + 1]; hi0 = o[2 * t + 8]; hi1 = o[2 * t + 9]; }
+            ca[mt][0][h] = pack_h2(lo0, lo1);
+            ca[mt][0][2 + h] = pack_h2(hi0, hi1);
+        }
+}
+
 // geo features (sigma net outputs in the permuted order [geo0..14, logit]) -> colour k-step 1;
 // column 15 (the logit; the colour net's padded input 31) is cleared.
 template <int MT>
@@ -437,6 +482,7 @@ static inline int fill_field_params(nsig::FieldParams& p, const float* xyzs, con
                              const int32_t* M_dev, float density_scale, const void* const* tables_h2 = nullptr,
                              const float* h2_inv_scale = nullptr) {
     if (!xyzs || !tables || !resolutions || !sigma_w) return NSIG_EINVAL;
+    if ((((uintptr_t)sigma_w) | ((uintptr_t)color_w)) & 15) return NSIG_EINVAL;   // 16-byte weight staging
     if ((tables_h2 == nullptr) != (h2_inv_scale == nullptr)) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f)) return NSIG_EINVAL;
     p.xyzs = xyzs;
