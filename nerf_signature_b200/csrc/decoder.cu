@@ -181,9 +181,24 @@ k_dec_conv(const ConvParams p) {
     __half* tile = reinterpret_cast<__half*>(smem_raw);                      // [(R+2)*(W+2)][STRIDE]
     BnCoef* coef = reinterpret_cast<BnCoef*>(tile + (size_t)(p.R + 2) * (p.W + 2) * STRIDE);
     BnCoef* coef_out = coef + CIN;                                           // [COUT], data-gradient convs with out_bsums
+    // the layer's weights [COUT][9*CIN], rows padded by 16 bytes (ldmatrix rows of an n-tile then sit in distinct banks)
+    constexpr int WROW = 9 * CIN, WSTR = WROW + 8;
+    __half* wsm = reinterpret_cast<__half*>(coef_out + COUT);
     const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
     const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
+    // Asynchronous copy of the weights (up to 74 KB from L2), issued first: it completes while the BatchNorm
+    // coefficients are derived and the input tile is staged and transformed.  Reading every weight fragment straight from
+    // global memory inside the k-loop instead exposed an L2 round trip every few k-steps on a kernel whose math is ~1 us.
+    {
+        constexpr int CHUNKS = WROW / 8;                                     // 16-byte chunks per row
+        for (int i = threadIdx.x; i < COUT * CHUNKS; i += blockDim.x) {
+            const int row = i / CHUNKS, ck = i - row * CHUNKS;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + (size_t)row * WSTR + ck * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(p.w + (size_t)row * WROW + ck * 8) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     if (MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
@@ -192,6 +207,7 @@ k_dec_conv(const ConvParams p) {
         __syncthreads();
     }
     stage_tile<CIN, SCH, MODE>(tile, p.src, p.src2, coef, b, r0, R, p.H, p.W);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int P = R * p.W, TW = p.W + 2, m_tiles = (P + 15) / 16, m_groups = (m_tiles + MB - 1) / MB;
@@ -213,23 +229,36 @@ k_dec_conv(const ConvParams p) {
             arow[m] = tile + ((size_t)(ra + 1) * TW + (wa + 1)) * STRIDE + (lane >> 4) * 8;
         }
         const int mcount = min(MB, m_tiles - mg * MB);
-        const __half* wrow = p.w + (size_t)(nt * 8 + g) * (9 * CIN) + 2 * tig;
+        // B fragments by ldmatrix: lane l addresses row (l & 7) of the n-tile, 8 halfs at k offset 8 * (l >> 3);
+        // an x4 covers two consecutive k-steps (k is flat over taps x input channels: k-step kk = tap * KS + ks)
+        const __half* wlane = wsm + (size_t)(nt * 8 + (lane & 7)) * WSTR + (lane >> 3) * 8;
         float c[MB][4];
 #pragma unroll
         for (int m = 0; m < MB; ++m) { c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f; }
+        constexpr int KK = 9 * KS;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int off = ((t / 3 - 1) * TW + (t % 3 - 1)) * STRIDE;
+        for (int kp = 0; kp < (KK + 1) / 2; ++kp) {
+            uint32_t bf[4];
+            if (2 * kp + 1 < KK) {
+                ldsm_x4(bf, wlane + kp * 32);
+            } else {   // odd tail (CIN == 16: 9 k-steps): lanes 16..31 re-address the first two matrices
+                uint32_t b2[2];
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(wlane - ((lane >> 4) * 16) + kp * 32);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b2[0]), "=r"(b2[1]) : "r"(a));
+                bf[0] = b2[0]; bf[1] = b2[1]; bf[2] = 0u; bf[3] = 0u;
+            }
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16));
-                const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + t * CIN + ks * 16 + 8));
+            for (int half_ = 0; half_ < 2; ++half_) {
+                const int kk = 2 * kp + half_;
+                if (kk >= KK) break;
+                const int t = kk / KS, ks = kk - t * KS;
+                const int off = ((t / 3 - 1) * TW + (t % 3 - 1)) * STRIDE;
 #pragma unroll
                 for (int m = 0; m < MB; ++m) {
                     if (m < mcount) {
                         uint32_t a[4];
                         ldsm_x4(a, arow[m] + off + ks * 16);
-                        mma_16816(c[m], a, b0, b1);
+                        mma_16816(c[m], a, bf[2 * half_], bf[2 * half_ + 1]);
                     }
                 }
             }
@@ -629,7 +658,8 @@ int wgrad_rows(int H, int W, int cin, int cout) {
 template <int CIN, int SCH, int COUT, int MODE>
 int launch_conv(ConvParams p, cudaStream_t st) {
     p.R = conv_rows(p.B, p.H, p.W);
-    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + (size_t)(CIN + COUT) * sizeof(BnCoef);
+    const size_t smem = (size_t)(p.R + 2) * (p.W + 2) * (CIN + 8) * 2 + (size_t)(CIN + COUT) * sizeof(BnCoef) +
+                        (size_t)COUT * (9 * CIN + 8) * 2;
     if (smem > 200 * 1024) return NSIG_EINVAL;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_conv<CIN, SCH, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }

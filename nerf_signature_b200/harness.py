@@ -232,17 +232,25 @@ class Scene:
     def _capture(self, batch, message):
         """Warm up on a side stream, then record one step into a CUDA graph with static input buffers."""
         from . import _lib
-        self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in batch.items()}
-        self._static["message"] = torch.empty(self.cfg["message_dim"], dtype=torch.float32, device=self.device)
+        # ONE flat static input buffer; the per-key entries are views of it.  Layout (floats):
+        #   [rays_o_block | rays_o | rays_d_block | rays_d | gt | message]
+        # so [block rays | content rays] are already concatenated for the merged render (no torch.cat in the captured
+        # step) and a host batch packed the same way (`pinned_batch`) needs a single H2D copy per step.
+        md = self.cfg["message_dim"]
+        order = ["rays_o_block", "rays_o", "rays_d_block", "rays_d", "gt"]
+        batch = {k: batch[k] for k in order}
+        self._layout, o = {}, 0
+        for k in order:
+            self._layout[k] = (o, tuple(batch[k].shape))
+            o += batch[k].numel()
+        self._layout["message"] = (o, (md,))
+        self._static_flat = torch.empty(o + md, dtype=torch.float32, device=self.device)
+        self._static = {k: self._static_flat[a:a + math.prod(shp)].view(shp) for k, (a, shp) in self._layout.items()}
         if self.merged_render:
-            # [block rays | content rays] live concatenated in the static buffers; the per-key entries are views of them,
-            # so the input copies of a replay land in place and the captured step needs no torch.cat
             nb, nc = batch["rays_o_block"].numel() // 3, batch["rays_o"].numel() // 3
             for a in ("o", "d"):
-                full = torch.empty(1, nb + nc, 3, dtype=torch.float32, device=self.device)
-                self._static[f"rays_{a}_all"] = full
-                self._static[f"rays_{a}_block"] = full[0, :nb].view(batch[f"rays_{a}_block"].shape)
-                self._static[f"rays_{a}"] = full[:, nb:].view(batch[f"rays_{a}"].shape)
+                lo = self._layout[f"rays_{a}_block"][0]
+                self._static[f"rays_{a}_all"] = self._static_flat[lo:lo + 3 * (nb + nc)].view(1, nb + nc, 3)
         self._copy_inputs(batch, message)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -262,9 +270,28 @@ class Scene:
         self._graph_rows = [(ls - k) % 16 for k in range(n_calls, 0, -1)]  # the march counters baked into the graph
 
     def _copy_inputs(self, batch, message):
+        flat = batch.get("_flat") if isinstance(batch, dict) else None
+        if flat is not None and flat.numel() == self._static_flat.numel():
+            self._static_flat.copy_(flat, non_blocking=True)   # packed host batch (pinned_batch): one H2D copy
+            return
         for k, v in batch.items():
-            self._static[k].copy_(v, non_blocking=True)
+            if k != "_flat":
+                self._static[k].copy_(v, non_blocking=True)
         self._static["message"].copy_(message, non_blocking=True)
+
+    def pinned_batch(self, batch_np):
+        """A host batch in pinned memory, packed in the layout of the captured step's static input buffer (what a data
+        loader with pin_memory would hand over): dict of views + "_flat" (the whole buffer) + "message" (view to fill
+        with the step's message).  train_step(pb, pb["message"]) then moves it to the device with one copy."""
+        if self._graph is None:
+            raise RuntimeError("pinned_batch needs the captured step (graph=True, after the first train_step)")
+        flat = torch.empty(self._static_flat.numel(), dtype=torch.float32).pin_memory()
+        out = {"_flat": flat}
+        for k, (a, shp) in self._layout.items():
+            out[k] = flat[a:a + math.prod(shp)].view(shp)
+            if k != "message":
+                out[k].copy_(torch.from_numpy(batch_np[k]))
+        return out
 
     def train_step(self, batch, message):
         """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here).  Configs with
@@ -279,7 +306,8 @@ class Scene:
 
     def _train_step(self, batch, message):
         if not self.use_graph:
-            batch = {k: (v if v.is_cuda else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
+            batch = {k: (v if v.is_cuda else v.to(self.device, non_blocking=True)) for k, v in batch.items()
+                     if k not in ("_flat", "message")}
             return self._step_impl(batch, message)
         if self._graph is None:
             self._capture(batch, message)

@@ -206,3 +206,25 @@ def test_decoder_on_side_stream_matches_sequential_step():
         _close_frac(x, y, rtol=1e-3, atol=1e-5, max_bad=5e-2)
     for x, y in zip(_msg_tables(a), _msg_tables(c)):
         _close_frac(x, y, rtol=1e-3, atol=1e-5, max_bad=5e-2)
+
+
+def test_packed_pinned_batch_single_copy_matches_per_tensor_copies():
+    """Scene.pinned_batch: the host batch packed like the captured step's static input buffer and moved with ONE H2D copy
+    (bench.py's e2e path) drives exactly the same step as handing over the tensors one by one."""
+    from nerf_signature_b200 import harness
+    a = _scene(optimizer="fused", graph=True, merged_render=True, fused_decoder=True, fused_losses=True)
+    b = _scene(optimizer="fused", graph=True, merged_render=True, fused_decoder=True, fused_losses=True)
+    host = [harness.make_batch(a.cfg, seed=70 + i) for i in range(2)]
+    dev = [a.to_device(h) for h in host]
+    gen = torch.Generator().manual_seed(13)
+    m0 = a.new_message(gen)
+    a.train_step(dev[0], m0)
+    b.train_step(dev[0], m0)          # captures; pinned_batch needs the static layout
+    pool = [b.pinned_batch(h) for h in host]
+    for i in range(4):
+        m = a.new_message(gen)
+        la = [float(x) for x in a.train_step(dev[i % 2], m)]
+        pb = pool[i % 2]
+        pb["message"].copy_(m)
+        lb = [float(x) for x in b.train_step(pb, pb["message"])]
+        np.testing.assert_allclose(lb, la, rtol=5e-3 if i else 1e-4, atol=1e-5)
