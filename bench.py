@@ -426,7 +426,7 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_port_run(cfg, steps=2, warmup=1, rays_per_pass=args.cpu_rays or 64)
+        line["cpu_baseline"] = cpu_port_run(cfg, steps=12, warmup=1, rays_per_pass=args.cpu_rays or 64)  # ~12 s of CPU work
     print(json.dumps(line), flush=True)
     _finish(world)
 
