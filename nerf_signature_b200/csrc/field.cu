@@ -259,8 +259,12 @@ constexpr int kStageSlots = 64;
 // per-warp staging (floats): xyz[64][3] + dt[64] + dreal[64] + sigma[32] + rgb[32][3]
 constexpr int kStageFloats = kStageSlots * 5 + 32 * 4;
 
+#ifndef NSIG_RENDER_MINB
+#define NSIG_RENDER_MINB 4   // resident CTAs per SM the frame renderer is compiled for: 128 registers (40 B of spills) and
+                             // 16 warps/SM beat 188 registers at 8 warps/SM: 800x800 frame 25.0 -> 23.5 ms
+#endif
 template <bool H2>
-__global__ void __launch_bounds__(kRenderWarps * 32)
+__global__ void __launch_bounds__(kRenderWarps * 32, NSIG_RENDER_MINB)
 k_render_rays(const RenderParams p) {
     constexpr int MT = 2;
     extern __shared__ __align__(16) __half sm[];
