@@ -287,12 +287,27 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     }
     float T = 1.0f, t_acc = 0.f;           // transmittance / accumulated real delta before the chunk
     float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
+    // the loads of chunk k+1 are issued before the scans of chunk k (a ray is a serial chain of ~10 chunks, each of
+    // which would otherwise wait for its own L2/HBM round trip)
+    float n_sigma = 0.f, n_r = 0.f, n_g = 0.f, n_b = 0.f;
+    float2 n_dl = make_float2(0.f, 0.f);
+    auto fetch = [&](uint32_t base) {
+        const uint32_t s = base + lane;
+        n_sigma = 0.f; n_dl = make_float2(0.f, 0.f); n_r = n_g = n_b = 0.f;
+        if (s < num_steps) {
+            const size_t i = (size_t)offset + s;
+            n_sigma = sigmas[i];
+            n_dl = *reinterpret_cast<const float2*>(deltas + i * 2);
+            n_r = rgbs[i * 3]; n_g = rgbs[i * 3 + 1]; n_b = rgbs[i * 3 + 2];
+        }
+    };
+    fetch(0);
     for (uint32_t base = 0; base < num_steps; base += 32) {
         const uint32_t s = base + lane;
         const bool valid = s < num_steps;
-        const size_t i = (size_t)offset + s;
-        const float sigma = valid ? sigmas[i] : 0.f;
-        const float2 dl = valid ? *reinterpret_cast<const float2*>(deltas + i * 2) : make_float2(0.f, 0.f);
+        const float sigma = n_sigma, cr = n_r, cg = n_g, cb = n_b;
+        const float2 dl = n_dl;
+        if (base + 32 < num_steps) fetch(base + 32);
         const float alpha = 1.0f - __expf(-sigma * dl.x);
         const float one_m = valid ? (1.0f - alpha) : 1.0f;
         const float Tincl = T * warp_scan_mul(one_m, lane);       // T after this sample
@@ -304,7 +319,7 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
         const int stop = dead ? (__ffs(dead) - 1) : 32;  // first lane that triggers the break
         if (valid && lane <= stop) {
             const float w = alpha * Tbefore;
-            r += w * rgbs[i * 3]; g += w * rgbs[i * 3 + 1]; b += w * rgbs[i * 3 + 2];
+            r += w * cr; g += w * cg; b += w * cb;
             d += w * tcum;
             ws += w;
         }
@@ -342,14 +357,24 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
     const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
     const float ws_term = gws * (1.0f - weights_sum[index]);
     float T = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f;  // state before the chunk
+    float n_sigma = 0.f, n_d0 = 0.f, n_r = 0.f, n_g = 0.f, n_b = 0.f;   // next chunk's inputs (see the forward kernel)
+    auto fetch = [&](uint32_t base) {
+        const uint32_t s = base + lane;
+        n_sigma = n_d0 = n_r = n_g = n_b = 0.f;
+        if (s < num_steps) {
+            const size_t i = (size_t)offset + s;
+            n_sigma = sigmas[i];
+            n_d0 = deltas[i * 2];
+            n_r = rgbs[i * 3]; n_g = rgbs[i * 3 + 1]; n_b = rgbs[i * 3 + 2];
+        }
+    };
+    fetch(0);
     for (uint32_t base = 0; base < num_steps; base += 32) {
         const uint32_t s = base + lane;
         const bool valid = s < num_steps;
         const size_t i = (size_t)offset + s;
-        const float sigma = valid ? sigmas[i] : 0.f;
-        const float d0 = valid ? deltas[i * 2] : 0.f;
-        float cr = 0.f, cg = 0.f, cb = 0.f;
-        if (valid) { cr = rgbs[i * 3]; cg = rgbs[i * 3 + 1]; cb = rgbs[i * 3 + 2]; }
+        const float sigma = n_sigma, d0 = n_d0, cr = n_r, cg = n_g, cb = n_b;
+        if (base + 32 < num_steps) fetch(base + 32);
         const float alpha = 1.0f - __expf(-sigma * d0);
         const float one_m = valid ? (1.0f - alpha) : 1.0f;
         const float Tincl = T * warp_scan_mul(one_m, lane);
