@@ -114,38 +114,66 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 // tile[(R+2)*(W+2)][C + 8], applying the input transform.  src/src2: [B,H,W,C] fp16 (src2 = z for IN_DZ, src = da).
 // ---------------------------------------------------------------------------------------------------------------
 // SCH = channels per pixel in memory (<= C); tile channels [SCH, C) are zero.
+// Two phases so the caller can put independent work between them: `issue` starts the global loads of up to kStagePF
+// positions x chunks per thread (items base + j*blockDim + tid), `commit` applies the transform and writes the tile.
+constexpr int kStagePF = 4;
+
 template <int C, int SCH, int MODE>
-__device__ __forceinline__ void stage_tile(__half* tile, const __half* __restrict__ src, const __half* __restrict__ src2,
-                                           const BnCoef* __restrict__ coef, int b, int r0, int R, int H, int W) {
-    constexpr int STRIDE = C + 8;
-    const int TW = W + 2, n_pos = (R + 2) * TW, chunks = C / 8;
-    for (int i = threadIdx.x; i < n_pos * chunks; i += blockDim.x) {
-        const int pos = i / chunks, ck = i - pos * chunks;
-        const int tr = pos / TW, tc = pos - tr * TW;
-        const int r = r0 - 1 + tr, w = tc - 1;
-        uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (r >= 0 && r < H && w >= 0 && w < W && ck * 8 < SCH) {
-            const size_t off = (((size_t)b * H + r) * W + w) * SCH + ck * 8;
-            const uint4 v = *reinterpret_cast<const uint4*>(src + off);
-            if (MODE == IN_RAW) {
-                out = v;
-            } else {
-                const __half* hv = reinterpret_cast<const __half*>(&v);
-                __half* ho = reinterpret_cast<__half*>(&out);
-                if (MODE == IN_BNGELU) {
+struct TileStager {
+    static constexpr int STRIDE = C + 8, CHUNKS = C / 8;
+    uint4 v[kStagePF], v2[kStagePF];
+    uint32_t valid;
+
+    __device__ __forceinline__ void issue(const __half* __restrict__ src, const __half* __restrict__ src2, int base, int b,
+                                          int r0, int R, int H, int W) {
+        const int TW = W + 2, total = (R + 2) * TW * CHUNKS;
+        valid = 0u;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) ho[k] = act_from_z(hv[k], coef[ck * 8 + k]);
-                } else {
-                    const uint4 v2 = *reinterpret_cast<const uint4*>(src2 + off);
-                    const __half* hz = reinterpret_cast<const __half*>(&v2);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ho[k] = dz_from(hv[k], hz[k], coef[ck * 8 + k]);
-                }
+        for (int j = 0; j < kStagePF; ++j) {
+            const int i = base + j * (int)blockDim.x + (int)threadIdx.x;
+            v[j] = make_uint4(0u, 0u, 0u, 0u);
+            v2[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i >= total) continue;
+            const int pos = i / CHUNKS, ck = i - pos * CHUNKS;
+            const int tr = pos / TW, tc = pos - tr * TW;
+            const int r = r0 - 1 + tr, w = tc - 1;
+            if (r >= 0 && r < H && w >= 0 && w < W && ck * 8 < SCH) {
+                const size_t off = (((size_t)b * H + r) * W + w) * SCH + ck * 8;
+                v[j] = *reinterpret_cast<const uint4*>(src + off);
+                if (MODE == IN_DZ) v2[j] = *reinterpret_cast<const uint4*>(src2 + off);
+                valid |= 1u << j;
             }
         }
-        *reinterpret_cast<uint4*>(tile + (size_t)pos * STRIDE + ck * 8) = out;
     }
-}
+
+    __device__ __forceinline__ void commit(__half* tile, const BnCoef* __restrict__ coef, int base, int R, int W) const {
+        const int TW = W + 2, total = (R + 2) * TW * CHUNKS;
+#pragma unroll
+        for (int j = 0; j < kStagePF; ++j) {
+            const int i = base + j * (int)blockDim.x + (int)threadIdx.x;
+            if (i >= total) continue;
+            const int pos = i / CHUNKS, ck = i - pos * CHUNKS;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);   // outside the image / padded channels: zero
+            if (valid & (1u << j)) {
+                if (MODE == IN_RAW) {
+                    out = v[j];
+                } else {
+                    const __half* hv = reinterpret_cast<const __half*>(&v[j]);
+                    __half* ho = reinterpret_cast<__half*>(&out);
+                    if (MODE == IN_BNGELU) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ho[k] = act_from_z(hv[k], coef[ck * 8 + k]);
+                    } else {
+                        const __half* hz = reinterpret_cast<const __half*>(&v2[j]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ho[k] = dz_from(hv[k], hz[k], coef[ck * 8 + k]);
+                    }
+                }
+            }
+            *reinterpret_cast<uint4*>(tile + (size_t)pos * STRIDE + ck * 8) = out;
+        }
+    }
+};
 
 struct ConvParams {
     const __half* src;     // [B,H,W,SCH]   activation (IN_RAW), z of the producing layer (IN_BNGELU) or da (IN_DZ)
@@ -200,13 +228,24 @@ k_dec_conv(const ConvParams p) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
+    // the first batch of input-tile loads is in flight while the BatchNorm coefficients (their own L2 round trip +
+    // fp64 arithmetic) are derived: one exposed memory latency in the prologue instead of two
+    TileStager<CIN, SCH, MODE> stager;
+    stager.issue(p.src, p.src2, 0, b, r0, R, p.H, p.W);
     if (MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
         if (bstats)
             for (int ch = threadIdx.x; ch < COUT; ch += blockDim.x) coef_out[ch] = bn_coef(p.bn_out, ch, false);
         __syncthreads();
     }
-    stage_tile<CIN, SCH, MODE>(tile, p.src, p.src2, coef, b, r0, R, p.H, p.W);
+    stager.commit(tile, coef, 0, R, p.W);
+    {
+        const int total = (R + 2) * (p.W + 2) * (CIN / 8), step = kStagePF * (int)blockDim.x;
+        for (int base = step; base < total; base += step) {
+            stager.issue(p.src, p.src2, base, b, r0, R, p.H, p.W);
+            stager.commit(tile, coef, base, R, p.W);
+        }
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
