@@ -51,6 +51,7 @@ struct MarchCfg {
     float Hm1f;  // (float)(H-1)
     float Cf;    // (float)C
     double Hd;   // (double)H
+    float mb0, rmb0;  // level-0 mip_bound = fminf(1, bound) and its reciprocal (the only level when C == 1)
 };
 
 __device__ __forceinline__ MarchCfg make_cfg(float bound, float dt_gamma, uint32_t max_steps,
@@ -68,6 +69,8 @@ __device__ __forceinline__ MarchCfg make_cfg(float bound, float dt_gamma, uint32
     c.Hm1f = (float)(H - 1);
     c.Cf = (float)C;
     c.Hd = (double)H;
+    c.mb0 = fminf(scalbnf(1.0f, 0), bound);
+    c.rmb0 = __fdiv_rn(1.0f, c.mb0);
     return c;
 }
 
@@ -128,17 +131,22 @@ __device__ __forceinline__ Point eval_point(float t, const RayConst& r, const Ma
     p.z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
     p.dt = step_dt(t, c);
 
-    // mip_from_pos / mip_from_dt (raymarching.cu:42-54)
-    int ep, ed;
-    frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &ep);
-    const int lp = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ep));
-    const float mxd = __double2float_rn(__dmul_rn((double)__fmul_rn(p.dt, c.Hf), 0.5));
-    frexpf(mxd, &ed);
-    const int ld = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ed));
-    const int level = max(lp, ld);
-
-    const float mip_bound = fminf(scalbnf(1.0f, level), c.bound);
-    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    // mip_from_pos / mip_from_dt (raymarching.cu:42-54).  With one cascade both are clamped to [0, C-1] = {0}: the
+    // two frexpf, the fp64 product, scalbnf and the IEEE division cannot change the result, so the (warp-uniform)
+    // C == 1 case takes level 0 and the precomputed level-0 bound (same operations, evaluated once in make_cfg).
+    int level = 0;
+    float mip_bound = c.mb0, mip_rbound = c.rmb0;
+    if (c.Cf != 1.0f) {
+        int ep, ed;
+        frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &ep);
+        const int lp = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ep));
+        const float mxd = __double2float_rn(__dmul_rn((double)__fmul_rn(p.dt, c.Hf), 0.5));
+        frexpf(mxd, &ed);
+        const int ld = (int)fminf(c.Cf - 1.0f, fmaxf(0.0f, (float)ed));
+        level = max(lp, ld);
+        mip_bound = fminf(scalbnf(1.0f, level), c.bound);
+        mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    }
 
     const int nx = grid_coord(p.x, mip_rbound, c);
     const int ny = grid_coord(p.y, mip_rbound, c);
