@@ -68,6 +68,21 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert h.nsig_hash_encode_forward(p, 1, tabs, res, 16, 31, p, None, None) == -1   # log2_T out of range
     assert h.nsig_march_rays_train(p, p, p, 1.0, 0.0, 1024, 4, 0, 128, 64, p, p, p, p, p, p, p, None, p, None) == -1  # C=0
     assert h.nsig_march_rays_train_scratch_bytes(1000) == 8000
+    # entry points added for the fused step: loss head, composite epilogue, decoder
+    assert h.nsig_split_clamp_forward(None, 0, 0, None, None, None) == 0
+    assert h.nsig_split_clamp_forward(p, 9, 6, p, p, None) == -1                       # more block floats than floats
+    assert h.nsig_split_clamp_backward(None, None, None, 3, 6, p, None) == -1
+    assert h.nsig_wtmk_loss_forward(p, p, 6, p, p, 2, 0.005, 1.0, 10.0, None, p, p, None) == -1   # no output
+    assert h.nsig_wtmk_loss_backward(p, p, 6, 2, None, p, p, None) == -1                   # no incoming gradient
+    assert h.nsig_composite_rays_train_blend_forward(p, p, p, p, 8, 8, 1e-4, 1.0, None, None, p, p, p, p, p, None) == -1
+    assert h.nsig_composite_rays_train_blend_backward(None, None, p, p, p, p, p, p, 8, 8, 1e-4, 1.0, p, p, None) == -1
+    assert h.nsig_decoder_workspace_bytes(32, 12, 12, 0) == 0 and h.nsig_decoder_workspace_bytes(32, 12, 12, 8) > 0
+    assert h.nsig_decoder_forward(p, 2, 4, 4, 8, 9, 1, tabs, p, p, None) == -1             # num_bits*redundancy > 8
+    # the fused field kernels stage the fp16 MLP weights with 16-byte copies: misaligned weight pointers are rejected
+    buf = (ctypes.c_float * 64)()
+    base = ctypes.addressof(buf)
+    aligned, odd = V(base + (-base) % 16), V(base + (-base) % 16 + 2)
+    assert h.nsig_field_backward(p, p, 4, 1.0, p, p, p, odd, aligned, 1.0, None, 2048.0, 19, p, None, None, None, None) == -1
 
 
 def test_python_layer_has_no_cpu_path(lib):
