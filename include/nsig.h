@@ -177,6 +177,15 @@ int nsig_msg_encode_forward_perbit(const float* x, uint32_t B, const float* cons
                                    float resolution, uint32_t log2_T, float* out,
                                    nsig_stream_t stream);
 
+/* Parity probe: the hashed slots (hash_encoding.py:43-44) exactly as the FUSED kernels
+ * (nsig_field_forward / nsig_render_rays / nsig_grid_sweep) derive them — same device
+ * function, csrc/hash_common.cuh locate_fused — in the layout of nsig_hash_encode_forward's
+ * `slots` ([B, n_levels, 8] int32).  weights (optional): [B, n_levels, 3] interpolation
+ * weights of the fused path.  Used by tests/test_hash_gpu.py to pin the fused path's
+ * integer outputs to the reference-order encoder on cell-boundary inputs. */
+int nsig_fused_hash_slots(const float* x, uint32_t B, const float* resolutions, uint32_t n_levels,
+                          uint32_t log2_T, int32_t* slots, float* weights, nsig_stream_t stream);
+
 /* half2 shadow copies of n_levels base tables for the fused kernels (BASELINE north_star kernel 2: "vectorised
  * half2 loads"): tables_h2[l][i] = fp16(tables[l][i] * 2^k_l) with 2^k_l the power of two that puts the level's
  * largest magnitude in [2^14, 2^15); inv_scale[l] = 2^-k_l (device float[n_levels]).  absmax_scratch: device

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "nsig_hash_encode_backward": ([_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp], 1),
     "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _vp], 1),
     "nsig_msg_encode_forward_perbit": ([_vp, _u32, _vp, _u32, _vp, _f32, _u32, _vp, _vp], 1),
+    "nsig_fused_hash_slots": ([_vp, _u32, _vp, _u32, _u32, _vp, _vp], 1),
     "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp], 1),
     "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp], 1),

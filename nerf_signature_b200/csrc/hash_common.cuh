@@ -103,7 +103,9 @@ struct TablePtrs {
 //     (g a power of two) or at relative distance >= 2^-49 from every fp32 rounding midpoint (a midpoint m has
 //     25 significant bits with the last one set; m*g == x would need m*g to fit in 24 bits, impossible for a g
 //     whose mantissa is not 1).  One DMUL + one conversion instead of an IEEE division (~10 instructions with
-//     a guarded slow path); checked exhaustively around every cell boundary in tests/test_hash_gpu.py.
+//     a guarded slow path).  Checked at every cell boundary of all 17 resolutions +-40 ulp and on 10^7 random points:
+//     on the device through nsig_fused_hash_slots (tests/test_hash_gpu.py::test_fused_slots_equal_reference_order_slots),
+//     in numpy in tests/test_host_cpu.py::test_fused_index_identity_double_multiply_equals_fp32_division.
 //   * weight: (x - vmin) * fl(1/g) instead of (x - vmin) / (vmax - vmin)  (relative difference <= 2e-7).
 //   * trilinear interpolation with FMA contraction (a*(1-w) + b*w -> fma(b, w, a*(1-w))).
 // ---------------------------------------------------------------------------------------------------

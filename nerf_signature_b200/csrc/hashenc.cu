@@ -174,6 +174,27 @@ k_msg_encode_perbit(const float* __restrict__ x, uint32_t B, MsgTablePtrs tp, ui
     out[(size_t)b * 2 + 1] = a1;
 }
 
+
+// ---- parity probe of the FUSED kernels' per-level geometry ------------------------------------------------------------
+// k_field_fwd / k_render_rays / k_grid_sweep locate a sample's voxel with locate_fused (hash_common.cuh: one double
+// multiply instead of the reference's IEEE fp32 division).  This kernel evaluates exactly that device function and
+// writes the 8 hashed slots (and the three interpolation weights) in the layout of k_hash_encode_fwd's `slots`, so a
+// test can assert slot-for-slot equality with the reference-order encoder on adversarial inputs (cell boundaries +-k ulp).
+struct GeomLevels { LevelGeom g[NSIG_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(256)
+k_fused_hash_slots(const float* __restrict__ x, uint32_t B, GeomLevels gl, uint32_t n_levels, uint32_t mask,
+                   int32_t* __restrict__ slots, float* __restrict__ weights) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)B * n_levels;
+    if (gid >= total) return;
+    const uint32_t b = (uint32_t)(gid / n_levels), l = (uint32_t)(gid % n_levels);
+    const Voxel v = locate_fused(x[(size_t)b * 3], x[(size_t)b * 3 + 1], x[(size_t)b * 3 + 2], gl.g[l]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) slots[gid * 8 + k] = (int32_t)corner_slot(v, k, mask);
+    if (weights) { weights[gid * 3] = v.wx; weights[gid * 3 + 1] = v.wy; weights[gid * 3 + 2] = v.wz; }
+}
+
 }  // namespace nsig
 
 using namespace nsig;
@@ -270,6 +291,23 @@ int nsig_tables_to_half2(const float* const* tables, uint32_t n_levels, uint32_t
     k_shadow_absmax<<<grid, 256, 0, st>>>(tp, n_vec4, absmax_scratch);
     NSIG_LAUNCH_CHECK();
     k_shadow_convert<<<grid, 256, 0, st>>>(tp, n_vec4, absmax_scratch, inv_scale);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_fused_hash_slots(const float* x, uint32_t B, const float* resolutions, uint32_t n_levels, uint32_t log2_T,
+                          int32_t* slots, float* weights, nsig_stream_t stream) {
+    if (B == 0) return 0;
+    if (!x || !resolutions || !slots) return NSIG_EINVAL;
+    if (n_levels == 0 || n_levels > NSIG_MAX_LEVELS || log2_T == 0 || log2_T > 30) return NSIG_EINVAL;
+    GeomLevels gl;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        if (!(resolutions[l] > 0.0f)) return NSIG_EINVAL;
+        gl.g[l] = make_level_geom(resolutions[l]);   // the same host helper fill_field_params uses
+    }
+    const uint64_t total = (uint64_t)B * n_levels;
+    k_fused_hash_slots<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, gl, n_levels, (1u << log2_T) - 1u, slots, weights);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -125,3 +125,16 @@ class HashEmbedder(nn.Module):
         _lib.call("nsig_hash_encode_forward", _P(x), B, _lib.pointer_array(tabs), _lib.float_array(self.resolutions),
                   self.n_levels, self.log2_hashmap_size, _P(out), _P(slots))
         return slots
+
+    @torch.no_grad()
+    def fused_hashed_indices(self, x, resolutions=None, want_weights=False):
+        """int32 [B, L, 8] slots as the FUSED field kernels derive them (csrc/hash_common.cuh locate_fused: one
+        double multiply instead of the reference's fp32 division) — must equal `hashed_indices` bit for bit.
+        `resolutions` overrides the level list (e.g. [2048.0] for the message encoder's geometry)."""
+        x = x.contiguous().float()
+        res = list(self.resolutions if resolutions is None else resolutions)
+        B, L = x.shape[0], len(res)
+        slots = torch.empty(B, L, 8, dtype=torch.int32, device=x.device)
+        w = torch.empty(B, L, 3, dtype=torch.float32, device=x.device) if want_weights else None
+        _lib.call("nsig_fused_hash_slots", _P(x), B, _lib.float_array(res), L, self.log2_hashmap_size, _P(slots), _P(w))
+        return (slots, w) if want_weights else slots

@@ -99,3 +99,77 @@ def test_msg_encoder_golden(golden_hash, tag):
         # gradients of different tables must not alias (GradScaler.unscale_ works in place)
         ptrs = {enc.embeddings[2 * i + bits[i]].weight.grad.data_ptr() for i in range(md)}
         assert len(ptrs) == md
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The FUSED kernels (k_field_fwd / k_render_rays / k_grid_sweep: the benchmarked path) derive the voxel index with
+# one double multiply (hash_common.cuh locate_axis_fused) instead of the reference's fp32 division.  north_star wants
+# hash slots bit-exact: compare that device function against the reference-order encoder (pinned to the reference
+# module's goldens above) where a one-ulp difference of the quotient would flip the cell.
+# ---------------------------------------------------------------------------------------------------------
+def _boundary_points(res, ulps):
+    """Every cell boundary k/res' (k = 0..res) of one level, stepped by -ulps..+ulps fp32 ulps, for both candidate
+    boundary values: the fp32 product k*gs and the fp32 quotient k/res."""
+    gs = np.float32(1.0) / np.float32(res)
+    k = np.arange(0, int(res) + 2, dtype=np.float32)
+    base = np.concatenate([k * gs, (k / np.float32(res)).astype(np.float32)])
+    base = np.clip(base, 0.0, 1.0).astype(np.float32)
+    pts = [base]
+    up, dn = base.copy(), base.copy()
+    for _ in range(ulps):
+        up = np.nextafter(up, np.float32(2.0)); dn = np.nextafter(dn, np.float32(-1.0))
+        pts += [up.copy(), dn.copy()]
+    return np.unique(np.clip(np.concatenate(pts), 0.0, 1.0).astype(np.float32))
+
+
+def test_fused_slots_equal_reference_order_slots():
+    from nerf_signature_b200.hash_encoding import HashEmbedder
+    enc = HashEmbedder(bounding_box=(0, 1), n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+                       base_resolution=16, finest_resolution=2048).cuda()
+    # (a) all 16 base resolutions + the message encoder's (2048): every boundary +-40 ulp, placed on each axis in turn
+    #     against pseudo-random other coordinates
+    rs = np.random.RandomState(0)
+    total = 0
+    for res in sorted(set(enc.resolutions + [2048.0])):
+        b = _boundary_points(res, 40)
+        for axis in range(3):
+            x = rs.uniform(0, 1, size=(b.size, 3)).astype(np.float32)
+            x[:, axis] = b
+            xt = torch.from_numpy(x).cuda()
+            want = enc.hashed_indices(xt)
+            got = enc.fused_hashed_indices(xt)
+            assert torch.equal(got, want), f"fused slot mismatch at a cell boundary of resolution {res}"
+            total += x.shape[0] * 16
+        # the level's own geometry, all three axes on boundaries at once
+        x = np.stack([rs.choice(b, b.size), rs.choice(b, b.size), b], axis=1).astype(np.float32)
+        xt = torch.from_numpy(x).cuda()
+        assert torch.equal(enc.fused_hashed_indices(xt), enc.hashed_indices(xt))
+    assert total > 10 ** 7
+    # (b) 10^7 random points (uniform, plus a batch that includes values outside [0,1]: the clamp path)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for i in range(10):
+        xt = torch.rand(10 ** 6, 3, device="cuda", generator=g)
+        if i == 9:
+            xt = xt * 1.2 - 0.1
+        assert torch.equal(enc.fused_hashed_indices(xt), enc.hashed_indices(xt))
+    # (c) interpolation weights of the fused path: within 4 fp32 ulp-of-one of the reference expression
+    xt = torch.rand(200000, 3, device="cuda", generator=g)
+    _, w = enc.fused_hashed_indices(xt, want_weights=True)
+    res_t = torch.tensor(enc.resolutions, device="cuda")
+    gs = (1.0 / res_t).view(1, -1, 1)
+    xx = xt.view(-1, 1, 3)
+    vmin = torch.floor(xx / gs) * gs
+    w_ref = (xx - vmin) / ((vmin + gs) - vmin)
+    assert float((w - w_ref).abs().max()) <= 5e-7 * 2048  # |dw| <= ~2 ulp(x) * res
+
+
+def test_fused_slots_message_geometry():
+    """The message encoder's single resolution (2048) through the fused geometry (FieldParams.msg_geom)."""
+    from nerf_signature_b200.hash_encoding import HashEmbedder
+    enc = HashEmbedder(bounding_box=(0, 1), n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+                       base_resolution=16, finest_resolution=2048).cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xt = torch.rand(500000, 3, device="cuda", generator=g)
+    got = enc.fused_hashed_indices(xt, resolutions=[2048.0])
+    assert enc.resolutions[15] == 2048.0
+    assert torch.equal(got, enc.hashed_indices(xt)[:, 15:16])   # level 15 has resolution 2048

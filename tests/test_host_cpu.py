@@ -91,3 +91,32 @@ def test_synthetic_batch_shapes_match_the_reference_provider():
     np.testing.assert_allclose(np.linalg.norm(b["rays_o"], axis=-1), 4.0311 * 0.8, atol=1e-4)
     b2 = harness.make_batch(cfg, seed=0)
     assert all(np.array_equal(b[k], b2[k]) for k in b)  # seeded
+
+
+def test_fused_index_identity_double_multiply_equals_fp32_division():
+    """csrc/hash_common.cuh locate_axis_fused obtains fl32(x / g) as fl32(fl64(x) * fl64(1/g)).  The identity is
+    checked here in numpy (IEEE fp32 division vs the double-multiply form) at every cell boundary of all 17
+    resolutions +-40 ulp and on 2 M random points; the device function itself is checked in tests/test_hash_gpu.py."""
+    from nerf_signature_b200.hash_encoding import level_resolutions
+    base, finest = torch.tensor(16), torch.tensor(2048)
+    b = torch.exp((torch.log(finest) - torch.log(base)) / 15)
+    resolutions = sorted(set(level_resolutions(base, b, 16) + [2048.0]))
+    assert resolutions[0] == 16.0 and resolutions[-1] == 2048.0
+    rs = np.random.RandomState(0)
+    rnd = rs.uniform(0, 1, size=2_000_000).astype(np.float32)
+    n = 0
+    for res in resolutions:
+        gs = np.float32(1.0) / np.float32(res)
+        k = np.arange(0, int(res) + 2, dtype=np.float32)
+        pts = [np.clip(k * gs, 0, 1).astype(np.float32), np.clip(k / np.float32(res), 0, 1).astype(np.float32)]
+        for seed in list(pts):
+            up, dn = seed.copy(), seed.copy()
+            for _ in range(40):
+                up = np.nextafter(up, np.float32(2.0)); dn = np.nextafter(dn, np.float32(-1.0))
+                pts += [up, dn]
+        x = np.clip(np.concatenate(pts + [rnd]), 0.0, 1.0).astype(np.float32)
+        q_ref = x / gs                                                    # IEEE fp32 division (hash_encoding.py:39)
+        q_fused = (x.astype(np.float64) * (1.0 / np.float64(gs))).astype(np.float32)
+        assert np.array_equal(q_ref.view(np.uint32), q_fused.view(np.uint32)), res
+        n += x.size
+    assert n > 3 * 10 ** 7
