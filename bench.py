@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--config", default="blender_wtmk")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame inference leg")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the secondary legs (configs[2] 360 training, configs[4] sharded 262144-ray step, gradient "
+                         "check, reference-composed CUDA step, configs[0] CPU render)")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph-captured one")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = optim.WatermarkAdam; torch = torch.optim.Adam over get_params (implies --no-graph)")
@@ -192,8 +195,36 @@ def cpu_port_run(cfg, steps, warmup, rays_per_pass, num_steps=512):
     total = sum(times)
     return {"value": n_rays * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{rays_per_pass} content + {md}x{px}x{px} watermark-block rays per step, {num_steps} uniform "
-                      f"samples/ray (non-cuda_ray NeRFRenderer.run), {len(times)} timed steps, torch {cores} threads",
+                      f"samples/ray (non-cuda_ray NeRFRenderer.run), {len(times)} timed steps, torch {cores} threads; "
+                      "rays/s is per-ray work, so the full 8704-ray step extrapolates linearly (factor "
+                      f"{8704 / n_rays:.0f}x the step time)",
             "ms_per_step": 1e3 * total / len(times), "rays_per_step": n_rays}
+
+
+def cpu_configs0(repeats=2, n_rays=4096, num_steps=512):
+    """BASELINE configs[0] AS STATED: random-init clean HashNeRF (hash_encoding.py, 16 levels, 2^19 tables, network_hash
+    MLPs), non-cuda_ray render (NeRFRenderer.run, 512 uniform samples per ray, no upsampling) of 4096 synthetic
+    Blender-camera rays on the host cores, forward only."""
+    import torch
+    from nerf_signature_b200 import harness
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(harness.CONFIGS["blender_wtmk"])
+    b = harness.make_batch(cfg, seed=77, num_rays=n_rays, n_blocks=1)
+    o, d = torch.from_numpy(b["rays_o"][0]), torch.from_numpy(b["rays_d"][0])
+    field = tp.PortField(bound=cfg["bound"], message_dim=0, seed=0, train_msg=False)
+    with torch.no_grad():
+        tp.render_run(field, o[:256], d[:256], None, num_steps=num_steps)   # warm-up (thread pool, allocator)
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            tp.render_run(field, o, d, None, num_steps=num_steps)
+            times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"workload": "configs[0]: clean HashNeRF, non-cuda_ray render, forward only", "rays": n_rays,
+            "samples_per_ray": num_steps, "ms_per_render": 1e3 * best, "rays_per_s": n_rays / best, "cores": cores,
+            "kind": "port", "repeats": repeats}
 
 
 def run_reference(args):
@@ -215,26 +246,273 @@ def run_reference(args):
                        "sample": r["sample"]},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "configs0_cpu_render": cpu_configs0(repeats=1)}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+ALG_FWD = 24 + 1024 + 64 + 16   # SURVEY 8d bytes/sample of the field forward: xyz+dir in, 16x8x8 B base gather, msg gather, out
+ALG_BWD = 64 + 16 + 128         # field backward (watermark mode): saved features + incoming grads + 8 x 16 B RMW scatter
+FLOP_BWD = 2 * 20480            # recomputed forward + dgrad of the 5 padded GEMMs
+ALG_RENDER = 24 + 1024 + 64     # frame renderer: no sample ever leaves the SM
+
+
+class Ctx:
+    pass
+
+
+def _max_over_ranks(ms, cx):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=cx.dev, dtype=torch.float64)
+    if cx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(cx):
+    import torch
+    import torch.distributed as dist
+    if cx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_replays=8, clocks=None):
+    """W warm-up steps, then EXACTLY K steps between barrier+synchronize pairs, device-timed, max over ranks.
+    Then (outside the timed region, same graph, same batches) `roofline_replays` synchronised replays in which the two field
+    kernels' event times AND the march counter are read after EVERY replay, so bytes and time cover the same launches."""
+    import torch
+    from nerf_signature_b200 import _lib
+    n_pool = len(host_batches)
+    dev_batches = [scene.to_device(b) for b in host_batches]
+    md = scene.cfg["message_dim"]
+    names = ["nsig_field_forward", "nsig_field_backward"]
+    _lib.timing_enable(names)   # external event nodes when the step is captured
+    for i in range(W):
+        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+    if not scene.use_graph:
+        _lib.timing_enable(names)
+    if clocks is not None:
+        clocks.start()
+    _barrier(cx)
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+    e1.record()
+    _barrier(cx)
+    out = {"ms": _max_over_ranks(e0.elapsed_time(e1), cx)}
+    out["launches"] = (scene.launches_per_step * K) if scene.use_graph else (_lib.launch_count - launches0)
+    # ---- per-replay kernel time + sample count (sum of bytes / sum of time over the SAME launches) ----
+    acc = {n: {"ms": 0.0, "n": 0} for n in names}
+    samples = rays = 0
+    if not scene.use_graph:
+        _lib.timing_enable(names)
+    for i in range(roofline_replays):
+        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+        t = _lib.timing_read()          # synchronises; in graph mode = this replay's event pairs
+        s_, r_ = scene.samples_per_step()
+        samples += s_; rays += r_
+        if scene.use_graph:
+            for n in names:
+                if n in t:
+                    acc[n]["ms"] += t[n]["ms"]; acc[n]["n"] += t[n]["n"]
+    if not scene.use_graph:
+        t = _lib.timing_read()
+        for n in names:
+            if n in t:
+                acc[n] = t[n]
+    out.update(kernel_ms=acc, kernel_samples=samples, kernel_rays=rays, kernel_steps=roofline_replays)
+    # ---- host inputs through the public API: pinned host batch -> ONE H2D copy -> step -> D2H loss ----
+    if want_e2e:
+        pool = [scene.pinned_batch(b) for b in host_batches] if scene.use_graph else None
+        pinned = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in host_batches[0].items()}
+        pinned_msg = torch.empty(md, dtype=torch.float32).pin_memory()
+        out["h2d_bytes"] = (pool[0]["_flat"].numel() * 4) if pool is not None else \
+            (sum(v.nbytes for v in host_batches[0].values()) + md * 4)
+
+        def host_step(i):
+            if pool is not None:
+                pb = pool[i % n_pool]
+                pb["message"].copy_(scene.new_message(gen))
+                loss, _, _ = scene.train_step(pb, pb["message"])
+                return float(loss)
+            for k, v in host_batches[i % n_pool].items():
+                pinned[k].copy_(torch.from_numpy(v))
+            pinned_msg.copy_(scene.new_message(gen))
+            loss, _, _ = scene.train_step(pinned, pinned_msg)
+            return float(loss)
+
+        for i in range(3):
+            host_step(i)
+        _barrier(cx)
+        e0.record()
+        for i in range(K):
+            out["loss"] = host_step(i)
+        e1.record()
+        _barrier(cx)
+        out["ms_e2e"] = _max_over_ranks(e0.elapsed_time(e1), cx)
+    _lib.timing_collect()
+    return out
+
+
+def _peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return pk["hbm_gbs"], pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)), \
+            "measured (MEASURED_PEAKS.json: copy burst; bf16 GEMM sustained)"
+    except Exception:
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def rooflines(res, step_ms):
+    """Roofline entries from time_scene's per-replay accounting."""
+    peak_gbs, peak_tf, src = _peaks()
+    fwd, bwd = res["kernel_ms"]["nsig_field_forward"], res["kernel_ms"]["nsig_field_backward"]
+    S, steps = res["kernel_samples"], res["kernel_steps"]
+    traffic = {}
+    try:  # ncu dram__bytes_read+write per launch from the committed capture of this round (not the live launch)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
+    fwd_s = fwd["ms"] * 1e-3
+    ach = ALG_FWD * S / fwd_s / 1e9 if fwd_s > 0 else 0.0
+    main = {"bound": "hbm", "kernel": "k_field_fwd (nsig_field_forward)", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+            "frac": ach / peak_gbs, "traffic": traffic.get("k_field_fwd_bytes_per_launch"),
+            "traffic_note": "ncu --set full capture committed under profiles/ (a launch of %s samples), not the live launch"
+                            % traffic.get("k_field_fwd_samples", "?"),
+            "peak_source": src, "avg_launch_ms": fwd["ms"] / max(fwd["n"], 1),
+            "samples_per_launch": S / max(fwd["n"], 1), "alg_bytes_per_sample": ALG_FWD,
+            "share_of_step": (fwd["ms"] / steps) / step_ms if step_ms > 0 else None,
+            "timed": "CUDA events around the launch on the launching stream (external event nodes inside the captured "
+                     f"step graph); SUM of algorithmic bytes / SUM of launch time over the same {steps} replays, march "
+                     "counter read after every replay"}
+    bwd_s = bwd["ms"] * 1e-3
+    tf = FLOP_BWD * S / bwd_s / 1e12 if bwd_s > 0 else 0.0
+    gb = ALG_BWD * S / bwd_s / 1e9 if bwd_s > 0 else 0.0
+    other = [{"bound": "tensor", "kernel": "k_field_bwd (nsig_field_backward)", "achieved": tf, "peak": peak_tf,
+              "unit": "TFLOP/s", "frac": tf / peak_tf, "hbm_achieved_gbs": gb, "hbm_frac": gb / peak_gbs,
+              "traffic": traffic.get("k_field_bwd_bytes_per_launch"), "avg_launch_ms": bwd["ms"] / max(bwd["n"], 1),
+              "alg_flop_per_sample": FLOP_BWD, "alg_bytes_per_sample": ALG_BWD,
+              "share_of_step": (bwd["ms"] / steps) / step_ms if step_ms > 0 else None,
+              "note": "neither roofline is close: the kernel is bound by dependent-MMA latency / issue (ncu under profiles/)"}]
+    return main, other
+
+
+def frames_leg(cx, n_views=10):
+    """Second half of BASELINE's metric (configs[3]): the 10 test views sharded over the ranks, HiDDeN bit extraction
+    from every frame inside the timed region, plus a roofline entry for the persistent frame kernel."""
+    from nerf_signature_b200 import _lib, harness
+    peak_gbs, _, src = _peaks()
+    mine = [v for v in range(n_views) if v % cx.world == cx.rank] or [cx.rank % n_views]
+    render = {}
+    for name in ("blender_800x800", "llff_1008x756"):
+        _lib.timing_enable(["nsig_render_rays"])
+        r = harness.time_frames(name, cx.dev, mine)
+        kt = _lib.timing_collect().get("nsig_render_rays", {"ms": 0.0, "n": 0})
+        # the warm-up frame's events are included in kt: average over all recorded launches
+        k_ms = kt["ms"] / max(kt["n"], 1)
+        fms = _max_over_ranks(r["ms_per_frame"], cx)
+        ach = ALG_RENDER * (r["samples_per_frame"] or 0) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        render[name] = {"ms_per_frame": fms, "views": n_views, "frames_per_s_all_gpus": cx.world * 1e3 / fms,
+                        "samples_per_frame": r["samples_per_frame"], "bit_accuracy_random_init": r["bit_accuracy"],
+                        "launches_per_frame": r["launches_per_frame"],
+                        "path": "NeRFRenderer.render(eval) -> nsig_render_rays (one persistent kernel per frame) -> "
+                                "message_dim blocks of the frame -> fused HiDDeN decoder -> bits (utils_wtmk_disen.py:935)",
+                        "roofline": {"bound": "hbm", "kernel": "k_render_rays", "achieved": ach, "peak": peak_gbs,
+                                     "unit": "GB/s", "frac": ach / peak_gbs, "kernel_ms": k_ms,
+                                     "alg_bytes_per_sample": ALG_RENDER, "peak_source": src}}
+    return render
+
+
+def ref_cuda_leg(config, steps=20, warmup=3):
+    """The reference-composed CUDA step (tools/bench_ref_cuda.py) in a SUBPROCESS: north_star's ">= 10x the reference
+    torch-ngp/tcnn CUDA path" denominator, timed on the same GPU right after our arm."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_ref_cuda.py"), "--steps", str(steps), "--warmup", str(warmup),
+           "--config", config]
+    try:
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        for ln in reversed(p.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (p.stderr or "no output")[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def exchange_check(cx, scene):
+    """The custom one-kernel exchange against ncclAllReduce(AVG) on the same data (outside any timed region)."""
+    import torch
+    import torch.distributed as dist
+    sync = scene.sync
+    if not sync.enabled or sync.bucket is None:
+        return {"exchange": sync.exchange, "checked": False}
+    g = torch.Generator(device=cx.dev).manual_seed(1234 + cx.rank)
+    x = torch.randn(sync.bucket.n, device=cx.dev, generator=g)
+    ref = x.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+    sync.bucket.buf.copy_(x)
+    sync.bucket.all_reduce_mean()
+    torch.cuda.synchronize()
+    err = float((sync.bucket.buf - ref).abs().max())
+    t = torch.tensor([err], device=cx.dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sync.bucket.buf.zero_()
+    return {"exchange": sync.exchange, "checked": True, "max_abs_err_vs_nccl_avg": float(t.item()),
+            "elements": int(sync.bucket.n)}
+
+
+def grad_check_1_vs_n(cx, content_rays=16384):
+    """N-GPU == 1-GPU semantics: one GLOBAL batch (message_dim 48 blocks + `content_rays` rays) is
+    (a) sharded over the N ranks - contiguous ray ranges, block pixels all-gathered before the decoder, one gradient
+    exchange - and (b) processed whole by every rank with the process group ignored.  Returns the relative L2 distance of
+    the exchanged dL/dS and decoder gradients from the single-GPU ones (fp32 atomics: not bit-equal)."""
+    import torch
+    from nerf_signature_b200 import harness
+    cfg = dict(harness.CONFIGS["shard262144_wtmk"])
+    cfg["num_rays"] = content_rays
+    gbatch = harness.make_batch(cfg, seed=31337)
+    msg = torch.randint(0, 2, (cfg["message_dim"],), generator=torch.Generator().manual_seed(3)).float()
+    kw = dict(seed=0, optimizer="fused", graph=False, merged_render=True, fused_decoder=True, fused_losses=True)
+    local, bshape, counts = harness.shard_batch(gbatch, cx.rank, cx.world)
+    lcfg = dict(cfg); lcfg["num_rays"] = local["rays_o"].shape[1]
+    sn = harness.Scene(lcfg, cx.dev, shard_blocks=(bshape, counts), **kw)
+    scale = sn.scaler.get_scale()
+    ln, _, _ = sn.train_step(sn.to_device(local), msg)
+    Gn = (sn.optimizer.G / scale).clone()
+    Dn = torch.cat([p.grad.reshape(-1) for p in sn._decoder_params]) / scale
+    s1 = harness.Scene(cfg, cx.dev, distributed=False, **kw)
+    l1, _, _ = s1.train_step(s1.to_device(gbatch), msg)
+    G1 = s1.optimizer.G / scale
+    D1 = torch.cat([p.grad.reshape(-1) for p in s1._decoder_params]) / scale
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    out = {"content_rays": content_rays, "block_rays": int(sum(counts)), "dLdS_rel_l2": rel(Gn, G1),
+           "decoder_grads_rel_l2": rel(Dn, D1), "lossw_1gpu": None}
+    del sn, s1
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
+    cx = Ctx()
+    cx.rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: nerf_signature_b200 has no CPU path "
                          "(use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cx.dev = dev = torch.device("cuda", local_rank)
+    rank, world = cx.rank, cx.world
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -244,170 +522,111 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     cfg = dict(harness.CONFIGS[args.config])
-    if args.config.startswith("shard"):
-        cfg["num_rays"] = cfg["num_rays"] // world
     if args.split_render:
         args.render_mode = "split"
     use_graph = (not args.no_graph) and args.optimizer == "fused"
-    scene = harness.Scene(cfg, dev, seed=0, optimizer=args.optimizer, graph=use_graph,
-                          merged_render=args.render_mode == "merged", overlap_decoder=args.render_mode == "overlap",
-                          fused_decoder=not args.torch_decoder,
-                          fused_losses=not args.torch_losses)
+    skw = dict(seed=0, optimizer=args.optimizer, graph=use_graph, merged_render=args.render_mode == "merged",
+               overlap_decoder=args.render_mode == "overlap", fused_decoder=not args.torch_decoder,
+               fused_losses=not args.torch_losses)
     md = cfg["message_dim"]
     n_pool = 4  # distinct host batches cycled through (fresh rays every step)
-    seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
-    host_batches = [harness.make_batch(cfg, seed=1000 * seed_rank + i) for i in range(n_pool)]
-    pinned = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in host_batches[0].items()}
-    pinned_msg = torch.empty(md, dtype=torch.float32).pin_memory()
-    dev_batches = [scene.to_device(b) for b in host_batches]
-    rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
-    h2d_bytes = sum(v.nbytes for v in host_batches[0].values()) + md * 4
+    W, K = max(args.warmup, 3), max(args.steps, 1)
     gen = torch.Generator().manual_seed(7)  # identical message stream on every rank
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- phase A: device-resident inputs -> `value` --------------------------------------------------
-    W, K = max(args.warmup, 3), max(args.steps, 1)
-    _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])  # external events when captured
-    for i in range(W):
-        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
-    if not use_graph:
-        _lib.timing_enable(["nsig_field_forward", "nsig_field_backward"])  # drop the warm-up events
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()  # NVML start-up (tens of ms, rank 0 only) BEFORE the barrier: ranks enter the timed region together
-    barrier()
-    launches0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
-    e1.record()
-    barrier()
-    launches = (scene.launches_per_step * K) if use_graph else (_lib.launch_count - launches0)
-    ktimes = _lib.timing_read()
-    n_samples_step, _ = scene.samples_per_step()
-    spr = n_samples_step / rays_per_step
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    if use_graph:
-        # events inside a graph are re-recorded by every replay: the read above is the LAST timed step; average a
-        # few more synchronised replays of the same graph for a steadier per-launch figure
-        acc = {}
-        for i in range(8):
-            scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
-            for name, d in _lib.timing_read().items():
-                a = acc.setdefault(name, {"ms": 0.0, "n": 0})
-                a["ms"] += d["ms"]; a["n"] += d["n"]
-        for name, d in ktimes.items():
-            acc[name]["ms"] += d["ms"]; acc[name]["n"] += d["n"]
-        ktimes_avg, steps_timed = acc, 9
+    # ---- main workload: BASELINE configs[1] per GPU (weak scaling for N > 1) --------------------------------------
+    sharded_main = args.config.startswith("shard")
+    if sharded_main:   # strong scaling: ONE global batch sharded as SURVEY 8(e) prescribes
+        shards = [harness.shard_batch(harness.make_batch(cfg, seed=500 + i), rank, world) for i in range(n_pool)]
+        host_batches = [s_[0] for s_ in shards]
+        cfg["num_rays"] = host_batches[0]["rays_o"].shape[1]
+        scene = harness.Scene(cfg, dev, shard_blocks=(shards[0][1], shards[0][2]), **skw)
     else:
-        ktimes_avg, steps_timed = ktimes, K
+        seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
+        host_batches = [harness.make_batch(cfg, seed=1000 * seed_rank + i) for i in range(n_pool)]
+        scene = harness.Scene(cfg, dev, **skw)
+    rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    res = time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, clocks=clocks)
+    clk = clocks.stop() if clocks is not None else None
+    ms, ms_e2e = res["ms"], res["ms_e2e"]
+    xchk = exchange_check(cx, scene) if world > 1 else None
+    exchange_name = scene.sync.exchange
+    launches = res["launches"]
+    del scene
+    torch.cuda.empty_cache()
 
-    # ---- phase B: host inputs through the public API, H2D in, loss D2H out -> `e2e` ----------------------
-    # the host batches wait in pinned memory, packed like the captured step's input buffer (a pin_memory data loader):
-    # a step is then ONE H2D copy (rays, ground truth and the fresh message) + graph replay + D2H read of the loss
-    pool = [scene.pinned_batch(b) for b in host_batches] if use_graph else None
-    if pool is not None:
-        h2d_bytes = pool[0]["_flat"].numel() * 4
+    render = frames_leg(cx) if not args.no_render else {}
 
-    def host_step(i):
-        if pool is not None:
-            pb = pool[i % n_pool]
-            pb["message"].copy_(scene.new_message(gen))
-            loss, _, _ = scene.train_step(pb, pb["message"])
-            return float(loss)
-        for k, v in host_batches[i % n_pool].items():
-            pinned[k].copy_(torch.from_numpy(v))
-        pinned_msg.copy_(scene.new_message(gen))
-        loss, _, _ = scene.train_step(pinned, pinned_msg)   # H2D of the batch + message from pinned memory
-        return float(loss)                                   # D2H read of the step's result
-
-    for i in range(3):
-        host_step(i)
-    barrier()
-    e0.record()
-    for i in range(K):
-        loss_host = host_step(i)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
-    clk = clocks.stop() if rank == 0 else None
-    _lib.timing_collect()
-
-    # ---- full-frame inference (second half of BASELINE's metric): the 10 test views sharded over the ranks ------
-    render = {}
-    if not args.no_render:
-        n_views = 10
-        mine = [v for v in range(n_views) if v % world == rank] or [rank % n_views]
-        for name in ("blender_800x800", "llff_1008x756"):
-            fms, fsamples = harness.time_frames(name, dev, mine)
-            t = torch.tensor([fms], device=dev, dtype=torch.float64)
+    extra = {}
+    if not args.no_extra:
+        # ---- BASELINE configs[2]: 360-shaped training with the occupancy-grid update every 16 iterations (N = 1) ----
+        if world == 1 and args.config == "blender_wtmk":
+            c2 = dict(harness.CONFIGS["360_wtmk"])
+            s2 = harness.Scene(c2, dev, **skw)
+            hb2 = [harness.make_batch(c2, seed=2000 + i) for i in range(n_pool)]
+            r2 = time_scene(cx, s2, hb2, 32, 16, gen, want_e2e=False, roofline_replays=4)
+            rays2 = hb2[0]["rays_o"].shape[1] + int(np.prod(hb2[0]["rays_o_block"].shape[:-1]))
+            extra["configs2_360_wtmk"] = {
+                "workload": "360_wtmk (bound 2, scale 0.33, 4096 content + 32x23x31 block rays), occupancy-grid update "
+                            "(update_extra_state, fused sweep) every 16 iterations INSIDE the timed region",
+                "steps": 32, "grid_updates_in_timed_region": 2, "ms_per_step": r2["ms"] / 32, "rays_per_step": rays2,
+                "value": rays2 * 32 / (r2["ms"] * 1e-3), "unit": UNIT,
+                "mean_samples_per_ray": r2["kernel_samples"] / max(r2["kernel_rays"], 1)}
+            del s2
+            torch.cuda.empty_cache()
+        # ---- BASELINE configs[4]: 262 144 content rays/step + 48 watermark blocks, md 48, sharded over the N ranks -------
+        if args.config == "blender_wtmk":
+            c4 = dict(harness.CONFIGS["shard262144_wtmk"])
+            shards = [harness.shard_batch(harness.make_batch(c4, seed=4000 + i), rank, world) for i in range(2)]
+            hb4 = [s_[0] for s_ in shards]
+            c4l = dict(c4); c4l["num_rays"] = hb4[0]["rays_o"].shape[1]
+            s4 = harness.Scene(c4l, dev, shard_blocks=(shards[0][1], shards[0][2]), **skw)
+            K4 = 10
+            r4 = time_scene(cx, s4, hb4, K4, 3, gen, want_e2e=True, roofline_replays=2)
+            total4 = c4["num_rays"] + int(np.prod(shards[0][1]))
+            m4, o4 = rooflines(r4, r4["ms"] / K4)
+            extra["configs4_shard262144"] = {
+                "workload": "shard262144_wtmk: ONE global batch of 262144 content rays + 48 blocks x 12 x 12 watermark rays, "
+                            "message_dim 48; contiguous ray ranges per rank, block pixels all-gathered before the decoder "
+                            "(global BatchNorm statistics), one gradient exchange per step",
+                "scaling": "strong", "n_gpus": world, "steps": K4, "ms_per_step": r4["ms"] / K4,
+                "value": total4 * K4 / (r4["ms"] * 1e-3), "unit": UNIT, "rays_per_step_global": total4,
+                "rays_per_step_per_gpu": hb4[0]["rays_o"].shape[1] + hb4[0]["rays_o_block"].shape[0],
+                "e2e": {"value": total4 * K4 / (r4["ms_e2e"] * 1e-3), "ms_per_step": r4["ms_e2e"] / K4,
+                        "h2d_bytes_per_step": r4["h2d_bytes"], "d2h_bytes_per_step": 4},
+                "mean_samples_per_ray": r4["kernel_samples"] / max(r4["kernel_rays"], 1),
+                "roofline_field_fwd_frac": m4["frac"], "field_fwd_ms": m4["avg_launch_ms"],
+                "field_bwd_ms": o4[0]["avg_launch_ms"], "exchange": s4.sync.exchange}
+            del s4
+            torch.cuda.empty_cache()
             if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fms_max = float(t.item())
-            render[name] = {"ms_per_frame": fms_max, "views": n_views, "frames_per_s_all_gpus": world * 1e3 / fms_max,
-                            "samples_per_frame": fsamples,
-                            "path": "NeRFRenderer.render(eval) -> nsig_render_rays (one persistent kernel per frame)"}
+                extra["grad_check_1_vs_n"] = grad_check_1_vs_n(cx)
+    if xchk is not None:
+        extra["exchange_check"] = xchk
 
     if rank != 0:
         _finish(world)
         return
 
-    # ---- roofline of the dominant kernel (fused field forward) -------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json, copy burst)") if "hbm_gbs" in peaks \
-        else (6650.0, "fallback (B200_PROFILING.md)")
-    fwd = ktimes_avg.get("nsig_field_forward", {"ms": 0.0, "n": 0})
-    bwd = ktimes_avg.get("nsig_field_backward", {"ms": 0.0, "n": 0})
-    samples_per_step = n_samples_step  # both render passes, read from the march counters
-    # SURVEY 8d algorithmic bytes per sample of the field forward: 24 (xyz, dir in) + 1024 (16 levels x 8 corners
-    # x 8 B) + 64 (pre-summed message table gather) + 16 (sigma, rgb out)
-    alg_bytes_per_sample = 24 + 1024 + 64 + 16
-    calls_per_step = max(fwd["n"] / steps_timed, 1e-9)
-    avg_ms = fwd["ms"] / max(fwd["n"], 1)
-    samples_per_launch = samples_per_step / calls_per_step
-    achieved = alg_bytes_per_sample * samples_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     step_ms = ms / K
-    traffic = None
-    try:  # ncu dram__bytes_read+write per launch of this kernel, from the committed capture of this round
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["k_field_fwd_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "k_field_fwd (nsig_field_forward)", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": avg_ms, "samples_per_launch": samples_per_launch,
-                "alg_bytes_per_sample": alg_bytes_per_sample,
-                "share_of_step": (fwd["ms"] / steps_timed) / step_ms if step_ms > 0 else None,
-                "field_backward_avg_launch_ms": bwd["ms"] / max(bwd["n"], 1),
-                "field_backward_share_of_step": (bwd["ms"] / steps_timed) / step_ms if step_ms > 0 else None,
-                "timed": "CUDA events around the launches on the launching stream" +
-                         (" (external event nodes inside the captured step graph; mean of 9 replays)" if use_graph else "")}
-
-    total_rays = rays_per_step * world
+    roofline, roofline_other = rooflines(res, step_ms)
+    for name, r in render.items():
+        roofline_other.append(dict(r["roofline"], workload=name))
+    spr = res["kernel_samples"] / max(res["kernel_rays"], 1)
+    total_rays = rays_per_step * (1 if sharded_main else world)
+    if sharded_main:
+        total_rays = cfg_global_rays(harness, args.config)
     line = {
         "metric": METRIC, "value": total_rays * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if sharded_main else "weak",
+        "vs_baseline": None,
         "dtype": "f16 MMA operands / f32 accumulate, f32 encoder+march+composite", "data": "synthetic",
         "config": {"workload": args.config, "bound": cfg["bound"], "scale": cfg["scale"], "dt_gamma": cfg["dt_gamma"],
                    "message_dim": md, "codebook": f'{cfg["num_rows"]}x{cfg["num_cols"]}',
                    "content_rays_per_gpu": cfg["num_rays"], "watermark_rays_per_gpu": rays_per_step - cfg["num_rays"],
-                   "rays_per_step_per_gpu": rays_per_step, "mean_samples_per_ray": spr, "occupancy": cfg["occupancy"],
+                   "rays_per_step_per_gpu": rays_per_step, "mean_samples_per_ray": spr,
+                   "mean_samples_per_ray_note": f"mean over the {res['kernel_steps']} roofline replays (all {n_pool} pool batches)",
+                   "occupancy": cfg["occupancy"],
                    "weights": "random-init (tables U(+-1e-4), Xavier MLPs)",
                    "optimizer": ("WatermarkAdam (fused message-table Adam + torch fused Adam for the decoder)"
                                  if args.optimizer == "fused" else "torch.optim.Adam(fused)") + " + GradScaler",
@@ -418,17 +637,33 @@ def run_ours(args):
                                        "next to the content pass"}[args.render_mode],
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
-                   "decoder": "fused kernels (csrc/decoder.cu)" if scene.fused_decoder else "plain PyTorch module (autocast)",
-                   "losses": "loss-head kernels (csrc/wtmk_loss.cu)" if scene.fused_losses else "plain torch expressions",
-                   "parallelism": f"ray-sharded dp{world}", "exchange": scene.sync.exchange},
+                   "decoder": "plain PyTorch module (autocast)" if args.torch_decoder else "fused kernels (csrc/decoder.cu)",
+                   "losses": "plain torch expressions" if args.torch_losses else "loss-head kernels (csrc/wtmk_loss.cu)",
+                   "parallelism": f"ray-sharded dp{world}", "exchange": exchange_name},
         "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
+                "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 4,
+                "staging": "host batches wait in pinned memory packed like the step's input buffer (what a pin_memory data "
+                           "loader hands over); packing is outside the timed region, the H2D copy, the step and the D2H loss "
+                           "read are inside"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_other": roofline_other, "render": render,
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
+        if not args.no_extra:
+            rc = ref_cuda_leg(args.config)
+            line["ref_cuda"] = rc
+            if "value" in rc:
+                line["ref_cuda"]["ours_e2e_over_ref_cuda"] = line["e2e"]["value"] / rc["value"]
         line["cpu_baseline"] = cpu_port_run(cfg, steps=12, warmup=1, rays_per_pass=args.cpu_rays or 64)  # ~12 s of CPU work
+        if not args.no_extra:
+            line["cpu_baseline"]["configs0"] = cpu_configs0(repeats=1)
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def cfg_global_rays(harness, name):
+    c = harness.CONFIGS[name]
+    return c["num_rays"] + c["message_dim"] * (c["H"] // c["num_rows"]) * (c["W"] // c["num_cols"])
 
 
 def _finish(world):

@@ -408,11 +408,15 @@ int nsig_allreduce_mean_inplace(void* const* bufs, void* const* flags, void* mul
  *   steps    : device float[n_tables], per-table step counts (incremented for the selected tables)
  *   coef     : device float[n_tables][2] scratch (bias-correction scalars)
  *   grad_scale / found_inf: optional device scalars with torch.amp.GradScaler's meaning (G is divided
- *   by *grad_scale; the whole step is skipped when *found_inf != 0). */
+ *   by *grad_scale; the whole step is skipped when *found_inf != 0).
+ *   lr_dev   : optional device float; when non-NULL the learning rate is read from it at execution
+ *   time instead of `lr`, so a per-step scheduler (the reference's LambdaLR, scheduler_update_every_step)
+ *   keeps acting on a step that is replayed from a CUDA graph. */
 int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
                        const float* message, const float* G, float* steps, float* coef,
                        const float* grad_scale, const float* found_inf, float lr, float beta1,
-                       float beta2, float eps, uint32_t log2_T, nsig_stream_t stream);
+                       float beta2, float eps, uint32_t log2_T, const float* lr_dev,
+                       nsig_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ _SIGNATURES = {
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
-    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp], 2),
+    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp, _vp], 2),
     "nsig_field_backward": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp, _vp,
                              _vp, _vp], 1),
 }
@@ -116,15 +116,28 @@ def load():
     return _lib
 
 
+class _Ptr:
+    """A device pointer argument that keeps its tensor alive until the call has been enqueued.  Call sites often pass
+    temporaries (`_P(x.contiguous())`); with a bare integer the temporary would be released as soon as data_ptr()
+    returns and the caching allocator could hand the same block to the next temporary of the same argument list, so
+    two arguments would alias.  ctypes converts the object through `_as_parameter_`."""
+    __slots__ = ("_as_parameter_", "tensor")
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self._as_parameter_ = ctypes.c_void_p(tensor.data_ptr())
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA and contiguous."""
+    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA and contiguous; it stays referenced by the
+    returned argument object for the duration of the call."""
     if t is None:
         return None
     if not t.is_cuda:
         raise NsigError("nerf_signature_b200 kernels need CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
         raise NsigError("tensor must be contiguous")
-    return t.data_ptr()
+    return _Ptr(t)
 
 
 def stream():
@@ -214,7 +227,8 @@ def side_stream(device=None, which=0):
 
 def pointer_array(tensors):
     """Host array of device pointers (const float* const*) for a list of tensors."""
-    arr = (_vp * len(tensors))(*[ptr(t) for t in tensors])
+    arr = (_vp * len(tensors))(*[None if t is None else ptr(t).tensor.data_ptr() for t in tensors])
+    arr._keep = list(tensors)   # the array only holds integers: keep the tensors (often temporaries) alive with it
     return arr
 
 

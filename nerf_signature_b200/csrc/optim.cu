@@ -18,10 +18,11 @@ namespace nsig {
 // torch's fused Adam evaluates its bias corrections).
 __global__ void k_msg_adam_prepare(uint32_t md, const float* __restrict__ message, float* __restrict__ steps,
                                    float* __restrict__ coef, const float* __restrict__ found_inf, double lr,
-                                   double beta1, double beta2) {
+                                   const float* __restrict__ lr_dev, double beta1, double beta2) {
     const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i >= md) return;
     if (found_inf && *found_inf != 0.0f) return;  // GradScaler: skip the whole step
+    if (lr_dev) lr = (double)*lr_dev;  // learning rate read on the device: schedulers keep working under graph replay
     const uint32_t t = 2 * i + (((uint32_t)(int)message[i]) & 1u);
     const float s = steps[t] + 1.0f;
     steps[t] = s;
@@ -96,13 +97,14 @@ using namespace nsig;
 extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
                                   const float* message, const float* G, float* steps, float* coef,
                                   const float* grad_scale, const float* found_inf, float lr, float beta1,
-                                  float beta2, float eps, uint32_t log2_T, nsig_stream_t stream) {
+                                  float beta2, float eps, uint32_t log2_T, const float* lr_dev,
+                                  nsig_stream_t stream) {
     if (!ptr_table || !message || !G || !steps || !coef) return NSIG_EINVAL;
     if (message_dim == 0 || 2 * message_dim > n_tables || n_tables > NSIG_MAX_MSG_TABLES) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || (((uintptr_t)G) & 15)) return NSIG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message, steps, coef, found_inf,
-                                                                 (double)lr, (double)beta1, (double)beta2);
+                                                                 (double)lr, lr_dev, (double)beta1, (double)beta2);
     NSIG_LAUNCH_CHECK();
     const uint32_t n_vec4 = (1u << log2_T) / 2;  // T entries x 2 floats / 4
     AdamPtrs ptrs{ptr_table, n_tables};

@@ -70,6 +70,27 @@ def make_batch(cfg, seed, num_rays=None, n_blocks=None):
     }
 
 
+def shard_batch(batch_np, rank, world_size):
+    """SURVEY 8(e) partitioning of ONE global batch: rank r takes the contiguous ray range [r*N/k, (r+1)*N/k) of the
+    content rays (with their ground truth) and of the flattened watermark-block rays.  Returns (local batch, block_shape,
+    per-rank block-ray counts); the block rays come back flat ([n_local, 3]) - the rendered pixels are all-gathered into
+    the full [md, pH, pW, 3] image before the decoder (parallel.all_gather_pixels)."""
+    bo, bd = batch_np["rays_o_block"], batch_np["rays_d_block"]
+    block_shape = tuple(bo.shape[:-1])
+    nb = int(np.prod(block_shape))
+    n = batch_np["rays_o"].shape[1]
+    blo, bhi = parallel.shard_range(nb, rank, world_size)
+    clo, chi = parallel.shard_range(n, rank, world_size)
+    counts = [parallel.shard_range(nb, r, world_size)[1] - parallel.shard_range(nb, r, world_size)[0]
+              for r in range(world_size)]
+    local = {"rays_o_block": np.ascontiguousarray(bo.reshape(-1, 3)[blo:bhi]),
+             "rays_d_block": np.ascontiguousarray(bd.reshape(-1, 3)[blo:bhi]),
+             "rays_o": np.ascontiguousarray(batch_np["rays_o"][:, clo:chi]),
+             "rays_d": np.ascontiguousarray(batch_np["rays_d"][:, clo:chi]),
+             "gt": np.ascontiguousarray(batch_np["gt"][:, clo:chi])}
+    return local, block_shape, counts
+
+
 def occupancy(cfg, cascade, seed=0):
     if cfg["occupancy"] == "sphere":
         return syn.sphere_grid(cascade)
@@ -80,7 +101,8 @@ class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
-                 merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False):
+                 merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
+                 shard_blocks=None, distributed=True):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -90,7 +112,11 @@ class Scene:
         overlap_decoder (two render calls, like the reference step): the decoder runs on a side stream.  Its forward
         and backward are chains of ~10 small latency-bound kernels each that leave most SMs idle; with the watermark
         blocks rendered first, the content pass (march, field forward, composite - and in the backward pass its field
-        backward) executes next to them.  In the captured step these are parallel branches of one graph."""
+        backward) executes next to them.  In the captured step these are parallel branches of one graph.
+        shard_blocks: (block_shape, per-rank block-ray counts) from shard_batch - the batch holds this rank's slice of
+        ONE global batch: block pixels are all-gathered before the decoder so that every rank decodes the
+        full batch (global BatchNorm statistics) and N GPUs compute what one GPU would.
+        distributed=False: ignore the process group (single-GPU semantics inside a multi-rank job; gradient checks)."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
         from .optim import WatermarkAdam
         torch.manual_seed(seed)
@@ -116,6 +142,9 @@ class Scene:
                              "with every message under torch.optim.Adam)")
         self.fused = optimizer == "fused"
         self.sync = parallel.GradSync()
+        if not distributed:
+            self.sync.enabled, self.sync.exchange = False, "none"
+        self.shard_blocks = shard_blocks
         self._decoder_params = [p for p in self.model.msg_decoder.parameters()]
         # one flat [dL/dS | decoder gradients] buffer whenever the fused optimizer is used: a single fill per step
         # instead of one zeros/add pair per decoder parameter, and the bucket of the multi-GPU exchange
@@ -139,6 +168,8 @@ class Scene:
         self.fused_losses = fused_losses
         self.overlap_decoder = overlap_decoder and not merged_render
         self.iteration = 0
+        self.keep_outputs = False   # parity tests: keep the step's rendered pixels and decoder logits in self.last
+        self.last = None
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -175,6 +206,13 @@ class Scene:
         from .nerf.loss_ops import split_clamp, wtmk_loss
         ob = batch["rays_o_block"]
         nb = ob.numel() // 3
+        block_shape = tuple(ob.shape)
+        gather = None
+        if self.shard_blocks is not None:   # this rank's slice of the block rays; pixels are gathered before the decoder
+            block_shape = tuple(self.shard_blocks[0]) + (3,)
+            if self.sync.enabled:
+                ws = parallel.world()[1]
+                gather = lambda px: parallel.all_gather_pixels(px.reshape(-1, 3), self.shard_blocks[1], grad_scale=ws)
         if self.merged_render:
             # the two render passes of the reference step (utils_wtmk_disen.py:592,641) see the same network and the
             # same message and rays are independent: one launch chain over [block rays | content rays]
@@ -187,16 +225,19 @@ class Scene:
                                **self.opt)
             if self.fused_losses:
                 pred, image_c = split_clamp(out["image"], nb)
-                pred, image_c = pred.view(ob.shape), image_c.view(batch["rays_o"].shape)
+                image_c = image_c.view(batch["rays_o"].shape)
             else:
-                image_w, image_c = out["image"][0, :nb].reshape(ob.shape), out["image"][:, nb:]
+                image_w, image_c = out["image"][0, :nb], out["image"][:, nb:]
         else:
-            image_w = model.render(batch["rays_o_block"], batch["rays_d_block"], message, staged=False, bg_color=1,
-                                   perturb=False, force_all_rays=True, **self.opt)["image"]
+            image_w = model.render(batch["rays_o_block"].reshape(1, nb, 3), batch["rays_d_block"].reshape(1, nb, 3), message,
+                                   staged=False, bg_color=1, perturb=False, force_all_rays=True, **self.opt)["image"]
             if self.fused_losses:
-                pred = split_clamp(image_w, nb)[0].view(ob.shape)
+                pred = split_clamp(image_w, nb)[0]
         if not self.fused_losses:
             pred = torch.clamp(image_w, min=0, max=1)
+        if gather is not None:
+            pred = gather(pred)
+        pred = pred.reshape(block_shape)
         side = _lib.side_stream(self.device, 2) if self.overlap_decoder else None
         main = torch.cuda.current_stream()
         if side is not None:     # fork: the decoder chain runs next to the content pass below
@@ -220,6 +261,8 @@ class Scene:
             lossi = F.mse_loss(image_c, batch["gt"], reduction="none").mean()
             lossw = F.binary_cross_entropy_with_logits(decoded.float() * 10.0, msg_dev.unsqueeze(-1), reduction="mean")
             loss = self.lambda_w * lossw + self.lambda_i * lossi
+        if self.keep_outputs:
+            self.last = {"pred": pred.detach(), "image_c": image_c.detach(), "decoded": decoded.detach()}
         self.scaler.scale(loss).backward()
         if self.flat_sync:
             self.sync.reduce_flat()
@@ -312,7 +355,12 @@ class Scene:
         if self._graph is None:
             self._capture(batch, message)
         self._copy_inputs(batch, message)
+        if self.fused:
+            self.optimizer.sync_lr()        # lr schedulers act on host floats; the captured kernels read device scalars
         self._graph.replay()
+        # the replayed Adam kernel rewrote the message tables through raw pointers: neither optimizer.step()'s cache
+        # invalidation nor an autograd version bump happened, so drop the cached summed table S here
+        self.model._S_cache = None
         return self._static_out
 
     def _counter_rows(self):
@@ -349,10 +397,25 @@ def frame_rays(fc, view):
     return syn.camera_rays(pose, fc["H"], fc["W"], focal, np.arange(fc["H"] * fc["W"]))
 
 
-def time_frames(name, device, views, message_dim=32, seed=0, fused=True, staged=False):
+def frame_block_ids(fc, message_dim, num_rows=32, num_cols=32, seed=0):
+    """Flat pixel ids of `message_dim` randomly chosen (seeded randperm, provider_wtmk.py:199-204) blocks of
+    pH x pW = (H // num_rows) x (W // num_cols) pixels of a full frame: [md * pH * pW] int64 + the block shape."""
+    H, W = fc["H"], fc["W"]
+    pH, pW = H // num_rows, W // num_cols
+    rs = np.random.RandomState(seed)
+    blocks = rs.permutation(num_rows * num_cols)[:message_dim]
+    ii, jj = np.meshgrid(np.arange(pH), np.arange(pW), indexing="ij")
+    ids = np.concatenate([(((b // num_cols) * pH + ii) * W + ((b % num_cols) * pW + jj)).reshape(-1) for b in blocks])
+    return ids.astype(np.int64), (message_dim, pH, pW)
+
+
+def time_frames(name, device, views, message_dim=32, seed=0, fused=True, staged=False, extract_bits=True):
     """Render `views` (list of view ids) of frame config `name` through NeRFRenderer.render in eval mode
     (main_nerf_wtmk.py --test path: renderer_wtmk.py:541-574 -> run_cuda inference branch) with a random-init
-    watermark network and the sphere occupancy fixture.  Returns (ms per frame, samples per frame)."""
+    watermark network and the sphere occupancy fixture, and - BASELINE configs[3] "+ HiDDeN bit extraction" - decode the
+    message from message_dim blocks of every rendered frame (Trainer.test_bitacc -> eval_step, utils_wtmk_disen.py:935,
+    663-669: clamp, normalise, msg_decoder; bit = logit > 0) inside the timed region.
+    Returns a dict: ms per frame, samples per frame, bit accuracy (random-init weights: ~0.5), launches per frame."""
     from .nerf.network_wtmk_tcnn import NeRFNetwork
     fc = FRAME_CONFIGS[name]
     torch.manual_seed(seed)
@@ -362,22 +425,38 @@ def time_frames(name, device, views, message_dim=32, seed=0, fused=True, staged=
     net.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, 0.5)))
     net.fused_inference = fused
     msg = torch.randint(0, 2, (message_dim,)).float().to(device)
+    ids, bshape = frame_block_ids(fc, message_dim)
+    ids = torch.from_numpy(ids).to(device)
     frames = []
     for v in views:
         o, d = frame_rays(fc, v)
         frames.append((torch.from_numpy(o)[None].to(device), torch.from_numpy(d)[None].to(device)))
     kw = dict(staged=staged, bg_color=1, perturb=False, dt_gamma=0.0, max_steps=1024)
     counts = []
+    hits = torch.zeros((), dtype=torch.float32, device=device)
+
+    def one(f):
+        out = net.render(*f, msg, **kw)
+        if extract_bits:
+            blocks = torch.clamp(out["image"].view(-1, 3)[ids].view(*bshape, 3), min=0, max=1)
+            logits = net.decode_blocks(blocks)
+            hits.add_(((logits.float().view(-1) > 0) == (msg > 0.5)).float().mean())
+        return out
+
     with torch.no_grad():
-        net.render(*frames[0], msg, **kw)  # warm-up
+        one(frames[0])  # warm-up
         torch.cuda.synchronize()
+        hits.zero_()
+        n0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for f in frames:
-            net.render(*f, msg, **kw)
+            one(f)
             if fused and not staged:
                 counts.append(net.last_render_samples)
         e1.record()
         torch.cuda.synchronize()
     samples = float(sum(int(c) for c in counts)) / max(len(counts), 1) if counts else None
-    return e0.elapsed_time(e1) / len(frames), samples
+    return {"ms_per_frame": e0.elapsed_time(e1) / len(frames), "samples_per_frame": samples,
+            "bit_accuracy": float(hits) / len(frames) if extract_bits else None,
+            "launches_per_frame": (_lib.launch_count - n0) / len(frames)}

@@ -55,6 +55,14 @@ class _fused_decode(Function):
 
     @staticmethod
     def backward(ctx, dlogits):
+        """RESTRICTION (deliberate): parameter gradients are ACCUMULATED INTO `p.grad` here and `None` is returned for the
+        parameters, instead of handing tensors to autograd's accumulator - that is what lets every decoder gradient land
+        directly in the flat all-reduce bucket with zero extra kernels.  Consequences: `torch.autograd.grad`, per-parameter
+        hooks and DistributedDataParallel's reducer do not see these gradients (use the plain module, harness
+        fused_decoder=False, for those), and the saved workspace is released after the first backward."""
+        if ctx.ws is None:
+            raise RuntimeError("fused HiDDeN decoder: backward called twice on the same graph (retain_graph is not "
+                               "supported: the activation workspace is released after the first backward)")
         B, H, W, num_blocks, num_bits, redundancy = ctx.meta
         dev = dlogits.device
         params = ctx.params

@@ -35,28 +35,25 @@ def custom_meshgrid(*args):
 
 
 def sample_pdf(bins, weights, n_samples, det=False):
-    """Inverse-CDF sampling of the original NeRF (reference renderer_wtmk.py:12-46)."""
-    weights = weights + 1e-5
-    pdf = weights / torch.sum(weights, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
-    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
-    if det:
-        u = torch.linspace(0. + 0.5 / n_samples, 1. - 0.5 / n_samples, steps=n_samples).to(weights.device)
-        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    """Draw `n_samples` depths per ray from the piecewise-constant density that `weights` [N, B-1] puts on the intervals
+    between the `bins` [N, B] (hierarchical sampling of the original NeRF; same signature and arithmetic as the reference
+    helper, renderer_wtmk.py:12-46, so the non-cuda_ray renderer resamples the same depths)."""
+    pdf = weights + 1e-5
+    pdf = pdf / pdf.sum(dim=-1, keepdim=True)
+    cdf = torch.nn.functional.pad(torch.cumsum(pdf, dim=-1), (1, 0))            # [N, B], starts at 0
+    n_rays, n_edges = cdf.shape[0], cdf.shape[-1]
+    if det:   # centres of n_samples equal probability bins
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=cdf.device).expand(n_rays, n_samples)
     else:
-        u = torch.rand(list(cdf.shape[:-1]) + [n_samples]).to(weights.device)
+        u = torch.rand(n_rays, n_samples, device=cdf.device)
     u = u.contiguous()
-    inds = torch.searchsorted(cdf, u, right=True)
-    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
-    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
-    inds_g = torch.stack([below, above], -1)
-    matched_shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
-    cdf_g = torch.gather(cdf.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    bins_g = torch.gather(bins.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    denom = (cdf_g[..., 1] - cdf_g[..., 0])
-    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-    t = (u - cdf_g[..., 0]) / denom
-    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+    hi = torch.searchsorted(cdf, u, right=True).clamp(max=n_edges - 1)          # first edge with cdf > u
+    lo = (hi - 1).clamp(min=0)
+    cdf_lo, cdf_hi = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
+    bin_lo, bin_hi = torch.gather(bins, 1, lo), torch.gather(bins, 1, hi)
+    span = cdf_hi - cdf_lo
+    frac = (u - cdf_lo) / torch.where(span < 1e-5, torch.ones_like(span), span)
+    return bin_lo + frac * (bin_hi - bin_lo)
 
 
 class NeRFRenderer(nn.Module):
@@ -131,95 +128,59 @@ class NeRFRenderer(nn.Module):
         self.local_step = 0
 
     # ------------------------------------------------------------------------------------------
-    # non-cuda_ray path (reference renderer_wtmk.py:125-253): uniform samples, density() + color()
+    # non-cuda_ray path: uniform (+ optionally importance-resampled) depths, no occupancy grid.
+    # Same results as the reference's NeRFRenderer.run (renderer_wtmk.py:125-253); evaluated differently: the
+    # resampling pass is a no-grad density query, and the final, depth-sorted sample set goes through ONE fused,
+    # DIFFERENTIABLE field evaluation (sigma and colour together) instead of density() + masked color().
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _alpha_weights(depths, sigmas, last_delta):
+        """Per-sample compositing weights alpha_i * prod_{j<i}(1 - alpha_j + 1e-15) for depths [N,S], sigmas [N,S]."""
+        gaps = torch.cat([depths[:, 1:] - depths[:, :-1], last_delta.expand(depths.shape[0], 1)], dim=-1)
+        alpha = 1 - torch.exp(-gaps * sigmas)
+        trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1 - alpha + 1e-15], dim=-1), dim=-1)[:, :-1]
+        return alpha * trans, gaps
+
     def run(self, rays_o, rays_d, message=None, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
-        prefix = rays_o.shape[:-1]
-        rays_o = rays_o.contiguous().view(-1, 3)
-        rays_d = rays_d.contiguous().view(-1, 3)
+        lead = rays_o.shape[:-1]
+        o = rays_o.contiguous().view(-1, 3).float()
+        d = rays_d.contiguous().view(-1, 3).float()
+        n_rays, dev = o.shape[0], o.device
+        box = self.aabb_train if self.training else self.aabb_infer
+        near, far = raymarching.near_far_from_aabb(o, d, box, self.min_near)
+        near, far = near.unsqueeze(-1), far.unsqueeze(-1)
+        step = (far - near) / num_steps
 
-        N = rays_o.shape[0]
-        device = rays_o.device
+        def points(t):   # [N,S] depths -> [N,S,3] positions clamped into the box
+            return torch.min(torch.max(o.unsqueeze(1) + d.unsqueeze(1) * t.unsqueeze(-1), box[:3]), box[3:])
 
-        aabb = self.aabb_train if self.training else self.aabb_infer
-
-        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
-        nears = nears.unsqueeze(-1)
-        fars = fars.unsqueeze(-1)
-
-        z_vals = torch.linspace(0.0, 1.0, num_steps, device=device).unsqueeze(0)
-        z_vals = z_vals.expand((N, num_steps))
-        z_vals = nears + (fars - nears) * z_vals
-
-        sample_dist = (fars - nears) / num_steps
+        depths = near + (far - near) * torch.linspace(0.0, 1.0, num_steps, device=dev).unsqueeze(0)
         if perturb:
-            z_vals = z_vals + (torch.rand(z_vals.shape, device=device) - 0.5) * sample_dist
-
-        xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
-        xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
-
-        density_outputs = self.density(xyzs.reshape(-1, 3), message)
-        for k, v in density_outputs.items():
-            density_outputs[k] = v.view(N, num_steps, -1)
-
+            depths = depths + (torch.rand(depths.shape, device=dev) - 0.5) * step
         if upsample_steps > 0:
-            with torch.no_grad():
-                deltas = z_vals[..., 1:] - z_vals[..., :-1]
-                deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
-                alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs['sigma'].squeeze(-1))
-                alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-                weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
-                z_vals_mid = (z_vals[..., :-1] + 0.5 * deltas[..., :-1])
-                new_z_vals = sample_pdf(z_vals_mid, weights[:, 1:-1], upsample_steps, det=not self.training).detach()
-                new_xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * new_z_vals.unsqueeze(-1)
-                new_xyzs = torch.min(torch.max(new_xyzs, aabb[:3]), aabb[3:])
-
-            new_density_outputs = self.density(new_xyzs.reshape(-1, 3), message)
-            for k, v in new_density_outputs.items():
-                new_density_outputs[k] = v.view(N, upsample_steps, -1)
-
-            z_vals = torch.cat([z_vals, new_z_vals], dim=1)
-            z_vals, z_index = torch.sort(z_vals, dim=1)
-            xyzs = torch.cat([xyzs, new_xyzs], dim=1)
-            xyzs = torch.gather(xyzs, dim=1, index=z_index.unsqueeze(-1).expand_as(xyzs))
-            for k in density_outputs:
-                tmp_output = torch.cat([density_outputs[k], new_density_outputs[k]], dim=1)
-                density_outputs[k] = torch.gather(tmp_output, dim=1, index=z_index.unsqueeze(-1).expand_as(tmp_output))
-
-        deltas = z_vals[..., 1:] - z_vals[..., :-1]
-        deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
-        alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs['sigma'].squeeze(-1))
-        alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-        weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
-
-        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
-        for k, v in density_outputs.items():
-            density_outputs[k] = v.view(-1, v.shape[-1])
-
-        mask = weights > 1e-4
-        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
-        rgbs = rgbs.view(N, -1, 3)
-
+            with torch.no_grad():   # coarse densities only steer the resampling
+                coarse = self.density(points(depths).reshape(-1, 3), message)["sigma"].view(n_rays, num_steps)
+                w, gaps = self._alpha_weights(depths, self.density_scale * coarse, step)
+                mids = depths[:, :-1] + 0.5 * gaps[:, :-1]
+                fine = sample_pdf(mids, w[:, 1:-1], upsample_steps, det=not self.training).detach()
+            depths, _ = torch.sort(torch.cat([depths, fine], dim=1), dim=1)
+        n_samples = depths.shape[1]
+        xyz = points(depths)
+        dirs = d.unsqueeze(1).expand_as(xyz)
+        # `field` returns density_scale * sigma and rgb; gradients flow to whatever the network trains
+        sigma, rgb = self.field(xyz.reshape(-1, 3).contiguous(), dirs.reshape(-1, 3).contiguous(), message)
+        weights, _ = self._alpha_weights(depths, sigma.view(n_rays, n_samples), step)
+        # the reference evaluates colour only where weight > 1e-4 and leaves zeros elsewhere
+        lit = (weights > 1e-4).to(weights.dtype)
+        image = torch.sum((weights * lit).unsqueeze(-1) * rgb.view(n_rays, n_samples, 3), dim=1)
         weights_sum = weights.sum(dim=-1)
-        ori_z_vals = ((z_vals - nears) / (fars - nears)).clamp(0, 1)
-        depth = torch.sum(weights * ori_z_vals, dim=-1)
-        image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2)
-
+        depth = torch.sum(weights * ((depths - near) / (far - near)).clamp(0, 1), dim=-1)
         if self.bg_radius > 0:
-            sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
-            bg_color = self.background(sph, rays_d.reshape(-1, 3))
+            bg_color = self.background(raymarching.sph_from_ray(o, d, self.bg_radius), d)
         elif bg_color is None:
             bg_color = 1
-
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-        image = image.view(*prefix, 3)
-        depth = depth.view(*prefix)
-
-        return {
-            'depth': depth,
-            'image': image,
-            'weights_sum': weights_sum,
-        }
+        return {'depth': depth.view(*lead), 'image': image.view(*lead, 3), 'weights_sum': weights_sum}
 
     # ------------------------------------------------------------------------------------------
     # cuda_ray path (reference renderer_wtmk.py:256-377)
@@ -282,10 +243,7 @@ class NeRFRenderer(nn.Module):
             else:
                 composite = raymarching.raymarching.composite_rays_train_live if live else raymarching.composite_rays_train
                 weights_sum, depth, image = composite(sigmas, rgbs, deltas, rays, T_thresh)
-                image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-            image = image.view(*prefix, 3)
-            depth = depth.view(*prefix)
+                image, depth = self._blend_and_normalise(image, depth, weights_sum, nears, fars, bg_color)
 
             results['weights_sum'] = weights_sum
 
@@ -298,47 +256,46 @@ class NeRFRenderer(nn.Module):
                 rays_o, rays_d, self.aabb_infer, self.min_near, self.density_bitfield, self.cascade, self.grid_size,
                 dt_gamma, max_steps, T_thresh, noises, S, cfg, sigma_mlp, color_mlp, tables)
             self.last_render_samples = n_samples  # device int32 scalar (for throughput accounting)
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-            depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-            image = image.view(*prefix, 3)
-            depth = depth.view(*prefix)
+            image, depth = self._blend_and_normalise(image, depth, weights_sum, nears, fars, bg_color)
 
         else:
-            dtype = torch.float32
+            weights_sum, depth, image = self._alive_ray_loop(rays_o, rays_d, nears, fars, message, perturb, dt_gamma,
+                                                             max_steps, T_thresh)
+            image, depth = self._blend_and_normalise(image, depth, weights_sum, nears, fars, bg_color)
 
-            weights_sum = torch.zeros(N, dtype=dtype, device=device)
-            depth = torch.zeros(N, dtype=dtype, device=device)
-            image = torch.zeros(N, 3, dtype=dtype, device=device)
-
-            n_alive = N
-            rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
-            rays_t = nears.clone()
-
-            step = 0
-            while step < max_steps:
-                n_alive = rays_alive.shape[0]
-                if n_alive <= 0:
-                    break
-                n_step = max(min(N // n_alive, 8), 1)
-
-                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
-
-                sigmas, rgbs = self.field(xyzs, dirs, message)
-
-                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
-
-                rays_alive = rays_alive[rays_alive >= 0]
-                step += n_step
-
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-            depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-            image = image.view(*prefix, 3)
-            depth = depth.view(*prefix)
-
-        results['depth'] = depth
-        results['image'] = image
-
+        results['depth'] = depth.view(*prefix)
+        results['image'] = image.view(*prefix, 3)
         return results
+
+    @staticmethod
+    def _blend_and_normalise(image, depth, weights_sum, nears, fars, bg_color):
+        """Composite over the background and map the accumulated depth into [0, 1] along the ray's box segment
+        (the tail of every run_cuda branch, reference renderer_wtmk.py:316-320, 368-372)."""
+        return image + (1 - weights_sum).unsqueeze(-1) * bg_color, torch.clamp(depth - nears, min=0) / (fars - nears)
+
+    def _alive_ray_loop(self, rays_o, rays_d, nears, fars, message, perturb, dt_gamma, max_steps, T_thresh):
+        """Host-driven inference through the drop-in march_rays / composite_rays pair, with the reference's schedule
+        (renderer_wtmk.py:323-372): every pass advances each surviving ray by k = clamp(N // survivors, 1, 8) samples,
+        composite_rays marks finished rays with -1, survivors are compacted, until max_steps samples per ray.  Kept for
+        API fidelity and as the parity baseline of the one-kernel frame renderer (fused_inference=True)."""
+        n_rays, dev = rays_o.shape[0], rays_o.device
+        acc_w = torch.zeros(n_rays, dtype=torch.float32, device=dev)
+        acc_depth = torch.zeros(n_rays, dtype=torch.float32, device=dev)
+        acc_rgb = torch.zeros(n_rays, 3, dtype=torch.float32, device=dev)
+        survivors = torch.arange(n_rays, dtype=torch.int32, device=dev)
+        ray_t = nears.clone()
+        taken = 0
+        while taken < max_steps and survivors.numel() > 0:
+            alive = survivors.numel()
+            k = min(max(n_rays // alive, 1), 8)
+            xyzs, dirs, deltas = raymarching.march_rays(alive, k, survivors, ray_t, rays_o, rays_d, self.bound,
+                                                        self.density_bitfield, self.cascade, self.grid_size, nears, fars,
+                                                        128, bool(perturb) and taken == 0, dt_gamma, max_steps)
+            sigmas, rgbs = self.field(xyzs, dirs, message)
+            raymarching.composite_rays(alive, k, survivors, ray_t, sigmas, rgbs, deltas, acc_w, acc_depth, acc_rgb, T_thresh)
+            survivors = survivors[survivors >= 0]
+            taken += k
+        return acc_w, acc_depth, acc_rgb
 
     def field(self, xyzs, dirs, message, count=None):
         """(density_scale * sigma, rgb) of the samples; implemented by the network subclasses."""
@@ -417,32 +374,19 @@ class NeRFRenderer(nn.Module):
         self._mean_count = v
 
     def render(self, rays_o, rays_d, message=None, staged=False, max_ray_batch=4096, **kwargs):
-        # rays_o, rays_d: [B, N, 3]  (reference renderer_wtmk.py:541-574)
-        if self.cuda_ray:
-            _run = self.run_cuda
-        else:
-            _run = self.run
-
-        B, N = rays_o.shape[:2]
-        device = rays_o.device
-
-        if staged:
-            depth = torch.empty((B, N), device=device)
-            image = torch.empty((B, N, 3), device=device)
-
-            for b in range(B):
-                head = 0
-                while head < N:
-                    tail = min(head + max_ray_batch, N)
-                    results_ = _run(rays_o[b:b+1, head:tail], rays_d[b:b+1, head:tail], message, **kwargs)
-                    depth[b:b+1, head:tail] = results_['depth']
-                    image[b:b+1, head:tail] = results_['image']
-                    head += max_ray_batch
-
-            results = {}
-            results['depth'] = depth
-            results['image'] = image
-        else:
-            results = _run(rays_o, rays_d, message, **kwargs)
-
-        return results
+        """rays_o, rays_d: [B, N, 3] -> {'image': [B, N, 3], 'depth': [B, N], ...} (reference signature,
+        renderer_wtmk.py:541-574).  staged=True walks every batch entry in chunks of max_ray_batch rays and returns only
+        image and depth, like the reference; otherwise the whole ray set goes through one call."""
+        runner = self.run_cuda if self.cuda_ray else self.run
+        if not staged:
+            return runner(rays_o, rays_d, message, **kwargs)
+        n_batch, n_rays = rays_o.shape[:2]
+        out = {'depth': torch.empty((n_batch, n_rays), device=rays_o.device),
+               'image': torch.empty((n_batch, n_rays, 3), device=rays_o.device)}
+        for b in range(n_batch):
+            for lo in range(0, n_rays, max_ray_batch):
+                hi = min(lo + max_ray_batch, n_rays)
+                part = runner(rays_o[b:b + 1, lo:hi], rays_d[b:b + 1, lo:hi], message, **kwargs)
+                out['depth'][b:b + 1, lo:hi] = part['depth']
+                out['image'][b:b + 1, lo:hi] = part['image']
+        return out

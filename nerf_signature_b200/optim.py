@@ -42,12 +42,22 @@ class WatermarkAdam(torch.optim.Optimizer):
         self.G = torch.zeros_like(tables[0]) if grad_buffer is None else grad_buffer.view_as(tables[0])
         self._proxy = torch.nn.Parameter(torch.empty_like(tables[0]), requires_grad=True)
         self._proxy.grad = self.G
-        groups = list(others)
+        groups = [{"params": g["params"], "lr": g["lr"]} for g in others]   # outer groups: what lr schedulers act on
         if self._train_tables:
             groups.append({"params": [self._proxy], "lr": lr, "msg_tables": True})
         super().__init__(groups, dict(lr=lr, betas=betas, eps=eps))
-        self.inner = torch.optim.Adam(others, lr=lr, betas=betas, eps=eps, fused=True, capturable=capturable) \
-            if others else None
+        # capturable: learning rates live in device scalars (tensor lr for the inner fused Adam, `_lr_dev` for the table
+        # kernel) so that a per-step scheduler acting on param_groups[...]["lr"] still takes effect when the step is
+        # replayed from a CUDA graph: call sync_lr() before each replay (harness.Scene does)
+        self.capturable = capturable
+        self.inner = None
+        if others:
+            inner_groups = [{"params": g["params"],
+                             "lr": torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev) if capturable else g["lr"]}
+                            for g in others]
+            self.inner = torch.optim.Adam(inner_groups, lr=lr, betas=betas, eps=eps, fused=True, capturable=capturable)
+        self._lr_dev = torch.tensor([float(lr)], dtype=torch.float32, device=dev) if capturable else None
+        self._lr_host = [float(g["lr"]) for g in self.param_groups]
         self.enc = enc
         self._model = model
         self.tables = tables
@@ -67,6 +77,84 @@ class WatermarkAdam(torch.optim.Optimizer):
     def set_message(self, message_dev):
         self.message = message_dev
 
+    def sync_lr(self):
+        """Propagate the learning rates of the outer param_groups (what lr schedulers modify) to the inner Adam and, in
+        capturable mode, to the device scalars the captured kernels read.  Host-side no-op while nothing changed."""
+        n_inner = len(self.inner.param_groups) if self.inner is not None else 0
+        for i, g in enumerate(self.param_groups):
+            lr = float(g["lr"])
+            changed = lr != self._lr_host[i]
+            self._lr_host[i] = lr
+            if i < n_inner:
+                g_in = self.inner.param_groups[i]
+                if isinstance(g_in["lr"], torch.Tensor):
+                    if changed:
+                        g_in["lr"].fill_(lr)
+                else:
+                    g_in["lr"] = lr
+            elif g.get("msg_tables") and self._lr_dev is not None and changed:
+                self._lr_dev.fill_(lr)
+
+    # ---- checkpointing: the layout torch.optim.Adam(model.get_params(lr)).state_dict() has ---------------------------
+    def state_dict(self):
+        """Same structure as the reference's optimizer checkpoint (nerf/utils_wtmk_disen.py:1410, an Adam over
+        get_params): parameter indices follow get_params order - the 2*message_dim message tables first, then the
+        decoder - and state[i] = {step, exp_avg, exp_avg_sq} exists for every parameter that has been updated."""
+        n_t = len(self.tables) if self._train_tables else 0
+        groups, state = [], {}
+        if self._train_tables:
+            g = {k: v for k, v in self.param_groups[-1].items() if k not in ("params", "msg_tables")}
+            groups.append({**g, "params": list(range(n_t))})
+            steps = self.steps.detach().cpu()
+            for t in range(n_t):
+                if float(steps[t]) > 0:
+                    state[t] = {"step": steps[t].clone(), "exp_avg": self.exp_avg[t].detach().clone(),
+                                "exp_avg_sq": self.exp_avg_sq[t].detach().clone()}
+        if self.inner is not None:
+            sd = self.inner.state_dict()
+            for g in sd["param_groups"]:
+                g = dict(g)
+                g["lr"] = float(g["lr"])
+                g["params"] = [i + n_t for i in g["params"]]
+                groups.append(g)
+            for k, v in sd["state"].items():
+                state[k + n_t] = v
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Accepts state_dict() of this class and of a torch.optim.Adam built over the same get_params groups."""
+        n_t = len(self.tables) if self._train_tables else 0
+        groups, state = state_dict["param_groups"], state_dict["state"]
+        if self._train_tables:
+            tg = groups[0]
+            if list(tg["params"]) != list(range(n_t)):
+                raise ValueError(f"first param group must hold the {n_t} message tables (get_params order)")
+            self.steps.zero_()
+            for t in range(n_t):
+                st = state.get(t)
+                self.exp_avg[t].zero_(); self.exp_avg_sq[t].zero_()
+                if st is not None:
+                    self.exp_avg[t].copy_(st["exp_avg"]); self.exp_avg_sq[t].copy_(st["exp_avg_sq"])
+                    self.steps[t] = float(st["step"])
+            for k in ("lr", "betas", "eps"):
+                if k in tg:
+                    self.param_groups[-1][k] = float(tg[k]) if k != "betas" else tuple(tg[k])
+            groups = groups[1:]
+        if self.inner is not None:
+            sd = {"param_groups": [], "state": {k - n_t: v for k, v in state.items() if k >= n_t}}
+            for g, g_in, g_out in zip(groups, self.inner.param_groups, self.param_groups):
+                g2 = dict(g)
+                g2["params"] = [i - n_t for i in g["params"]]
+                g_out["lr"] = float(g["lr"])
+                if isinstance(g_in["lr"], torch.Tensor):   # keep the device scalar the captured step reads
+                    g_in["lr"].fill_(float(g["lr"]))
+                    g2["lr"] = g_in["lr"]
+                sd["param_groups"].append(g2)
+            self.inner.load_state_dict(sd)
+        self._lr_host = [float("nan")] * len(self.param_groups)   # force a refresh of the device scalars
+        self.sync_lr()
+
     def zero_grad(self, set_to_none=True):
         if self.inner is not None:
             self.inner.zero_grad(set_to_none=set_to_none)
@@ -80,9 +168,8 @@ class WatermarkAdam(torch.optim.Optimizer):
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
         side = None
+        self.sync_lr()
         if self.inner is not None:
-            for g_out, g_in in zip(self.param_groups, self.inner.param_groups):
-                g_in["lr"] = g_out["lr"]  # lr schedulers act on the outer groups
             self.inner.grad_scale, self.inner.found_inf = grad_scale, found_inf
             # the decoder's (tiny, latency-bound) Adam runs next to the HBM-bound message-table Adam
             side = _lib.side_stream(self.G.device, 1) if self._train_tables else None
@@ -105,7 +192,7 @@ class WatermarkAdam(torch.optim.Optimizer):
             md = self.enc.message_dim
             _lib.call("nsig_msg_adam_step", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(self.G),
                       _P(self.steps), _P(self._coef), _P(grad_scale), _P(found_inf), float(group["lr"]), float(beta1),
-                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size)
+                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size, _P(self._lr_dev))
             # the kernel writes the tables through raw pointers (no autograd version bump): drop the model's
             # cached S so the next forward re-sums the updated tables
             self._model._S_cache = None

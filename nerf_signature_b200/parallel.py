@@ -146,27 +146,34 @@ class GradSync:
             o += n
 
 
-def all_gather_pixels(local_pixels, counts, group=None):
+def all_gather_pixels(local_pixels, counts, group=None, grad_scale=1.0):
     """Concatenate per-rank [n_r, 3] pixel blocks (n_r = counts[r]) into the full [sum, 3] tensor on every
-    rank, differentiably: the backward pass hands each rank the gradient slice of its own pixels."""
-    return _AllGatherPixels.apply(local_pixels, tuple(int(c) for c in counts), group)
+    rank, differentiably: the backward pass hands each rank the gradient slice of its own pixels, multiplied by
+    `grad_scale`.  Every rank evaluates the decoder loss on the FULL gathered batch, so the slice already is the complete
+    d(loss)/d(own pixels); the step's gradient exchange averages over ranks, hence callers pass grad_scale = world size
+    to make the rank-mean of the table gradient equal the single-GPU gradient."""
+    return _AllGatherPixels.apply(local_pixels, tuple(int(c) for c in counts), group, float(grad_scale))
 
 
 class _AllGatherPixels(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, counts, group):
+    def forward(ctx, x, counts, group, grad_scale):
         rank, ws = world()
-        ctx.counts, ctx.rank = counts, rank
+        ctx.counts, ctx.rank, ctx.grad_scale = counts, rank, grad_scale
         if ws == 1:
             return x.clone()
         mx = max(counts)
         pad = torch.zeros(mx, *x.shape[1:], dtype=x.dtype, device=x.device)
         pad[:x.shape[0]] = x
-        out = [torch.empty_like(pad) for _ in range(ws)]
-        dist.all_gather(out, pad, group=group)
-        return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+        full = torch.empty(ws * mx, *x.shape[1:], dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(full, pad, group=group)   # one collective, capturable in the step graph
+        if all(c == mx for c in counts):
+            return full
+        return torch.cat([full[r * mx:r * mx + c] for r, c in enumerate(counts)], dim=0)
 
     @staticmethod
     def backward(ctx, g):
         lo = sum(ctx.counts[:ctx.rank])
-        return g[lo:lo + ctx.counts[ctx.rank]].contiguous(), None, None
+        gl = g[lo:lo + ctx.counts[ctx.rank]]
+        gl = gl * ctx.grad_scale if ctx.grad_scale != 1.0 else gl.contiguous()
+        return gl, None, None, None

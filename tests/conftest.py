@@ -38,3 +38,15 @@ def oracle_cpu():
     from oracle import cpu
     cpu.build()
     return cpu
+
+
+def record_parity(name, metrics):
+    """Append measured parity errors to gpurun_out/parity_metrics.jsonl (when that directory exists: GPU runs under
+    gpurun) so the tolerances written in the tests can be audited against what was actually observed; the summary is
+    committed under profiles/."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    with open(os.path.join(out, "parity_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **metrics}) + "\n")

@@ -7,7 +7,16 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import record_parity
+
 pytestmark = pytest.mark.gpu
+
+
+def _rel(got, want):
+    """(max-norm relative error, relative L2 error) of a tensor against its reference."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return (float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)),
+            float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)))
 
 
 def _points(M, bound, seed):
@@ -61,11 +70,17 @@ def test_field_forward_and_density(oracle_cpu, bound, md, M):
         colm = net.color(xt, dt, mask=mask, geo_feat=dens["geo_feat"])
     for m_, (s_, c_) in ((msg, (sigma, rgb)), (None, (sigma0, rgb0))):
         _, _, osig, orgb, ogeo = _oracle_forward(net, x, dirs, m_, oracle_cpu)
+        record_parity(f"field_forward[{bound},{md},{M},msg={m_ is not None}]",
+                      {"sigma_max_rel_elementwise": float(np.abs(s_.cpu().numpy() / osig.detach().numpy() - 1).max()),
+                       "rgb_max_abs": float(np.abs(c_.cpu().numpy() - orgb.detach().numpy()).max())})
         np.testing.assert_allclose(s_.cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
         np.testing.assert_allclose(c_.cpu().numpy(), orgb.detach().numpy(), rtol=0, atol=2e-3)
     assert float((sigma - sigma0).abs().max()) > 0  # the message does change the field
     _, _, osig, orgb, ogeo = _oracle_forward(net, x, dirs, msg, oracle_cpu)
     np.testing.assert_allclose(dens["sigma"].cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
+    record_parity(f"field_density[{bound},{md},{M}]",
+                  {"geo_max_abs": float(np.abs(dens["geo_feat"].float().cpu().numpy() - ogeo.detach().numpy()).max()),
+                   "geo_scale": float(np.abs(ogeo.detach().numpy()).max())})
     np.testing.assert_allclose(dens["geo_feat"].float().cpu().numpy(), ogeo.detach().numpy(), rtol=0, atol=3e-3)
     np.testing.assert_allclose(col.cpu().numpy(), rgb.cpu().numpy(), rtol=0, atol=1e-5)
     assert torch.equal(colm[mask], col[mask]) and float(colm[~mask].abs().sum()) == 0
@@ -96,6 +111,7 @@ def test_field_backward_message_tables(oracle_cpu, bound, md, M):
         assert uns.grad is None
         np.testing.assert_allclose(sel.grad.cpu().numpy(), G, rtol=0, atol=1e-2 * gmax)
     got = net.msg_encoder.embeddings[int(msg[0])].weight.grad.cpu().numpy()
+    record_parity(f"field_backward_G[{bound},{md},{M}]", dict(zip(("max_rel", "rel_l2"), _rel(got, G))))
     rel_l2 = np.linalg.norm(got - G) / np.linalg.norm(G)
     assert rel_l2 < 5e-3, rel_l2
     # frozen parts stay grad-free
@@ -138,6 +154,7 @@ def test_clean_model_backward_weights_and_base_tables(oracle_cpu, M):
 
     for name, got, want in (("sigma_net", net.sigma_net.params.grad, sp.grad), ("color_net", net.color_net.params.grad, cp.grad)):
         got, want = got.cpu().numpy(), want.numpy()
+        record_parity(f"clean_wgrad[{M},{name}]", dict(zip(("max_rel", "rel_l2"), _rel(got, want))))
         rel = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert rel < 1e-2, (name, rel)
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-2 * np.abs(want).max(), err_msg=name)
@@ -149,5 +166,6 @@ def test_clean_model_backward_weights_and_base_tables(oracle_cpu, M):
     gt = oracle_cpu.hash_encode_backward(xn, featt.grad.numpy(), net.encoder.resolutions, 16, 19)
     for l in (0, 7, 15):
         got = net.encoder.embeddings[l].weight.grad.cpu().numpy()
+        record_parity(f"clean_base_table_grad[{M},level{l}]", dict(zip(("max_rel", "rel_l2"), _rel(got, gt[l]))))
         rel = np.linalg.norm(got - gt[l]) / np.linalg.norm(gt[l])
         assert rel < 1e-2, (l, rel)

@@ -70,6 +70,27 @@ def _worker(rank, world, port, results):
         w = torch.arange(sum(counts) * 3, dtype=torch.float32).view(-1, 3)
         (full * w).sum().backward()
         assert torch.equal(x.grad, w[lo:lo + counts[rank]])
+        # grad_scale = world: every rank differentiates the FULL-batch loss, the exchange then averages over ranks
+        x2 = x.detach().clone().requires_grad_(True)
+        (parallel.all_gather_pixels(x2, counts, grad_scale=world) * w).sum().backward()
+        assert torch.equal(x2.grad, world * w[lo:lo + counts[rank]])
+        # ---- watermark-block sharding: rank-mean of the sharded gradients == single-process gradient ----
+        torch.manual_seed(11)
+        table = torch.nn.Parameter(torch.randn(6, 3))          # stands in for the message table: pixel = f(table)
+        Wd = torch.nn.Parameter(torch.randn(3, 1))             # stands in for the decoder (sees the FULL batch)
+        sel = torch.tensor([0, 1, 2, 3, 4, 5, 0, 2])           # 8 "block pixels"
+        plo, phi = parallel.shard_range(8, rank, world)
+        pcounts = [parallel.shard_range(8, r, world)[1] - parallel.shard_range(8, r, world)[0] for r in range(world)]
+        local_px = torch.tanh(table[sel[plo:phi]])
+        full_px = parallel.all_gather_pixels(local_px, pcounts, grad_scale=world)
+        bn = (full_px - full_px.mean(0)) / full_px.std(0)       # batch statistics over ALL pixels, like BatchNorm
+        (bn @ Wd).pow(2).mean().backward()
+        sync.reduce_params([table, Wd])
+        t1, w1 = torch.nn.Parameter(table.detach().clone()), torch.nn.Parameter(Wd.detach().clone())
+        px = torch.tanh(t1[sel])
+        bn1 = (px - px.mean(0)) / px.std(0)
+        (bn1 @ w1).pow(2).mean().backward()
+        assert torch.allclose(table.grad, t1.grad, atol=1e-5) and torch.allclose(Wd.grad, w1.grad, atol=1e-5)
         # ---- equivalence: sharded mean-loss gradients == single-process gradients ----
         torch.manual_seed(7)
         W = torch.nn.Parameter(torch.randn(3, 4))

@@ -95,3 +95,62 @@ def test_fused_renderer_clean_model_and_edge_cases():
     with torch.no_grad():
         e = net.render(ro, rd, staged=False, bg_color=1, perturb=False)
     assert torch.all(e["image"] == 1.0) and int(net.last_render_samples) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# non-cuda_ray renderer (NeRFRenderer.run): BASELINE configs[0] shape against the CPU port of the reference's run()
+# ---------------------------------------------------------------------------------------------------------
+def _load_port_weights(net, field):
+    with torch.no_grad():
+        for e, t in zip(net.encoder.embeddings, field.base_tables):
+            e.weight.copy_(t)
+        net.sigma_net.params.copy_(torch.cat([w.reshape(-1) for w in field.Ws]))
+        net.color_net.params.copy_(torch.cat([w.reshape(-1) for w in field.Wc]))
+
+
+def test_run_non_cuda_ray_matches_reference_port():
+    """configs[0]: random-init clean HashNeRF, non-cuda_ray render with 512 uniform samples per ray, against
+    oracle/torch_port.render_run (the reference's NeRFRenderer.run, upsample_steps=0) on the CPU: 1e-3."""
+    from nerf_signature_b200.nerf.network_hash import NeRFNetwork
+    from oracle import torch_port as tp
+    field = tp.PortField(bound=1.0, message_dim=0, seed=3, train_msg=False)
+    for t in field.base_tables:
+        t.mul_(300.0)     # features O(0.03): the MLPs matter
+    net = NeRFNetwork(bound=1.0, cuda_ray=False)
+    _load_port_weights(net, field)
+    net = net.cuda().eval()
+    o, d = syn.blender_rays(192, seed=5)
+    with torch.no_grad():
+        want, want_ws = tp.render_run(field, torch.from_numpy(o), torch.from_numpy(d), None, num_steps=512)
+        got = net.render(torch.from_numpy(o)[None].cuda(), torch.from_numpy(d)[None].cuda(), staged=False, num_steps=512,
+                         upsample_steps=0, bg_color=1, perturb=False)
+    np.testing.assert_allclose(got["image"][0].cpu().numpy(), want.numpy(), rtol=0, atol=1e-3)
+    np.testing.assert_allclose(got["weights_sum"].cpu().numpy(), want_ws.numpy(), rtol=0, atol=1e-3)
+    # staged == unstaged, importance resampling runs and keeps the image close (same field, more samples)
+    with torch.no_grad():
+        st = net.render(torch.from_numpy(o)[None].cuda(), torch.from_numpy(d)[None].cuda(), staged=True, max_ray_batch=50,
+                        num_steps=512, upsample_steps=0, bg_color=1, perturb=False)
+        up = net.render(torch.from_numpy(o)[None].cuda(), torch.from_numpy(d)[None].cuda(), staged=False, num_steps=256,
+                        upsample_steps=128, bg_color=1, perturb=False)
+    assert torch.allclose(st["image"], got["image"], atol=1e-6)
+    assert up["image"].shape == got["image"].shape and float((up["image"] - got["image"]).abs().max()) < 0.05
+
+
+def test_run_non_cuda_ray_is_differentiable_in_watermark_training():
+    """with cuda_ray=False the reference trains through run(); the message tables must receive a gradient."""
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+    torch.manual_seed(0)
+    net = NeRFNetwork(bound=1.0, cuda_ray=False, message_dim=4).cuda().train()
+    with torch.no_grad():
+        for e in list(net.encoder.embeddings) + list(net.msg_encoder.embeddings):
+            e.weight.mul_(300.0)
+    o, d = syn.blender_rays(64, seed=6)
+    msg = torch.tensor([1.0, 0.0, 1.0, 1.0]).cuda()
+    out = net.render(torch.from_numpy(o)[None].cuda(), torch.from_numpy(d)[None].cuda(), msg, staged=False, num_steps=64,
+                     upsample_steps=32, bg_color=1, perturb=True)
+    out["image"].square().mean().backward()
+    bits = [1, 0, 1, 1]
+    for i, b in enumerate(bits):
+        g = net.msg_encoder.embeddings[2 * i + b].weight.grad
+        assert g is not None and float(g.abs().sum()) > 0
+        assert net.msg_encoder.embeddings[2 * i + 1 - b].weight.grad is None

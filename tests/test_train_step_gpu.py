@@ -228,3 +228,72 @@ def test_packed_pinned_batch_single_copy_matches_per_tensor_copies():
         pb["message"].copy_(m)
         lb = [float(x) for x in b.train_step(pb, pb["message"])]
         np.testing.assert_allclose(lb, la, rtol=5e-3 if i else 1e-4, atol=1e-5)
+
+
+def test_optimizer_state_dict_round_trip_and_torch_adam_layout():
+    """WatermarkAdam.state_dict() carries the message tables' moments and step counts in the layout of
+    torch.optim.Adam(model.get_params(lr)).state_dict() (what the reference Trainer checkpoints); a resumed optimizer
+    continues exactly like the uninterrupted one, and a torch-Adam checkpoint loads."""
+    from nerf_signature_b200.optim import WatermarkAdam
+    a, b = _scene(optimizer="fused"), _scene(optimizer="fused")
+    batches = _batches(a, 2)
+    gen = torch.Generator().manual_seed(9)
+    msgs = [a.new_message(gen) for _ in range(6)]
+    for i in range(3):
+        a.train_step(batches[i % 2], msgs[i]); b.train_step(batches[i % 2], msgs[i])
+    sd = a.optimizer.state_dict()
+    md2 = 2 * SMALL["message_dim"]
+    assert sd["param_groups"][0]["params"] == list(range(md2))
+    touched = {t for t in range(md2) if float(a.optimizer.steps[t]) > 0}
+    assert touched and touched == {k for k in sd["state"] if k < md2}
+    assert all({"step", "exp_avg", "exp_avg_sq"} <= set(sd["state"][t]) for t in touched)
+    n_dec = len(list(a.model.msg_decoder.parameters()))
+    assert sorted(k for k in sd["state"] if k >= md2) == list(range(md2, md2 + n_dec))
+    # resume: a fresh optimizer on a copy of the model state
+    c = _scene(optimizer="fused")
+    c.model.load_state_dict(a.model.state_dict())
+    c.optimizer.load_state_dict(sd)
+    c.scaler.load_state_dict(a.scaler.state_dict())
+    assert torch.equal(c.optimizer.steps, a.optimizer.steps)
+    for i in range(3, 6):
+        la = a.train_step(batches[i % 2], msgs[i]); lc = c.train_step(batches[i % 2], msgs[i])
+        np.testing.assert_allclose([float(x) for x in lc], [float(x) for x in la], rtol=1e-4, atol=1e-6)
+    for x, y in zip(_msg_tables(a), _msg_tables(c)):
+        _close_frac(x, y, rtol=1e-3, atol=1e-5)
+    # a torch.optim.Adam checkpoint over get_params (the reference's optimizer) has the same layout and loads
+    t = _scene(optimizer="torch")
+    for i in range(3):
+        t.train_step(batches[i % 2], msgs[i])
+    tsd = t.optimizer.state_dict()
+    assert tsd["param_groups"][0]["params"] == list(range(md2))
+    d = _scene(optimizer="fused")
+    d.optimizer.load_state_dict(tsd)
+    np.testing.assert_allclose(d.optimizer.steps.cpu().numpy(), b.optimizer.steps.cpu().numpy())
+    for t_ in touched:
+        torch.testing.assert_close(d.optimizer.exp_avg[t_], b.optimizer.exp_avg[t_], rtol=1e-3, atol=1e-7)
+
+
+def test_lr_schedule_acts_on_graph_replays():
+    """the reference steps a LambdaLR every iteration (scheduler_update_every_step); under CUDA-graph replay the
+    learning rate must be read from a device scalar.  lr -> 0 must freeze the tables and the decoder; and the cached
+    summed table must not survive a replay."""
+    g = _scene(optimizer="fused", graph=True, merged_render=True, fused_decoder=True, fused_losses=True)
+    batches = _batches(g, 2)
+    gen = torch.Generator().manual_seed(3)
+    g.train_step(batches[0], g.new_message(gen))            # capture + first replay at lr 1e-2
+    assert g.model._S_cache is None                          # dropped after the replay
+    before = _msg_tables(g)
+    dec_before = [p.detach().clone() for p in g.model.msg_decoder.parameters()]
+    sched = torch.optim.lr_scheduler.LambdaLR(g.optimizer, lambda it: 0.0)   # sets every group's lr to 0 immediately
+    g.train_step(batches[1], g.new_message(gen))
+    torch.cuda.synchronize()
+    for x, y in zip(before, _msg_tables(g)):
+        assert torch.equal(x, y)
+    for x, y in zip(dec_before, g.model.msg_decoder.parameters()):
+        assert torch.equal(x, y.detach())
+    for grp in g.optimizer.param_groups:
+        grp["lr"] = 1e-2                                     # what a scheduler step does
+    g.train_step(batches[0], g.new_message(gen))
+    torch.cuda.synchronize()
+    assert any(not torch.equal(x, y) for x, y in zip(before, _msg_tables(g)))
+    del sched
