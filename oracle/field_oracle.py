@@ -44,9 +44,12 @@ def split_params(sigma_params, color_params):
     return [_q(w) for w in Ws], [_q(w) for w in Wc]
 
 
-def mlp_forward(feat, dirs, sigma_params, color_params, density_scale=1.0):
+def mlp_forward(feat, dirs, sigma_params, color_params, density_scale=1.0, pad_value=0.0):
     """feat [M,32] fp32 encoder output (incl. message feature), dirs [M,3].  Returns sigma [M], rgb [M,3],
-    and the pre-activation outputs (logit [M], geo [M,15]).  network_wtmk_tcnn.py:107-124."""
+    and the pre-activation outputs (logit [M], geo [M,15]).  network_wtmk_tcnn.py:107-124.
+    pad_value: what the colour net's 32nd (padding) input holds.  0 = this repo's native parameterisation;
+    1 = tiny-cuda-nn's convention as recalled in SURVEY 8c (inputs padded to a multiple of 16 with the constant 1, which
+    turns weight column 31 into a bias) - used by the checkpoint-conversion test."""
     Ws, Wc = split_params(sigma_params, color_params)
     x = _q(feat)
     h = _q(torch.relu(x @ Ws[0].t()))
@@ -55,7 +58,7 @@ def mlp_forward(feat, dirs, sigma_params, color_params, density_scale=1.0):
     sigma = density_scale * torch.exp(logit)
     d = (dirs + 1) / 2            # network_wtmk_tcnn.py:114
     v = d * 2 - 1                 # tcnn's SphericalHarmonics maps [0,1] back to [-1,1]
-    cin = torch.cat([_q(sh4(v)), _q(geo), torch.zeros_like(geo[:, :1])], -1)
+    cin = torch.cat([_q(sh4(v)), _q(geo), torch.full_like(geo[:, :1], float(pad_value))], -1)
     h1 = _q(torch.relu(cin @ Wc[0].t()))
     h2 = _q(torch.relu(h1 @ Wc[1].t()))
     o = h2 @ Wc[2].t()
