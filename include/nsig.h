@@ -395,6 +395,15 @@ uint32_t nsig_allreduce_grid(void);
 int nsig_allreduce_mean_inplace(void* const* bufs, void* const* flags, void* multicast, uint32_t n,
                                 uint32_t rank, uint32_t world, nsig_stream_t stream);
 
+/* The watermark-mode case of nsig_field_backward (G only: no full feature gradient, no weight gradients - SURVEY F13:
+ * everything but the message tables is frozen) on the 5th-generation tensor cores: every MLP layer of a 128-sample
+ * tile is one tcgen05.mma chain with the accumulator in TMEM (csrc/field_tc.cu).  Same arguments, same result up to
+ * fp32 summation order; `feat` must be 16-byte aligned. */
+int nsig_field_backward_tc(const float* xyzs, const float* dirs, uint32_t M, float bound, const void* feat,
+                           const float* grad_sigmas, const float* grad_rgbs, const void* sigma_w,
+                           const void* color_w, float density_scale, const int32_t* M_dev,
+                           float msg_resolution, uint32_t log2_T, float* G, nsig_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* optimizer step of the message tables — nerf/utils_wtmk_disen.py:1175-1181   */
 /* ------------------------------------------------------------------------- */
@@ -417,6 +426,25 @@ int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t me
                        const float* grad_scale, const float* found_inf, float lr, float beta1,
                        float beta2, float eps, uint32_t log2_T, const float* lr_dev,
                        nsig_stream_t stream);
+
+/* torch.amp.GradScaler's per-step work (utils_wtmk_disen.py:1175-1181) over the flat gradient bucket in one launch:
+ * non-finite check of flat[0..n) -> *found_inf (0/1); *step_scale = the scale this step's gradients carry (what the
+ * optimizer kernels divide by); then _amp_update_scale_ on *scale / *growth_tracker (backoff on overflow, growth after
+ * growth_interval clean steps); *adam_step (optional) += 1 when the step is not skipped.  scratch: uint32[2], zero-
+ * initialised once by the caller, left zeroed.  flat must be 16-byte aligned.
+ * enabled (optional): device word; when it is 0 no optimizer step is pending (the harness' deferred-step mode after a
+ * flush): *found_inf = 1 so that the optimizer kernels skip, scaler state untouched. */
+int nsig_grad_check_update_scale(const float* flat, uint32_t n, float* scale, int32_t* growth_tracker,
+                                 float growth_factor, float backoff_factor, int32_t growth_interval,
+                                 float* found_inf, float* step_scale, float* adam_step, uint32_t* scratch,
+                                 const uint32_t* enabled, nsig_stream_t stream);
+
+/* torch.optim.Adam (no weight decay / amsgrad) over one flat fp32 parameter vector (the HiDDeN decoder's tensors viewed
+ * as one buffer).  step: device float holding this step's count (>= 1); grad_scale / found_inf / lr_dev as in
+ * nsig_msg_adam_step. */
+int nsig_flat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, uint32_t n,
+                        const float* step, const float* grad_scale, const float* found_inf, float lr,
+                        const float* lr_dev, float beta1, float beta2, float eps, nsig_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.normpath(os.path.join(_HERE, "..", "include"))
 LIB = os.path.join(_HERE, "libnsig_b200.so")
-SOURCES = ["raymarch.cu", "hashenc.cu", "field.cu", "grid.cu", "collective.cu", "decoder.cu", "wtmk_loss.cu", "optim.cu", "version.cu"]
+SOURCES = ["raymarch.cu", "hashenc.cu", "field.cu", "field_tc.cu", "grid.cu", "collective.cu", "decoder.cu", "wtmk_loss.cu", "optim.cu", "version.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE] + os.environ.get("NSIG_NVCC_EXTRA", "").split()
 

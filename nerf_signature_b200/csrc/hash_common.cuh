@@ -183,33 +183,17 @@ __device__ __forceinline__ float2 encode_level_fused(const float2* __restrict__ 
 // 32 lanes x 4 B per wavefront, so this halves the wavefronts of the gather against the fp32 (8 B per lane) tables.
 // Interpolation stays fp32; the result is multiplied by 1/scale_l (exact).  Absolute error per feature
 // <= 2^-11 * max|corner|, the same size as the fp16 rounding the MMA operands get anyway.
-// x-pair gather (NSIG_XPAIR): the hash is ix ^ iy*P1 ^ iz*P2, so when ix is EVEN the two x-neighbours of a (y,z) corner
-// pair occupy one aligned pair of table entries {s & ~1, s | 1} (their slots differ in bit 0 only).  Those lanes fetch both
-// with ONE 8-byte load: 4 load instructions per level instead of 8, i.e. half the L1 tag lookups for half of all
-// (sample, level) pairs, for the same number of bytes.  Lanes with an odd ix keep the 8 single loads (their x+1
-// neighbour flips higher index bits).  Values and interpolation order are unchanged, so results are bit-identical.
 __device__ __forceinline__ float2 encode_level_fused_h2(const __half2* __restrict__ table, const Voxel& v, uint32_t mask,
                                                         float inv_scale) {
+    // (An x-pair variant - ONE aligned 8-byte load for both x-neighbours when ix is even, whose slots differ in bit 0 only -
+    // was measured in round 2: 0.302 vs 0.221 ms per 1.07 M samples.  The divergent even/odd paths execute 12 instead of 8
+    // load instructions per level and the L1 tag stage counts SECTORS, not instructions: tag requests stayed at 55 per
+    // sample.  profiles/r02_experiments.txt.)
     float2 e[8];
-#ifdef NSIG_XPAIR
-    if ((v.hx0 & 1u) == 0u) {
-        const uint2* pairs = reinterpret_cast<const uint2*>(table);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // k = (y,z) corner; corner k has x = 0, corner k + 4 has x = 1
-            const uint32_t s = corner_slot(v, k, mask);
-            const uint2 raw = __ldg(pairs + (s >> 1));
-            const uint32_t a = (s & 1u) ? raw.y : raw.x, b = (s & 1u) ? raw.x : raw.y;
-            e[k] = __half22float2(*reinterpret_cast<const __half2*>(&a));
-            e[k + 4] = __half22float2(*reinterpret_cast<const __half2*>(&b));
-        }
-    } else
-#endif
-    {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(table) + corner_slot(v, k, mask));
-            e[k] = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-        }
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(table) + corner_slot(v, k, mask));
+        e[k] = __half22float2(*reinterpret_cast<const __half2*>(&raw));
     }
     const float2 r = trilerp_fma(e, v);
     return make_float2(r.x * inv_scale, r.y * inv_scale);

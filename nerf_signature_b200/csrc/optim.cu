@@ -90,6 +90,92 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// torch.amp.GradScaler's per-step work as ONE kernel over the flat gradient bucket [dL/dS | decoder gradients]
+// (nerf/utils_wtmk_disen.py:1175-1181: scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()):
+//   * the non-finite check of every gradient (GradScaler._unscale_grads_ -> _amp_foreach_non_finite_check_and_unscale_:
+//     a multi-tensor launch over ~40 tensors, 15 us) as one vectorised pass over 5 MB that is still in L2;
+//   * the last CTA to finish publishes found_inf and the scale THIS step's optimizer kernels must divide by, bumps the
+//     Adam step count of the flat parameter group, and applies _amp_update_scale_ (backoff on overflow, growth after
+//     growth_interval clean steps) right away - the optimizer kernels read the published copy, so nothing has to run
+//     after them.  Replaces 2 fills + the check + a reduction of found_inf + amp_update_scale (6 launches).
+// scratch: uint32[2] {flag, ticket}, zero-initialised once; the kernel leaves it zeroed.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_grad_check_update_scale(const float* __restrict__ flat, uint32_t n4, uint32_t n, float* __restrict__ scale,
+                          int32_t* __restrict__ growth_tracker, float growth_factor, float backoff_factor,
+                          int32_t growth_interval, float* __restrict__ found_inf, float* __restrict__ step_scale,
+                          float* __restrict__ adam_step, uint32_t* __restrict__ scratch,
+                          const uint32_t* __restrict__ enabled) {
+    bool bad = false;
+    const float4* f4 = reinterpret_cast<const float4*>(flat);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 v = f4[i];
+        // non-finite <=> exponent bits all set
+        bad |= ((__float_as_uint(v.x) & 0x7f800000u) == 0x7f800000u) | ((__float_as_uint(v.y) & 0x7f800000u) == 0x7f800000u) |
+               ((__float_as_uint(v.z) & 0x7f800000u) == 0x7f800000u) | ((__float_as_uint(v.w) & 0x7f800000u) == 0x7f800000u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) bad |= (__float_as_uint(flat[n4 * 4 + threadIdx.x]) & 0x7f800000u) == 0x7f800000u;
+    const bool any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (any_bad) atomicOr(scratch, 1u);
+        __threadfence();
+        const uint32_t ticket = atomicAdd(scratch + 1, 1u);
+        if (ticket == gridDim.x - 1) {   // last CTA: every flag update is visible
+            __threadfence();
+            const bool inf = atomicOr(scratch, 0u) != 0u;
+            const float s = *scale;
+            *step_scale = s;
+            if (enabled && *enabled == 0u) {
+                // no optimizer step is pending (deferred-step mode after a flush): make the optimizer kernels skip and leave
+                // the scaler state alone
+                *found_inf = 1.0f;
+                scratch[0] = 0u;
+                scratch[1] = 0u;
+                return;
+            }
+            *found_inf = inf ? 1.0f : 0.0f;
+            if (inf) {
+                *scale = s * backoff_factor;
+                *growth_tracker = 0;
+            } else {
+                if (adam_step) *adam_step += 1.0f;
+                const int32_t ok = *growth_tracker + 1;
+                if (ok == growth_interval) {
+                    const float grown = s * growth_factor;
+                    if (isfinite(grown)) *scale = grown;
+                    *growth_tracker = 0;
+                } else {
+                    *growth_tracker = ok;
+                }
+            }
+            scratch[0] = 0u;
+            scratch[1] = 0u;
+        }
+    }
+}
+
+// Adam (torch.optim.Adam semantics: no weight decay, no amsgrad) over ONE flat parameter vector - the HiDDeN decoder's
+// 38 tensors re-pointed at a single buffer - instead of torch's two multi-tensor launches.  step: device float already
+// incremented for this step by k_grad_check_update_scale.
+__global__ void __launch_bounds__(256)
+k_flat_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint32_t n,
+            const float* __restrict__ step, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
+            float lr, const float* __restrict__ lr_dev, float beta1, float beta2, float eps) {
+    if (found_inf && *found_inf != 0.0f) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = (double)*step;
+    const double lr_now = lr_dev ? (double)*lr_dev : (double)lr;
+    const float step_size = (float)(lr_now / (1.0 - pow((double)beta1, s)));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, s));
+    const float inv = grad_scale ? 1.0f / *grad_scale : 1.0f;
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_elem(pp, mm, vv, g[i] * inv, 1.0f - beta1, beta2, 1.0f - beta2, step_size, bc2_sqrt, eps);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+}
+
 }  // namespace nsig
 
 using namespace nsig;
@@ -110,6 +196,32 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
     AdamPtrs ptrs{ptr_table, n_tables};
     k_msg_adam<<<div_up(n_vec4, 256), 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
                                                     beta1, beta2, eps, n_vec4);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsig_grad_check_update_scale(const float* flat, uint32_t n, float* scale, int32_t* growth_tracker,
+                                            float growth_factor, float backoff_factor, int32_t growth_interval,
+                                            float* found_inf, float* step_scale, float* adam_step, uint32_t* scratch,
+                                            const uint32_t* enabled, nsig_stream_t stream) {
+    if (!flat || !scale || !growth_tracker || !found_inf || !step_scale || !scratch) return NSIG_EINVAL;
+    if ((((uintptr_t)flat) & 15) || growth_interval < 1) return NSIG_EINVAL;
+    const uint32_t n4 = n / 4;
+    const uint32_t grid = max(1u, min(div_up(n4, 256u * 4u), 148u * 4u));
+    k_grad_check_update_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(flat, n4, n, scale, growth_tracker, growth_factor,
+                                                                        backoff_factor, growth_interval, found_inf,
+                                                                        step_scale, adam_step, scratch, enabled);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsig_flat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, uint32_t n,
+                                   const float* step, const float* grad_scale, const float* found_inf, float lr,
+                                   const float* lr_dev, float beta1, float beta2, float eps, nsig_stream_t stream) {
+    if (n == 0) return 0;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !step) return NSIG_EINVAL;
+    k_flat_adam<<<div_up(n, 256u), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, step, grad_scale,
+                                                                    found_inf, lr, lr_dev, beta1, beta2, eps);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -10,6 +10,7 @@ restates only what they feed the hot path with, on synthetic data (no datasets o
     (force_all_rays=True, perturb=False, bg_color=1), HiDDeN decoder, BCE(temp 10) + MSE, backward, Adam.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -102,7 +103,7 @@ class Scene:
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
                  merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
-                 shard_blocks=None, distributed=True):
+                 shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -116,7 +117,12 @@ class Scene:
         shard_blocks: (block_shape, per-rank block-ray counts) from shard_batch - the batch holds this rank's slice of
         ONE global batch: block pixels are all-gathered before the decoder so that every rank decodes the
         full batch (global BatchNorm statistics) and N GPUs compute what one GPU would.
-        distributed=False: ignore the process group (single-GPU semantics inside a multi-rank job; gradient checks)."""
+        distributed=False: ignore the process group (single-GPU semantics inside a multi-rank job; gradient checks).
+        defer_optimizer: software-pipeline the optimizer: the Adam update of step t (HBM-bound, ~0.14 ms) is issued at the START
+        of step t+1 on the side stream that also builds the summed message table, next to the latency-bound march of step t+1
+        (which needs neither the tables nor G).  Every kernel sees exactly the data it would see in the sequential order -
+        Adam(t) still completes before the table sum of step t+1 - so results are unchanged; reads of the message tables
+        from outside (evaluation, checkpoints, update_extra_state) must call flush_optimizer() first (train_step does)."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
         from .optim import WatermarkAdam
         torch.manual_seed(seed)
@@ -154,11 +160,19 @@ class Scene:
             if self.flat_sync:  # one flat bucket [dL/dS | decoder grads] -> one all-reduce per step
                 gbuf = self.sync.make_flat_buffer(self.model.msg_encoder.tables()[0].numel(), self._decoder_params, device)
             self.optimizer = WatermarkAdam(self.model, lr=lr, betas=(0.9, 0.99), eps=1e-15, capturable=graph,
-                                           grad_buffer=gbuf)
+                                           grad_buffer=gbuf, flat_bucket=self.sync.flat if self.flat_sync else None)
         else:
             self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
         self.fp16 = fp16
-        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
+        # fused_scaler (default with the fused optimizer): GradScaler's check / found_inf / scale update as one kernel over
+        # the flat bucket (optim.FusedGradScaler); False keeps torch.amp.GradScaler (what the reference uses)
+        use_fs = (self.fused and fp16 and os.environ.get("NSIG_TORCH_SCALER") != "1") if fused_scaler is None \
+            else (fused_scaler and self.fused and fp16)
+        if use_fs:
+            from .optim import FusedGradScaler
+            self.scaler = FusedGradScaler(device)
+        else:
+            self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.lambda_w, self.lambda_i = 0.005, 1.0  # README.md:40,45
         self.opt = dict(dt_gamma=cfg["dt_gamma"], max_steps=1024, T_thresh=1e-4)
         _hmsg.grad_reducer = self.sync.reduce_table_grad if (self.sync.enabled and not self.flat_sync) else None
@@ -167,6 +181,9 @@ class Scene:
         self.fused_decoder = fused_decoder and fp16  # the kernels implement the float16-autocast arithmetic
         self.fused_losses = fused_losses
         self.overlap_decoder = overlap_decoder and not merged_render
+        self.defer_optimizer = bool(defer_optimizer) and self.fused and use_fs   # needs the one-kernel scaler's skip flag
+        if self.defer_optimizer:   # [message of the step whose update is pending (md) | pending flag (1)]
+            self._opt_state = torch.zeros(cfg["message_dim"] + 1, dtype=torch.float32, device=device)
         self.iteration = 0
         self.keep_outputs = False   # parity tests: keep the step's rendered pixels and decoder logits in self.last
         self.last = None
@@ -195,12 +212,30 @@ class Scene:
         select which tables receive a gradient) or a device tensor (fused path: nothing on the host depends
         on the bits)."""
         model = self.model
-        if self.flat_sync:
+        if self.defer_optimizer:
+            pass                      # cleared after the deferred optimizer step below
+        elif self.flat_sync:
             self.sync.zero_flat()
         else:
             self.optimizer.zero_grad(set_to_none=True)
         msg_dev = message.to(self.device, non_blocking=True) if not message.is_cuda else message
-        if self.fused:
+        if self.defer_optimizer:
+            # the PREVIOUS step's optimizer update, on the stream the summed-table prefetch uses (so the table sum is ordered
+            # after it) while this step's near/far + march run on the main stream; then the bucket is cleared for this
+            # step's backward.  The render call joins the side stream before the first field kernel.
+            md = self.cfg["message_dim"]
+            side = _lib.side_stream(self.device, 0)
+            main = torch.cuda.current_stream()
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                self.optimizer.set_message(self._opt_state[:md])
+                self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
+                self.sync.zero_flat()
+            if side is not None:
+                self._opt_side = side
+            message = msg_dev
+        elif self.fused:
             self.optimizer.set_message(msg_dev)
             message = msg_dev
         from .nerf.loss_ops import split_clamp, wtmk_loss
@@ -268,9 +303,26 @@ class Scene:
             self.sync.reduce_flat()
         else:
             self.sync.reduce_params(self._decoder_params)
-        self.scaler.step(self.optimizer)
-        self.scaler.update()
+        if self.defer_optimizer:   # remember whose update is pending; it runs at the start of the next step (or in flush)
+            md = self.cfg["message_dim"]
+            self._opt_state[:md].copy_(msg_dev)
+            self._opt_state[md:].fill_(1.0)
+        else:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
         return loss, lossi, lossw
+
+    def flush_optimizer(self):
+        """Apply the pending (deferred) optimizer update now; no-op otherwise.  After it the message tables and the decoder
+        hold what a sequential step would have left, and the next step's leading update is skipped on the device."""
+        if not self.defer_optimizer:
+            return
+        md = self.cfg["message_dim"]
+        with torch.no_grad():
+            self.optimizer.set_message(self._opt_state[:md])
+            self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
+            self._opt_state[md:].zero_()
+        self.model._S_cache = None
 
     def _capture(self, batch, message):
         """Warm up on a side stream, then record one step into a CUDA graph with static input buffers."""
@@ -344,6 +396,7 @@ class Scene:
         self.iteration += 1
         every = self.cfg.get("grid_update_every", 0)
         if every and self.iteration % every == 0:
+            self.flush_optimizer()   # the occupancy sweep reads the message tables: they must be up to date
             self.model.update_extra_state(message.to(self.device) if not message.is_cuda else message)
         return out
 

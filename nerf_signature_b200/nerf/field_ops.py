@@ -3,6 +3,7 @@ tiny-cuda-nn modules the reference instantiates, and the autograd functions that
 nsig_field_forward / nsig_field_density / nsig_field_backward.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -11,6 +12,9 @@ from torch.autograd import Function
 from .. import _lib
 
 _P = _lib.ptr
+
+# A/B switch (tools, tests): NSIG_BWD_TC=0 keeps the mma.sync backward (csrc/field.cu) for the watermark-mode case too
+USE_TCGEN05_BACKWARD = os.environ.get("NSIG_BWD_TC", "1") != "0"
 
 
 class FusedMLP(nn.Module):
@@ -164,9 +168,14 @@ class _field_forward(Function):
         grad_feat = alloc(M, 32, dtype=torch.float32, device=dev) if any(need_tab) else None
         gsw = torch.zeros(sw.numel(), dtype=torch.float32, device=dev) if need_w else None
         gcw = torch.zeros(cw.numel(), dtype=torch.float32, device=dev) if need_w else None
-        _lib.call("nsig_field_backward", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
-                  _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G),
-                  _P(grad_feat), _P(gsw), _P(gcw))
+        if G is not None and grad_feat is None and gsw is None and USE_TCGEN05_BACKWARD:
+            # watermark training (the hot path): dL/dS only - tcgen05/TMEM kernel (csrc/field_tc.cu)
+            _lib.call("nsig_field_backward_tc", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
+                      _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G))
+        else:
+            _lib.call("nsig_field_backward", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
+                      _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G),
+                      _P(grad_feat), _P(gsw), _P(gcw))
         tab_grads = [None] * ctx.n_tables
         if any(need_tab):
             xn = (xyzs + cfg.bound) * (1.0 / (2.0 * cfg.bound))  # network_wtmk_tcnn.py:101

@@ -22,9 +22,13 @@ _P = _lib.ptr
 class WatermarkAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
 
-    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False, grad_buffer=None):
+    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False, grad_buffer=None, flat_bucket=None):
         """grad_buffer: optional pre-allocated [T*2] fp32 storage for G (the data-parallel harness passes a slice
-        of its flat all-reduce bucket)."""
+        of its flat all-reduce bucket).
+        flat_bucket: the WHOLE flat gradient bucket [dL/dS | gradients of every other trainable parameter, in get_params
+        order] (parallel.GradSync.make_flat_buffer).  When given, the other parameters (the HiDDeN decoder) are re-pointed
+        at ONE flat parameter buffer and updated by one Adam kernel (nsig_flat_adam_step) instead of torch's multi-tensor
+        Adam, and FusedGradScaler can check the whole bucket for non-finite values in one pass."""
         enc = model.msg_encoder
         tables = enc.tables()
         dev = tables[0].device
@@ -51,7 +55,25 @@ class WatermarkAdam(torch.optim.Optimizer):
         # replayed from a CUDA graph: call sync_lr() before each replay (harness.Scene does)
         self.capturable = capturable
         self.inner = None
-        if others:
+        self.flat_bucket = flat_bucket
+        self._flat = None
+        if others and flat_bucket is not None and len(others) == 1 and self._train_tables:
+            ps = others[0]["params"]
+            n_other = sum(p.numel() for p in ps)
+            ok = all(p.dtype == torch.float32 and p.is_contiguous() and p.requires_grad for p in ps)
+            if ok and flat_bucket.numel() >= tables[0].numel() + n_other:
+                flat_p = torch.empty(n_other, dtype=torch.float32, device=dev)
+                o = 0
+                for p in ps:   # the module keeps its parameters (names, shapes, state dict); their storage becomes one buffer
+                    flat_p[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                    p.data = flat_p[o:o + p.numel()].view(p.shape)
+                    o += p.numel()
+                self._flat = {"p": flat_p, "g": flat_bucket[tables[0].numel():tables[0].numel() + n_other],
+                              "m": torch.zeros_like(flat_p), "v": torch.zeros_like(flat_p),
+                              "step": torch.zeros(1, dtype=torch.float32, device=dev), "params": ps,
+                              "lr_dev": torch.tensor([float(others[0]["lr"])], dtype=torch.float32, device=dev)}
+                self.scaler_bumps_step = False   # FusedGradScaler increments _flat["step"] inside its check kernel
+        if others and self._flat is None:
             inner_groups = [{"params": g["params"],
                              "lr": torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev) if capturable else g["lr"]}
                             for g in others]
@@ -85,7 +107,10 @@ class WatermarkAdam(torch.optim.Optimizer):
             lr = float(g["lr"])
             changed = lr != self._lr_host[i]
             self._lr_host[i] = lr
-            if i < n_inner:
+            if self._flat is not None and not g.get("msg_tables"):
+                if changed:
+                    self._flat["lr_dev"].fill_(lr)
+            elif i < n_inner:
                 g_in = self.inner.param_groups[i]
                 if isinstance(g_in["lr"], torch.Tensor):
                     if changed:
@@ -110,6 +135,18 @@ class WatermarkAdam(torch.optim.Optimizer):
                 if float(steps[t]) > 0:
                     state[t] = {"step": steps[t].clone(), "exp_avg": self.exp_avg[t].detach().clone(),
                                 "exp_avg_sq": self.exp_avg_sq[t].detach().clone()}
+        if self._flat is not None:
+            f, g0 = self._flat, self.param_groups[0]
+            g = {k: v for k, v in g0.items() if k != "params"}
+            groups.append({**g, "params": list(range(n_t, n_t + len(f["params"])))})
+            if float(f["step"]) > 0:
+                o = 0
+                for j, p in enumerate(f["params"]):
+                    n = p.numel()
+                    state[n_t + j] = {"step": f["step"].detach().reshape(()).clone(),
+                                      "exp_avg": f["m"][o:o + n].view(p.shape).clone(),
+                                      "exp_avg_sq": f["v"][o:o + n].view(p.shape).clone()}
+                    o += n
         if self.inner is not None:
             sd = self.inner.state_dict()
             for g in sd["param_groups"]:
@@ -141,6 +178,19 @@ class WatermarkAdam(torch.optim.Optimizer):
                 if k in tg:
                     self.param_groups[-1][k] = float(tg[k]) if k != "betas" else tuple(tg[k])
             groups = groups[1:]
+        if self._flat is not None:
+            f = self._flat
+            f["m"].zero_(); f["v"].zero_(); f["step"].zero_()
+            o = 0
+            for j, p in enumerate(f["params"]):
+                st = state.get(n_t + j)
+                n = p.numel()
+                if st is not None:
+                    f["m"][o:o + n].copy_(st["exp_avg"].reshape(-1)); f["v"][o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    f["step"].fill_(float(st["step"]))
+                o += n
+            if groups:
+                self.param_groups[0]["lr"] = float(groups[0]["lr"])
         if self.inner is not None:
             sd = {"param_groups": [], "state": {k - n_t: v for k, v in state.items() if k >= n_t}}
             for g, g_in, g_out in zip(groups, self.inner.param_groups, self.param_groups):
@@ -159,7 +209,10 @@ class WatermarkAdam(torch.optim.Optimizer):
         if self.inner is not None:
             self.inner.zero_grad(set_to_none=set_to_none)
         # the field backward ACCUMULATES dL/dS into G (FieldConfig.S_sink); the proxy keeps pointing at it
-        self.G.zero_()
+        if self.flat_bucket is not None:
+            self.flat_bucket.zero_()   # one fill: G and the flat-mode decoder gradients live in the same bucket
+        else:
+            self.G.zero_()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -169,6 +222,19 @@ class WatermarkAdam(torch.optim.Optimizer):
         found_inf = getattr(self, "found_inf", None)
         side = None
         self.sync_lr()
+        if self._flat is not None:
+            f, group = self._flat, self.param_groups[0]
+            if not self.scaler_bumps_step:   # plain GradScaler / no scaler: count the step here (skipped steps do not count)
+                f["step"].add_(1.0 if found_inf is None else (1.0 - found_inf.reshape(1)))
+            side = _lib.side_stream(self.G.device, 1)
+            b1, b2 = group["betas"]
+            cur = torch.cuda.current_stream()
+            if side is not None:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side if side is not None else cur):   # next to the HBM-bound message-table Adam
+                _lib.call("nsig_flat_adam_step", _P(f["p"]), _P(f["g"]), _P(f["m"]), _P(f["v"]), f["p"].numel(),
+                          _P(f["step"]), _P(grad_scale), _P(found_inf), float(group["lr"]), _P(f["lr_dev"]), float(b1),
+                          float(b2), float(group["eps"]))
         if self.inner is not None:
             self.inner.grad_scale, self.inner.found_inf = grad_scale, found_inf
             # the decoder's (tiny, latency-bound) Adam runs next to the HBM-bound message-table Adam
@@ -199,3 +265,72 @@ class WatermarkAdam(torch.optim.Optimizer):
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         return None
+
+
+class _ScaledLoss:
+    """What FusedGradScaler.scale(loss) returns: `.backward()` seeds autograd with the device-resident scale instead of
+    multiplying the loss (no extra kernels; the loss-head backward kernel consumes the seed as d(loss))."""
+
+    def __init__(self, loss, scale):
+        self.loss, self.scale = loss, scale
+
+    def backward(self, **kw):
+        self.loss.backward(gradient=self.scale.reshape(self.loss.shape).to(self.loss.dtype), **kw)
+
+
+class FusedGradScaler:
+    """torch.amp.GradScaler semantics (the reference trains with --fp16: utils_wtmk_disen.py:1170-1181) for the flat-bucket
+    optimizer, as ONE kernel per step: non-finite check of every gradient, found_inf, the scale the optimizer kernels
+    divide by, and the scale update (backoff x0.5 on overflow, growth x2 after 2000 clean steps) - see
+    nsig_grad_check_update_scale.  `scale(loss).backward(); step(optimizer); update()` as usual; update() is a no-op
+    because the update already happened on the device.  state_dict() uses GradScaler's keys."""
+
+    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, int(growth_interval)
+        self._scale = torch.tensor([float(init_scale)], dtype=torch.float32, device=device)
+        self._growth_tracker = torch.zeros(1, dtype=torch.int32, device=device)
+        self._found_inf = torch.zeros(1, dtype=torch.float32, device=device)
+        self._step_scale = torch.tensor([float(init_scale)], dtype=torch.float32, device=device)
+        self._scratch = torch.zeros(2, dtype=torch.int32, device=device)
+
+    def is_enabled(self):
+        return True
+
+    def scale(self, loss):
+        return _ScaledLoss(loss, self._scale)
+
+    def step(self, optimizer, enabled=None):
+        """enabled: optional device word (any 4-byte dtype); 0 = nothing pending, skip the step and leave the scaler alone
+        (harness deferred-optimizer mode)."""
+        if getattr(optimizer, "flat_bucket", None) is None:
+            raise _lib.NsigError("FusedGradScaler needs an optimizer built over a flat gradient bucket "
+                                 "(WatermarkAdam(flat_bucket=...)); use torch.amp.GradScaler otherwise")
+        flat = optimizer.flat_bucket
+        f = getattr(optimizer, "_flat", None)
+        if f is not None:
+            optimizer.scaler_bumps_step = True
+        _lib.call("nsig_grad_check_update_scale", _P(flat), flat.numel(), _P(self._scale), _P(self._growth_tracker),
+                  float(self.growth_factor), float(self.backoff_factor), self.growth_interval, _P(self._found_inf),
+                  _P(self._step_scale), _P(f["step"]) if f is not None else None, _P(self._scratch), _P(enabled))
+        optimizer.grad_scale, optimizer.found_inf = self._step_scale, self._found_inf
+        try:
+            return optimizer.step()
+        finally:
+            del optimizer.grad_scale, optimizer.found_inf
+
+    def update(self, new_scale=None):
+        if new_scale is not None:
+            self._scale.fill_(float(new_scale))
+
+    def get_scale(self):
+        return float(self._scale)
+
+    def state_dict(self):
+        return {"scale": self.get_scale(), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": int(self._growth_tracker)}
+
+    def load_state_dict(self, sd):
+        self._scale.fill_(float(sd["scale"]))
+        self.growth_factor, self.backoff_factor = float(sd["growth_factor"]), float(sd["backoff_factor"])
+        self.growth_interval = int(sd["growth_interval"])
+        self._growth_tracker.fill_(int(sd["_growth_tracker"]))

@@ -1,8 +1,17 @@
 """-m gpu parity tests of the fused field kernels (NeRFNetwork.forward / density / color and the
 watermark-mode backward) against oracle/hash_oracle.c (features) + oracle/field_oracle.py (torch fp32
-restatement of the tcnn part).  Tolerances (MLP parity is unpinned): fp16 operands with fp32
-accumulation on both sides -> sigma 2e-3 relative, rgb 2e-3 absolute, table gradients 1e-2 of their max
-(fp16 gradient activations, per-row power-of-two scaled)."""
+restatement of the tcnn part).  MLP parity is unpinned; both sides use fp16 operands with fp32 accumulation.
+
+Tolerances = north_star's 1e-3 relative wherever the quantity allows it; measured errors on B200 (round 2,
+profiles/r02_parity_errors.md) in brackets:
+  sigma           1e-3 relative, element-wise                  [2.5e-5]
+  rgb             1e-3 absolute (values in [0,1])              [4.3e-5]
+  geo features    1e-3 of the feature scale                    [5.7e-4]
+  dL/dS, wgrads   1e-3 rel-L2 and max-norm at M >= 3000        [3.4e-4 .. 7.1e-4]
+                  2e-3 rel-L2 / 2.5e-3 max-norm for the bound-2, M=1500 case [1.2e-3 / 1.8e-3]: per-sample gradients go
+                  through a chain of fp16 activations (2^-11 = 4.9e-4 relative per rounding, 5 layers), which only averages
+                  down to 1e-3 when a table slot / weight sums enough samples; tiny-cuda-nn's own backward is fp16 as well
+  M = 117 case    5e-3: 117 samples, each slot receives one or two contributions (no averaging)     [1.2e-3 .. 4.3e-3]"""
 import numpy as np
 import pytest
 import torch
@@ -73,15 +82,16 @@ def test_field_forward_and_density(oracle_cpu, bound, md, M):
         record_parity(f"field_forward[{bound},{md},{M},msg={m_ is not None}]",
                       {"sigma_max_rel_elementwise": float(np.abs(s_.cpu().numpy() / osig.detach().numpy() - 1).max()),
                        "rgb_max_abs": float(np.abs(c_.cpu().numpy() - orgb.detach().numpy()).max())})
-        np.testing.assert_allclose(s_.cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
-        np.testing.assert_allclose(c_.cpu().numpy(), orgb.detach().numpy(), rtol=0, atol=2e-3)
+        np.testing.assert_allclose(s_.cpu().numpy(), osig.detach().numpy(), rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(c_.cpu().numpy(), orgb.detach().numpy(), rtol=0, atol=1e-3)
     assert float((sigma - sigma0).abs().max()) > 0  # the message does change the field
     _, _, osig, orgb, ogeo = _oracle_forward(net, x, dirs, msg, oracle_cpu)
-    np.testing.assert_allclose(dens["sigma"].cpu().numpy(), osig.detach().numpy(), rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(dens["sigma"].cpu().numpy(), osig.detach().numpy(), rtol=1e-3, atol=1e-6)
     record_parity(f"field_density[{bound},{md},{M}]",
                   {"geo_max_abs": float(np.abs(dens["geo_feat"].float().cpu().numpy() - ogeo.detach().numpy()).max()),
                    "geo_scale": float(np.abs(ogeo.detach().numpy()).max())})
-    np.testing.assert_allclose(dens["geo_feat"].float().cpu().numpy(), ogeo.detach().numpy(), rtol=0, atol=3e-3)
+    np.testing.assert_allclose(dens["geo_feat"].float().cpu().numpy(), ogeo.detach().numpy(), rtol=0,
+                               atol=1e-3 * float(np.abs(ogeo.detach().numpy()).max()))
     np.testing.assert_allclose(col.cpu().numpy(), rgb.cpu().numpy(), rtol=0, atol=1e-5)
     assert torch.equal(colm[mask], col[mask]) and float(colm[~mask].abs().sum()) == 0
 
@@ -109,11 +119,11 @@ def test_field_backward_message_tables(oracle_cpu, bound, md, M):
         sel = net.msg_encoder.embeddings[2 * i + int(msg[i])].weight
         uns = net.msg_encoder.embeddings[2 * i + 1 - int(msg[i])].weight
         assert uns.grad is None
-        np.testing.assert_allclose(sel.grad.cpu().numpy(), G, rtol=0, atol=1e-2 * gmax)
+        np.testing.assert_allclose(sel.grad.cpu().numpy(), G, rtol=0, atol=(1e-3 if M >= 3000 else 2.5e-3) * gmax)
     got = net.msg_encoder.embeddings[int(msg[0])].weight.grad.cpu().numpy()
     record_parity(f"field_backward_G[{bound},{md},{M}]", dict(zip(("max_rel", "rel_l2"), _rel(got, G))))
     rel_l2 = np.linalg.norm(got - G) / np.linalg.norm(G)
-    assert rel_l2 < 5e-3, rel_l2
+    assert rel_l2 < (1e-3 if M >= 3000 else 2e-3), rel_l2
     # frozen parts stay grad-free
     assert all(e.weight.grad is None for e in net.encoder.embeddings)
     assert net.sigma_net.params.grad is None and net.color_net.params.grad is None
@@ -149,15 +159,16 @@ def test_clean_model_backward_weights_and_base_tables(oracle_cpu, M):
     sp = net.sigma_net.params.detach().cpu().clone().requires_grad_(True)
     cp = net.color_net.params.detach().cpu().clone().requires_grad_(True)
     osig, orgb, _, _ = fo.mlp_forward(featt, torch.from_numpy(dirs), sp, cp)
-    np.testing.assert_allclose(sigma.detach().cpu().numpy(), osig.detach().numpy(), rtol=3e-3)
+    np.testing.assert_allclose(sigma.detach().cpu().numpy(), osig.detach().numpy(), rtol=1e-3)
     ((osig * torch.from_numpy(gs)).sum() + (orgb * torch.from_numpy(gc)).sum()).backward()
 
     for name, got, want in (("sigma_net", net.sigma_net.params.grad, sp.grad), ("color_net", net.color_net.params.grad, cp.grad)):
         got, want = got.cpu().numpy(), want.numpy()
         record_parity(f"clean_wgrad[{M},{name}]", dict(zip(("max_rel", "rel_l2"), _rel(got, want))))
         rel = np.linalg.norm(got - want) / np.linalg.norm(want)
-        assert rel < 1e-2, (name, rel)
-        np.testing.assert_allclose(got, want, rtol=0, atol=2e-2 * np.abs(want).max(), err_msg=name)
+        tol = 1e-3 if M >= 3000 else 5e-3
+        assert rel < tol, (name, rel)
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol * np.abs(want).max(), err_msg=name)
     # structurally zero entries: colour input column 31 (padding) and colour output rows 3..15
     gcw = net.color_net.params.grad.cpu().numpy()
     assert not gcw[:2048].reshape(64, 32)[:, 31].any()
@@ -168,4 +179,39 @@ def test_clean_model_backward_weights_and_base_tables(oracle_cpu, M):
         got = net.encoder.embeddings[l].weight.grad.cpu().numpy()
         record_parity(f"clean_base_table_grad[{M},level{l}]", dict(zip(("max_rel", "rel_l2"), _rel(got, gt[l]))))
         rel = np.linalg.norm(got - gt[l]) / np.linalg.norm(gt[l])
-        assert rel < 1e-2, (l, rel)
+        assert rel < (1e-3 if M >= 3000 else 5e-3), (l, rel)
+
+
+@pytest.mark.parametrize("M", [128 * 37 + 5, 9, 200000])
+def test_tcgen05_backward_matches_mma_sync_backward(M):
+    """csrc/field_tc.cu (tcgen05.mma + TMEM, one thread per sample row) against csrc/field.cu's mma.sync backward on the
+    same inputs: both use fp16 operands with fp32 accumulation and the same per-row power-of-two scaling, so dL/dS agrees
+    to fp32 summation order (atomics) plus the different rounding points of the two kernels' register layouts."""
+    from nerf_signature_b200.nerf import field_ops
+    net = _net(1.0, 8)
+    x, dirs = _points(M, 1.0, 11)
+    rs = np.random.RandomState(12)
+    msg = torch.from_numpy(rs.randint(0, 2, size=8).astype(np.float32)).cuda()
+    gs = (rs.normal(size=M) * np.exp(rs.normal(0, 3, size=M))).astype(np.float32)
+    gc = (rs.normal(size=(M, 3)) * np.exp(rs.normal(0, 3, size=(M, 1)))).astype(np.float32)
+    gs[::7] = 0; gc[::7] = 0
+    if M > 1000:
+        gs[256:384] = 0; gc[256:384] = 0     # a whole 128-row tile without gradient: skipped by the tcgen05 kernel
+    xt, dt = torch.from_numpy(x).cuda(), torch.from_numpy(dirs).cuda()
+    got = {}
+    for use_tc in (True, False):
+        field_ops.USE_TCGEN05_BACKWARD = use_tc
+        try:
+            for e in net.msg_encoder.embeddings:
+                e.weight.grad = None
+            sigma, rgb = net(xt, dt, msg)
+            ((sigma * torch.from_numpy(gs).cuda()).sum() + (rgb * torch.from_numpy(gc).cuda()).sum()).backward()
+            got[use_tc] = net.msg_encoder.embeddings[int(msg[0])].weight.grad.clone()
+        finally:
+            field_ops.USE_TCGEN05_BACKWARD = True
+    torch.cuda.synchronize()
+    a, b = got[True].double(), got[False].double()
+    assert float(b.abs().max()) > 0
+    record_parity(f"tcgen05_vs_mma_sync_backward[{M}]", dict(zip(("max_rel", "rel_l2"), _rel(a.cpu().numpy(), b.cpu().numpy()))))
+    assert float((a - b).norm() / b.norm()) < 1e-3
+    assert float((a - b).abs().max() / b.abs().max()) < 2e-3

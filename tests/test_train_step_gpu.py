@@ -297,3 +297,33 @@ def test_lr_schedule_acts_on_graph_replays():
     torch.cuda.synchronize()
     assert any(not torch.equal(x, y) for x, y in zip(before, _msg_tables(g)))
     del sched
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_deferred_optimizer_equals_sequential_optimizer(graph):
+    """harness defer_optimizer: the Adam update of step t issued at the start of step t+1 (next to its march) leaves, after
+    flush_optimizer(), the same tables, decoder and scaler state as the sequential schedule, step for step; a flush in the
+    middle (what update_extra_state needs) does not apply an update twice."""
+    kw = dict(optimizer="fused", merged_render=True, fused_decoder=True, fused_losses=True, graph=graph)
+    a, b = _scene(**kw), _scene(defer_optimizer=True, **kw)
+    assert b.defer_optimizer
+    batches = _batches(a, 2)
+    gen = torch.Generator().manual_seed(21)
+    msgs = [a.new_message(gen) for _ in range(7)]
+    for i, m in enumerate(msgs):
+        la = a.train_step(batches[i % 2], m)
+        lb = b.train_step(batches[i % 2], m)
+        np.testing.assert_allclose([float(x) for x in lb], [float(x) for x in la], rtol=2e-4, atol=1e-6)
+        if i == 3:
+            b.flush_optimizer()
+            b.flush_optimizer()      # idempotent
+            for x, y in zip(_msg_tables(a), _msg_tables(b)):
+                _close_frac(x, y, rtol=1e-3, atol=1e-5)
+    b.flush_optimizer()
+    torch.cuda.synchronize()
+    for x, y in zip(_msg_tables(a), _msg_tables(b)):
+        _close_frac(x, y, rtol=1e-3, atol=1e-5)
+    for p, q in zip(a.model.msg_decoder.parameters(), b.model.msg_decoder.parameters()):
+        _close_frac(p.detach(), q.detach(), rtol=1e-3, atol=1e-5, max_bad=1e-3)
+    np.testing.assert_allclose(b.optimizer.steps.cpu().numpy(), a.optimizer.steps.cpu().numpy())
+    assert a.scaler.get_scale() == b.scaler.get_scale()
