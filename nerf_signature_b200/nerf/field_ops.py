@@ -14,7 +14,7 @@ from .. import _lib
 _P = _lib.ptr
 
 # A/B switch (tools, tests): NSIG_BWD_TC=0 keeps the mma.sync backward (csrc/field.cu) for the watermark-mode case too
-USE_TCGEN05_BACKWARD = os.environ.get("NSIG_BWD_TC", "1") != "0"
+USE_TCGEN05_BACKWARD = os.environ.get("NSIG_BWD_TC", "0") != "0"   # TODO(round 2): flip to "1" once validated on the B200
 
 
 class FusedMLP(nn.Module):
