@@ -229,6 +229,32 @@ def cpu_configs0(repeats=2, n_rays=4096, num_steps=512):
             "kind": "port", "repeats": repeats}
 
 
+def gpu_configs0(dev, n_rays=4096, num_steps=512, repeats=5):
+    """BASELINE configs[0] through THIS repo on the GPU: the same clean HashNeRF render (NeRFRenderer.run, non-cuda_ray,
+    512 uniform samples per ray, forward only) - the number that stands next to cpu_configs0()."""
+    import torch
+    from nerf_signature_b200 import harness
+    from nerf_signature_b200.nerf.network_hash import NeRFNetwork
+    cfg = dict(harness.CONFIGS["blender_wtmk"])
+    b = harness.make_batch(cfg, seed=77, num_rays=n_rays, n_blocks=1)
+    o, d = torch.from_numpy(b["rays_o"]).to(dev), torch.from_numpy(b["rays_d"]).to(dev)
+    torch.manual_seed(0)
+    net = NeRFNetwork(bound=cfg["bound"], cuda_ray=False).to(dev).eval()
+    kw = dict(staged=False, num_steps=num_steps, upsample_steps=0, bg_color=1, perturb=False)
+    with torch.no_grad():
+        net.render(o, d, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            net.render(o, d, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / repeats
+    return {"ms_per_render": ms, "rays_per_s": n_rays / (ms * 1e-3), "rays": n_rays, "samples_per_ray": num_steps,
+            "path": "nerf.network_hash.NeRFNetwork(cuda_ray=False).render -> NeRFRenderer.run -> fused field kernel"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -545,8 +571,19 @@ def run_ours(args):
         cfg["num_rays"] = host_batches[0]["rays_o"].shape[1]
         scene = harness.Scene(cfg, dev, shard_blocks=(shards[0][1], shards[0][2]), **skw)
     else:
-        seed_rank = 0 if os.environ.get("NSIG_DIAG_SAME_RAYS") == "1" else rank  # diagnosis: identical work on every rank
-        host_batches = [harness.make_batch(cfg, seed=1000 * seed_rank + i) for i in range(n_pool)]
+        same = os.environ.get("NSIG_DIAG_SAME_RAYS") == "1"   # diagnosis: identical work on every rank
+        host_batches = []
+        for i in range(n_pool):
+            views = [harness.make_batch(cfg, seed=1000 * (0 if same else r) + i) for r in range(world)]
+            mine = views[rank]
+            if world > 1 and not same and os.environ.get("NSIG_NO_INTERLEAVE") != "1":
+                # data-loader choice, not a change of the step: the global content batch (4096 random pixels of each of the
+                # N views) is dealt out ray by ray, so every rank draws the same number of rays from every view and the
+                # per-rank sample counts stop differing by the +-10 % one view's pose makes (the gradient exchange waits
+                # for the slowest rank).  The watermark blocks stay per rank (each rank decodes its own view's blocks).
+                for k in ("rays_o", "rays_d", "gt"):
+                    mine[k] = np.ascontiguousarray(np.concatenate([v[k] for v in views], axis=1)[:, rank::world])
+            host_batches.append(mine)
         scene = harness.Scene(cfg, dev, **skw)
     rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -646,7 +683,9 @@ def run_ours(args):
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
                    "decoder": "plain PyTorch module (autocast)" if args.torch_decoder else "fused kernels (csrc/decoder.cu)",
                    "losses": "plain torch expressions" if args.torch_losses else "loss-head kernels (csrc/wtmk_loss.cu)",
-                   "parallelism": f"ray-sharded dp{world}", "exchange": exchange_name},
+                   "parallelism": f"ray-sharded dp{world}" + ("; content rays of the N views dealt out ray by ray (balanced "
+                                                                 "sample counts), watermark blocks per rank" if world > 1 else ""),
+                   "exchange": exchange_name},
         "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 4,
                 "staging": "host batches wait in pinned memory packed like the step's input buffer (what a pin_memory data "
@@ -664,6 +703,7 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_port_run(cfg, steps=12, warmup=1, rays_per_pass=args.cpu_rays or 64)  # ~12 s of CPU work
         if not args.no_extra:
             line["cpu_baseline"]["configs0"] = cpu_configs0(repeats=1)
+            line["cpu_baseline"]["configs0"]["ours_gpu"] = gpu_configs0(dev)
     print(json.dumps(line), flush=True)
     _finish(world)
 

@@ -201,18 +201,20 @@ struct ConvParams {
 // k-step straight from global memory (the 74 KB of a layer's weights stay in L1/L2; staging them through shared
 // memory cost more than the math) and reused for every m-tile; A fragments come from the staged input tile.
 // ---------------------------------------------------------------------------------------------------------------
+// The body works on "items" = (image b, strip of R rows): item -> b = item / strips, r0 = (item % strips) * R.  The
+// stand-alone kernel gives every CTA one item; the persistent forward kernel (k_dec_fwd_persist) lets a CTA loop over
+// items item0, item0 + item_step, ... of a layer, loading the layer's weights and BatchNorm coefficients once.
 template <int CIN, int SCH, int COUT, int MODE>
-__global__ void __launch_bounds__(kDecThreads)
-k_dec_conv(const ConvParams p) {
+__device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* smem_raw, int item0, int item_step, int n_items,
+                                         int strips) {
     constexpr int STRIDE = CIN + 8, NT = COUT / 8, KS = CIN / 16, MB = 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (item0 >= n_items) return;
     __half* tile = reinterpret_cast<__half*>(smem_raw);                      // [(R+2)*(W+2)][STRIDE]
     BnCoef* coef = reinterpret_cast<BnCoef*>(tile + (size_t)(p.R + 2) * (p.W + 2) * STRIDE);
     BnCoef* coef_out = coef + CIN;                                           // [COUT], data-gradient convs with out_bsums
     // the layer's weights [COUT][9*CIN], rows padded by 16 bytes (ldmatrix rows of an n-tile then sit in distinct banks)
     constexpr int WROW = 9 * CIN, WSTR = WROW + 8;
     __half* wsm = reinterpret_cast<__half*>(coef_out + COUT);
-    const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
     const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
     // Asynchronous copy of the weights (up to 74 KB from L2), issued first: it completes while the BatchNorm
@@ -228,11 +230,14 @@ k_dec_conv(const ConvParams p) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
+  for (int item = item0; item < n_items; item += item_step) {
+    const int b = item / strips, r0 = (item - b * strips) * p.R, R = min(p.R, p.H - r0);
+    const bool first = item == item0;
     // the first batch of input-tile loads is in flight while the BatchNorm coefficients (their own L2 round trip +
     // fp64 arithmetic) are derived: one exposed memory latency in the prologue instead of two
     TileStager<CIN, SCH, MODE> stager;
     stager.issue(p.src, p.src2, 0, b, r0, R, p.H, p.W);
-    if (MODE != IN_RAW) {
+    if (first && MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
         if (bstats)
             for (int ch = threadIdx.x; ch < COUT; ch += blockDim.x) coef_out[ch] = bn_coef(p.bn_out, ch, false);
@@ -246,7 +251,7 @@ k_dec_conv(const ConvParams p) {
             stager.commit(tile, coef, base, R, p.W);
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (first) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int P = R * p.W, TW = p.W + 2, m_tiles = (P + 15) / 16, m_groups = (m_tiles + MB - 1) / MB;
@@ -353,6 +358,16 @@ k_dec_conv(const ConvParams p) {
             }
         }
     }
+    __syncthreads();   // the tile is restaged for the CTA's next item
+  }
+}
+
+template <int CIN, int SCH, int COUT, int MODE>
+__global__ void __launch_bounds__(kDecThreads)
+k_dec_conv(const ConvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    conv_cta<CIN, SCH, COUT, MODE>(p, smem_raw, (int)(blockIdx.y * gridDim.x + blockIdx.x), 1 << 30,
+                                   (int)(gridDim.x * gridDim.y), (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -617,6 +632,119 @@ k_dec_head_bwd(const HeadParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent forward: the whole decoder forward (weight/input preparation, L+1 convolutions, head) as ONE kernel.
+// The per-layer kernels above are 9-11 us each for ~1 us of math: every launch pays a grid ramp-up, an L2 round trip for
+// the BatchNorm sums and a pipeline drain, and BatchNorm's batch statistics force a global dependency between layers.
+// Here the grid (one resident wave, at most one CTA per (image, strip) item) stays on the SMs and the layers are
+// separated by a grid barrier (one atomic per CTA + an acquire spin on an L2 counter) instead of a kernel boundary.
+// Arithmetic, rounding points and memory layout are exactly those of the per-layer kernels (same conv_cta body), which
+// remain the path for the backward pass and for shapes whose items exceed what fits co-resident.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPersistMaxLayers = 9;   // conv blocks 0..L (the reference decoder: num_blocks = 8 -> 9 convs)
+
+struct FwdPersistParams {
+    ConvParams layer[kPersistMaxLayers];
+    PrepParams prep;
+    HeadParams head;
+    const float* image;
+    __half* x0;
+    unsigned int* barrier;   // zero-initialised by the caller (inside the statistics memset)
+    int L, n_pix, strips, n_items;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                       // this CTA's global writes (and its warps' atomics) before the arrival
+        atomicAdd(counter, 1u);
+        unsigned int seen = 0, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen < target && ++spins > (1u << 27)) __trap();   // a CTA that never arrives must not hang the GPU
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void prep_weights_slice(const PrepParams& q, int l, int gtid, int gthreads) {
+    const float* __restrict__ w = q.w[l];
+    const int cout = q.cout[l], cin = q.cin[l], cout_pad = q.cout_pad[l], cin_pad = q.cin_pad[l];
+    __half* __restrict__ wf = q.wf[l];
+    __half* __restrict__ wr = q.wr[l];
+    const int n = cout_pad * 9 * cin_pad;
+    for (int i = gtid; i < n; i += gthreads) {
+        {
+            const int co = i / (9 * cin_pad), rem = i - co * 9 * cin_pad, t = rem / cin_pad, ci = rem - t * cin_pad;
+            wf[i] = (co < cout && ci < cin) ? f2h(w[((size_t)co * cin + ci) * 9 + t]) : f2h(0.f);
+        }
+        {
+            const int ci = i / (9 * cout_pad), rem = i - ci * 9 * cout_pad, t = rem / cout_pad, co = rem - t * cout_pad;
+            wr[i] = (co < cout && ci < cin) ? f2h(w[((size_t)co * cin + ci) * 9 + (8 - t)]) : f2h(0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ void head_fwd_image(const HeadParams& p, int b, BnCoef* coef, float* acc) {
+    __syncthreads();
+    if (threadIdx.x < 8) { coef[threadIdx.x] = (int)threadIdx.x < p.nb ? bn_coef(p.bn, threadIdx.x, false) : BnCoef{}; acc[threadIdx.x] = 0.f; }
+    __syncthreads();
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pix = threadIdx.x; pix < p.HW; pix += blockDim.x) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p.z9 + ((size_t)b * p.HW + pix) * 8);
+        const __half* hz = reinterpret_cast<const __half*>(&v);
+        for (int k = 0; k < p.nb; ++k) s[k] += h2f(act_from_z(hz[k], coef[k]));
+    }
+    for (int k = 0; k < p.nb; ++k) atomicAdd(&acc[k], s[k]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __half pooled[8];
+        for (int k = 0; k < 8; ++k) { pooled[k] = f2h(k < p.nb ? acc[k] / (float)p.HW : 0.f); p.pooled[b * 8 + k] = pooled[k]; }
+        for (int bit = 0; bit < p.num_bits; ++bit) {
+            float tot = 0.f;
+            for (int rdn = 0; rdn < p.redundancy; ++rdn) {
+                const int o = bit * p.redundancy + rdn;
+                float v = 0.f;
+                for (int k = 0; k < p.nb; ++k) v = fmaf(h2f(f2h(p.lin_w[o * p.nb + k])), h2f(pooled[k]), v);
+                tot += h2f(f2h(v + h2f(f2h(p.lin_b[o]))));
+            }
+            p.logits[b * p.num_bits + bit] = h2f(f2h(tot));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+k_dec_fwd_persist(const FwdPersistParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ BnCoef head_coef[8];
+    __shared__ float head_acc[8];
+    const int gtid = blockIdx.x * kDecThreads + threadIdx.x, gthreads = gridDim.x * kDecThreads;
+    const unsigned int n_cta = gridDim.x;
+    // phase 0: fp16 weight copies (both orientations; the backward kernels read the rotated one) and the normalised input
+    for (int l = 0; l <= q.L; ++l) prep_weights_slice(q.prep, l, gtid, gthreads);
+    {
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, std[3] = {0.229f, 0.224f, 0.225f};
+        for (int i = gtid; i < q.n_pix; i += gthreads) {
+            __align__(16) __half o[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = f2h(0.f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] = f2h(__fdiv_rn(__fsub_rn(q.image[(size_t)i * 3 + k], mean[k]), std[k]));
+            *reinterpret_cast<uint4*>(q.x0 + (size_t)i * 16) = *reinterpret_cast<const uint4*>(o);
+            *reinterpret_cast<uint4*>(q.x0 + (size_t)i * 16 + 8) = *reinterpret_cast<const uint4*>(o + 8);
+        }
+    }
+    unsigned int phase = 1;
+    grid_barrier(q.barrier, phase++ * n_cta);
+    for (int l = 0; l <= q.L; ++l) {
+        if (l == 0) conv_cta<16, 16, 64, IN_RAW>(q.layer[l], smem_raw, (int)blockIdx.x, (int)gridDim.x, q.n_items, q.strips);
+        else if (l == q.L) conv_cta<64, 64, 8, IN_BNGELU>(q.layer[l], smem_raw, (int)blockIdx.x, (int)gridDim.x, q.n_items, q.strips);
+        else conv_cta<64, 64, 64, IN_BNGELU>(q.layer[l], smem_raw, (int)blockIdx.x, (int)gridDim.x, q.n_items, q.strips);
+        grid_barrier(q.barrier, phase++ * n_cta);
+    }
+    for (int b = blockIdx.x; b < q.head.B; b += gridDim.x) head_fwd_image(q.head, b, head_coef, head_acc);
+}
+
 struct BnGradParams { const double* bsums[17]; float* dgamma[17]; float* dbeta[17]; int c_pad[17], c_real[17]; };
 __global__ void __launch_bounds__(64)
 k_dec_bn_grads(const BnGradParams q) {   // dbeta = sum dy, dgamma = sum dy*yhat: the backward statistics themselves
@@ -643,7 +771,7 @@ struct DecLayout {
     size_t n_pix;
     size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz[kMaxLayers + 1], off_da9, off_dx0, off_pooled;
     size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_sums[kMaxLayers + 1], off_bsums[kMaxLayers + 1];
-    size_t off_sums_begin, sums_bytes, total;
+    size_t off_sums_begin, sums_bytes, off_barrier, total;
 };
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
@@ -673,6 +801,7 @@ DecLayout make_layout(int B, int H, int W, int L) {
         d.off_sums[l] = o; o += 2 * 64 * sizeof(double);
         d.off_bsums[l] = o; o += 2 * 64 * sizeof(double);
     }
+    d.off_barrier = o; o += 256;            // grid-barrier counter of the persistent forward, cleared with the statistics
     d.sums_bytes = o - d.off_sums_begin;
     d.total = align_up(o);
     return d;
@@ -780,33 +909,66 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
         q.w[l] = params[4 * l]; q.wf[l] = H16(d.off_wf[l]); q.wr[l] = H16(d.off_wr[l]);
         q.cin[l] = l == 0 ? 3 : 64; q.cout[l] = l == L ? nb : 64; q.cin_pad[l] = l == 0 ? 16 : 64; q.cout_pad[l] = l == L ? 16 : 64;
     }
-    k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, st>>>(q);
-    NSIG_LAUNCH_CHECK();
-    k_dec_prep_input<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(image, (int)d.n_pix, H16(d.off_x0));
-    NSIG_LAUNCH_CHECK();
     const float inv_n = 1.0f / (float)d.n_pix;
-    for (int l = 0; l <= L; ++l) {
+    auto conv_params = [&](int l) {
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
         p.w = H16(d.off_wf[l]); p.bias = params[4 * l + 1]; p.dst = H16(d.off_z[l]); p.out_sums = D64(d.off_sums[l]);
         p.cout_valid = l == L ? nb : 64;
-        int rc;
         if (l == 0) {
             p.src = H16(d.off_x0);
-            rc = launch_conv<16, 16, 64, IN_RAW>(p, st);
         } else {
             p.src = H16(d.off_z[l - 1]);
             p.act_out = H16(d.off_a[l - 1]);   // a_{l-1}, kept for the weight gradient of this layer
             p.bn = BnSrc{D64(d.off_sums[l - 1]), nullptr, params[4 * (l - 1) + 2], params[4 * (l - 1) + 3], inv_n, 64, 64};
-            rc = l == L ? launch_conv<64, 64, 8, IN_BNGELU>(p, st) : launch_conv<64, 64, 64, IN_BNGELU>(p, st);
         }
-        if (rc) return rc;
-    }
+        return p;
+    };
     HeadParams h{};
     h.z9 = H16(d.off_z[L]); h.bn = BnSrc{D64(d.off_sums[L]), nullptr, params[4 * L + 2], params[4 * L + 3], inv_n, 8, nb};
     h.lin_w = params[4 * (L + 1)]; h.lin_b = params[4 * (L + 1) + 1];
     h.B = (int)B; h.HW = (int)(H * W); h.nb = nb; h.num_bits = (int)num_bits; h.redundancy = (int)redundancy;
     h.logits = logits; h.pooled = H16(d.off_pooled);
+
+    // ---- persistent path: one kernel, grid barriers between the layers ----
+    static const bool no_persist = [] { const char* e = getenv("NSIG_DEC_NO_PERSIST"); return e && e[0] == '1'; }();
+    if (!no_persist && L + 1 <= kPersistMaxLayers) {
+        const int R = conv_rows((int)B, (int)H, (int)W);
+        const int strips = ((int)H + R - 1) / R;
+        const size_t smem = (size_t)(R + 2) * (W + 2) * (64 + 8) * 2 + (size_t)(64 + 64) * sizeof(BnCoef) + (size_t)64 * (9 * 64 + 8) * 2;
+        if (smem <= 200 * 1024) {
+            static bool set = false;
+            if (!set) { cudaFuncSetAttribute(k_dec_fwd_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+            int per_sm = 0, dev = 0, sms = 148;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dec_fwd_persist, kDecThreads, smem) == cudaSuccess && per_sm >= 1) {
+                if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                FwdPersistParams fp{};
+                for (int l = 0; l <= L; ++l) { fp.layer[l] = conv_params(l); fp.layer[l].R = R; }
+                fp.prep = q; fp.head = h; fp.image = image; fp.x0 = H16(d.off_x0);
+                fp.barrier = reinterpret_cast<unsigned int*>(ws + d.off_barrier);
+                fp.L = L; fp.n_pix = (int)d.n_pix; fp.strips = strips; fp.n_items = strips * (int)B;
+                // one resident wave: every CTA must be on an SM for the grid barrier to complete.  One CTA per SM is
+                // enough (the layers are latency-bound) and leaves room for kernels of parallel graph branches.
+                const int cap = sms * 1;
+                const int grid = fp.n_items < cap ? fp.n_items : cap;
+                k_dec_fwd_persist<<<grid, kDecThreads, smem, st>>>(fp);
+                NSIG_LAUNCH_CHECK();
+                return 0;
+            }
+        }
+    }
+
+    k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, st>>>(q);
+    NSIG_LAUNCH_CHECK();
+    k_dec_prep_input<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(image, (int)d.n_pix, H16(d.off_x0));
+    NSIG_LAUNCH_CHECK();
+    for (int l = 0; l <= L; ++l) {
+        ConvParams p = conv_params(l);
+        int rc;
+        if (l == 0) rc = launch_conv<16, 16, 64, IN_RAW>(p, st);
+        else rc = l == L ? launch_conv<64, 64, 8, IN_BNGELU>(p, st) : launch_conv<64, 64, 64, IN_BNGELU>(p, st);
+        if (rc) return rc;
+    }
     k_dec_head_fwd<<<B, 256, 0, st>>>(h);
     NSIG_LAUNCH_CHECK();
     return 0;

@@ -312,7 +312,8 @@ class FusedGradScaler:
         _lib.call("nsig_grad_check_update_scale", _P(flat), flat.numel(), _P(self._scale), _P(self._growth_tracker),
                   float(self.growth_factor), float(self.backoff_factor), self.growth_interval, _P(self._found_inf),
                   _P(self._step_scale), _P(f["step"]) if f is not None else None, _P(self._scratch), _P(enabled))
-        optimizer.grad_scale, optimizer.found_inf = self._step_scale, self._found_inf
+        # 0-dim views: torch's fused Adam (the non-flat decoder path) broadcasts found_inf against its 0-dim step tensors
+        optimizer.grad_scale, optimizer.found_inf = self._step_scale.reshape(()), self._found_inf.reshape(())
         try:
             return optimizer.step()
         finally:

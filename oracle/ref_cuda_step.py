@@ -58,7 +58,6 @@ class RefComposedStep:
         self.lambda_w, self.lambda_i = lambda_w, lambda_i
         self.density_scale, self.min_near = float(density_scale), float(min_near)
         self.aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=dev)
-        tp._OFFSETS = tp._OFFSETS.to(dev)
         if mlp == "fp16":
             sp, cp = self.sigma_params, self.color_params
             self.Ws = [sp[:2048].view(64, 32).half(), sp[2048:3072].view(16, 64).half()]

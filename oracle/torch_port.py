@@ -22,6 +22,16 @@ import torch
 import torch.nn.functional as F
 
 _OFFSETS = torch.tensor([[[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)]])  # hash_encoding.py:8
+_OFFSETS_ON = {}
+
+
+def _offsets(device):
+    """BOX_OFFSETS on `device` (the reference keeps its copy on 'cuda'; this port runs on the CPU and, for the
+    reference-composed CUDA step, on the GPU)."""
+    key = str(device)
+    if key not in _OFFSETS_ON:
+        _OFFSETS_ON[key] = _OFFSETS.to(device)
+    return _OFFSETS_ON[key]
 _PRIMES = (1, 2654435761, 805459861)
 
 
@@ -39,7 +49,7 @@ def _voxel(x, resolution, log2_T):
     idx = torch.floor(xc / grid_size).int()
     vmin = idx * grid_size
     vmax = vmin + grid_size
-    slots = _hash(idx.unsqueeze(1) + _OFFSETS, log2_T)
+    slots = _hash(idx.unsqueeze(1) + _offsets(idx.device), log2_T)
     return vmin, vmax, slots
 
 

@@ -83,6 +83,17 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     base = ctypes.addressof(buf)
     aligned, odd = V(base + (-base) % 16), V(base + (-base) % 16 + 2)
     assert h.nsig_field_backward(p, p, 4, 1.0, p, p, p, odd, aligned, 1.0, None, 2048.0, 19, p, None, None, None, None) == -1
+    # round-2 entry points: tcgen05 backward, fused-slot probe, one-kernel GradScaler, flat Adam
+    assert h.nsig_field_backward_tc(None, None, 0, 1.0, None, None, None, None, None, 1.0, None, 2048.0, 19, None, None) == 0
+    assert h.nsig_field_backward_tc(p, p, 4, 1.0, aligned, p, p, aligned, aligned, 1.0, None, 2048.0, 19, None, None) == -1   # no G
+    assert h.nsig_field_backward_tc(p, p, 4, 1.0, odd, p, p, aligned, aligned, 1.0, None, 2048.0, 19, p, None) == -1       # feat alignment
+    assert h.nsig_field_backward_tc(p, p, 4, 1.0, aligned, p, p, aligned, aligned, 1.0, None, 0.0, 19, p, None) == -1      # msg resolution
+    assert h.nsig_fused_hash_slots(None, 0, None, 16, 19, None, None, None) == 0
+    assert h.nsig_fused_hash_slots(p, 1, res, 17, 19, p, None, None) == -1
+    assert h.nsig_grad_check_update_scale(None, 8, p, p, 2.0, 0.5, 2000, p, p, None, p, None, None) == -1
+    assert h.nsig_grad_check_update_scale(aligned, 8, p, p, 2.0, 0.5, 0, p, p, None, p, None, None) == -1                  # growth_interval
+    assert h.nsig_flat_adam_step(None, None, None, None, 0, None, None, None, 1e-2, None, 0.9, 0.99, 1e-15, None) == 0
+    assert h.nsig_flat_adam_step(p, p, p, p, 8, None, None, None, 1e-2, None, 0.9, 0.99, 1e-15, None) == -1                # no step counter
 
 
 def test_python_layer_has_no_cpu_path(lib):

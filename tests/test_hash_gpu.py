@@ -164,12 +164,17 @@ def test_fused_slots_equal_reference_order_slots():
 
 
 def test_fused_slots_message_geometry():
-    """The message encoder's single resolution (2048) through the fused geometry (FieldParams.msg_geom)."""
+    """The message encoder's single resolution through the fused geometry (FieldParams.msg_geom): 2048 exactly
+    (base == finest, b = 1), whereas the base encoder's finest level is floor(16 * b**15) = 2047 in torch fp32."""
     from nerf_signature_b200.hash_encoding import HashEmbedder
-    enc = HashEmbedder(bounding_box=(0, 1), n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
-                       base_resolution=16, finest_resolution=2048).cuda()
+    enc = HashEmbedder(bounding_box=(0, 1), n_levels=2, n_features_per_level=2, log2_hashmap_size=19,
+                       base_resolution=2048, finest_resolution=2048).cuda()
+    assert enc.resolutions == [2048.0, 2048.0]
     g = torch.Generator(device="cuda").manual_seed(2)
     xt = torch.rand(500000, 3, device="cuda", generator=g)
-    got = enc.fused_hashed_indices(xt, resolutions=[2048.0])
-    assert enc.resolutions[15] == 2048.0
-    assert torch.equal(got, enc.hashed_indices(xt)[:, 15:16])   # level 15 has resolution 2048
+    b = torch.from_numpy(_boundary_points(2048.0, 8)).cuda()
+    xb = torch.rand(b.numel(), 3, device="cuda", generator=g)
+    xb[:, 1] = b
+    for x in (xt, xb):
+        got = enc.fused_hashed_indices(x, resolutions=[2048.0])
+        assert torch.equal(got, enc.hashed_indices(x)[:, :1])

@@ -299,31 +299,43 @@ def test_lr_schedule_acts_on_graph_replays():
     del sched
 
 
+def _bad_frac(x, y, rtol=1e-3, atol=1e-5):
+    return ((x - y).abs() > atol + rtol * y.abs()).float().mean().item()
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_deferred_optimizer_equals_sequential_optimizer(graph):
     """harness defer_optimizer: the Adam update of step t issued at the start of step t+1 (next to its march) leaves, after
     flush_optimizer(), the same tables, decoder and scaler state as the sequential schedule, step for step; a flush in the
-    middle (what update_extra_state needs) does not apply an update twice."""
+    middle (what update_extra_state needs) does not apply an update twice.  The scatter-add order of dL/dS is not
+    deterministic and Adam's update is sign-like for near-zero gradients (see _close_frac), so the yardstick is the
+    run-to-run difference of two IDENTICAL sequential scenes."""
     kw = dict(optimizer="fused", merged_render=True, fused_decoder=True, fused_losses=True, graph=graph)
-    a, b = _scene(**kw), _scene(defer_optimizer=True, **kw)
+    a, a2, b = _scene(**kw), _scene(**kw), _scene(defer_optimizer=True, **kw)
     assert b.defer_optimizer
     batches = _batches(a, 2)
     gen = torch.Generator().manual_seed(21)
     msgs = [a.new_message(gen) for _ in range(7)]
+
+    def check_tables():
+        floor = max(_bad_frac(x, y) for x, y in zip(_msg_tables(a2), _msg_tables(a)))
+        worst = max(_bad_frac(x, y) for x, y in zip(_msg_tables(b), _msg_tables(a)))
+        assert worst <= max(1e-4, 3.0 * floor), (worst, floor)
+
     for i, m in enumerate(msgs):
         la = a.train_step(batches[i % 2], m)
+        a2.train_step(batches[i % 2], m)
         lb = b.train_step(batches[i % 2], m)
         np.testing.assert_allclose([float(x) for x in lb], [float(x) for x in la], rtol=2e-4, atol=1e-6)
         if i == 3:
             b.flush_optimizer()
             b.flush_optimizer()      # idempotent
-            for x, y in zip(_msg_tables(a), _msg_tables(b)):
-                _close_frac(x, y, rtol=1e-3, atol=1e-5)
+            check_tables()
     b.flush_optimizer()
     torch.cuda.synchronize()
-    for x, y in zip(_msg_tables(a), _msg_tables(b)):
-        _close_frac(x, y, rtol=1e-3, atol=1e-5)
-    for p, q in zip(a.model.msg_decoder.parameters(), b.model.msg_decoder.parameters()):
-        _close_frac(p.detach(), q.detach(), rtol=1e-3, atol=1e-5, max_bad=1e-3)
+    check_tables()
+    floor = max(_bad_frac(p.detach(), q.detach()) for p, q in zip(a2.model.msg_decoder.parameters(), a.model.msg_decoder.parameters()))
+    worst = max(_bad_frac(p.detach(), q.detach()) for p, q in zip(b.model.msg_decoder.parameters(), a.model.msg_decoder.parameters()))
+    assert worst <= max(1e-3, 3.0 * floor), (worst, floor)
     np.testing.assert_allclose(b.optimizer.steps.cpu().numpy(), a.optimizer.steps.cpu().numpy())
     assert a.scaler.get_scale() == b.scaler.get_scale()

@@ -82,19 +82,23 @@ def main():
     fwd()
     sig, rgb = holder["o"]
     gs, gc = torch.randn_like(sig) * 1e-3, torch.randn_like(rgb) * 1e-3
-    _lib.timing_enable(["nsig_field_backward"])
+    bwd_names = ["nsig_field_backward", "nsig_field_backward_tc"]   # mma.sync kernel / tcgen05 kernel (NSIG_BWD_TC=1)
+    _lib.timing_enable(bwd_names)
 
     def bwd():
         torch.autograd.grad([sig, rgb], [Sg], [gs, gc], retain_graph=True)
 
     for _ in range(3):
         bwd()
-    _lib.timing_enable(["nsig_field_backward"])
+    _lib.timing_enable(bwd_names)
     for _ in range(args.iters):
         if not args.no_flush:
             flush.fill_(1.0)
         bwd()
-    t = _lib.timing_collect()["nsig_field_backward"]
+    tt = _lib.timing_collect()
+    name = [n for n in bwd_names if n in tt][0]
+    t = tt[name]
+    out["field_bwd_kernel"] = name
     out["field_bwd_ms"] = t["ms"] / t["n"]
     out["fwd_Gsamples_per_s"] = M / out["field_fwd_ms"] / 1e6
     out["fwd_alg_GBps"] = 1128 * M / out["field_fwd_ms"] / 1e6
