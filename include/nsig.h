@@ -218,7 +218,10 @@ int nsig_tables_to_half2(const float* const* tables, uint32_t n_levels, uint32_t
  *          kernel processes min(M, *M_dev) rows, so no host sync is needed to size the launch
  * outputs: sigmas[M] fp32, rgbs[M,3] fp32 (sigmoid applied)
  *          feat_out (optional) [M,32] fp16: encoder output incl. message feature, saved for
- *          the backward pass.
+ *          nsig_field_backward / nsig_field_backward_tc (which recompute the MLPs from it).
+ *          masks_out (optional) [M,4] x 8 bytes: the ReLU sign masks of the three hidden layers in the
+ *          fragment order of the kernels (entry (row, q) = {m1s | m1c << 16, m2c} of quad thread q;
+ *          bit 2*nt + e <-> hidden unit nt*8 + 2*q + e), saved for nsig_field_backward_masks.
  *   tables_h2 / h2_inv_scale (optional, both or neither): half2 shadow copies of the 16 base tables and their
  *          device float[16] de-scaling factors, as nsig_tables_to_half2 writes them.  When given, the kernel
  *          gathers those (one 32-bit load per corner) instead of the fp32 tables; hash slots are unchanged, the
@@ -227,8 +230,8 @@ int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float b
                        const float* const* tables, const float* resolutions, uint32_t log2_T,
                        const float* S, float msg_resolution, const void* sigma_w,
                        const void* color_w, float density_scale, const int32_t* M_dev,
-                       float* sigmas, float* rgbs, void* feat_out, const void* const* tables_h2,
-                       const float* h2_inv_scale, nsig_stream_t stream);
+                       float* sigmas, float* rgbs, void* feat_out, void* masks_out,
+                       const void* const* tables_h2, const float* h2_inv_scale, nsig_stream_t stream);
 
 /* Density-only variant: NeRFNetwork.density (network_wtmk_tcnn.py:126-143);
  * geo_feat (optional) [M,15] fp16. */
@@ -394,6 +397,17 @@ int nsig_wtmk_loss_backward(const float* g_image, const float* g_logits, uint32_
 uint32_t nsig_allreduce_grid(void);
 int nsig_allreduce_mean_inplace(void* const* bufs, void* const* flags, void* multicast, uint32_t n,
                                 uint32_t rank, uint32_t world, nsig_stream_t stream);
+
+/* Watermark-mode backward from what the forward already produced (the default hot path): `masks` as written by
+ * nsig_field_forward(masks_out), the forward outputs sigmas / rgbs (sigmoid'(z) = rgb (1 - rgb), exp(logit) = sigma /
+ * density_scale) and the incoming gradients.  No MLP recomputation: only the five data-gradient GEMMs run, then dL/dS is
+ * scatter-added into G ([2^log2_T, 2] fp32, accumulated).  Same result as nsig_field_backward(G only) up to 1 ulp of the
+ * exp() factor. */
+int nsig_field_backward_masks(const float* xyzs, uint32_t M, float bound, const void* masks, const float* sigmas,
+                              const float* rgbs, const float* grad_sigmas, const float* grad_rgbs,
+                              const void* sigma_w, const void* color_w, float density_scale,
+                              const int32_t* M_dev, float msg_resolution, uint32_t log2_T, float* G,
+                              nsig_stream_t stream);
 
 /* The watermark-mode case of nsig_field_backward (G only: no full feature gradient, no weight gradients - SURVEY F13:
  * everything but the message tables is frozen) on the 5th-generation tensor cores: every MLP layer of a 128-sample

@@ -46,8 +46,9 @@ _SIGNATURES = {
     "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _vp], 1),
     "nsig_msg_encode_forward_perbit": ([_vp, _u32, _vp, _u32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_fused_hash_slots": ([_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp], 1),
-    "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp,
+    "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp], 1),
+    "nsig_field_backward_masks": ([_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_tables_to_half2": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp], 2),
     "nsig_grid_sweep": ([_vp, _vp, _vp, _u32, _vp, _u64, _u32, _u32, _f64, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32,

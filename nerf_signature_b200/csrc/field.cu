@@ -29,7 +29,7 @@ namespace nsig {
 template <bool COLOR, bool H2>
 __global__ void __launch_bounds__(kFieldThreads, NSIG_FWD_MINB)
 k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__ rgbs, __half* __restrict__ feat_out,
-            __half* __restrict__ geo_out) {
+            __half* __restrict__ geo_out, uint2* __restrict__ mask_out) {
     constexpr int MT = 2;
     extern __shared__ __align__(16) __half sm[];
     uint32_t M = p.M;
@@ -80,9 +80,11 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
 #endif
         // sigma net: 32 -> 64 (ReLU) -> 16
         uint32_t h1[MT][4][4];
+        [[maybe_unused]] uint32_t mk[3][MT][2];   // ReLU sign masks of the three hidden layers (COLOR && mask_out)
         {
             float c[MT][8][4];
             layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
+            if (COLOR && mask_out) relu_mask_bits<MT>(mk[0], c);
             relu_to_a<MT, 8>(h1, c);
         }
         float so[MT][2][4];
@@ -122,9 +124,20 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
             {
                 float c[MT][8][4];
                 layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
+                if (mask_out) relu_mask_bits<MT>(mk[1], c);
                 relu_to_a<MT, 8>(h1, c);
                 layer<MT, 4, 8>(c, h1, sm + oWc1, kS64, g, tig);
+                if (mask_out) relu_mask_bits<MT>(mk[2], c);
                 relu_to_a<MT, 8>(h2, c);
+            }
+            if (mask_out) {   // 8 bytes per (row, quad thread): [m1s | m1c << 16, m2c]; a quad writes 32 contiguous bytes per row
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t r = frag_row<MT>(row0, mt, h, g);
+                        if (r < M) mask_out[(size_t)r * 4 + tig] = make_uint2(mk[0][mt][h] | (mk[1][mt][h] << 16), mk[2][mt][h]);
+                    }
             }
             float co[MT][1][4];
             layer<MT, 4, 1>(co, h2, sm + oWc2, kS64, g, tig);
@@ -824,6 +837,158 @@ k_field_bwd(const FieldBwdParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Watermark-mode backward from SAVED ReLU MASKS (the hot path: only dL/dS is needed).
+// k_field_bwd above recomputes the five forward GEMMs of a tile from the saved encoder output just to learn (a) which hidden
+// units were active and (b) sigmoid'(z), exp(logit).  (b) follows from the forward's own outputs (rgb, sigma), and (a) is 3 x 64
+// bits per sample, which k_field_fwd writes next to them (relu_mask_bits: 32 B per sample instead of the 64 B of features).
+// What is left is the five dgrad GEMMs: 60 instead of 136 m16n8k16 MMAs per 16 rows, no SH, no feature reload.
+// Bit-identical masks by construction (same accumulators, same rounding rule), so dL/dS differs from k_field_bwd's only by
+// exp(logit) being read back as sigma / density_scale (1 ulp).
+// ---------------------------------------------------------------------------------------
+struct FieldBwdMaskParams {
+    const float* xyzs;
+    uint32_t M;
+    float bound_add, bound_mul;
+    const uint2* masks;        // [M][4] (row, quad thread): x = m1s | m1c << 16, y = m2c
+    const float* sigmas;       // [M]   forward outputs
+    const float* rgbs;         // [M,3]
+    const float* grad_sigmas;  // [M]
+    const float* grad_rgbs;    // [M,3]
+    const __half* sigma_w;
+    const __half* color_w;
+    float msg_grid_size;
+    uint32_t mask;
+    float* G;
+    const int32_t* M_dev;
+    float density_scale;
+};
+
+__global__ void __launch_bounds__(kFieldThreads)
+k_field_bwd_masks(const FieldBwdMaskParams p) {
+    constexpr int MT = 1;
+    extern __shared__ __align__(16) __half sm[];
+    uint32_t M = p.M;
+    if (p.M_dev) M = min(M, (uint32_t)max(*p.M_dev, 0));
+    if (M == 0) return;
+    stage_backward_weights(sm, p.sigma_w, p.color_w);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const uint32_t rows_per_cta = kFieldWarps * 16 * MT;
+    const uint32_t n_tiles = div_up(M, rows_per_cta);
+    const float inv_ds = 1.0f / p.density_scale;
+    struct TileIn {
+        float gs[2], gc[2][2], act[2][2], sx[3];   // act: tig 3 -> sigma; tig 0 -> (r, g); tig 1 -> b
+        uint2 mk[2];
+    };
+    auto load_tile = [&](uint32_t tile, TileIn& t) {
+        const uint32_t row0 = tile * rows_per_cta + warp * 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = row0 + h * 8 + g;
+            t.gs[h] = 0.f; t.gc[h][0] = t.gc[h][1] = 0.f; t.act[h][0] = t.act[h][1] = 0.f;
+            t.mk[h] = make_uint2(0u, 0u);
+            if (r < M) {
+                if (tig == 3) { t.gs[h] = __ldg(p.grad_sigmas + r); t.act[h][0] = __ldg(p.sigmas + r); }
+                if (tig == 0) {
+                    t.gc[h][0] = __ldg(p.grad_rgbs + (size_t)r * 3); t.gc[h][1] = __ldg(p.grad_rgbs + (size_t)r * 3 + 1);
+                    t.act[h][0] = __ldg(p.rgbs + (size_t)r * 3); t.act[h][1] = __ldg(p.rgbs + (size_t)r * 3 + 1);
+                }
+                if (tig == 1) { t.gc[h][0] = __ldg(p.grad_rgbs + (size_t)r * 3 + 2); t.act[h][0] = __ldg(p.rgbs + (size_t)r * 3 + 2); }
+                t.mk[h] = __ldg(p.masks + (size_t)r * 4 + tig);
+            }
+        }
+        // the row whose 8 corners this thread scatters: quad thread `tig` takes row (h = tig & 1) of the tile's row pair
+        const uint32_t rs = row0 + (tig & 1) * 8 + g;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t.sx[a] = (tig < 2 && rs < M) ? __ldg(p.xyzs + (size_t)rs * 3 + a) : 0.f;
+    };
+    TileIn nxt;
+    if (blockIdx.x < n_tiles) load_tile(blockIdx.x, nxt);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileIn cur = nxt;
+        if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);
+        const uint32_t row0 = tile * rows_per_cta + warp * 16;
+        if (row0 >= M) continue;
+        bool any = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) any |= (cur.gs[h] != 0.f) | (cur.gc[h][0] != 0.f) | (cur.gc[h][1] != 0.f);
+        if (!__any_sync(NSIG_FULL_MASK, any)) continue;
+        // ---- output-activation gradients, normalised per row by a power of two ----
+        float d_rgb[2][2], d_logit[2], inv_scale[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float s0 = cur.act[h][0], s1 = cur.act[h][1];                // sigmoid'(z) = s (1 - s)
+            d_rgb[h][0] = (tig < 2) ? cur.gc[h][0] * s0 * (1.0f - s0) : 0.f;
+            d_rgb[h][1] = (tig == 0) ? cur.gc[h][1] * s1 * (1.0f - s1) : 0.f;
+            // trunc_exp backward: g * exp(clamp(x, -15, 15)) (activation.py:14-16), with exp(x) = sigma / density_scale
+            const float e = fminf(fmaxf(s0 * inv_ds, 3.0590232050182579e-7f), 3269017.3724721107f);
+            d_logit[h] = (tig == 3) ? cur.gs[h] * p.density_scale * e : 0.f;
+            float vmax = fmaxf(fmaxf(fabsf(d_rgb[h][0]), fabsf(d_rgb[h][1])), fabsf(d_logit[h]));
+            vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 1));
+            vmax = fmaxf(vmax, __shfl_xor_sync(NSIG_FULL_MASK, vmax, 2));
+            const float sc = pow2_scale(vmax);
+            inv_scale[h] = 1.0f / sc;
+            d_rgb[h][0] *= sc; d_rgb[h][1] *= sc; d_logit[h] *= sc;
+        }
+        uint32_t m1s[MT][2], m1c[MT][2], m2c[MT][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { m1s[0][h] = cur.mk[h].x & 0xffffu; m1c[0][h] = cur.mk[h].x >> 16; m2c[0][h] = cur.mk[h].y; }
+        // ---- colour net dgrad ----
+        uint32_t da[MT][1][4];
+        da[0][0][0] = pack_h2(d_rgb[0][0], d_rgb[0][1]);
+        da[0][0][1] = pack_h2(d_rgb[1][0], d_rgb[1][1]);
+        da[0][0][2] = 0u; da[0][0][3] = 0u;
+        uint32_t dh[MT][4][4];
+        float dgeo[MT][2][4];
+        {
+            float c[MT][8][4];
+            layer<MT, 1, 8>(c, da, sm + oWc2T, kS16, g, tig);        // d h2 = d out x W2
+            grad_to_a_bits<MT, 8>(dh, c, m2c);
+            layer<MT, 4, 8>(c, dh, sm + oWc1T, kS64, g, tig);        // d h1 = d h2 x W1
+            grad_to_a_bits<MT, 8>(dh, c, m1c);
+            layer<MT, 4, 2>(dgeo, dh, sm + oWc0T, kS64, g, tig);     // d geo = (d h1 x W0)[:, 16:32]
+        }
+        // ---- sigma net dgrad: d out' = [d geo0..14, d logit] ----
+        da[0][0][0] = pack_h2(dgeo[0][0][0], dgeo[0][0][1]);
+        da[0][0][1] = pack_h2(dgeo[0][0][2], dgeo[0][0][3]);
+        da[0][0][2] = pack_h2(dgeo[0][1][0], (tig == 3) ? d_logit[0] : dgeo[0][1][1]);
+        da[0][0][3] = pack_h2(dgeo[0][1][2], (tig == 3) ? d_logit[1] : dgeo[0][1][3]);
+        float gmsg[2][2];  // d feature 30,31 (valid on tig == 3)
+        {
+            float c[MT][8][4];
+            layer<MT, 1, 8>(c, da, sm + oWs1T, kS16, g, tig);        // d h1s = d out' x W1'
+            grad_to_a_bits<MT, 8>(dh, c, m1s);
+            float c2[MT][1][4];
+            layer<MT, 4, 1, 3>(c2, dh, sm + oWs0T, kS64, g, tig);    // d feat, channels 24..31 only
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                gmsg[h][0] = c2[0][0][2 * h] * inv_scale[h];
+                gmsg[h][1] = c2[0][0][2 * h + 1] * inv_scale[h];
+            }
+        }
+        // ---- scatter into G: quad threads 0 and 1 take rows g and g + 8 ----
+        float gx = 0.f, gy = 0.f;
+        uint32_t myrow = 0xffffffffu;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float vx = __shfl_sync(NSIG_FULL_MASK, gmsg[h][0], (g << 2) | 3);
+            const float vy = __shfl_sync(NSIG_FULL_MASK, gmsg[h][1], (g << 2) | 3);
+            if (tig == h) { gx = vx; gy = vy; myrow = row0 + h * 8 + g; }
+        }
+        if (myrow < M && (gx != 0.f || gy != 0.f)) {
+            float xn[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) xn[a] = __fmul_rn(__fadd_rn(cur.sx[a], p.bound_add), p.bound_mul);
+            const Voxel v = locate(xn[0], xn[1], xn[2], p.msg_grid_size);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                red_add_v2(p.G + (size_t)corner_slot(v, k, p.mask) * 2, corner_grad(v, k, gx), corner_grad(v, k, gy));
+        }
+    }
+}
+
 }  // namespace nsig
 
 using namespace nsig;
@@ -833,7 +998,7 @@ extern "C" {
 int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float bound, const float* const* tables,
                        const float* resolutions, uint32_t log2_T, const float* S, float msg_resolution,
                        const void* sigma_w, const void* color_w, float density_scale, const int32_t* M_dev,
-                       float* sigmas, float* rgbs, void* feat_out, const void* const* tables_h2,
+                       float* sigmas, float* rgbs, void* feat_out, void* masks_out, const void* const* tables_h2,
                        const float* h2_inv_scale, nsig_stream_t stream) {
     if (M == 0) return 0;
     if (!dirs || !color_w || !sigmas || !rgbs) return NSIG_EINVAL;
@@ -844,12 +1009,14 @@ int nsig_field_forward(const float* xyzs, const float* dirs, uint32_t M, float b
     const size_t smem = kFieldFwdSmem;
     cudaStream_t st = (cudaStream_t)stream;
     __half* feat = reinterpret_cast<__half*>(feat_out);
+    uint2* masks = reinterpret_cast<uint2*>(masks_out);
+    if (((uintptr_t)masks_out) & 7) return NSIG_EINVAL;
     if (tables_h2)
         k_field_fwd<true, true><<<field_grid(k_field_fwd<true, true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
-            p, sigmas, rgbs, feat, nullptr);
+            p, sigmas, rgbs, feat, nullptr, masks);
     else
         k_field_fwd<true, false><<<field_grid(k_field_fwd<true, false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
-            p, sigmas, rgbs, feat, nullptr);
+            p, sigmas, rgbs, feat, nullptr, masks);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -869,10 +1036,10 @@ int nsig_field_density(const float* xyzs, uint32_t M, float bound, const float* 
     __half* geo = reinterpret_cast<__half*>(geo_feat);
     if (tables_h2)
         k_field_fwd<false, true><<<field_grid(k_field_fwd<false, true>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
-            p, sigmas, nullptr, nullptr, geo);
+            p, sigmas, nullptr, nullptr, geo, nullptr);
     else
         k_field_fwd<false, false><<<field_grid(k_field_fwd<false, false>, smem, M, kFieldWarps * 32), kFieldThreads, smem, st>>>(
-            p, sigmas, nullptr, nullptr, geo);
+            p, sigmas, nullptr, nullptr, geo, nullptr);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -963,6 +1130,35 @@ int nsig_field_backward(const float* xyzs, const float* dirs, uint32_t M, float 
     } else {
         k_field_bwd<false, false><<<field_grid(k_field_bwd<false, false>, smem, M, kFieldWarps * 16), kFieldThreads, smem, st>>>(p);
     }
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+int nsig_field_backward_masks(const float* xyzs, uint32_t M, float bound, const void* masks, const float* sigmas,
+                              const float* rgbs, const float* grad_sigmas, const float* grad_rgbs, const void* sigma_w,
+                              const void* color_w, float density_scale, const int32_t* M_dev, float msg_resolution,
+                              uint32_t log2_T, float* G, nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyzs || !masks || !sigmas || !rgbs || !grad_sigmas || !grad_rgbs || !sigma_w || !color_w || !G) return NSIG_EINVAL;
+    if ((((uintptr_t)sigma_w) | ((uintptr_t)color_w)) & 15) return NSIG_EINVAL;   // 16-byte weight staging
+    if (((uintptr_t)masks) & 7) return NSIG_EINVAL;
+    if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f) || !(msg_resolution > 0.0f) || !(density_scale > 0.0f)) return NSIG_EINVAL;
+    FieldBwdMaskParams p;
+    p.xyzs = xyzs; p.M = M; p.bound_add = bound; p.bound_mul = 1.0f / (2.0f * bound);
+    p.masks = reinterpret_cast<const uint2*>(masks);
+    p.sigmas = sigmas; p.rgbs = rgbs; p.grad_sigmas = grad_sigmas; p.grad_rgbs = grad_rgbs;
+    p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
+    p.color_w = reinterpret_cast<const __half*>(color_w);
+    p.msg_grid_size = 1.0f / msg_resolution;
+    p.mask = (1u << log2_T) - 1u;
+    p.G = G; p.M_dev = M_dev; p.density_scale = density_scale;
+    const size_t smem = kBwdHalfsPad * sizeof(__half);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_field_bwd_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_field_bwd_masks<<<field_grid(k_field_bwd_masks, smem, M, kFieldWarps * 16), kFieldThreads, smem, (cudaStream_t)stream>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -99,6 +99,42 @@ __device__ __forceinline__ void relu_to_a(uint32_t (&a)[MT][NT / 2][4], const fl
         }
 }
 
+// Sign mask of a 16 x 64 layer output, for the backward pass: bit 2*nt + e of bits[mt][h] is set when the fp16-rounded ReLU
+// activation of row (h ? g + 8 : g), column nt*8 + 2*tig + e is positive.  fp16 round-to-nearest-even maps everything up to
+// and including 2^-25 to zero, so `c > 2^-25` on the fp32 accumulator is exactly `fp16(max(c, 0)) > 0`.
+template <int MT>
+__device__ __forceinline__ void relu_mask_bits(uint32_t (&bits)[MT][2], const float (&c)[MT][8][4]) {
+    constexpr float kHalfFlush = 2.98023223876953125e-8f;   // 2^-25
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t b = 0u;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                b |= (c[mt][nt][2 * h] > kHalfFlush ? 1u : 0u) << (2 * nt);
+                b |= (c[mt][nt][2 * h + 1] > kHalfFlush ? 1u : 0u) << (2 * nt + 1);
+            }
+            bits[mt][h] = b;
+        }
+}
+
+// gradient accumulators -> A fragments, masked by the sign bits the forward kernel saved (relu_mask_bits)
+template <int MT, int NT>
+__device__ __forceinline__ void grad_to_a_bits(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4],
+                                               const uint32_t (&bits)[MT][2]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {   // fragment register r: row half h = r & 1, n-tile 2*ks + (r >> 1)
+                const int h = r & 1, nt = 2 * ks + (r >> 1);
+                const uint32_t b = bits[mt][h] >> (2 * nt);
+                a[mt][ks][r] = pack_h2((b & 1u) ? c[mt][nt][2 * h] : 0.f, (b & 2u) ? c[mt][nt][2 * h + 1] : 0.f);
+            }
+}
+
 // gradient accumulators -> A fragments, masked by the forward activation (ReLU'(h) = h > 0)
 __device__ __forceinline__ uint32_t pack_masked(float a, float b, uint32_t act) {
     const __half2 h = *reinterpret_cast<const __half2*>(&act);

@@ -13,8 +13,11 @@ from .. import _lib
 
 _P = _lib.ptr
 
-# A/B switch (tools, tests): NSIG_BWD_TC=0 keeps the mma.sync backward (csrc/field.cu) for the watermark-mode case too
-USE_TCGEN05_BACKWARD = os.environ.get("NSIG_BWD_TC", "0") != "0"   # TODO(round 2): flip to "1" once validated on the B200
+# Watermark-mode backward (only dL/dS is needed), three interchangeable kernels (A/B switch NSIG_BWD for tools and tests):
+#   "masks" (default): the forward saves the ReLU sign masks (32 B/sample) and the backward runs the five dgrad GEMMs only;
+#   "recompute":       the forward saves the fp16 encoder output (64 B/sample), the backward recomputes the MLPs (mma.sync);
+#   "tc":              same data flow as "recompute" on tcgen05.mma + TMEM (csrc/field_tc.cu; validated, slower: DESIGN.md 4)
+BACKWARD_MODE = os.environ.get("NSIG_BWD", "tc" if os.environ.get("NSIG_BWD_TC", "0") == "1" else "masks")
 
 
 class FusedMLP(nn.Module):
@@ -130,14 +133,20 @@ class _field_forward(Function):
         need_w = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
         need_tab = any(ctx.needs_input_grad[_field_forward.N_FIXED:])
         save = need_S or need_tab or need_w
-        feat = torch.empty(M, 32, dtype=torch.float16, device=dev) if save else None
+        use_masks = need_S and not (need_w or need_tab) and BACKWARD_MODE == "masks"
+        feat = torch.empty(M, 32, dtype=torch.float16, device=dev) if (save and not use_masks) else None
+        masks = torch.empty(M, 4, 2, dtype=torch.int32, device=dev) if use_masks else None
         tabs = [t.contiguous() for t in tables]
         sw, cw = sigma_mlp.half_weights(), color_mlp.half_weights()
         Sc = S.contiguous() if S is not None else None
         _lib.call("nsig_field_forward", _P(xyzs), _P(dirs), M, cfg.bound, _lib.pointer_array(tabs),
                   _lib.float_array(cfg.resolutions), cfg.log2_T, _P(Sc), cfg.msg_resolution, _P(sw), _P(cw),
-                  cfg.density_scale, _P(count), _P(sigmas), _P(rgbs), _P(feat), *_shadow_args(cfg))
-        if save:
+                  cfg.density_scale, _P(count), _P(sigmas), _P(rgbs), _P(feat), _P(masks), *_shadow_args(cfg))
+        ctx.use_masks = use_masks
+        if use_masks:
+            ctx.save_for_backward(xyzs, masks, sigmas, rgbs, sw, cw)
+            ctx.cfg, ctx.count, ctx.S_shape = cfg, count, tuple(S.shape)
+        elif save:
             ctx.save_for_backward(xyzs, dirs, feat, sw, cw)
             ctx.cfg = cfg
             ctx.count = count
@@ -152,6 +161,15 @@ class _field_forward(Function):
         n_in = _field_forward.N_FIXED + ctx.n_tables
         if not ctx.has_graph:
             return (None,) * n_in
+        if ctx.use_masks:
+            xyzs, masks, sigmas, rgbs, sw, cw = ctx.saved_tensors
+            cfg = ctx.cfg
+            direct = cfg.S_sink is not None
+            G = cfg.S_sink if direct else torch.zeros(ctx.S_shape, dtype=torch.float32, device=xyzs.device)
+            _lib.call("nsig_field_backward_masks", _P(xyzs), xyzs.shape[0], cfg.bound, _P(masks), _P(sigmas), _P(rgbs),
+                      _P(grad_sigmas.contiguous().float()), _P(grad_rgbs.contiguous().float()), _P(sw), _P(cw),
+                      cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G))
+            return (None, None, None if direct else G) + (None,) * (n_in - 3)
         xyzs, dirs, feat, sw, cw = ctx.saved_tensors
         cfg = ctx.cfg
         M = xyzs.shape[0]
@@ -168,7 +186,7 @@ class _field_forward(Function):
         grad_feat = alloc(M, 32, dtype=torch.float32, device=dev) if any(need_tab) else None
         gsw = torch.zeros(sw.numel(), dtype=torch.float32, device=dev) if need_w else None
         gcw = torch.zeros(cw.numel(), dtype=torch.float32, device=dev) if need_w else None
-        if G is not None and grad_feat is None and gsw is None and USE_TCGEN05_BACKWARD:
+        if G is not None and grad_feat is None and gsw is None and BACKWARD_MODE == "tc":
             # watermark training (the hot path): dL/dS only - tcgen05/TMEM kernel (csrc/field_tc.cu)
             _lib.call("nsig_field_backward_tc", _P(xyzs), _P(dirs), M, cfg.bound, _P(feat), _P(grad_sigmas), _P(grad_rgbs),
                       _P(sw), _P(cw), cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G))

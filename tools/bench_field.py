@@ -82,7 +82,8 @@ def main():
     fwd()
     sig, rgb = holder["o"]
     gs, gc = torch.randn_like(sig) * 1e-3, torch.randn_like(rgb) * 1e-3
-    bwd_names = ["nsig_field_backward", "nsig_field_backward_tc"]   # mma.sync kernel / tcgen05 kernel (NSIG_BWD_TC=1)
+    # NSIG_BWD = masks (default) | recompute | tc selects the kernel
+    bwd_names = ["nsig_field_backward", "nsig_field_backward_tc", "nsig_field_backward_masks"]
     _lib.timing_enable(bwd_names)
 
     def bwd():
