@@ -167,8 +167,12 @@ int nsig_hash_encode_backward(const float* x, const float* grad_out, uint32_t B,
  *   out = trilerp(S)[x],  S = sum_i embeddings[2*i + bit_i].weight.
  * nsig_msg_table_sum builds S ([2^log2_T,2] fp32) from the DEVICE message vector
  * (float 0/1, read on device: no .item() sync, cf. hash_encoding_wtmk_bit.py:110). */
+/* elem_begin / elem_count (floats, multiples of 8; count 0 = the whole table): the slice of S to build - with the
+ * optimizer state sharded over the ranks of a data-parallel job every rank sums only the table slice it owns and the
+ * slices of S are all-gathered (parallel.py). */
 int nsig_msg_table_sum(const float* const* tables, uint32_t message_dim, const float* message,
-                       uint32_t log2_T, float* S, nsig_stream_t stream);
+                       uint32_t log2_T, float* S, uint32_t elem_begin, uint32_t elem_count,
+                       nsig_stream_t stream);
 
 /* The same encoder in the reference's literal per-bit form (message_dim gathers per
  * corner, summed in bit order) — kept for parity tests against the pre-summed form. */
@@ -220,8 +224,9 @@ int nsig_tables_to_half2(const float* const* tables, uint32_t n_levels, uint32_t
  *          feat_out (optional) [M,32] fp16: encoder output incl. message feature, saved for
  *          nsig_field_backward / nsig_field_backward_tc (which recompute the MLPs from it).
  *          masks_out (optional) [M,4] x 8 bytes: the ReLU sign masks of the three hidden layers in the
- *          fragment order of the kernels (entry (row, q) = {m1s | m1c << 16, m2c} of quad thread q;
- *          bit 2*nt + e <-> hidden unit nt*8 + 2*q + e), saved for nsig_field_backward_masks.
+ *          fragment order of the kernels (entry (row, q) = {m1s | m1c << 8, m2c} of quad thread q; within a
+ *          layer's 16 bits, bit nt <-> hidden unit nt*8 + 2*q, bit 16 + nt <-> unit nt*8 + 2*q + 1), saved for
+ *          nsig_field_backward_masks.
  *   tables_h2 / h2_inv_scale (optional, both or neither): half2 shadow copies of the 16 base tables and their
  *          device float[16] de-scaling factors, as nsig_tables_to_half2 writes them.  When given, the kernel
  *          gathers those (one 32-bit load per corner) instead of the fp32 tables; hash slots are unchanged, the
@@ -434,12 +439,14 @@ int nsig_field_backward_tc(const float* xyzs, const float* dirs, uint32_t M, flo
  *   by *grad_scale; the whole step is skipped when *found_inf != 0).
  *   lr_dev   : optional device float; when non-NULL the learning rate is read from it at execution
  *   time instead of `lr`, so a per-step scheduler (the reference's LambdaLR, scheduler_update_every_step)
- *   keeps acting on a step that is replayed from a CUDA graph. */
+ *   keeps acting on a step that is replayed from a CUDA graph.
+ *   elem_begin / elem_count (floats, multiples of 4; count 0 = everything): the slice of every selected table (and of
+ *   its moments) to update - ZeRO-style sharding of the optimizer over the ranks of a data-parallel job. */
 int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
                        const float* message, const float* G, float* steps, float* coef,
                        const float* grad_scale, const float* found_inf, float lr, float beta1,
                        float beta2, float eps, uint32_t log2_T, const float* lr_dev,
-                       nsig_stream_t stream);
+                       uint32_t elem_begin, uint32_t elem_count, nsig_stream_t stream);
 
 /* torch.amp.GradScaler's per-step work (utils_wtmk_disen.py:1175-1181) over the flat gradient bucket in one launch:
  * non-finite check of flat[0..n) -> *found_inf (0/1); *step_scale = the scale this step's gradients carry (what the

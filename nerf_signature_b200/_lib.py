@@ -43,7 +43,7 @@ _SIGNATURES = {
     "nsig_composite_rays": ([_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_hash_encode_forward": ([_vp, _u32, _vp, _vp, _u32, _u32, _vp, _vp, _vp], 1),
     "nsig_hash_encode_backward": ([_vp, _vp, _u32, _vp, _vp, _u32, _u32, _vp], 1),
-    "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _vp], 1),
+    "nsig_msg_table_sum": ([_vp, _u32, _vp, _u32, _vp, _u32, _u32, _vp], 1),
     "nsig_msg_encode_forward_perbit": ([_vp, _u32, _vp, _u32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_fused_hash_slots": ([_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp], 1),
     "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
@@ -68,7 +68,7 @@ _SIGNATURES = {
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
-    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp, _vp], 2),
+    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp, _u32, _u32, _vp], 2),
     "nsig_grad_check_update_scale": ([_vp, _u32, _vp, _vp, _f32, _f32, _c.c_int32, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_flat_adam_step": ([_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _f32, _vp, _f32, _f32, _f32, _vp], 1),
     "nsig_field_backward_tc": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),

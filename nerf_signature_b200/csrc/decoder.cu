@@ -661,7 +661,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
         unsigned int seen = 0, spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-            if (seen < target && ++spins > (1u << 27)) __trap();   // a CTA that never arrives must not hang the GPU
+            if (seen < target && ++spins > (1u << 23)) __trap();   // a CTA that never arrives must not hang the GPU
         } while (seen < target);
     }
     __syncthreads();
@@ -931,8 +931,11 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
     h.logits = logits; h.pooled = H16(d.off_pooled);
 
     // ---- persistent path: one kernel, grid barriers between the layers ----
-    static const bool no_persist = [] { const char* e = getenv("NSIG_DEC_NO_PERSIST"); return e && e[0] == '1'; }();
-    if (!no_persist && L + 1 <= kPersistMaxLayers) {
+    // Measured (round 2, B=32 blocks of 12x12, graph replay): persistent 118.8 us vs per-layer kernels 110.8 us - ten grid
+    // barriers (an L2 atomic + acquire spin each) cost more than ten kernel boundaries inside a CUDA graph, so the
+    // per-layer chain stays the default; NSIG_DEC_PERSIST=1 selects the persistent kernel (tools/bench_decoder.py).
+    static const bool persist = [] { const char* e = getenv("NSIG_DEC_PERSIST"); return e && e[0] == '1'; }();
+    if (persist && L + 1 <= kPersistMaxLayers) {
         const int R = conv_rows((int)B, (int)H, (int)W);
         const int strips = ((int)H + R - 1) / R;
         const size_t smem = (size_t)(R + 2) * (W + 2) * (64 + 8) * 2 + (size_t)(64 + 64) * sizeof(BnCoef) + (size_t)64 * (9 * 64 + 8) * 2;

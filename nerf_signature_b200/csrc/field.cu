@@ -80,12 +80,12 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
 #endif
         // sigma net: 32 -> 64 (ReLU) -> 16
         uint32_t h1[MT][4][4];
-        [[maybe_unused]] uint32_t mk[3][MT][2];   // ReLU sign masks of the three hidden layers (COLOR && mask_out)
+        [[maybe_unused]] uint32_t mk[2][MT][2] = {};   // ReLU sign masks: [0] = m1s | m1c << 8, [1] = m2c (COLOR && mask_out)
         {
             float c[MT][8][4];
             layer<MT, 2, 8>(c, fa, sm + oWs0, kS32, g, tig);
-            if (COLOR && mask_out) relu_mask_bits<MT>(mk[0], c);
             relu_to_a<MT, 8>(h1, c);
+            if (COLOR && mask_out) act_mask_bits<MT>(mk[0], h1, 0);
         }
         float so[MT][2][4];
         layer<MT, 4, 2>(so, h1, sm + oWs1, kS64, g, tig);
@@ -124,19 +124,19 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
             {
                 float c[MT][8][4];
                 layer<MT, 2, 8>(c, ca, sm + oWc0, kS32, g, tig);
-                if (mask_out) relu_mask_bits<MT>(mk[1], c);
                 relu_to_a<MT, 8>(h1, c);
+                if (mask_out) act_mask_bits<MT>(mk[0], h1, 8);
                 layer<MT, 4, 8>(c, h1, sm + oWc1, kS64, g, tig);
-                if (mask_out) relu_mask_bits<MT>(mk[2], c);
                 relu_to_a<MT, 8>(h2, c);
+                if (mask_out) act_mask_bits<MT>(mk[1], h2, 0);
             }
-            if (mask_out) {   // 8 bytes per (row, quad thread): [m1s | m1c << 16, m2c]; a quad writes 32 contiguous bytes per row
+            if (mask_out) {   // 8 bytes per (row, quad thread): {m1s | m1c << 8, m2c}; a quad writes 32 contiguous bytes per row
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t r = frag_row<MT>(row0, mt, h, g);
-                        if (r < M) mask_out[(size_t)r * 4 + tig] = make_uint2(mk[0][mt][h] | (mk[1][mt][h] << 16), mk[2][mt][h]);
+                        if (r < M) mask_out[(size_t)r * 4 + tig] = make_uint2(mk[0][mt][h], mk[1][mt][h]);
                     }
             }
             float co[MT][1][4];
@@ -851,7 +851,7 @@ struct FieldBwdMaskParams {
     const float* xyzs;
     uint32_t M;
     float bound_add, bound_mul;
-    const uint2* masks;        // [M][4] (row, quad thread): x = m1s | m1c << 16, y = m2c
+    const uint2* masks;        // [M][4] (row, quad thread): x = m1s | m1c << 8, y = m2c (bit layout: act_mask_bits)
     const float* sigmas;       // [M]   forward outputs
     const float* rgbs;         // [M,3]
     const float* grad_sigmas;  // [M]
@@ -932,9 +932,9 @@ k_field_bwd_masks(const FieldBwdMaskParams p) {
             inv_scale[h] = 1.0f / sc;
             d_rgb[h][0] *= sc; d_rgb[h][1] *= sc; d_logit[h] *= sc;
         }
-        uint32_t m1s[MT][2], m1c[MT][2], m2c[MT][2];
+        uint32_t m1[MT][2], m2[MT][2];   // m1 = m1s | m1c << 8, m2 = m2c (bit layout: act_mask_bits)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { m1s[0][h] = cur.mk[h].x & 0xffffu; m1c[0][h] = cur.mk[h].x >> 16; m2c[0][h] = cur.mk[h].y; }
+        for (int h = 0; h < 2; ++h) { m1[0][h] = cur.mk[h].x; m2[0][h] = cur.mk[h].y; }
         // ---- colour net dgrad ----
         uint32_t da[MT][1][4];
         da[0][0][0] = pack_h2(d_rgb[0][0], d_rgb[0][1]);
@@ -945,9 +945,9 @@ k_field_bwd_masks(const FieldBwdMaskParams p) {
         {
             float c[MT][8][4];
             layer<MT, 1, 8>(c, da, sm + oWc2T, kS16, g, tig);        // d h2 = d out x W2
-            grad_to_a_bits<MT, 8>(dh, c, m2c);
+            grad_to_a_bits<MT, 8>(dh, c, m2, 0);
             layer<MT, 4, 8>(c, dh, sm + oWc1T, kS64, g, tig);        // d h1 = d h2 x W1
-            grad_to_a_bits<MT, 8>(dh, c, m1c);
+            grad_to_a_bits<MT, 8>(dh, c, m1, 8);
             layer<MT, 4, 2>(dgeo, dh, sm + oWc0T, kS64, g, tig);     // d geo = (d h1 x W0)[:, 16:32]
         }
         // ---- sigma net dgrad: d out' = [d geo0..14, d logit] ----
@@ -959,7 +959,7 @@ k_field_bwd_masks(const FieldBwdMaskParams p) {
         {
             float c[MT][8][4];
             layer<MT, 1, 8>(c, da, sm + oWs1T, kS16, g, tig);        // d h1s = d out' x W1'
-            grad_to_a_bits<MT, 8>(dh, c, m1s);
+            grad_to_a_bits<MT, 8>(dh, c, m1, 0);
             float c2[MT][1][4];
             layer<MT, 4, 1, 3>(c2, dh, sm + oWs0T, kS64, g, tig);    // d feat, channels 24..31 only
 #pragma unroll

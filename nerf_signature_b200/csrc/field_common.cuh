@@ -99,30 +99,35 @@ __device__ __forceinline__ void relu_to_a(uint32_t (&a)[MT][NT / 2][4], const fl
         }
 }
 
-// Sign mask of a 16 x 64 layer output, for the backward pass: bit 2*nt + e of bits[mt][h] is set when the fp16-rounded ReLU
-// activation of row (h ? g + 8 : g), column nt*8 + 2*tig + e is positive.  fp16 round-to-nearest-even maps everything up to
-// and including 2^-25 to zero, so `c > 2^-25` on the fp32 accumulator is exactly `fp16(max(c, 0)) > 0`.
+// Sign masks of a 16 x 64 hidden layer, for the backward pass (k_field_bwd_masks).  Taken from the layer's A fragments
+// (post-ReLU, fp16-rounded - exactly the values whose sign k_field_bwd re-derives): one HSET2 + one LOP3 per fragment
+// register.  Bit layout of a row's 32-bit word: fragment register (ks, q) = n-tile nt = 2*ks + q holds hidden units
+// nt*8 + 2*tig (low half) and nt*8 + 2*tig + 1 (high half); the low half's sign goes to bit nt + shift, the high half's to
+// bit 16 + nt + shift.  shift = 0 / 8 lets two layers share one word.
 template <int MT>
-__device__ __forceinline__ void relu_mask_bits(uint32_t (&bits)[MT][2], const float (&c)[MT][8][4]) {
-    constexpr float kHalfFlush = 2.98023223876953125e-8f;   // 2^-25
+__device__ __forceinline__ void act_mask_bits(uint32_t (&bits)[MT][2], const uint32_t (&a)[MT][4][4], int shift) {
+    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            uint32_t b = 0u;
+            uint32_t b = bits[mt][h];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                b |= (c[mt][nt][2 * h] > kHalfFlush ? 1u : 0u) << (2 * nt);
-                b |= (c[mt][nt][2 * h + 1] > kHalfFlush ? 1u : 0u) << (2 * nt + 1);
-            }
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t m = __hgt2_mask(*reinterpret_cast<const __half2*>(&a[mt][ks][h + 2 * q]), zero);  // 0xffff per positive half
+                    b |= m & (0x00010001u << (2 * ks + q + shift));
+                }
             bits[mt][h] = b;
         }
 }
 
-// gradient accumulators -> A fragments, masked by the sign bits the forward kernel saved (relu_mask_bits)
+// gradient accumulators -> A fragments, masked by the sign bits the forward kernel saved (act_mask_bits): the selected
+// halves are kept, the others become +0 (a bitwise AND: inf/NaN in a masked-out unit cannot leak, exactly like a select)
 template <int MT, int NT>
 __device__ __forceinline__ void grad_to_a_bits(uint32_t (&a)[MT][NT / 2][4], const float (&c)[MT][NT][4],
-                                               const uint32_t (&bits)[MT][2]) {
+                                               const uint32_t (&bits)[MT][2], int shift) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -130,8 +135,8 @@ __device__ __forceinline__ void grad_to_a_bits(uint32_t (&a)[MT][NT / 2][4], con
 #pragma unroll
             for (int r = 0; r < 4; ++r) {   // fragment register r: row half h = r & 1, n-tile 2*ks + (r >> 1)
                 const int h = r & 1, nt = 2 * ks + (r >> 1);
-                const uint32_t b = bits[mt][h] >> (2 * nt);
-                a[mt][ks][r] = pack_h2((b & 1u) ? c[mt][nt][2 * h] : 0.f, (b & 2u) ? c[mt][nt][2 * h + 1] : 0.f);
+                const uint32_t sel = (bits[mt][h] >> (nt + shift)) & 0x00010001u;
+                a[mt][ks][r] = pack_h2(c[mt][nt][2 * h], c[mt][nt][2 * h + 1]) & (sel * 0xffffu);
             }
 }
 

@@ -79,10 +79,10 @@ __device__ __forceinline__ f8 ld_evict_first8(const float* p) {
 
 __global__ void __launch_bounds__(256)
 k_msg_table_sum(MsgTablePtrs tp, uint32_t message_dim, const float* __restrict__ message, uint32_t n_vec8,
-                float* __restrict__ S) {
+                float* __restrict__ S, uint32_t vec8_begin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vec8) return;
-    const size_t off = (size_t)i * 8;
+    const size_t off = (size_t)(vec8_begin + i) * 8;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -240,7 +240,7 @@ int nsig_hash_encode_backward(const float* x, const float* grad_out, uint32_t B,
 }
 
 int nsig_msg_table_sum(const float* const* tables, uint32_t message_dim, const float* message, uint32_t log2_T,
-                       float* S, nsig_stream_t stream) {
+                       float* S, uint32_t elem_begin, uint32_t elem_count, nsig_stream_t stream) {
     if (!tables || !message || !S) return NSIG_EINVAL;
     if (message_dim == 0 || 2 * message_dim > NSIG_MAX_MSG_TABLES || log2_T < 1 || log2_T > 30) return NSIG_EINVAL;
     MsgTablePtrs tp;
@@ -249,8 +249,11 @@ int nsig_msg_table_sum(const float* const* tables, uint32_t message_dim, const f
         tp.t[i] = tables[i];
     }
     if (log2_T < 2 || (((uintptr_t)S) & 31)) return NSIG_EINVAL;
-    const uint32_t n_vec8 = (1u << log2_T) / 4;  // T entries x 2 floats / 8
-    k_msg_table_sum<<<div_up(n_vec8, 256), 256, 0, (cudaStream_t)stream>>>(tp, message_dim, message, n_vec8, S);
+    const uint32_t total = 2u << log2_T;         // T entries x 2 floats
+    if (elem_count == 0) { elem_begin = 0; elem_count = total; }
+    if ((elem_begin | elem_count) & 7u || elem_begin > total || elem_count > total - elem_begin) return NSIG_EINVAL;
+    const uint32_t n_vec8 = elem_count / 8;
+    k_msg_table_sum<<<div_up(n_vec8, 256), 256, 0, (cudaStream_t)stream>>>(tp, message_dim, message, n_vec8, S, elem_begin / 8);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

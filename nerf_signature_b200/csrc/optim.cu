@@ -50,11 +50,12 @@ constexpr int kAdamUnroll = 4;
 __global__ void __launch_bounds__(256)
 k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const float* __restrict__ G,
            const float* __restrict__ coef, const float* __restrict__ grad_scale,
-           const float* __restrict__ found_inf, float beta1, float beta2, float eps, uint32_t n_vec4) {
+           const float* __restrict__ found_inf, float beta1, float beta2, float eps, uint32_t n_vec4,
+           uint32_t vec4_begin) {
     if (found_inf && *found_inf != 0.0f) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vec4) return;
-    const size_t off = (size_t)i * 4;
+    const size_t off = (size_t)(vec4_begin + i) * 4;   // this rank's slice of every table (sharded optimizer) or 0
     float4 g = ld4_stream(G + off);
     if (grad_scale) {
         const float inv = 1.0f / *grad_scale;  // GradScaler.unscale_: grad * (1/scale)
@@ -184,7 +185,7 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
                                   const float* message, const float* G, float* steps, float* coef,
                                   const float* grad_scale, const float* found_inf, float lr, float beta1,
                                   float beta2, float eps, uint32_t log2_T, const float* lr_dev,
-                                  nsig_stream_t stream) {
+                                  uint32_t elem_begin, uint32_t elem_count, nsig_stream_t stream) {
     if (!ptr_table || !message || !G || !steps || !coef) return NSIG_EINVAL;
     if (message_dim == 0 || 2 * message_dim > n_tables || n_tables > NSIG_MAX_MSG_TABLES) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || (((uintptr_t)G) & 15)) return NSIG_EINVAL;
@@ -192,10 +193,13 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
     k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message, steps, coef, found_inf,
                                                                  (double)lr, lr_dev, (double)beta1, (double)beta2);
     NSIG_LAUNCH_CHECK();
-    const uint32_t n_vec4 = (1u << log2_T) / 2;  // T entries x 2 floats / 4
+    const uint32_t total = 2u << log2_T;         // T entries x 2 floats
+    if (elem_count == 0) { elem_begin = 0; elem_count = total; }
+    if ((elem_begin | elem_count) & 3u || elem_begin > total || elem_count > total - elem_begin) return NSIG_EINVAL;
+    const uint32_t n_vec4 = elem_count / 4;
     AdamPtrs ptrs{ptr_table, n_tables};
     k_msg_adam<<<div_up(n_vec4, 256), 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
-                                                    beta1, beta2, eps, n_vec4);
+                                                    beta1, beta2, eps, n_vec4, elem_begin / 4);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -103,7 +103,7 @@ class Scene:
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
                  merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
-                 shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False):
+                 shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False, shard_optimizer=None):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -159,8 +159,12 @@ class Scene:
             gbuf = None
             if self.flat_sync:  # one flat bucket [dL/dS | decoder grads] -> one all-reduce per step
                 gbuf = self.sync.make_flat_buffer(self.model.msg_encoder.tables()[0].numel(), self._decoder_params, device)
+            # multi-GPU: the message tables' optimizer is sharded over the ranks (every rank sees the same exchanged G)
+            do_shard = (self.sync.enabled and os.environ.get("NSIG_NO_SHARD_OPT") != "1") if shard_optimizer is None \
+                else (shard_optimizer and self.sync.enabled)
             self.optimizer = WatermarkAdam(self.model, lr=lr, betas=(0.9, 0.99), eps=1e-15, capturable=graph,
-                                           grad_buffer=gbuf, flat_bucket=self.sync.flat if self.flat_sync else None)
+                                           grad_buffer=gbuf, flat_bucket=self.sync.flat if self.flat_sync else None,
+                                           shard=parallel.world() if do_shard else None)
         else:
             self.optimizer = torch.optim.Adam(self.model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
         self.fp16 = fp16

@@ -41,7 +41,7 @@ class _msg_table_sum(Function):
         msg = message.to(device=dev, dtype=torch.float32).contiguous()
         S = torch.empty_like(tables[0])
         tabs = [t.contiguous() for t in tables]
-        _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S))
+        _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), 0, 0)
         ctx.bits = bits
         ctx.n = len(tables)
         return S
@@ -64,12 +64,21 @@ class _msg_table_sum_sink(Function):
     the message — the whole training step can be captured in a CUDA graph."""
 
     @staticmethod
-    def forward(ctx, message, log2_T, sink, *tables):
+    def forward(ctx, message, log2_T, sink, shard, *tables):
         md = len(tables) // 2
         msg = message.to(device=tables[0].device, dtype=torch.float32).contiguous()
         S = torch.empty_like(tables[0])
         tabs = [t.contiguous() for t in tables]
-        _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S))
+        if shard is None:
+            _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), 0, 0)
+        else:
+            # sharded optimizer state (optim.WatermarkAdam(shard=...)): this rank holds the up-to-date values of its own
+            # slice of every table only, so it sums that slice and the slices of S are all-gathered (4 MiB in total)
+            import torch.distributed as dist
+            lo, n, group = shard
+            _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), lo, n)
+            flat = S.view(-1)
+            dist.all_gather_into_tensor(flat, flat[lo:lo + n].clone(), group=group)
         ctx.sink = sink
         ctx.n = len(tables)
         # the fused field backward scatter-adds dL/dS straight into `sink` (FieldConfig.S_sink) and returns no gradient
@@ -83,7 +92,7 @@ class _msg_table_sum_sink(Function):
             if grad_reducer is not None:
                 grad_S = grad_reducer(grad_S)
             ctx.sink.add_(grad_S)
-        return (None, None, None) + (None,) * ctx.n
+        return (None, None, None, None) + (None,) * ctx.n
 
 
 class HashEmbedder(nn.Module):
@@ -116,16 +125,20 @@ class HashEmbedder(nn.Module):
         self.resolution = res[0]
         # set by optim.WatermarkAdam: persistent [T,2] buffer that receives dL/dS (see _msg_table_sum_sink)
         self.grad_sink = None
+        # set by optim.WatermarkAdam(shard=...): (first float, float count, process group) of the table slice this rank owns
+        self.shard = None
 
     def tables(self):
         return [e.weight for e in self.embeddings[:2 * self.message_dim]]
 
     def summed_table(self, message, bits=None):
         """S [T,2] (differentiable w.r.t. the selected tables)."""
-        if self.grad_sink is not None and torch.is_grad_enabled():
+        if self.shard is not None or (self.grad_sink is not None and torch.is_grad_enabled()):
+            # (sharded optimizer: only the owner's slice of a table is current, so S is ALWAYS built slice-wise + all-gather,
+            # also for evaluation and the occupancy update - a collective every rank must enter)
             if message.shape[0] != self.message_dim:
                 raise ValueError(f"message has {message.shape[0]} bits, encoder was built for {self.message_dim}")
-            return _msg_table_sum_sink.apply(message, self.log2_hashmap_size, self.grad_sink, *self.tables())
+            return _msg_table_sum_sink.apply(message, self.log2_hashmap_size, self.grad_sink, self.shard, *self.tables())
         if bits is None:
             bits = message_bits(message)
         if len(bits) != self.message_dim:

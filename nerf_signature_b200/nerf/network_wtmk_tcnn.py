@@ -93,7 +93,7 @@ class NeRFNetwork(NeRFRenderer):
                tuple(t._version for t in tabs), tabs[0].data_ptr())
         if self._S_cache is not None and self._S_cache[0] == key:
             return self._S_cache[1]
-        sink_mode = self.msg_encoder.grad_sink is not None and torch.is_grad_enabled()
+        sink_mode = self.msg_encoder.shard is not None or (self.msg_encoder.grad_sink is not None and torch.is_grad_enabled())
         S = self.msg_encoder.summed_table(message, None if sink_mode else message_bits(message))
         self._S_cache = (key, S, message)  # keep `message` alive so id() stays unique
         return S

@@ -22,13 +22,20 @@ _P = _lib.ptr
 class WatermarkAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
 
-    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False, grad_buffer=None, flat_bucket=None):
+    def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, capturable=False, grad_buffer=None, flat_bucket=None,
+                 shard=None):
         """grad_buffer: optional pre-allocated [T*2] fp32 storage for G (the data-parallel harness passes a slice
         of its flat all-reduce bucket).
         flat_bucket: the WHOLE flat gradient bucket [dL/dS | gradients of every other trainable parameter, in get_params
         order] (parallel.GradSync.make_flat_buffer).  When given, the other parameters (the HiDDeN decoder) are re-pointed
         at ONE flat parameter buffer and updated by one Adam kernel (nsig_flat_adam_step) instead of torch's multi-tensor
-        Adam, and FusedGradScaler can check the whole bucket for non-finite values in one pass."""
+        Adam, and FusedGradScaler can check the whole bucket for non-finite values in one pass.
+        shard: (rank, world_size[, group]) - ZeRO-style sharding of the message tables' optimizer over a data-parallel job.
+        The exchanged gradient G is identical on every rank, so rank r updates only the r-th contiguous slice of every
+        selected table (and keeps moments for that slice only): the HBM-bound Adam pass costs 1/world.  The forward needs
+        nothing but the summed table S, which each rank builds for its slice and all-gathers (4 MiB per step instead of
+        broadcasting 2*message_dim tables).  A rank's copy of the OTHER slices goes stale: call gather_tables() before
+        anything reads the tables themselves (checkpoints, single-rank evaluation)."""
         enc = model.msg_encoder
         tables = enc.tables()
         dev = tables[0].device
@@ -83,6 +90,14 @@ class WatermarkAdam(torch.optim.Optimizer):
         self.enc = enc
         self._model = model
         self.tables = tables
+        self.shard = None
+        if shard is not None and self._train_tables and int(shard[1]) > 1:
+            rank, world = int(shard[0]), int(shard[1])
+            total = tables[0].numel()
+            if total % (8 * world):
+                raise ValueError("table size must be a multiple of 8 * world_size to shard the optimizer")
+            self.shard = (rank * (total // world), total // world, shard[2] if len(shard) > 2 else None)
+            enc.shard = self.shard
         self.message = None  # device float [md]; set by the training step before backward
         if self._train_tables:
             enc.grad_sink = self.G
@@ -120,6 +135,21 @@ class WatermarkAdam(torch.optim.Optimizer):
             elif g.get("msg_tables") and self._lr_dev is not None and changed:
                 self._lr_dev.fill_(lr)
 
+    @torch.no_grad()
+    def gather_tables(self, moments=True):
+        """Sharded mode: make every rank's message tables (and Adam moments) complete again by all-gathering the slices
+        their owners updated.  Collective; 2*message_dim x 4 MiB (x3 with moments): for checkpoints and evaluation only."""
+        if self.shard is None:
+            return
+        import torch.distributed as dist
+        lo, n, group = self.shard
+        sets = [self.tables] + ([self.exp_avg, self.exp_avg_sq] if moments else [])
+        for tensors in sets:
+            for t in tensors:
+                flat = t.data.view(-1)
+                dist.all_gather_into_tensor(flat, flat[lo:lo + n].clone(), group=group)
+        self._model._S_cache = None
+
     # ---- checkpointing: the layout torch.optim.Adam(model.get_params(lr)).state_dict() has ---------------------------
     def state_dict(self):
         """Same structure as the reference's optimizer checkpoint (nerf/utils_wtmk_disen.py:1410, an Adam over
@@ -127,6 +157,7 @@ class WatermarkAdam(torch.optim.Optimizer):
         decoder - and state[i] = {step, exp_avg, exp_avg_sq} exists for every parameter that has been updated."""
         n_t = len(self.tables) if self._train_tables else 0
         groups, state = [], {}
+        self.gather_tables()   # sharded mode: collective - every rank must call state_dict()
         if self._train_tables:
             g = {k: v for k, v in self.param_groups[-1].items() if k not in ("params", "msg_tables")}
             groups.append({**g, "params": list(range(n_t))})
@@ -258,7 +289,8 @@ class WatermarkAdam(torch.optim.Optimizer):
             md = self.enc.message_dim
             _lib.call("nsig_msg_adam_step", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(self.G),
                       _P(self.steps), _P(self._coef), _P(grad_scale), _P(found_inf), float(group["lr"]), float(beta1),
-                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size, _P(self._lr_dev))
+                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size, _P(self._lr_dev),
+                      self.shard[0] if self.shard else 0, self.shard[1] if self.shard else 0)
             # the kernel writes the tables through raw pointers (no autograd version bump): drop the model's
             # cached S so the next forward re-sums the updated tables
             self._model._S_cache = None

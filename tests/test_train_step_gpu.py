@@ -30,6 +30,10 @@ def _close_frac(x, y, rtol, atol, max_bad=1e-4):
     assert bad <= max_bad, bad
 
 
+def _bad_frac(x, y, rtol=1e-3, atol=1e-5):
+    return ((x - y).abs() > atol + rtol * y.abs()).float().mean().item()
+
+
 def _msg_tables(scene):
     return [e.weight.detach().clone() for e in scene.model.msg_encoder.embeddings]
 
@@ -255,11 +259,20 @@ def test_optimizer_state_dict_round_trip_and_torch_adam_layout():
     c.optimizer.load_state_dict(sd)
     c.scaler.load_state_dict(a.scaler.state_dict())
     assert torch.equal(c.optimizer.steps, a.optimizer.steps)
+    for p, q in zip(a.model.msg_decoder.parameters(), c.model.msg_decoder.parameters()):
+        assert torch.equal(p.detach(), q.detach())
+    # yardstick: `b` is an identical scene that was never interrupted - how far two runs of the same schedule drift apart
+    # (scatter-add order + Adam's sign-like updates of near-zero gradients) bounds what a correct resume may deviate by
     for i in range(3, 6):
-        la = a.train_step(batches[i % 2], msgs[i]); lc = c.train_step(batches[i % 2], msgs[i])
-        np.testing.assert_allclose([float(x) for x in lc], [float(x) for x in la], rtol=1e-4, atol=1e-6)
-    for x, y in zip(_msg_tables(a), _msg_tables(c)):
-        _close_frac(x, y, rtol=1e-3, atol=1e-5)
+        la = [float(x) for x in a.train_step(batches[i % 2], msgs[i])]
+        lb = [float(x) for x in b.train_step(batches[i % 2], msgs[i])]
+        lc = [float(x) for x in c.train_step(batches[i % 2], msgs[i])]
+        for k in range(3):
+            floor = abs(lb[k] - la[k]) / abs(la[k])
+            assert abs(lc[k] - la[k]) / abs(la[k]) <= max(1e-4, 3.0 * floor), (i, k, la, lb, lc)
+    floor = max(_bad_frac(x, y) for x, y in zip(_msg_tables(b), _msg_tables(a)))
+    worst = max(_bad_frac(x, y) for x, y in zip(_msg_tables(c), _msg_tables(a)))
+    assert worst <= max(1e-4, 3.0 * floor), (worst, floor)
     # a torch.optim.Adam checkpoint over get_params (the reference's optimizer) has the same layout and loads
     t = _scene(optimizer="torch")
     for i in range(3):
@@ -299,10 +312,6 @@ def test_lr_schedule_acts_on_graph_replays():
     del sched
 
 
-def _bad_frac(x, y, rtol=1e-3, atol=1e-5):
-    return ((x - y).abs() > atol + rtol * y.abs()).float().mean().item()
-
-
 @pytest.mark.parametrize("graph", [False, True])
 def test_deferred_optimizer_equals_sequential_optimizer(graph):
     """harness defer_optimizer: the Adam update of step t issued at the start of step t+1 (next to its march) leaves, after
@@ -323,10 +332,12 @@ def test_deferred_optimizer_equals_sequential_optimizer(graph):
         assert worst <= max(1e-4, 3.0 * floor), (worst, floor)
 
     for i, m in enumerate(msgs):
-        la = a.train_step(batches[i % 2], m)
-        a2.train_step(batches[i % 2], m)
-        lb = b.train_step(batches[i % 2], m)
-        np.testing.assert_allclose([float(x) for x in lb], [float(x) for x in la], rtol=2e-4, atol=1e-6)
+        la = [float(x) for x in a.train_step(batches[i % 2], m)]
+        la2 = [float(x) for x in a2.train_step(batches[i % 2], m)]
+        lb = [float(x) for x in b.train_step(batches[i % 2], m)]
+        for k in range(3):
+            floor = abs(la2[k] - la[k]) / abs(la[k])
+            assert abs(lb[k] - la[k]) / abs(la[k]) <= max(2e-4, 3.0 * floor), (i, k, la, la2, lb)
         if i == 3:
             b.flush_optimizer()
             b.flush_optimizer()      # idempotent
