@@ -317,7 +317,8 @@ def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_repla
     n_pool = len(host_batches)
     dev_batches = [scene.to_device(b) for b in host_batches]
     md = scene.cfg["message_dim"]
-    names = ["nsig_field_forward", "nsig_field_backward", "nsig_field_backward_masks", "nsig_field_backward_tc"]
+    names = ["nsig_field_forward", "nsig_field_backward", "nsig_field_backward_masks", "nsig_field_backward_tc",
+             "nsig_field_backward_tc_masks"]
     _lib.timing_enable(names)   # external event nodes when the step is captured
     for i in range(W):
         scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
@@ -403,11 +404,11 @@ def rooflines(res, step_ms):
     """Roofline entries from time_scene's per-replay accounting."""
     peak_gbs, peak_tf, src = _peaks()
     fwd = res["kernel_ms"]["nsig_field_forward"]
-    bwd_name = max(("nsig_field_backward_masks", "nsig_field_backward", "nsig_field_backward_tc"),
-                   key=lambda n: res["kernel_ms"][n]["n"])
+    bwd_kernels = {"nsig_field_backward_masks": "k_field_bwd_masks", "nsig_field_backward": "k_field_bwd",
+                   "nsig_field_backward_tc": "k_field_bwd_tc", "nsig_field_backward_tc_masks": "k_field_bwd_tc_masks"}
+    bwd_name = max(bwd_kernels, key=lambda n: res["kernel_ms"][n]["n"])
     bwd = res["kernel_ms"][bwd_name]
-    bwd_kernel = {"nsig_field_backward_masks": "k_field_bwd_masks", "nsig_field_backward": "k_field_bwd",
-                  "nsig_field_backward_tc": "k_field_bwd_tc"}[bwd_name]
+    bwd_kernel = bwd_kernels[bwd_name]
     S, steps = res["kernel_samples"], res["kernel_steps"]
     traffic = {}
     try:  # ncu dram__bytes_read+write per launch from the committed capture of this round (not the live launch)

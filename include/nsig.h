@@ -423,6 +423,14 @@ int nsig_field_backward_tc(const float* xyzs, const float* dirs, uint32_t M, flo
                            const void* color_w, float density_scale, const int32_t* M_dev,
                            float msg_resolution, uint32_t log2_T, float* G, nsig_stream_t stream);
 
+/* nsig_field_backward_masks on tcgen05 + TMEM: five UMMA layers per 128-row tile, one thread per sample row, six
+ * CTAs per SM (csrc/field_tc.cu).  Same arguments and result; `masks` must be 16-byte aligned. */
+int nsig_field_backward_tc_masks(const float* xyzs, uint32_t M, float bound, const void* masks,
+                                 const float* sigmas, const float* rgbs, const float* grad_sigmas,
+                                 const float* grad_rgbs, const void* sigma_w, const void* color_w,
+                                 float density_scale, const int32_t* M_dev, float msg_resolution,
+                                 uint32_t log2_T, float* G, nsig_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* optimizer step of the message tables — nerf/utils_wtmk_disen.py:1175-1181   */
 /* ------------------------------------------------------------------------- */

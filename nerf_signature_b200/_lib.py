@@ -48,6 +48,7 @@ _SIGNATURES = {
     "nsig_fused_hash_slots": ([_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp], 1),
     "nsig_field_forward": ([_vp, _vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp], 1),
+    "nsig_field_backward_tc_masks": ([_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_field_backward_masks": ([_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),
     "nsig_field_density": ([_vp, _u32, _f32, _vp, _vp, _u32, _vp, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_tables_to_half2": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp], 2),

@@ -29,6 +29,8 @@
 // Numerics: fp16 operands, fp32 accumulation (TMEM), per-row power-of-two gradient scaling as in field.cu.
 #include "field_common.cuh"
 
+#include <cstdlib>
+
 namespace nsig {
 namespace tc {
 
@@ -165,7 +167,7 @@ k_field_bwd_tc(const BwdTcParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -350,7 +352,189 @@ k_field_bwd_tc(const BwdTcParams p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same tcgen05 backward fed by SAVED ReLU MASKS (k_field_fwd's mask_out, see k_field_bwd_masks in field.cu): no MLP
+// recomputation, five UMMA layers per 128-row tile instead of ten, 32 KB of shared memory per CTA (backward weights + one
+// A operand) so six CTAs - six independent tiles - are resident per SM to hide the per-layer synchronisation.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t mBc2T = 0;                     // [64 x 16]
+constexpr uint32_t mBc1T = mBc2T + 64 * 16 * 2;   // [64 x 64]
+constexpr uint32_t mBc0T = mBc1T + 64 * 64 * 2;   // [16 x 64]
+constexpr uint32_t mBs1T = mBc0T + 16 * 64 * 2;   // [64 x 16]
+constexpr uint32_t mBs0T = mBs1T + 64 * 16 * 2;   // [16 x 64]
+constexpr uint32_t mA = mBs0T + 16 * 64 * 2;      // [128 x 64]
+constexpr uint32_t kSmemBytesMasks = mA + kRows * 64 * 2;
+constexpr int kMaskCtasPerSm = 6;
+
+struct BwdTcMaskParams {
+    const float* xyzs;
+    uint32_t M;
+    float bound_add, bound_mul;
+    const uint4* masks;        // [M][2] x 16 bytes: the row's four (quad-thread) entries {m1s | m1c << 8, m2c}
+    const float* sigmas;
+    const float* rgbs;
+    const float* grad_sigmas;
+    const float* grad_rgbs;
+    const __half* sigma_w;
+    const __half* color_w;
+    float msg_grid_size;
+    uint32_t mask;
+    float* G;
+    const int32_t* M_dev;
+    float density_scale;
+};
+
+// sign bit of hidden unit u of a layer (act_mask_bits layout): entry q = (u & 7) >> 1, bit 16*(u & 1) + (u >> 3) + shift
+template <int U>
+__device__ __forceinline__ bool unit_active(const uint32_t (&w)[4], int shift) {
+    return (w[(U & 7) >> 1] >> (16 * (U & 1) + (U >> 3) + shift)) & 1u;
+}
+
+__global__ void __launch_bounds__(kRows, kMaskCtasPerSm)
+k_field_bwd_tc_masks(const BwdTcMaskParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t mbar_storage;
+    __shared__ uint32_t tmem_slot;
+    uint32_t M = p.M;
+    if (p.M_dev) M = min(M, (uint32_t)max(*p.M_dev, 0));
+    if (M == 0) return;
+    const int t = threadIdx.x, warp = t >> 5;
+    const __half hz = __float2half(0.0f);
+    {
+        const __half* sw = p.sigma_w;
+        const __half* cw = p.color_w;
+        stage(sm + mBc2T, 64, 16, [&](int n, int k) { return k < 3 ? cw[6144 + k * 64 + n] : hz; });
+        stage(sm + mBc1T, 64, 64, [&](int n, int k) { return cw[2048 + k * 64 + n]; });
+        stage(sm + mBc0T, 16, 64, [&](int n, int k) { return n < 15 ? cw[k * 32 + 16 + n] : hz; });
+        stage(sm + mBs1T, 64, 16, [&](int n, int k) { return sw[2048 + ((k + 1) & 15) * 64 + n]; });
+        stage(sm + mBs0T, 16, 64, [&](int n, int k) { return sw[k * 32 + 16 + n]; });
+    }
+    const uint32_t mbar = smem_u32(&mbar_storage);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t my_tmem = tmem_d + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sbase = smem_u32(sm);
+    uint8_t* sA = sm + mA;
+    uint32_t parity = 0;
+    auto run_layer = [&](auto issue) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue();
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    const float inv_ds = 1.0f / p.density_scale;
+    const uint32_t n_tiles = div_up(M, (uint32_t)kRows);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t r = tile * kRows + t;
+        const bool live = r < M;
+        float gs = 0.f, gc[3] = {0.f, 0.f, 0.f}, sig = 1.f, rgb[3] = {0.f, 0.f, 0.f}, sx[3] = {0.f, 0.f, 0.f};
+        uint32_t w1[4] = {0u, 0u, 0u, 0u}, w2[4] = {0u, 0u, 0u, 0u};   // w1 = m1s | m1c << 8, w2 = m2c, per quad entry
+        if (live) {
+            gs = __ldg(p.grad_sigmas + r);
+            sig = __ldg(p.sigmas + r);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                gc[a] = __ldg(p.grad_rgbs + (size_t)r * 3 + a);
+                rgb[a] = __ldg(p.rgbs + (size_t)r * 3 + a);
+                sx[a] = __ldg(p.xyzs + (size_t)r * 3 + a);
+            }
+            const uint4 m0 = __ldg(p.masks + (size_t)r * 2), m1 = __ldg(p.masks + (size_t)r * 2 + 1);
+            w1[0] = m0.x; w2[0] = m0.y; w1[1] = m0.z; w2[1] = m0.w;
+            w1[2] = m1.x; w2[2] = m1.y; w1[3] = m1.z; w2[3] = m1.w;
+        }
+        const bool has_grad = (gs != 0.f) | (gc[0] != 0.f) | (gc[1] != 0.f) | (gc[2] != 0.f);
+        if (!__syncthreads_or(has_grad)) continue;
+
+        float v[32];
+        // gradient accumulators x saved ReLU mask -> fp16 A operand (K = 64), two halves of 32 columns
+        auto mask_store = [&](const uint32_t (&w)[4], int shift) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                NSIG_TMEM_LD16(my_tmem + hf * 32, v);
+                NSIG_TMEM_LD16(my_tmem + hf * 32 + 16, (&v[16]));
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = hf * 32 + c * 8 + 2 * j;     // hidden units u, u + 1: same quad entry, bits nt and 16 + nt
+                        const uint32_t sel = (w[(u & 7) >> 1] >> ((u >> 3) + shift)) & 0x00010001u;
+                        o[j] = pack_h2(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]) & (sel * 0xffffu);
+                    }
+                    store_a(sA, t, hf * 4 + c, 64, make_uint4(o[0], o[1], o[2], o[3]));
+                }
+            }
+        };
+        // ---- output-activation gradients from the forward's outputs, normalised per row by a power of two ----
+        float d_rgb[3], d_logit, inv_scale;
+        {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) d_rgb[a] = gc[a] * rgb[a] * (1.0f - rgb[a]);   // sigmoid'(z) = s (1 - s)
+            // trunc_exp backward: g * exp(clamp(x, -15, 15)) with exp(x) = sigma / density_scale
+            d_logit = gs * p.density_scale * fminf(fmaxf(sig * inv_ds, 3.0590232050182579e-7f), 3269017.3724721107f);
+            const float vmax = fmaxf(fmaxf(fabsf(d_rgb[0]), fabsf(d_rgb[1])), fmaxf(fabsf(d_rgb[2]), fabsf(d_logit)));
+            float sc = 1.0f;
+            if (vmax > 0.0f && isfinite(vmax)) { int e; frexpf(vmax, &e); sc = scalbnf(1.0f, -max(-100, min(100, e))); }
+            inv_scale = 1.0f / sc;
+            d_rgb[0] *= sc; d_rgb[1] *= sc; d_rgb[2] *= sc; d_logit *= sc;
+        }
+        // B5: d h2 = d out x Wc2
+        store_a(sA, t, 0, 16, make_uint4(pack_h2(d_rgb[0], d_rgb[1]), pack_h2(d_rgb[2], 0.f), 0u, 0u));
+        store_a(sA, t, 1, 16, make_uint4(0u, 0u, 0u, 0u));
+        run_layer([&] { issue_layer<64, 16>(sbase + mA, sbase + mBc2T, tmem_d, mbar); });
+        // B4: d h1 = (d h2 . relu') x Wc1
+        mask_store(w2, 0);
+        run_layer([&] { issue_layer<64, 64>(sbase + mA, sbase + mBc1T, tmem_d, mbar); });
+        // B3: d geo = ((d h1 . relu') x Wc0)[:, 16:31]
+        mask_store(w1, 8);
+        run_layer([&] { issue_layer<16, 64>(sbase + mA, sbase + mBc0T, tmem_d, mbar); });
+        // B2: d h1s = [d geo0..14, d logit] x Ws1'
+        NSIG_TMEM_LD16(my_tmem, v);
+        tmem_wait_ld();
+        store_a(sA, t, 0, 16, make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7])));
+        store_a(sA, t, 1, 16, make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], d_logit)));
+        run_layer([&] { issue_layer<64, 16>(sbase + mA, sbase + mBs1T, tmem_d, mbar); });
+        // B1: d feat[16..31] = (d h1s . relu') x Ws0[:, 16:32]
+        mask_store(w1, 0);
+        run_layer([&] { issue_layer<16, 64>(sbase + mA, sbase + mBs0T, tmem_d, mbar); });
+        NSIG_TMEM_LD16(my_tmem, v);
+        tmem_wait_ld();
+        const float gx = v[14] * inv_scale, gy = v[15] * inv_scale;
+        if (live && (gx != 0.f || gy != 0.f)) {
+            float xn[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) xn[a] = __fmul_rn(__fadd_rn(sx[a], p.bound_add), p.bound_mul);
+            const Voxel vx = locate(xn[0], xn[1], xn[2], p.msg_grid_size);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                red_add_v2(p.G + (size_t)corner_slot(vx, k, p.mask) * 2, corner_grad(vx, k, gx), corner_grad(vx, k, gy));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
 }
 
 }  // namespace tc
@@ -381,16 +565,51 @@ extern "C" int nsig_field_backward_tc(const float* xyzs, const float* dirs, uint
         cudaFuncSetAttribute(tc::k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
         attr_set = true;
     }
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::k_field_bwd_tc, tc::kRows, tc::kSmemBytes) != cudaSuccess ||
-        per_sm < 1)
-        per_sm = 1;
-    if (per_sm > (int)(512 / tc::kTmemCols)) per_sm = 512 / tc::kTmemCols;   // TMEM columns per SM
+    // Resident CTAs per SM: 4 by shared memory (4 x 52 KB), registers (__launch_bounds__(128, 4)) and TMEM (4 x 64 of 512
+    // columns).  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that allocates TMEM (it cannot see the
+    // column count and assumes the whole 512), which left 3/4 of every SM idle in the first measurement (ncu: grid 148,
+    // 6 % warps active, 432 us); tcgen05.alloc blocks until columns are free, so over-subscription is safe.
+    static const int per_sm = [] { const char* e = getenv("NSIG_TC_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t tiles = div_up(M, (uint32_t)tc::kRows);
     const uint32_t cap = (uint32_t)(sms * per_sm);
     tc::k_field_bwd_tc<<<tiles < cap ? tiles : cap, tc::kRows, tc::kSmemBytes, (cudaStream_t)stream>>>(p);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsig_field_backward_tc_masks(const float* xyzs, uint32_t M, float bound, const void* masks,
+                                            const float* sigmas, const float* rgbs, const float* grad_sigmas,
+                                            const float* grad_rgbs, const void* sigma_w, const void* color_w,
+                                            float density_scale, const int32_t* M_dev, float msg_resolution,
+                                            uint32_t log2_T, float* G, nsig_stream_t stream) {
+    if (M == 0) return 0;
+    if (!xyzs || !masks || !sigmas || !rgbs || !grad_sigmas || !grad_rgbs || !sigma_w || !color_w || !G) return NSIG_EINVAL;
+    if (((uintptr_t)masks) & 15) return NSIG_EINVAL;   // a row's masks are read as two 16-byte chunks
+    if (log2_T < 1 || log2_T > 30 || !(bound > 0.0f) || !(msg_resolution > 0.0f) || !(density_scale > 0.0f)) return NSIG_EINVAL;
+    tc::BwdTcMaskParams p;
+    p.xyzs = xyzs; p.M = M; p.bound_add = bound; p.bound_mul = 1.0f / (2.0f * bound);
+    p.masks = reinterpret_cast<const uint4*>(masks);
+    p.sigmas = sigmas; p.rgbs = rgbs; p.grad_sigmas = grad_sigmas; p.grad_rgbs = grad_rgbs;
+    p.sigma_w = reinterpret_cast<const __half*>(sigma_w);
+    p.color_w = reinterpret_cast<const __half*>(color_w);
+    p.msg_grid_size = 1.0f / msg_resolution;
+    p.mask = (1u << log2_T) - 1u;
+    p.G = G; p.M_dev = M_dev; p.density_scale = density_scale;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::k_field_bwd_tc_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytesMasks);
+        attr_set = true;
+    }
+    // resident CTAs per SM chosen by hand: the occupancy API answers 1 for kernels that allocate TMEM (see above)
+    static const int per_sm = [] { const char* e = getenv("NSIG_TC_CTAS_PER_SM"); const int v = e ? atoi(e) : 0;
+                                   return v > 0 ? v : tc::kMaskCtasPerSm; }();
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t tiles = div_up(M, (uint32_t)tc::kRows);
+    const uint32_t cap = (uint32_t)(sms * per_sm);
+    tc::k_field_bwd_tc_masks<<<tiles < cap ? tiles : cap, tc::kRows, tc::kSmemBytesMasks, (cudaStream_t)stream>>>(p);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -16,7 +16,8 @@ _P = _lib.ptr
 # Watermark-mode backward (only dL/dS is needed), three interchangeable kernels (A/B switch NSIG_BWD for tools and tests):
 #   "masks" (default): the forward saves the ReLU sign masks (32 B/sample) and the backward runs the five dgrad GEMMs only;
 #   "recompute":       the forward saves the fp16 encoder output (64 B/sample), the backward recomputes the MLPs (mma.sync);
-#   "tc":              same data flow as "recompute" on tcgen05.mma + TMEM (csrc/field_tc.cu; validated, slower: DESIGN.md 4)
+#   "tc":              same data flow as "recompute" on tcgen05.mma + TMEM (csrc/field_tc.cu)
+#   "tc_masks":        same data flow as "masks" on tcgen05.mma + TMEM (csrc/field_tc.cu)
 BACKWARD_MODE = os.environ.get("NSIG_BWD", "tc" if os.environ.get("NSIG_BWD_TC", "0") == "1" else "masks")
 
 
@@ -133,7 +134,7 @@ class _field_forward(Function):
         need_w = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
         need_tab = any(ctx.needs_input_grad[_field_forward.N_FIXED:])
         save = need_S or need_tab or need_w
-        use_masks = need_S and not (need_w or need_tab) and BACKWARD_MODE == "masks"
+        use_masks = need_S and not (need_w or need_tab) and BACKWARD_MODE in ("masks", "tc_masks")
         feat = torch.empty(M, 32, dtype=torch.float16, device=dev) if (save and not use_masks) else None
         masks = torch.empty(M, 4, 2, dtype=torch.int32, device=dev) if use_masks else None
         tabs = [t.contiguous() for t in tables]
@@ -166,7 +167,8 @@ class _field_forward(Function):
             cfg = ctx.cfg
             direct = cfg.S_sink is not None
             G = cfg.S_sink if direct else torch.zeros(ctx.S_shape, dtype=torch.float32, device=xyzs.device)
-            _lib.call("nsig_field_backward_masks", _P(xyzs), xyzs.shape[0], cfg.bound, _P(masks), _P(sigmas), _P(rgbs),
+            entry = "nsig_field_backward_tc_masks" if BACKWARD_MODE == "tc_masks" else "nsig_field_backward_masks"
+            _lib.call(entry, _P(xyzs), xyzs.shape[0], cfg.bound, _P(masks), _P(sigmas), _P(rgbs),
                       _P(grad_sigmas.contiguous().float()), _P(grad_rgbs.contiguous().float()), _P(sw), _P(cw),
                       cfg.density_scale, _P(ctx.count), cfg.msg_resolution, cfg.log2_T, _P(G))
             return (None, None, None if direct else G) + (None,) * (n_in - 3)

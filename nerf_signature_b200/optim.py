@@ -223,7 +223,11 @@ class WatermarkAdam(torch.optim.Optimizer):
             if groups:
                 self.param_groups[0]["lr"] = float(groups[0]["lr"])
         if self.inner is not None:
-            sd = {"param_groups": [], "state": {k - n_t: v for k, v in state.items() if k >= n_t}}
+            # torch's Optimizer.load_state_dict keeps a tensor that already has the right dtype/device BY REFERENCE; a state dict
+            # taken from a live optimizer (not from torch.load) would then share its moments with this one: copy them
+            def _copy(v):
+                return {kk: (vv.detach().clone() if isinstance(vv, torch.Tensor) else vv) for kk, vv in v.items()}
+            sd = {"param_groups": [], "state": {k - n_t: _copy(v) for k, v in state.items() if k >= n_t}}
             for g, g_in, g_out in zip(groups, self.inner.param_groups, self.param_groups):
                 g2 = dict(g)
                 g2["params"] = [i - n_t for i in g["params"]]

@@ -88,6 +88,10 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert h.nsig_field_backward_tc(p, p, 4, 1.0, aligned, p, p, aligned, aligned, 1.0, None, 2048.0, 19, None, None) == -1   # no G
     assert h.nsig_field_backward_tc(p, p, 4, 1.0, odd, p, p, aligned, aligned, 1.0, None, 2048.0, 19, p, None) == -1       # feat alignment
     assert h.nsig_field_backward_tc(p, p, 4, 1.0, aligned, p, p, aligned, aligned, 1.0, None, 0.0, 19, p, None) == -1      # msg resolution
+    assert h.nsig_field_backward_masks(None, 0, 1.0, None, None, None, None, None, None, None, 1.0, None, 2048.0, 19, None, None) == 0
+    assert h.nsig_field_backward_masks(p, 4, 1.0, aligned, p, p, p, p, odd, aligned, 1.0, None, 2048.0, 19, p, None) == -1   # weights
+    assert h.nsig_field_backward_tc_masks(p, 4, 1.0, odd, p, p, p, p, aligned, aligned, 1.0, None, 2048.0, 19, p, None) == -1  # masks
+    assert h.nsig_field_backward_tc_masks(p, 4, 1.0, aligned, p, p, p, p, aligned, aligned, 0.0, None, 2048.0, 19, p, None) == -1
     assert h.nsig_fused_hash_slots(None, 0, None, 16, 19, None, None, None) == 0
     assert h.nsig_fused_hash_slots(p, 1, res, 17, 19, p, None, None) == -1
     assert h.nsig_grad_check_update_scale(None, 8, p, p, 2.0, 0.5, 2000, p, p, None, p, None, None) == -1

@@ -187,7 +187,8 @@ def test_backward_kernels_agree(M):
     """The three interchangeable watermark-mode backward kernels on the same inputs:
       recompute: csrc/field.cu k_field_bwd (saved fp16 features, MLPs recomputed, mma.sync) - the round-1 kernel;
       masks:     csrc/field.cu k_field_bwd_masks (saved ReLU sign masks + forward outputs, dgrad GEMMs only) - the default;
-      tc:        csrc/field_tc.cu (tcgen05.mma + TMEM, one thread per sample row).
+      tc:        csrc/field_tc.cu (tcgen05.mma + TMEM, one thread per sample row), data flow of `recompute`;
+      tc_masks:  csrc/field_tc.cu, data flow of `masks` (five UMMA layers per tile).
     Same fp16 operands / fp32 accumulation / per-row power-of-two scaling everywhere; `masks` uses bit-identical activation
     patterns by construction, so it agrees with `recompute` to summation order (atomics) and 1 ulp of exp(); `tc` rounds
     at the same points with a different register layout."""
@@ -203,7 +204,7 @@ def test_backward_kernels_agree(M):
         gs[256:384] = 0; gc[256:384] = 0     # a whole 128-row tile without gradient: skipped by the tcgen05 kernel
     xt, dt = torch.from_numpy(x).cuda(), torch.from_numpy(dirs).cuda()
     got, prev = {}, field_ops.BACKWARD_MODE
-    for mode in ("recompute", "masks", "tc"):
+    for mode in ("recompute", "masks", "tc", "tc_masks"):
         field_ops.BACKWARD_MODE = mode
         try:
             for e in net.msg_encoder.embeddings:
@@ -216,7 +217,7 @@ def test_backward_kernels_agree(M):
     torch.cuda.synchronize()
     b = got["recompute"].double()
     assert float(b.abs().max()) > 0
-    for mode, tol_l2, tol_max in (("masks", 1e-5, 1e-5), ("tc", 1e-3, 2e-3)):
+    for mode, tol_l2, tol_max in (("masks", 1e-5, 1e-5), ("tc", 1e-3, 2e-3), ("tc_masks", 1e-3, 2e-3)):
         a = got[mode].double()
         record_parity(f"backward_{mode}_vs_recompute[{M}]", dict(zip(("max_rel", "rel_l2"), _rel(a.cpu().numpy(), b.cpu().numpy()))))
         assert float((a - b).norm() / b.norm()) < tol_l2, mode

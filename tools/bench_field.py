@@ -83,7 +83,7 @@ def main():
     sig, rgb = holder["o"]
     gs, gc = torch.randn_like(sig) * 1e-3, torch.randn_like(rgb) * 1e-3
     # NSIG_BWD = masks (default) | recompute | tc selects the kernel
-    bwd_names = ["nsig_field_backward", "nsig_field_backward_tc", "nsig_field_backward_masks"]
+    bwd_names = ["nsig_field_backward", "nsig_field_backward_tc", "nsig_field_backward_masks", "nsig_field_backward_tc_masks"]
     _lib.timing_enable(bwd_names)
 
     def bwd():
