@@ -527,8 +527,17 @@ def grad_check_1_vs_n(cx, content_rays=16384):
     D1 = torch.cat([p.grad.reshape(-1) for p in s1._decoder_params]) / scale
     torch.cuda.synchronize()
     rel = lambda a, b: float((a - b).norm() / b.norm())
+    # the optimizer of the message tables is sharded over the ranks: after the step every rank holds the updated slice it
+    # owns; gather_tables() makes the tables whole again and they must equal the single-GPU update
+    sn.optimizer.gather_tables()
+    bits = [int(b) for b in msg.tolist()]
+    tabs_n, tabs_1 = sn.model.msg_encoder.tables(), s1.model.msg_encoder.tables()
+    upd = max(float((tabs_n[2 * i + b] - tabs_1[2 * i + b]).abs().max()) for i, b in enumerate(bits))
+    untouched = max(float((tabs_n[2 * i + 1 - b] - tabs_1[2 * i + 1 - b]).abs().max()) for i, b in enumerate(bits))
     out = {"content_rays": content_rays, "block_rays": int(sum(counts)), "dLdS_rel_l2": rel(Gn, G1),
-           "decoder_grads_rel_l2": rel(Dn, D1), "lossw_1gpu": None}
+           "decoder_grads_rel_l2": rel(Dn, D1), "loss_rel": abs(float(ln) - float(l1)) / abs(float(l1)),
+           "updated_tables_max_abs_diff": upd, "untouched_tables_max_abs_diff": untouched, "lr": 1e-2,
+           "optimizer_sharded": sn.optimizer.shard is not None}
     del sn, s1
     torch.cuda.empty_cache()
     return out
