@@ -5,6 +5,8 @@
 #include "hash_common.cuh"
 #include "march_common.cuh"
 
+#include <cstdlib>
+
 namespace nsig {
 
 // ---- shared-memory weight layout (halfs); row strides padded by 8 halfs: conflict-free B loads
@@ -557,6 +559,10 @@ static inline int field_grid(K kernel, size_t smem, uint32_t M, uint32_t rows_pe
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, nsig::kFieldThreads, smem) != cudaSuccess ||
         ctas_per_sm < 1)
         ctas_per_sm = 1;
+    // experiment switch: cap the resident CTAs per SM of the persistent field kernels so that kernels of a parallel graph
+    // branch (the decoder chain in the harness' `overlap` render mode) find free registers / shared memory
+    static const int cap_env = [] { const char* e = getenv("NSIG_FIELD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (cap_env > 0 && ctas_per_sm > cap_env) ctas_per_sm = cap_env;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t tiles = nsig::div_up(M, rows_per_cta);
