@@ -355,14 +355,23 @@ int nsig_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, 
  * linear.bias.  workspace: nsig_decoder_workspace_bytes() bytes, kept between forward and backward.
  * forward writes logits [B, num_bits] fp32 (HiddenDecoder_multi_views.forward's return value).
  * backward takes dlogits [B, num_bits] fp32, ACCUMULATES every parameter gradient into grads (same order and
- * shapes as params, fp32) and writes dimage [B,H,W,3] fp32 (optional). */
+ * shapes as params, fp32) and writes dimage [B,H,W,3] fp32 (optional).  Weight gradients are reduced in a fixed order
+ * (per-CTA partials in the workspace + a ticket per tap): results are run-to-run deterministic.
+ * prepared_weights (optional, may be NULL): nsig_decoder_weights_bytes() bytes filled by nsig_decoder_prepare_weights
+ * from the SAME params - the fp16 copies of the conv weights the kernels consume.  With NULL the forward converts the
+ * weights itself (one more kernel on the critical path of every call); a caller that knows when the weights change
+ * (the optimizer) converts them once per update instead.  backward must get what forward got. */
 size_t nsig_decoder_workspace_bytes(uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks);
+size_t nsig_decoder_weights_bytes(uint32_t num_blocks);
+int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks, uint32_t num_bits,
+                                 uint32_t redundancy, void* weights, nsig_stream_t stream);
 int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
                          uint32_t num_bits, uint32_t redundancy, const float* const* params, void* workspace,
-                         float* logits, nsig_stream_t stream);
+                         float* logits, const void* prepared_weights, nsig_stream_t stream);
 int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
                           uint32_t num_bits, uint32_t redundancy, const float* const* params,
-                          float* const* grads, void* workspace, float* dimage, nsig_stream_t stream);
+                          float* const* grads, void* workspace, float* dimage, const void* prepared_weights,
+                          nsig_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* loss head of the watermark training step — nerf/utils_wtmk_disen.py:592-593, 636-644 */

@@ -63,9 +63,11 @@ _SIGNATURES = {
     # kernels per call as a function of the arguments (args[4] = num_blocks): weight prep, input prep, num_blocks+1
     # convs, head / head, last-block statistics, num_blocks+1 data-gradient convs and weight-gradient kernels,
     # BatchNorm parameter gradients, input gradient
-    "nsig_decoder_forward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp], lambda a: a[4] + 4),
-    "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+    "nsig_decoder_forward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+                             lambda a: a[4] + (3 if a[10] is not None else 4)),
+    "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
                               lambda a: 2 * (a[4] + 1) + 3 + (1 if a[10] is not None else 0)),
+    "nsig_decoder_prepare_weights": ([_vp, _u32, _u32, _u32, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
@@ -79,7 +81,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes",
                                                 "nsig_grid_sample_cells_scratch_bytes", "nsig_allreduce_grid",
-                                                "nsig_decoder_workspace_bytes"])
+                                                "nsig_decoder_workspace_bytes", "nsig_decoder_weights_bytes"])
 
 _lib = None
 _lock = threading.Lock()
@@ -115,6 +117,8 @@ def load():
         lib.nsig_grid_sample_cells_scratch_bytes.argtypes = [_u32, _u32]
         lib.nsig_decoder_workspace_bytes.restype = _sz
         lib.nsig_decoder_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32]
+        lib.nsig_decoder_weights_bytes.restype = _sz
+        lib.nsig_decoder_weights_bytes.argtypes = [_u32]
         lib.nsig_allreduce_grid.restype = _u32
         lib.nsig_allreduce_grid.argtypes = []
         _lib = lib

@@ -378,8 +378,7 @@ template <int C>
 __global__ void __launch_bounds__(kDecThreads)
 k_dec_bwd_stats(const __half* __restrict__ da, const __half* __restrict__ z, BnSrc bn, double* __restrict__ bsums, int n_pix) {
     __shared__ BnCoef coef[C];
-    __shared__ float red[2][C];
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) { coef[ch] = bn_coef(bn, ch, false); red[0][ch] = 0.f; red[1][ch] = 0.f; }
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) coef[ch] = bn_coef(bn, ch, false);
     __syncthreads();
     constexpr int CK = C / 8;                       // 16-byte chunks per pixel
     const int slot = threadIdx.x % CK;               // this thread always handles the same 8 channels
@@ -408,14 +407,19 @@ k_dec_bwd_stats(const __half* __restrict__ da, const __half* __restrict__ z, BnS
 #pragma unroll
         for (int o = 16; o >= CK; o >>= 1) { a1[k] += __shfl_xor_sync(NSIG_FULL_MASK, a1[k], o); a2[k] += __shfl_xor_sync(NSIG_FULL_MASK, a2[k], o); }
     }
+    // per-warp partials, then a fixed-order sum over the warps (no shared-memory float atomics: results are reproducible)
+    __shared__ float part[2][kDecWarps][C];
     if ((threadIdx.x & 31) < CK) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { atomicAdd(&red[0][slot * 8 + k], a1[k]); atomicAdd(&red[1][slot * 8 + k], a2[k]); }
+        for (int k = 0; k < 8; ++k) { part[0][threadIdx.x >> 5][slot * 8 + k] = a1[k]; part[1][threadIdx.x >> 5][slot * 8 + k] = a2[k]; }
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-        atomicAdd(bsums + ch, (double)red[0][ch]);
-        atomicAdd(bsums + C + ch, (double)red[1][ch]);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kDecWarps; ++w) { s1 += part[0][w][ch]; s2 += part[1][w][ch]; }
+        atomicAdd(bsums + ch, (double)s1);
+        atomicAdd(bsums + C + ch, (double)s2);
     }
 }
 
@@ -432,6 +436,12 @@ struct WgradParams {
     const __half* dz;      // gradient wrt the conv output  [B,H,W,DCH] (materialised by the data-gradient conv)
     float* dW;             // [cout_real][cin_real][3][3]
     float* db;             // [cout_real]
+    // two-phase reduction (null: one atomicAdd per element and CTA instead): every CTA stores its [COUT x CIN] partial to
+    // partial[(group * 9 + tap)] with plain coalesced stores and takes a ticket of its tap; the CTA that draws the last
+    // ticket sums the groups IN GROUP ORDER and adds the result to dW - deterministic, and 9*G*COUT*CIN scattered L2
+    // atomics (stride 36 B) become 8-byte stores plus one read-modify-write of dW
+    float* partial;        // [G][9][COUT][CIN] fp32
+    unsigned int* tickets; // [9] (+1 for the bias), zero before the launch
     int B, H, W, R, cin_real, cout_real;
 };
 
@@ -495,19 +505,73 @@ k_dec_wgrad(const WgradParams p) {
             }
         }
     }
-    if (t == 4 && bco < p.cout_real) atomicAdd(p.db + bco, dbias);
+    if (p.partial == nullptr) {
+        if (t == 4 && bco < p.cout_real) atomicAdd(p.db + bco, dbias);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < NT_PER; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int co = mt * 16 + h * 8 + g;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int ci = (nt0 + j) * 8 + 2 * tig + e;
+                        if (co < p.cout_real && ci < p.cin_real) atomicAdd(p.dW + ((size_t)co * p.cin_real + ci) * 9 + t, c[j][2 * h + e]);
+                    }
+                }
+        }
+        return;
+    }
+    // slot (group, tap) of the partials; slot (group, 9) holds the group's bias partial (written by its centre-tap CTA)
+    float* mine = p.partial + ((size_t)blockIdx.y * 10 + t) * (COUT * CIN);
+    __shared__ float s_db[kDecThreads];
+    if (t == 4) {
+        s_db[threadIdx.x] = dbias;
+        __syncthreads();
+        if (threadIdx.x < 64 && threadIdx.x < COUT) {
+            float acc = 0.f;
+            for (int part = 0; part < kDecThreads / 64; ++part) acc += s_db[part * 64 + threadIdx.x];
+            p.partial[((size_t)blockIdx.y * 10 + 9) * (COUT * CIN) + threadIdx.x] = acc;
+        }
+    }
     if (active) {
 #pragma unroll
         for (int j = 0; j < NT_PER; ++j)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int co = mt * 16 + h * 8 + g;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ci = (nt0 + j) * 8 + 2 * tig + e;
-                    if (co < p.cout_real && ci < p.cin_real) atomicAdd(p.dW + ((size_t)co * p.cin_real + ci) * 9 + t, c[j][2 * h + e]);
-                }
+                const int co = mt * 16 + h * 8 + g, ci = (nt0 + j) * 8 + 2 * tig;
+                *reinterpret_cast<float2*>(mine + co * CIN + ci) = make_float2(c[j][2 * h], c[j][2 * h + 1]);
             }
+    }
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + t, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.y - 1) return;
+    __threadfence();   // acquire: the other groups' partials were fenced before their tickets
+    const float* base = p.partial + (size_t)t * (COUT * CIN);
+    constexpr int NE = COUT * CIN / kDecThreads;     // elements per thread: all their loads of one group are in flight at once
+    float acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+    for (unsigned int grp = 0; grp < gridDim.y; ++grp) {
+        float v[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[e] = __ldcg(base + (size_t)grp * 10 * (COUT * CIN) + e * kDecThreads + threadIdx.x);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) acc[e] += v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int i = e * kDecThreads + (int)threadIdx.x, co = i / CIN, ci = i - co * CIN;
+        if (co < p.cout_real && ci < p.cin_real) p.dW[((size_t)co * p.cin_real + ci) * 9 + t] += acc[e];   // sole writer of tap t
+    }
+    if (t == 4 && (int)threadIdx.x < p.cout_real) {
+        float acc = 0.f;
+        for (unsigned int grp = 0; grp < gridDim.y; ++grp)
+            acc += __ldcg(p.partial + ((size_t)grp * 10 + 9) * (COUT * CIN) + threadIdx.x);
+        p.db[threadIdx.x] += acc;
     }
 }
 
@@ -589,7 +653,21 @@ k_dec_head_fwd(const HeadParams p) {
         const __half* hz = reinterpret_cast<const __half*>(&v);
         for (int k = 0; k < p.nb; ++k) s[k] += h2f(act_from_z(hz[k], coef[k]));
     }
-    for (int k = 0; k < p.nb; ++k) atomicAdd(&acc[k], s[k]);
+    {   // block sum in a fixed order: warp shuffles, then the per-warp partials one after the other
+        __shared__ float wpart[kDecWarps][8];
+        for (int k = 0; k < p.nb; ++k) {
+            float v = s[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NSIG_FULL_MASK, v, o);
+            if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5][k] = v;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < p.nb) {
+            float v = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += wpart[w][threadIdx.x];
+            acc[threadIdx.x] = v;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __half pooled[8];
@@ -616,13 +694,19 @@ k_dec_head_bwd(const HeadParams p) {
         float dp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int o = 0; o < p.nb; ++o) {
             const float dlo = h2f(f2h(p.dlogits[b * p.num_bits + o / p.redundancy]));   // gradient arrives in fp16 under autocast
-            atomicAdd(p.dlin_b + o, dlo);
-            for (int k = 0; k < p.nb; ++k) {
-                atomicAdd(p.dlin_w + o * p.nb + k, dlo * h2f(p.pooled[b * 8 + k]));
-                dp[k] += dlo * h2f(f2h(p.lin_w[o * p.nb + k]));
-            }
+            for (int k = 0; k < p.nb; ++k) dp[k] += dlo * h2f(f2h(p.lin_w[o * p.nb + k]));
         }
         for (int k = 0; k < 8; ++k) dpool[k] = h2f(f2h(dp[k])) / (float)p.HW;
+    }
+    // gradients of the linear layer: CTA 0, one thread per element, images summed in order (deterministic; nb <= 8)
+    if (b == 0 && threadIdx.x >= 32 && (int)threadIdx.x - 32 < p.nb * (p.nb + 1)) {
+        const int e = (int)threadIdx.x - 32, o = e / (p.nb + 1), k = e - o * (p.nb + 1);   // k == nb: the bias
+        float acc = 0.f;
+        for (int bb = 0; bb < p.B; ++bb) {
+            const float dlo = h2f(f2h(p.dlogits[bb * p.num_bits + o / p.redundancy]));
+            acc += k < p.nb ? dlo * h2f(p.pooled[bb * 8 + k]) : dlo;
+        }
+        if (k < p.nb) p.dlin_w[o * p.nb + k] += acc; else p.dlin_b[o] += acc;
     }
     __syncthreads();
     for (int pix = threadIdx.x; pix < p.HW; pix += blockDim.x) {
@@ -695,7 +779,21 @@ __device__ __forceinline__ void head_fwd_image(const HeadParams& p, int b, BnCoe
         const __half* hz = reinterpret_cast<const __half*>(&v);
         for (int k = 0; k < p.nb; ++k) s[k] += h2f(act_from_z(hz[k], coef[k]));
     }
-    for (int k = 0; k < p.nb; ++k) atomicAdd(&acc[k], s[k]);
+    {   // block sum in a fixed order: warp shuffles, then the per-warp partials one after the other
+        __shared__ float wpart[kDecWarps][8];
+        for (int k = 0; k < p.nb; ++k) {
+            float v = s[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NSIG_FULL_MASK, v, o);
+            if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5][k] = v;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < p.nb) {
+            float v = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += wpart[w][threadIdx.x];
+            acc[threadIdx.x] = v;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __half pooled[8];
@@ -771,10 +869,11 @@ struct DecLayout {
     size_t n_pix;
     size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz[kMaxLayers + 1], off_da9, off_dx0, off_pooled;
     size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_sums[kMaxLayers + 1], off_bsums[kMaxLayers + 1];
-    size_t off_sums_begin, sums_bytes, off_barrier, total;
+    size_t off_sums_begin, sums_bytes, off_barrier, off_tickets, off_partial[kMaxLayers + 1], total;
 };
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
+constexpr int kWgradGroupsMax = 32;   // upper bound of the weight-gradient grid's image groups (NSIG_DEC_WGRAD_G)
 
 DecLayout make_layout(int B, int H, int W, int L) {
     DecLayout d{};
@@ -802,9 +901,38 @@ DecLayout make_layout(int B, int H, int W, int L) {
         d.off_bsums[l] = o; o += 2 * 64 * sizeof(double);
     }
     d.off_barrier = o; o += 256;            // grid-barrier counter of the persistent forward, cleared with the statistics
+    d.off_tickets = o; o += (size_t)(kMaxLayers + 1) * 16 * sizeof(unsigned int);   // weight-gradient tickets, per layer x tap
     d.sums_bytes = o - d.off_sums_begin;
+    o = align_up(o);
+    for (int l = 0; l <= L; ++l) {   // per-layer partials of the weight-gradient reduction (layers run concurrently)
+        const int cin = l == 0 ? 16 : 64, cout = l == L ? 16 : 64;
+        d.off_partial[l] = o; o = align_up(o + (size_t)kWgradGroupsMax * 10 * cout * cin * sizeof(float));
+    }
     d.total = align_up(o);
     return d;
+}
+
+// fp16 weights of every layer in both orientations, as one buffer (nsig_decoder_prepare_weights): offsets of layer l
+struct WeightLayout { size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], total; };
+WeightLayout make_weight_layout(int L) {
+    WeightLayout w{};
+    size_t o = 0;
+    for (int l = 0; l <= L; ++l) {
+        const int cin = l == 0 ? 16 : 64, cout = l == L ? 16 : 64;
+        w.off_wf[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
+        w.off_wr[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
+    }
+    w.total = o;
+    return w;
+}
+PrepParams make_prep(const float* const* params, int L, int nb, unsigned char* base, const size_t* off_wf, const size_t* off_wr) {
+    PrepParams q{};
+    for (int l = 0; l <= L; ++l) {
+        q.w[l] = params[4 * l];
+        q.wf[l] = reinterpret_cast<__half*>(base + off_wf[l]); q.wr[l] = reinterpret_cast<__half*>(base + off_wr[l]);
+        q.cin[l] = l == 0 ? 3 : 64; q.cout[l] = l == L ? nb : 64; q.cin_pad[l] = l == 0 ? 16 : 64; q.cout_pad[l] = l == L ? 16 : 64;
+    }
+    return q;
 }
 
 // image rows per conv CTA: at most 64 pixels (4 m-tiles per warp pass), at least ~148 CTAs when the batch allows it
@@ -843,7 +971,11 @@ int launch_wgrad(WgradParams p, cudaStream_t st) {
     const size_t smem = (size_t)((p.R * p.W + 15) / 16 * 16) * (CIN + 8 + COUT + 8) * 2;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    static const int g_max = [] { const char* e = getenv("NSIG_DEC_WGRAD_G"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    static const int g_max = [] {
+        const char* e = getenv("NSIG_DEC_WGRAD_G");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? (v < kWgradGroupsMax ? v : kWgradGroupsMax) : 16;
+    }();
     const int G = p.B < g_max ? p.B : g_max;   // image groups: 9*G CTAs, each adds its [COUT x CIN] partial with atomics
     k_dec_wgrad<CIN, COUT, DCH><<<dim3(9, G), kDecThreads, smem, st>>>(p);
     NSIG_LAUNCH_CHECK();
@@ -855,10 +987,12 @@ int launch_wgrad(WgradParams p, cudaStream_t st) {
 // layer l), and nothing downstream of it but the optimizer.  It is launched on a second stream that forks from the
 // caller's stream after that conv and joins it at the end of the call: in a stream capture this becomes a parallel
 // branch of the graph, eagerly the kernels simply overlap (neither chain fills the 148 SMs).
+constexpr int kMaxSideStreams = 4;
 struct SideStream {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream[kMaxSideStreams] = {};   // layer l's weight gradient goes to stream[l % n]
     cudaEvent_t fork[kMaxLayers + 1] = {};
-    cudaEvent_t join = nullptr;
+    cudaEvent_t join[kMaxSideStreams] = {};
+    int n = 0;
     bool ok = false;
 };
 std::mutex g_side_mutex;   // one backward launch chain at a time: the fork/join events are shared per device
@@ -868,12 +1002,23 @@ SideStream* side_stream_for_current_device() {
     static const bool disabled = [] { const char* e = getenv("NSIG_DEC_NO_SIDE"); return e && e[0] == '1'; }();
     int dev = 0;
     if (disabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    // one weight-gradient kernel is 9 x 16 CTAs of latency-bound work (two staged images, 36 MMAs per warp, 4096 atomics
+    // per CTA): consecutive layers' kernels do not compete for anything, so they alternate between n streams and the
+    // weight-gradient chain stops being longer than the data-gradient chain it hangs off
+    static const int n_streams = [] {
+        const char* e = getenv("NSIG_DEC_SIDE_STREAMS");
+        const int v = e ? atoi(e) : 3;
+        return v < 1 ? 1 : (v > kMaxSideStreams ? kMaxSideStreams : v);
+    }();
     SideStream& s = side[dev];
     if (!s.ok) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int k = 0; k < n_streams; ++k) {
+            if (cudaStreamCreateWithFlags(&s.stream[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&s.join[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
         for (int l = 0; l <= kMaxLayers; ++l)
             if (cudaEventCreateWithFlags(&s.fork[l], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.n = n_streams;
         s.ok = true;
     }
     return &s;
@@ -888,12 +1033,31 @@ size_t nsig_decoder_workspace_bytes(uint32_t B, uint32_t H, uint32_t W, uint32_t
     return make_layout((int)B, (int)H, (int)W, (int)num_blocks).total;
 }
 
+size_t nsig_decoder_weights_bytes(uint32_t num_blocks) {
+    if (num_blocks == 0 || num_blocks > (uint32_t)kMaxLayers) return 0;
+    return make_weight_layout((int)num_blocks).total;
+}
+
+// The fp16 copies of the conv weights (forward layout + rotated/transposed data-gradient layout) only change when the
+// optimizer changes the weights: a caller that knows when that happens converts them once, off the critical path (e.g.
+// right behind the optimizer kernel on its side stream), and hands the buffer to forward/backward as `prepared_weights`.
+int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks, uint32_t num_bits, uint32_t redundancy,
+                                 void* weights, nsig_stream_t stream) {
+    const int L = (int)num_blocks, nb = (int)(num_bits * redundancy);
+    if (!params || !weights || L < 1 || L > kMaxLayers || nb < 1 || nb > 8) return NSIG_EINVAL;
+    const WeightLayout wl = make_weight_layout(L);
+    const PrepParams q = make_prep(params, L, nb, reinterpret_cast<unsigned char*>(weights), wl.off_wf, wl.off_wr);
+    k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, (cudaStream_t)stream>>>(q);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
 // params (HOST array of device pointers, fp32), per conv block l = 0..num_blocks (the last one has nb outputs):
 //   params[4l+0] conv weight [cout,cin,3,3], [4l+1] conv bias, [4l+2] BN weight, [4l+3] BN bias;
 //   then linear weight [nb,nb], linear bias [nb].
 int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks, uint32_t num_bits,
                          uint32_t redundancy, const float* const* params, void* workspace, float* logits,
-                         nsig_stream_t stream) {
+                         const void* prepared_weights, nsig_stream_t stream) {
     if (B == 0) return 0;
     const int L = (int)num_blocks, nb = (int)(num_bits * redundancy);
     if (!image || !params || !workspace || !logits || L < 1 || L > kMaxLayers || nb < 1 || nb > 8 || H == 0 || W == 0) return NSIG_EINVAL;
@@ -904,16 +1068,15 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
     auto D64 = [&](size_t off) { return reinterpret_cast<double*>(ws + off); };
     cudaError_t e = cudaMemsetAsync(ws + d.off_sums_begin, 0, d.sums_bytes, st);
     if (e != cudaSuccess) return (int)e;
-    PrepParams q{};
-    for (int l = 0; l <= L; ++l) {
-        q.w[l] = params[4 * l]; q.wf[l] = H16(d.off_wf[l]); q.wr[l] = H16(d.off_wr[l]);
-        q.cin[l] = l == 0 ? 3 : 64; q.cout[l] = l == L ? nb : 64; q.cin_pad[l] = l == 0 ? 16 : 64; q.cout_pad[l] = l == L ? 16 : 64;
-    }
+    const PrepParams q = make_prep(params, L, nb, ws, d.off_wf, d.off_wr);
+    const WeightLayout wl = make_weight_layout(L);
+    const unsigned char* pw = reinterpret_cast<const unsigned char*>(prepared_weights);
+    auto WF = [&](int l) { return pw ? reinterpret_cast<const __half*>(pw + wl.off_wf[l]) : H16(d.off_wf[l]); };
     const float inv_n = 1.0f / (float)d.n_pix;
     auto conv_params = [&](int l) {
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
-        p.w = H16(d.off_wf[l]); p.bias = params[4 * l + 1]; p.dst = H16(d.off_z[l]); p.out_sums = D64(d.off_sums[l]);
+        p.w = WF(l); p.bias = params[4 * l + 1]; p.dst = H16(d.off_z[l]); p.out_sums = D64(d.off_sums[l]);
         p.cout_valid = l == L ? nb : 64;
         if (l == 0) {
             p.src = H16(d.off_x0);
@@ -935,7 +1098,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
     // barriers (an L2 atomic + acquire spin each) cost more than ten kernel boundaries inside a CUDA graph, so the
     // per-layer chain stays the default; NSIG_DEC_PERSIST=1 selects the persistent kernel (tools/bench_decoder.py).
     static const bool persist = [] { const char* e = getenv("NSIG_DEC_PERSIST"); return e && e[0] == '1'; }();
-    if (persist && L + 1 <= kPersistMaxLayers) {
+    if (persist && !pw && L + 1 <= kPersistMaxLayers) {
         const int R = conv_rows((int)B, (int)H, (int)W);
         const int strips = ((int)H + R - 1) / R;
         const size_t smem = (size_t)(R + 2) * (W + 2) * (64 + 8) * 2 + (size_t)(64 + 64) * sizeof(BnCoef) + (size_t)64 * (9 * 64 + 8) * 2;
@@ -961,8 +1124,10 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
         }
     }
 
-    k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, st>>>(q);
-    NSIG_LAUNCH_CHECK();
+    if (!pw) {
+        k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, st>>>(q);
+        NSIG_LAUNCH_CHECK();
+    }
     k_dec_prep_input<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(image, (int)d.n_pix, H16(d.off_x0));
     NSIG_LAUNCH_CHECK();
     for (int l = 0; l <= L; ++l) {
@@ -981,7 +1146,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
 // dimage (optional) [B,H,W,3] fp32: gradient wrt the (un-normalised) input image.
 int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks, uint32_t num_bits,
                           uint32_t redundancy, const float* const* params, float* const* grads, void* workspace,
-                          float* dimage, nsig_stream_t stream) {
+                          float* dimage, const void* prepared_weights, nsig_stream_t stream) {
     if (B == 0) return 0;
     const int L = (int)num_blocks, nb = (int)(num_bits * redundancy);
     if (!dlogits || !params || !grads || !workspace || L < 1 || L > kMaxLayers || nb < 1 || nb > 8) return NSIG_EINVAL;
@@ -992,6 +1157,9 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
     auto D64 = [&](size_t off) { return reinterpret_cast<double*>(ws + off); };
     const float inv_n = 1.0f / (float)d.n_pix;
     const int n_pix = (int)d.n_pix;
+    const WeightLayout wl = make_weight_layout(L);
+    const unsigned char* pw = reinterpret_cast<const unsigned char*>(prepared_weights);   // must be what the forward used
+    auto WR = [&](int l) { return pw ? reinterpret_cast<const __half*>(pw + wl.off_wr[l]) : H16(d.off_wr[l]); };
 
     HeadParams h{};
     h.lin_w = params[4 * (L + 1)]; h.B = (int)B; h.HW = (int)(H * W); h.nb = nb; h.num_bits = (int)num_bits;
@@ -1002,6 +1170,8 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
 
     std::lock_guard<std::mutex> lock(g_side_mutex);
     SideStream* side = side_stream_for_current_device();
+    // weight-gradient reduction: tickets + partials (deterministic, default) or fp32 atomics (NSIG_DEC_WGRAD_ATOMIC=1)
+    static const bool two_phase = [] { const char* e = getenv("NSIG_DEC_WGRAD_ATOMIC"); return !(e && e[0] == '1'); }();
     const __half* da = H16(d.off_da9);
     const int stat_blocks = n_pix / 64 < 64 ? (n_pix / 64 > 0 ? n_pix / 64 : 1) : 64;
     for (int l = L; l >= 0; --l) {
@@ -1015,7 +1185,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         // (2) data gradient da_{l-1} = conv(dz_l, rotated weights); the staged dz_l is written out for (3)
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
-        p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = H16(d.off_wr[l]); p.act_out = H16(d.off_dz[l]);
+        p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = WR(l); p.act_out = H16(d.off_dz[l]);
         __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
         p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
         if (l > 0) {   // outputs are da_{l-1}: accumulate layer l-1's backward statistics on the way out
@@ -1032,14 +1202,18 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         cudaStream_t wst = st;
         if (side) {
             cudaError_t e = cudaEventRecord(side->fork[l], st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork[l], 0);
+            wst = side->stream[l % side->n];
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(wst, side->fork[l], 0);
             if (e != cudaSuccess) return (int)e;
-            wst = side->stream;
         }
         WgradParams w{};
         w.dz = H16(d.off_dz[l]); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
         w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
         w.a = l == 0 ? H16(d.off_x0) : H16(d.off_a[l - 1]);
+        if (two_phase) {
+            w.partial = reinterpret_cast<float*>(ws + d.off_partial[l]);
+            w.tickets = reinterpret_cast<unsigned int*>(ws + d.off_tickets) + 16 * l;
+        }
         if (l == 0) rc = launch_wgrad<16, 64, 64>(w, wst);
         else if (l == L) rc = launch_wgrad<64, 16, 8>(w, wst);
         else rc = launch_wgrad<64, 64, 64>(w, wst);
@@ -1047,9 +1221,11 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         da = out;
     }
     if (side) {
-        cudaError_t e = cudaEventRecord(side->join, side->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
-        if (e != cudaSuccess) return (int)e;
+        for (int k = 0; k < side->n && k <= L; ++k) {
+            cudaError_t e = cudaEventRecord(side->join[k], side->stream[k]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join[k], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     BnGradParams q{};
     for (int l = 0; l <= L; ++l) {

@@ -10,6 +10,7 @@
 // p, m, v in and out: 6 x 4 MiB per table, HBM-bound, with the table choice made on the device from the
 // message vector (no host round trip, CUDA-graph capturable).
 #include "nsig_common.cuh"
+#include <cstdlib>
 
 namespace nsig {
 
@@ -35,7 +36,26 @@ struct AdamPtrs {  // device array layout: [3][n_tables] of pointers (param, exp
     uint32_t n_tables;
 };
 
-__device__ __forceinline__ float4 ld4_stream(const float* p) { return ld_stream4(reinterpret_cast<const float4*>(p)); }
+// Streaming accesses of the table Adam: no L1 allocation and EVICT-FIRST in L2, loads and stores alike.  The kernel moves
+// ~0.8 GB per step through a 126 MB L2; with the default policy it evicts everything else - the half2 shadow tables the field
+// forward gathers, the occupancy bitfield and rays of the march running beside it, and the instruction lines of every
+// kernel that starts while it runs (a 2 us kernel of the parallel branch then took 50-100 us to get going because each
+// instruction-cache miss went to a saturated HBM).
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld4_stream(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st4_stream(float* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, float w1, float beta2, float omb2,
                                           float step_size, float bc2_sqrt, float eps) {
@@ -53,10 +73,14 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
            const float* __restrict__ found_inf, float beta1, float beta2, float eps, uint32_t n_vec4,
            uint32_t vec4_begin) {
     if (found_inf && *found_inf != 0.0f) return;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_vec4) return;
+    // Grid-stride over a SMALL resident grid (a couple of CTAs per SM, chosen by the host): the kernel is HBM-bound and needs
+    // ~50 KB of loads in flight per SM, not the whole register file.  Launched as one CTA per 256 elements it parks 5 long-lived
+    // (~100 us) CTAs on every SM, and the kernels of the parallel graph branch (near/far, march) only get SM slots once its
+    // last wave has been dispatched - the two branches ran back to back instead of side by side (profiles/r02_timeline_step*).
+    const uint64_t pol = evict_first_policy();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += gridDim.x * blockDim.x) {
     const size_t off = (size_t)(vec4_begin + i) * 4;   // this rank's slice of every table (sharded optimizer) or 0
-    float4 g = ld4_stream(G + off);
+    float4 g = ld4_stream(G + off, pol);
     if (grad_scale) {
         const float inv = 1.0f / *grad_scale;  // GradScaler.unscale_: grad * (1/scale)
         g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
@@ -72,9 +96,9 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
         for (int u = 0; u < kAdamUnroll; ++u) {
             const uint32_t mi = min(m0 + u, md - 1);
             t[u] = 2 * mi + (((uint32_t)(int)__ldg(message + mi)) & 1u);
-            p[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(P + t[u])) + off);
-            m[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(M + t[u])) + off);
-            v[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(V + t[u])) + off);
+            p[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(P + t[u])) + off, pol);
+            m[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(M + t[u])) + off, pol);
+            v[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(V + t[u])) + off, pol);
         }
 #pragma unroll
         for (int u = 0; u < kAdamUnroll; ++u) {
@@ -84,10 +108,11 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
             adam_elem(p[u].y, m[u].y, v[u].y, g.y, w1, beta2, omb2, step_size, bc2_sqrt, eps);
             adam_elem(p[u].z, m[u].z, v[u].z, g.z, w1, beta2, omb2, step_size, bc2_sqrt, eps);
             adam_elem(p[u].w, m[u].w, v[u].w, g.w, w1, beta2, omb2, step_size, bc2_sqrt, eps);
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(P + t[u])) + off) = p[u];
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(M + t[u])) + off) = m[u];
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(V + t[u])) + off) = v[u];
+            st4_stream(reinterpret_cast<float*>(__ldg(P + t[u])) + off, p[u], pol);
+            st4_stream(reinterpret_cast<float*>(__ldg(M + t[u])) + off, m[u], pol);
+            st4_stream(reinterpret_cast<float*>(__ldg(V + t[u])) + off, v[u], pol);
         }
+    }
     }
 }
 
@@ -198,8 +223,10 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
     if ((elem_begin | elem_count) & 3u || elem_begin > total || elem_count > total - elem_begin) return NSIG_EINVAL;
     const uint32_t n_vec4 = elem_count / 4;
     AdamPtrs ptrs{ptr_table, n_tables};
-    k_msg_adam<<<div_up(n_vec4, 256), 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
-                                                    beta1, beta2, eps, n_vec4, elem_begin / 4);
+    static const uint32_t per_sm = [] { const char* e = getenv("NSIG_ADAM_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 4); }();
+    const uint32_t grid = min(div_up(n_vec4, 256u), 148u * per_sm);
+    k_msg_adam<<<grid, 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
+                                     beta1, beta2, eps, n_vec4, elem_begin / 4);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

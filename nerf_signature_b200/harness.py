@@ -184,6 +184,10 @@ class Scene:
         self.merged_render = merged_render  # one render call over [block rays | content rays] instead of two
         self.fused_decoder = fused_decoder and fp16  # the kernels implement the float16-autocast arithmetic
         self.fused_losses = fused_losses
+        if self.fused_decoder and self.fused and os.environ.get("NSIG_NO_DEC_PREP") != "1":
+            # fp16 weight copies of the decoder: converted behind every optimizer update (on its side stream) instead of at the
+            # head of every decoder forward, i.e. off the step's critical path
+            self.model.prepare_decoder_weights()
         self.overlap_decoder = overlap_decoder and not merged_render
         self.defer_optimizer = bool(defer_optimizer) and self.fused and use_fs   # needs the one-kernel scaler's skip flag
         if self.defer_optimizer:   # [message of the step whose update is pending (md) | pending flag (1)]

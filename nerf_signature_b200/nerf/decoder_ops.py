@@ -37,7 +37,7 @@ def decoder_params(decoder):
 
 class _fused_decode(Function):
     @staticmethod
-    def forward(ctx, image, meta, *params):
+    def forward(ctx, image, meta, prepared, *params):
         num_blocks, num_bits, redundancy = meta
         image = image.contiguous().float()
         B, H, W, _ = image.shape
@@ -46,7 +46,8 @@ class _fused_decode(Function):
         logits = torch.empty(B, num_bits, dtype=torch.float32, device=dev)
         flat = [p.detach().contiguous() for p in params]
         _lib.call("nsig_decoder_forward", _P(image), B, H, W, num_blocks, num_bits, redundancy, _lib.pointer_array(flat),
-                  _P(ws), _P(logits))
+                  _P(ws), _P(logits), _P(prepared))
+        ctx.prepared = prepared
         ctx.meta = (B, H, W, num_blocks, num_bits, redundancy)
         ctx.ws = ws
         ctx.params = params
@@ -84,20 +85,43 @@ class _fused_decode(Function):
         dimage = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if ctx.need_image else None
         _lib.call("nsig_decoder_backward", _P(dlogits.contiguous().float()), B, H, W, num_blocks, num_bits, redundancy,
                   _lib.pointer_array([p.detach().contiguous() for p in params]), _lib.pointer_array(grads), _P(ctx.ws),
-                  _P(dimage))
+                  _P(dimage), _P(ctx.prepared))
         for g, tmp in fixups:
             g.add_(tmp)
         ctx.ws = None
-        return (dimage, None) + (None,) * len(params)
+        return (dimage, None, None) + (None,) * len(params)
 
 
-def decode(decoder, image):
+class PreparedWeights:
+    """fp16 copies of a decoder's conv weights in the two layouts the kernels consume (nsig_decoder_prepare_weights), kept
+    in one persistent buffer so the conversion runs once per optimizer update instead of inside every forward.  The owner
+    must call `refresh()` after ANY change of the decoder's conv weights (optim.WatermarkAdam does after its flat-bucket
+    step; checkpoint loads and manual edits must do it themselves) - nothing here can detect a write through a raw pointer."""
+
+    def __init__(self, decoder):
+        ps = decoder_params(decoder)
+        if ps is None:
+            raise ValueError("decoder does not have the architecture the fused kernels cover")
+        self.decoder = decoder
+        self.num_blocks = len(ps) // 4 - 1
+        self.buffer = torch.empty(_lib.load().nsig_decoder_weights_bytes(self.num_blocks), dtype=torch.uint8, device=ps[0].device)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        ps = decoder_params(self.decoder)
+        _lib.call("nsig_decoder_prepare_weights", _lib.pointer_array([p.detach().contiguous() for p in ps]), self.num_blocks,
+                  self.decoder.num_bits, self.decoder.redundancy, _P(self.buffer))
+
+
+def decode(decoder, image, prepared=None):
     """logits [B, num_bits] of `image` [B,H,W,3] (fp32, in [0,1]); fused kernels when the decoder has the
-    reference architecture, the plain module (under autocast) otherwise."""
+    reference architecture, the plain module (under autocast) otherwise.  prepared: optional PreparedWeights of `decoder`."""
     ps = decoder_params(decoder) if image.is_cuda else None
     if ps is None:
         from .hidden_models import normalize_img
         with torch.autocast("cuda", dtype=torch.float16, enabled=image.is_cuda):
             return decoder(normalize_img(image.permute(0, 3, 1, 2)))
     num_blocks = len(ps) // 4 - 1
-    return _fused_decode.apply(image, (num_blocks, decoder.num_bits, decoder.redundancy), *ps)
+    return _fused_decode.apply(image, (num_blocks, decoder.num_bits, decoder.redundancy),
+                               prepared.buffer if prepared is not None else None, *ps)

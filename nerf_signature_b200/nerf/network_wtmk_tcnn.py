@@ -166,7 +166,22 @@ class NeRFNetwork(NeRFRenderer):
         """msg_decoder(normalization(image.permute(0, 3, 1, 2))) for rendered blocks `image` [B,H,W,3] in [0,1], with
         float16-autocast arithmetic (utils_wtmk_disen.py:592-595), through the fused decoder kernels."""
         from .decoder_ops import decode
-        return decode(self.msg_decoder, image)
+        return decode(self.msg_decoder, image, getattr(self, "_dec_prepared", None))
+
+    def prepare_decoder_weights(self, enable=True):
+        """Keep the decoder's fp16 weight copies in a persistent buffer (decoder_ops.PreparedWeights) instead of converting
+        them inside every decode_blocks call.  Whoever changes the conv weights afterwards must call
+        `refresh_decoder_weights()`; optim.WatermarkAdam does so after each of its steps."""
+        from .decoder_ops import PreparedWeights
+        self._dec_prepared = PreparedWeights(self.msg_decoder) if enable else None
+        if enable and not getattr(self, "_dec_prepared_hook", False):   # state-dict loads change the weights too
+            self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.refresh_decoder_weights())
+            self._dec_prepared_hook = True
+        return self._dec_prepared
+
+    def refresh_decoder_weights(self):
+        if getattr(self, "_dec_prepared", None) is not None:
+            self._dec_prepared.refresh()
 
     def get_params(self, lr):
         if self.finetune_decoder:

@@ -240,6 +240,11 @@ class WatermarkAdam(torch.optim.Optimizer):
         self._lr_host = [float("nan")] * len(self.param_groups)   # force a refresh of the device scalars
         self.sync_lr()
 
+    def _refresh_decoder(self):
+        fn = getattr(self._model, "refresh_decoder_weights", None)
+        if fn is not None:
+            fn()
+
     def zero_grad(self, set_to_none=True):
         if self.inner is not None:
             self.inner.zero_grad(set_to_none=set_to_none)
@@ -270,6 +275,7 @@ class WatermarkAdam(torch.optim.Optimizer):
                 _lib.call("nsig_flat_adam_step", _P(f["p"]), _P(f["g"]), _P(f["m"]), _P(f["v"]), f["p"].numel(),
                           _P(f["step"]), _P(grad_scale), _P(found_inf), float(group["lr"]), _P(f["lr_dev"]), float(b1),
                           float(b2), float(group["eps"]))
+                self._refresh_decoder()   # fp16 weight copies of the fused decoder, behind the update
         if self.inner is not None:
             self.inner.grad_scale, self.inner.found_inf = grad_scale, found_inf
             # the decoder's (tiny, latency-bound) Adam runs next to the HBM-bound message-table Adam
@@ -279,8 +285,10 @@ class WatermarkAdam(torch.optim.Optimizer):
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
                         self.inner.step()
+                        self._refresh_decoder()
                 else:
                     self.inner.step()
+                    self._refresh_decoder()
             finally:
                 del self.inner.grad_scale, self.inner.found_inf
         if self._train_tables:

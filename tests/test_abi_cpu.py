@@ -77,7 +77,10 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert h.nsig_composite_rays_train_blend_forward(p, p, p, p, 8, 8, 1e-4, 1.0, None, None, p, p, p, p, p, None) == -1
     assert h.nsig_composite_rays_train_blend_backward(None, None, p, p, p, p, p, p, 8, 8, 1e-4, 1.0, p, p, None) == -1
     assert h.nsig_decoder_workspace_bytes(32, 12, 12, 0) == 0 and h.nsig_decoder_workspace_bytes(32, 12, 12, 8) > 0
-    assert h.nsig_decoder_forward(p, 2, 4, 4, 8, 9, 1, tabs, p, p, None) == -1             # num_bits*redundancy > 8
+    assert h.nsig_decoder_forward(p, 2, 4, 4, 8, 9, 1, tabs, p, p, None, None) == -1       # num_bits*redundancy > 8
+    assert h.nsig_decoder_weights_bytes(0) == 0 and h.nsig_decoder_weights_bytes(8) > 2 * 7 * 64 * 9 * 64 * 2
+    assert h.nsig_decoder_prepare_weights(tabs, 8, 1, 1, None, None) == -1                  # no output buffer
+    assert h.nsig_decoder_prepare_weights(tabs, 0, 1, 1, p, None) == -1                     # no conv block
     # the fused field kernels stage the fp16 MLP weights with 16-byte copies: misaligned weight pointers are rejected
     buf = (ctypes.c_float * 64)()
     base = ctypes.addressof(buf)

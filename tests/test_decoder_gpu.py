@@ -91,3 +91,44 @@ def test_fused_decoder_accumulates_into_existing_grads_and_skips_frozen():
     img = image.clone().requires_grad_(True)
     decoder_ops.decode(dec, img).sum().backward()    # frozen decoder: only the image gradient
     assert img.grad is not None and all(p.grad is None for p in dec.parameters())
+
+
+def test_weight_gradients_are_deterministic_and_prepared_weights_change_nothing():
+    """(1) The weight-gradient reduction sums the per-CTA partials in a fixed order: two backward passes over the same inputs
+    give bit-identical parameter gradients.  (2) Handing the kernels fp16 weights converted ahead of time
+    (decoder_ops.PreparedWeights) is the same arithmetic as converting them inside the forward: bit-identical outputs and
+    gradients; after a weight update a refresh() is needed and sufficient."""
+    from nerf_signature_b200.nerf import decoder_ops
+    dec = _decoder(3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    image = torch.rand(32, 12, 12, 3, device="cuda", generator=g)
+    gout = torch.randn(32, 1, device="cuda", generator=g) * 64.0
+    o1, di1, gp1 = _run_fused(dec, image, gout)
+    o2, di2, gp2 = _run_fused(dec, image, gout)
+    assert torch.equal(o1, o2) and torch.equal(di1, di2)
+    for a, b in zip(gp1, gp2):
+        assert torch.equal(a, b)
+
+    def run_prepared(prep):
+        dec.zero_grad(set_to_none=True)
+        img = image.clone().requires_grad_(True)
+        out = decoder_ops.decode(dec, img, prep)
+        (out * gout).sum().backward()
+        return out.detach(), img.grad.detach(), [p.grad.detach().clone() for p in dec.parameters()]
+
+    prep = decoder_ops.PreparedWeights(dec)
+    o3, di3, gp3 = run_prepared(prep)
+    assert torch.equal(o1, o3) and torch.equal(di1, di3)
+    for a, b in zip(gp1, gp3):
+        assert torch.equal(a, b)
+    with torch.no_grad():
+        for p in dec.parameters():
+            p.add_(0.01 * torch.randn(p.shape, device="cuda", generator=g))
+    o4, di4, gp4 = _run_fused(dec, image, gout)          # converts the new weights itself
+    o_stale, _, _ = run_prepared(prep)                    # still the old conv weights
+    assert not torch.equal(o4, o_stale)
+    prep.refresh()
+    o5, di5, gp5 = run_prepared(prep)
+    assert torch.equal(o4, o5) and torch.equal(di4, di5)
+    for a, b in zip(gp4, gp5):
+        assert torch.equal(a, b)
