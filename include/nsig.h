@@ -458,12 +458,28 @@ int nsig_field_backward_tc_masks(const float* xyzs, uint32_t M, float bound, con
  *   time instead of `lr`, so a per-step scheduler (the reference's LambdaLR, scheduler_update_every_step)
  *   keeps acting on a step that is replayed from a CUDA graph.
  *   elem_begin / elem_count (floats, multiples of 4; count 0 = everything): the slice of every selected table (and of
- *   its moments) to update - ZeRO-style sharding of the optimizer over the ranks of a data-parallel job. */
+ *   its moments) to update - ZeRO-style sharding of the optimizer over the ranks of a data-parallel job.
+ *   steps_prepared: 1 when nsig_msg_adam_lookahead_sum was already called for THIS update (it advanced steps / coef);
+ *   0 otherwise. */
 int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
                        const float* message, const float* G, float* steps, float* coef,
                        const float* grad_scale, const float* found_inf, float lr, float beta1,
                        float beta2, float eps, uint32_t log2_T, const float* lr_dev,
-                       uint32_t elem_begin, uint32_t elem_count, nsig_stream_t stream);
+                       uint32_t elem_begin, uint32_t elem_count, uint32_t steps_prepared, nsig_stream_t stream);
+
+/* Look-ahead table sum for a software-pipelined optimizer: S [2^log2_T,2] = sum_i table[2i + next_i] with the values the
+ * tables WILL hold after the pending nsig_msg_adam_step(message = message_applied, same G / scalars / range) - computed
+ * from (param, exp_avg, exp_avg_sq, G) with the update's own arithmetic, nothing but S (and steps / coef) written.
+ * Bit-identical to running the update and then nsig_msg_table_sum(message_next).  The next step's field forward then
+ * depends on ~0.26 GB of reads instead of the update's ~0.8 GB of traffic, and the update itself (call nsig_msg_adam_step
+ * with steps_prepared = 1) may run any time before G is written again.  Replaces, for that schedule, the call pair
+ * hash_encoding_wtmk_bit.py:99-116 (per-bit table selection) after optimizer.step() (utils_wtmk_disen.py:1178). */
+int nsig_msg_adam_lookahead_sum(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
+                                const float* message_applied, const float* message_next, const float* G,
+                                float* steps, float* coef, const float* grad_scale, const float* found_inf,
+                                float lr, float beta1, float beta2, float eps, uint32_t log2_T,
+                                const float* lr_dev, uint32_t elem_begin, uint32_t elem_count, float* S,
+                                nsig_stream_t stream);
 
 /* torch.amp.GradScaler's per-step work (utils_wtmk_disen.py:1175-1181) over the flat gradient bucket in one launch:
  * non-finite check of flat[0..n) -> *found_inf (0/1); *step_scale = the scale this step's gradients carry (what the

@@ -71,7 +71,10 @@ _SIGNATURES = {
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
-    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp, _u32, _u32, _vp], 2),
+    "nsig_msg_adam_step": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp, _u32, _u32, _u32,
+                            _vp], lambda a: 1 if a[17] else 2),
+    "nsig_msg_adam_lookahead_sum": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp,
+                                     _u32, _u32, _vp, _vp], 2),
     "nsig_grad_check_update_scale": ([_vp, _u32, _vp, _vp, _f32, _f32, _c.c_int32, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_flat_adam_step": ([_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _f32, _vp, _f32, _f32, _f32, _vp], 1),
     "nsig_field_backward_tc": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),

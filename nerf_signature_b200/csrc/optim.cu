@@ -57,12 +57,14 @@ __device__ __forceinline__ void st4_stream(float* p, const float4& v, uint64_t p
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
+// One rounded operation per line, spelled with intrinsics: the update kernel and the look-ahead sum must produce the SAME
+// bits, and left to itself the compiler contracts `beta2*v + omb2*g*g` into different FMAs in the two kernels.
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, float w1, float beta2, float omb2,
                                           float step_size, float bc2_sqrt, float eps) {
-    m = m + w1 * (g - m);                       // lerp(exp_avg, grad, 1 - beta1)
-    v = beta2 * v + omb2 * g * g;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - step_size * (m / denom);
+    m = __fmaf_rn(w1, __fsub_rn(g, m), m);                                  // lerp(exp_avg, grad, 1 - beta1)
+    v = __fmaf_rn(__fmul_rn(omb2, g), g, __fmul_rn(beta2, v));              // beta2 * v + (1 - beta2) * g * g
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+    p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);
 }
 
 constexpr int kAdamUnroll = 4;
@@ -113,6 +115,67 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
             st4_stream(reinterpret_cast<float*>(__ldg(V + t[u])) + off, v[u], pol);
         }
     }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Look-ahead table sum: S = sum_i table[2i + next_i] AS IT WILL BE once k_msg_adam has applied the pending update (the one
+// selected by `applied`), without writing anything but S.  A table that the pending update touches AND the next message
+// selects (next_i == applied_i) contributes p_new computed from (p, m, v, G) with the very same adam_elem; any other table
+// contributes its current p.  The accumulation order is k_msg_table_sum's (bit 0 first), so S is bit-identical to running
+// the update and then the table sum - but the field forward of the next step no longer has to wait for the 0.8 GB of
+// Adam traffic, which can then run anywhere before the next backward touches G (harness: next to the decoder).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_msg_sum_ahead(AdamPtrs ptrs, uint32_t md, const float* __restrict__ applied, const float* __restrict__ next,
+                const float* __restrict__ G, const float* __restrict__ coef, const float* __restrict__ grad_scale,
+                const float* __restrict__ found_inf, float beta1, float beta2, float eps, uint32_t n_vec4,
+                uint32_t vec4_begin, float* __restrict__ S) {
+    const bool skip = found_inf && *found_inf != 0.0f;   // the pending update will be skipped: sum the tables as they are
+    const uint64_t pol = evict_first_policy();
+    const float w1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    const uint64_t* P = ptrs.table;
+    const uint64_t* M = ptrs.table + ptrs.n_tables;
+    const uint64_t* V = ptrs.table + 2 * ptrs.n_tables;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += gridDim.x * blockDim.x) {
+        const size_t off = (size_t)(vec4_begin + i) * 4;
+        float4 g = ld4_stream(G + off, pol);
+        if (grad_scale) {
+            const float inv = 1.0f / *grad_scale;
+            g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t m0 = 0; m0 < md; m0 += kAdamUnroll) {
+            float4 p[kAdamUnroll], m[kAdamUnroll], v[kAdamUnroll];
+            uint32_t t[kAdamUnroll];
+            bool upd[kAdamUnroll];
+#pragma unroll
+            for (int u = 0; u < kAdamUnroll; ++u) {
+                const uint32_t mi = min(m0 + u, md - 1);
+                const uint32_t bn = ((uint32_t)(int)__ldg(next + mi)) & 1u, ba = ((uint32_t)(int)__ldg(applied + mi)) & 1u;
+                t[u] = 2 * mi + bn;
+                upd[u] = !skip && bn == ba;       // uniform over the grid
+                p[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(P + t[u])) + off, pol);
+                if (upd[u]) {
+                    m[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(M + t[u])) + off, pol);
+                    v[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(V + t[u])) + off, pol);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kAdamUnroll; ++u) {
+                if (m0 + u >= md) break;
+                if (upd[u]) {
+                    const float step_size = __ldg(coef + 2 * t[u]), bc2_sqrt = __ldg(coef + 2 * t[u] + 1);
+                    adam_elem(p[u].x, m[u].x, v[u].x, g.x, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].y, m[u].y, v[u].y, g.y, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].z, m[u].z, v[u].z, g.z, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].w, m[u].w, v[u].w, g.w, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                }
+                acc.x += p[u].x; acc.y += p[u].y; acc.z += p[u].z; acc.w += p[u].w;
+            }
+        }
+        *reinterpret_cast<float4*>(S + off) = acc;
     }
 }
 
@@ -206,27 +269,64 @@ k_flat_adam(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 using namespace nsig;
 
+namespace {
+uint32_t adam_ctas_per_sm() {
+    static const uint32_t per_sm = [] { const char* e = getenv("NSIG_ADAM_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 4); }();
+    return per_sm;
+}
+int adam_range(uint32_t log2_T, uint32_t& elem_begin, uint32_t& elem_count) {
+    const uint32_t total = 2u << log2_T;         // T entries x 2 floats
+    if (elem_count == 0) { elem_begin = 0; elem_count = total; }
+    if ((elem_begin | elem_count) & 3u || elem_begin > total || elem_count > total - elem_begin) return NSIG_EINVAL;
+    return 0;
+}
+}  // namespace
+
 extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
                                   const float* message, const float* G, float* steps, float* coef,
                                   const float* grad_scale, const float* found_inf, float lr, float beta1,
                                   float beta2, float eps, uint32_t log2_T, const float* lr_dev,
-                                  uint32_t elem_begin, uint32_t elem_count, nsig_stream_t stream) {
+                                  uint32_t elem_begin, uint32_t elem_count, uint32_t steps_prepared,
+                                  nsig_stream_t stream) {
     if (!ptr_table || !message || !G || !steps || !coef) return NSIG_EINVAL;
     if (message_dim == 0 || 2 * message_dim > n_tables || n_tables > NSIG_MAX_MSG_TABLES) return NSIG_EINVAL;
     if (log2_T < 1 || log2_T > 30 || (((uintptr_t)G) & 15)) return NSIG_EINVAL;
+    if (adam_range(log2_T, elem_begin, elem_count)) return NSIG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message, steps, coef, found_inf,
-                                                                 (double)lr, lr_dev, (double)beta1, (double)beta2);
-    NSIG_LAUNCH_CHECK();
-    const uint32_t total = 2u << log2_T;         // T entries x 2 floats
-    if (elem_count == 0) { elem_begin = 0; elem_count = total; }
-    if ((elem_begin | elem_count) & 3u || elem_begin > total || elem_count > total - elem_begin) return NSIG_EINVAL;
+    if (!steps_prepared) {   // (a preceding nsig_msg_adam_lookahead_sum for this update already advanced steps / coef)
+        k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message, steps, coef, found_inf,
+                                                                     (double)lr, lr_dev, (double)beta1, (double)beta2);
+        NSIG_LAUNCH_CHECK();
+    }
     const uint32_t n_vec4 = elem_count / 4;
     AdamPtrs ptrs{ptr_table, n_tables};
-    static const uint32_t per_sm = [] { const char* e = getenv("NSIG_ADAM_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 4); }();
-    const uint32_t grid = min(div_up(n_vec4, 256u), 148u * per_sm);
+    const uint32_t grid = min(div_up(n_vec4, 256u), 148u * adam_ctas_per_sm());
     k_msg_adam<<<grid, 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
                                      beta1, beta2, eps, n_vec4, elem_begin / 4);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsig_msg_adam_lookahead_sum(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
+                                           const float* message_applied, const float* message_next, const float* G,
+                                           float* steps, float* coef, const float* grad_scale, const float* found_inf,
+                                           float lr, float beta1, float beta2, float eps, uint32_t log2_T,
+                                           const float* lr_dev, uint32_t elem_begin, uint32_t elem_count, float* S,
+                                           nsig_stream_t stream) {
+    if (!ptr_table || !message_applied || !message_next || !G || !steps || !coef || !S) return NSIG_EINVAL;
+    if (message_dim == 0 || 2 * message_dim > n_tables || n_tables > NSIG_MAX_MSG_TABLES) return NSIG_EINVAL;
+    if (log2_T < 1 || log2_T > 30 || (((uintptr_t)G) & 15) || (((uintptr_t)S) & 15)) return NSIG_EINVAL;
+    if (adam_range(log2_T, elem_begin, elem_count)) return NSIG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message_applied, steps, coef, found_inf,
+                                                                 (double)lr, lr_dev, (double)beta1, (double)beta2);
+    NSIG_LAUNCH_CHECK();
+    const uint32_t n_vec4 = elem_count / 4;
+    AdamPtrs ptrs{ptr_table, n_tables};
+    static const uint32_t per_sm = [] { const char* e = getenv("NSIG_SUM_AHEAD_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : 2); }();
+    const uint32_t grid = min(div_up(n_vec4, 256u), 148u * per_sm);
+    k_msg_sum_ahead<<<grid, 256, 0, st>>>(ptrs, message_dim, message_applied, message_next, G, coef, grad_scale, found_inf,
+                                          beta1, beta2, eps, n_vec4, elem_begin / 4, S);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

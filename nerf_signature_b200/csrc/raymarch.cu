@@ -15,6 +15,7 @@
 // and FMA contraction the reference build produces (nvcc default -fmad=true, IEEE div), so the
 // compiler cannot re-associate or re-contract it.
 #include "march_common.cuh"
+#include <cstdlib>
 
 namespace nsig {
 
@@ -203,6 +204,118 @@ k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d
     const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
     warp_march<true>(r, c, grid, t0, fars[n], num_steps, xyzs + (size_t)off * 3,
                      dirs + (size_t)off * 3, deltas + (size_t)off * 2, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-launch march: count -> offsets -> write in ONE kernel.  A CTA (8 rays) counts its rays, publishes the CTA total,
+// obtains its exclusive prefix over all earlier CTAs by decoupled look-back (aggregate / inclusive-prefix words, one warp
+// looking back 32 CTAs at a time) and marches its rays again to write them - the second walk re-reads occupancy bytes the
+// first one just pulled into L1.  Offsets are the same exclusive scan in ray order as k_march_scan computes, so rays /
+// xyzs / dirs / deltas / counter are bit-identical to the three-kernel path; what goes away is the single-CTA scan kernel
+// and two kernel boundaries in a chain that sits on the step's critical path.  CTA ids are drawn from a ticket so that a
+// CTA only ever waits for CTAs that started before it.
+// state: uint64[n_blocks] (flag << 32 | value; flag 1 = CTA total, 2 = inclusive prefix), ticket: uint32 - zeroed by the host.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMarchWarps * 32)
+k_march_fused(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+              const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+              unsigned long long* __restrict__ state, uint32_t* __restrict__ ticket, float* __restrict__ xyzs,
+              float* __restrict__ dirs, float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter) {
+    __shared__ uint32_t s_vb, s_cnt[kMarchWarps], s_excl;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_vb = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t vb = s_vb, n_blocks = gridDim.x;
+    const uint32_t n = vb * kMarchWarps + wid;
+    const bool live = n < N;
+    const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
+    RayConst r{};
+    float t0 = 0.f, far = 0.f;
+    uint32_t cnt = 0;
+    if (live) {
+        r = load_ray(rays_o, rays_d, n);
+        t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
+        far = fars[n];
+        cnt = warp_march<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr, lane);
+    }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kMarchWarps; ++w) total += s_cnt[w];
+        uint32_t excl = 0;
+        if (vb == 0) {
+            excl = (uint32_t)counter[0];                      // the reference's running sample counter (normally 0)
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state, (2ull << 32) | (unsigned long long)(excl + total));
+            }
+        } else {
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state + vb, (1ull << 32) | (unsigned long long)total);
+            }
+            // look back: lanes inspect CTAs vb-1-lane of the current window; stop at the first inclusive prefix
+            int base = (int)vb - 1;
+            while (true) {
+                const int idx = base - lane;
+                unsigned long long w = idx >= 0 ? *((volatile unsigned long long*)(state + idx)) : (2ull << 32);
+                const uint32_t flag = (uint32_t)(w >> 32);
+                const uint32_t ready = __ballot_sync(NSIG_FULL_MASK, flag != 0u);
+                const uint32_t pref = __ballot_sync(NSIG_FULL_MASK, flag == 2u);
+                // usable lanes: the contiguous run of published entries from lane 0 up to (and including) the first prefix
+                const uint32_t first_gap = ~ready ? (uint32_t)__ffs(~ready) - 1u : 32u;
+                const uint32_t first_pref = pref ? (uint32_t)__ffs(pref) - 1u : 32u;
+                if (first_pref < first_gap) {                 // a prefix is reachable through published aggregates
+                    uint32_t v = (uint32_t)lane <= first_pref ? (uint32_t)w : 0u;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(NSIG_FULL_MASK, v, d);
+                    excl += v;
+                    break;
+                }
+                if (first_gap == 32u) {                       // 32 aggregates, no prefix yet: take them and move on
+                    uint32_t v = (uint32_t)w;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(NSIG_FULL_MASK, v, d);
+                    excl += v;
+                    base -= 32;
+                }
+                // else: an earlier CTA has not published yet - poll the same window again
+            }
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state + vb, (2ull << 32) | (unsigned long long)(excl + total));
+            }
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (vb == n_blocks - 1) {                          // the reference's atomics: counter[0] += samples, counter[1] += N
+                counter[0] = (int)(excl + total);
+                counter[1] += (int)N;
+            }
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    uint32_t off = s_excl;
+    for (int w = 0; w < wid; ++w) off += s_cnt[w];
+    if (lane == 0) {
+        rays[n * 3] = (int)n;
+        rays[n * 3 + 1] = (int)off;
+        rays[n * 3 + 2] = (int)cnt;
+    }
+    if (cnt == 0) return;
+    if (off + cnt > M) {   // reservation overflow: see k_march_write
+        for (uint32_t i = off + lane; i < M; i += 32) {
+            xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
+            dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
+            deltas[(size_t)i * 2] = deltas[(size_t)i * 2 + 1] = 0.f;
+        }
+        return;
+    }
+    warp_march<true>(r, c, grid, t0, far, cnt, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2, lane);
 }
 
 // zero rows [counter[0], end) with end = min(align_up(counter[0]), M), or M when align == 0
@@ -513,6 +626,24 @@ int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
     uint32_t* counts = (uint32_t*)scratch;
     uint32_t* offsets = counts + N;
     const uint32_t blocks = div_up(N, kMarchWarps);
+    // Measured (round 2, call Q): inside the training step the single-launch kernel is SLOWER than the three-kernel chain
+    // (1.000 vs 0.967 ms per step; the march branch takes ~220 us either way next to the HBM-bound table Adam, and CTAs that
+    // spin in the look-back keep SM slots the Adam and the remaining rays are waiting for), so it is opt-in: NSIG_MARCH_FUSED=1.
+    static const bool fused = [] { const char* e = getenv("NSIG_MARCH_FUSED"); return e && e[0] == '1'; }();
+    if (fused) {
+        // scratch (2N words) as [ticket | pad | look-back state: one 64-bit word per CTA]
+        const size_t state_bytes = 16 + (size_t)blocks * sizeof(unsigned long long);
+        if (state_bytes <= (size_t)N * 2 * sizeof(uint32_t) && (((uintptr_t)scratch) & 7) == 0) {
+            cudaError_t e = cudaMemsetAsync(scratch, 0, state_bytes, st);
+            if (e != cudaSuccess) return (int)e;
+            k_march_fused<<<blocks, kMarchWarps * 32, 0, st>>>(
+                rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises,
+                reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(scratch) + 16), counts, xyzs, dirs,
+                deltas, rays, counter);
+            NSIG_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     k_march_count<<<blocks, kMarchWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
                                                        C, H, nears, fars, noises, counts);
     NSIG_LAUNCH_CHECK();

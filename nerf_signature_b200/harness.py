@@ -98,12 +98,28 @@ def occupancy(cfg, cascade, seed=0):
     return syn.bernoulli_grid(cascade, p=0.5, seed=seed)
 
 
+class _join_on_backward(torch.autograd.Function):
+    """Identity whose backward makes the current stream wait for `stream` first: placed on the rendered block pixels, the
+    wait lands between the decoder's backward and the composite / field backward."""
+
+    @staticmethod
+    def forward(ctx, x, stream):
+        ctx.stream = stream
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        torch.cuda.current_stream().wait_stream(ctx.stream)
+        return g, None
+
+
 class Scene:
     """Model + optimizer + GradScaler as main_nerf_wtmk.py:92-117 sets them up."""
 
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
                  merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
-                 shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False, shard_optimizer=None):
+                 shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False, shard_optimizer=None,
+                 lookahead=None):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -190,6 +206,13 @@ class Scene:
             self.model.prepare_decoder_weights()
         self.overlap_decoder = overlap_decoder and not merged_render
         self.defer_optimizer = bool(defer_optimizer) and self.fused and use_fs   # needs the one-kernel scaler's skip flag
+        # look-ahead schedule of the deferred optimizer (see _step_impl).  Opt-in (lookahead=True or NSIG_LOOKAHEAD=1): measured
+        # SLOWER than the plain deferred order (1.02 vs 0.97 ms) - the field forward does start 80 us earlier, but the table
+        # Adam saturates HBM and every latency-bound kernel that runs beside it crawls (the decoder forward took 238-285 us
+        # instead of 113, finishing ~90 us after the Adam whatever its grid) - profiles/r02_experiments.txt
+        if lookahead is None:
+            lookahead = os.environ.get("NSIG_LOOKAHEAD") == "1"
+        self.lookahead = self.defer_optimizer and bool(lookahead) and merged_render
         if self.defer_optimizer:   # [message of the step whose update is pending (md) | pending flag (1)]
             self._opt_state = torch.zeros(cfg["message_dim"] + 1, dtype=torch.float32, device=device)
         self.iteration = 0
@@ -238,8 +261,21 @@ class Scene:
                 side.wait_stream(main)
             with torch.cuda.stream(side if side is not None else main):
                 self.optimizer.set_message(self._opt_state[:md])
-                self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
-                self.sync.zero_flat()
+                if self.lookahead:
+                    # look-ahead schedule: only what the field forward needs happens here - the scaler's check, the
+                    # decoder's Adam (+ its fp16 weights) and S as the tables WILL be after the pending update, read-only
+                    # (~0.26 GB instead of the update's ~0.8 GB); the table update itself is issued after the composite
+                    # forward, next to the latency-bound decoder chain, and joined before the field backward writes G
+                    self.scaler.check(self.optimizer, enabled=self._opt_state[md:])
+                    self.optimizer.step_decoder()
+                    ds = self.optimizer._decoder_side
+                    if ds is not None:
+                        torch.cuda.current_stream().wait_stream(ds)
+                    self.sync.zero_decoder_grads()
+                    self.optimizer.lookahead_sum(msg_dev)
+                else:
+                    self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
+                    self.sync.zero_flat()
             if side is not None:
                 self._opt_side = side
             message = msg_dev
@@ -278,6 +314,19 @@ class Scene:
                 pred = split_clamp(image_w, nb)[0]
         if not self.fused_losses:
             pred = torch.clamp(image_w, min=0, max=1)
+        if self.defer_optimizer and self.lookahead:
+            # the pending table update (reads G and the tables, writes the tables) + the clear of G: a branch that starts
+            # here, after the field forward (which holds every SM) and ends before the field backward writes G
+            tail = _lib.side_stream(self.device, 3)
+            main = torch.cuda.current_stream()
+            if tail is not None:
+                tail.wait_stream(main)
+            with torch.cuda.stream(tail if tail is not None else main):
+                self.optimizer.step_tables()
+                self.sync.zero_table_grad()
+                self.scaler.release(self.optimizer)
+            if tail is not None:
+                pred = _join_on_backward.apply(pred, tail)
         if gather is not None:
             pred = gather(pred)
         pred = pred.reshape(block_shape)
@@ -331,6 +380,7 @@ class Scene:
             self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
             self._opt_state[md:].zero_()
         self.model._S_cache = None
+        self.model.msg_encoder.presummed = None
 
     def _capture(self, batch, message):
         """Warm up on a side stream, then record one step into a CUDA graph with static input buffers."""

@@ -64,19 +64,23 @@ class _msg_table_sum_sink(Function):
     the message — the whole training step can be captured in a CUDA graph."""
 
     @staticmethod
-    def forward(ctx, message, log2_T, sink, shard, *tables):
+    def forward(ctx, message, log2_T, sink, shard, pre, *tables):
         md = len(tables) // 2
         msg = message.to(device=tables[0].device, dtype=torch.float32).contiguous()
-        S = torch.empty_like(tables[0])
+        # pre: S already computed for exactly this message by the optimizer's look-ahead (optim.WatermarkAdam.lookahead_sum;
+        # with a sharded optimizer only this rank's slice of it): no kernel here
+        S = pre.view_as(pre) if pre is not None else torch.empty_like(tables[0])
         tabs = [t.contiguous() for t in tables]
         if shard is None:
-            _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), 0, 0)
+            if pre is None:
+                _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), 0, 0)
         else:
             # sharded optimizer state (optim.WatermarkAdam(shard=...)): this rank holds the up-to-date values of its own
             # slice of every table only, so it sums that slice and the slices of S are all-gathered (4 MiB in total)
             import torch.distributed as dist
             lo, n, group = shard
-            _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), lo, n)
+            if pre is None:
+                _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, _P(msg), log2_T, _P(S), lo, n)
             flat = S.view(-1)
             dist.all_gather_into_tensor(flat, flat[lo:lo + n].clone(), group=group)
         ctx.sink = sink
@@ -92,7 +96,7 @@ class _msg_table_sum_sink(Function):
             if grad_reducer is not None:
                 grad_S = grad_reducer(grad_S)
             ctx.sink.add_(grad_S)
-        return (None, None, None, None) + (None,) * ctx.n
+        return (None, None, None, None, None) + (None,) * ctx.n
 
 
 class HashEmbedder(nn.Module):
@@ -127,6 +131,8 @@ class HashEmbedder(nn.Module):
         self.grad_sink = None
         # set by optim.WatermarkAdam(shard=...): (first float, float count, process group) of the table slice this rank owns
         self.shard = None
+        # set by optim.WatermarkAdam.lookahead_sum: (message tensor, S) - consumed by the next summed_table(message) call
+        self.presummed = None
 
     def tables(self):
         return [e.weight for e in self.embeddings[:2 * self.message_dim]]
@@ -138,7 +144,12 @@ class HashEmbedder(nn.Module):
             # also for evaluation and the occupancy update - a collective every rank must enter)
             if message.shape[0] != self.message_dim:
                 raise ValueError(f"message has {message.shape[0]} bits, encoder was built for {self.message_dim}")
-            return _msg_table_sum_sink.apply(message, self.log2_hashmap_size, self.grad_sink, self.shard, *self.tables())
+            pre = None
+            if self.presummed is not None:
+                if self.presummed[0] is message:
+                    pre = self.presummed[1]
+                self.presummed = None      # one use; a different message means the look-ahead does not apply
+            return _msg_table_sum_sink.apply(message, self.log2_hashmap_size, self.grad_sink, self.shard, pre, *self.tables())
         if bits is None:
             bits = message_bits(message)
         if len(bits) != self.message_dim:

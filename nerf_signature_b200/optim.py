@@ -258,6 +258,14 @@ class WatermarkAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("closures are not supported")
+        self.step_decoder()
+        self.step_tables()
+        return None
+
+    @torch.no_grad()
+    def step_decoder(self):
+        """The decoder's share of step(): Adam over the flat parameter vector (or torch's fused Adam over the decoder's
+        tensors), on a side stream that is joined before returning, then the refresh of the fused decoder's fp16 weights."""
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
         side = None
@@ -291,24 +299,62 @@ class WatermarkAdam(torch.optim.Optimizer):
                     self._refresh_decoder()
             finally:
                 del self.inner.grad_scale, self.inner.found_inf
+        self._decoder_side = side
+
+    def _table_call_args(self):
+        if self.message is None:
+            raise RuntimeError("WatermarkAdam.set_message(message) must be called before step()")
+        if tuple(t.data_ptr() for t in self.tables) != self._ptr_key:
+            raise RuntimeError("message tables were re-allocated after the optimizer was built")
+        group = self.param_groups[-1]
+        beta1, beta2 = group["betas"]
+        return group, float(beta1), float(beta2)
+
+    @torch.no_grad()
+    def lookahead_sum(self, next_message):
+        """S = sum_i table[2i + next_message_i] with the values the tables WILL hold after the pending step_tables() (for the
+        message given to set_message), computed without touching the tables (nsig_msg_adam_lookahead_sum), and handed to the
+        encoder as the pre-summed table of `next_message`.  Must be followed by exactly one step_tables() before anything
+        else writes G; grad_scale / found_inf are read from the attributes a scaler's check() left on this optimizer."""
+        if not self._train_tables:
+            return None
+        group, beta1, beta2 = self._table_call_args()
+        self.sync_lr()
+        md = self.enc.message_dim
+        if getattr(self, "_S_ahead", None) is None:
+            self._S_ahead = torch.empty_like(self.tables[0])
+        nxt = next_message.to(device=self.G.device, dtype=torch.float32)
+        _lib.call("nsig_msg_adam_lookahead_sum", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(nxt), _P(self.G),
+                  _P(self.steps), _P(self._coef), _P(getattr(self, "grad_scale", None)), _P(getattr(self, "found_inf", None)),
+                  float(group["lr"]), beta1, beta2, float(group["eps"]), self.enc.log2_hashmap_size, _P(self._lr_dev),
+                  self.shard[0] if self.shard else 0, self.shard[1] if self.shard else 0, _P(self._S_ahead))
+        self._steps_prepared = True
+        self.enc.presummed = (next_message, self._S_ahead)
+        self._model._S_cache = None
+        return self._S_ahead
+
+    @torch.no_grad()
+    def step_tables(self):
+        """The message tables' share of step(): one Adam kernel over the tables the message selects; joins the decoder's
+        side stream (step_decoder) into the current stream."""
         if self._train_tables:
-            if self.message is None:
-                raise RuntimeError("WatermarkAdam.set_message(message) must be called before step()")
-            if tuple(t.data_ptr() for t in self.tables) != self._ptr_key:
-                raise RuntimeError("message tables were re-allocated after the optimizer was built")
-            group = self.param_groups[-1]
-            beta1, beta2 = group["betas"]
+            group, beta1, beta2 = self._table_call_args()
             md = self.enc.message_dim
+            prepared = 1 if getattr(self, "_steps_prepared", False) else 0
+            self._steps_prepared = False
             _lib.call("nsig_msg_adam_step", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(self.G),
-                      _P(self.steps), _P(self._coef), _P(grad_scale), _P(found_inf), float(group["lr"]), float(beta1),
-                      float(beta2), float(group["eps"]), self.enc.log2_hashmap_size, _P(self._lr_dev),
-                      self.shard[0] if self.shard else 0, self.shard[1] if self.shard else 0)
+                      _P(self.steps), _P(self._coef), _P(getattr(self, "grad_scale", None)),
+                      _P(getattr(self, "found_inf", None)), float(group["lr"]), beta1, beta2, float(group["eps"]),
+                      self.enc.log2_hashmap_size, _P(self._lr_dev), self.shard[0] if self.shard else 0,
+                      self.shard[1] if self.shard else 0, prepared)
             # the kernel writes the tables through raw pointers (no autograd version bump): drop the model's
             # cached S so the next forward re-sums the updated tables
-            self._model._S_cache = None
+            if not prepared:
+                self._model._S_cache = None
+        side = getattr(self, "_decoder_side", None)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
-        return None
+            self._decoder_side = None
 
 
 class _ScaledLoss:
@@ -343,9 +389,11 @@ class FusedGradScaler:
     def scale(self, loss):
         return _ScaledLoss(loss, self._scale)
 
-    def step(self, optimizer, enabled=None):
-        """enabled: optional device word (any 4-byte dtype); 0 = nothing pending, skip the step and leave the scaler alone
-        (harness deferred-optimizer mode)."""
+    def check(self, optimizer, enabled=None):
+        """The per-step kernel alone (non-finite check, found_inf, the scale this step's gradients carry, scale update) and
+        the hand-over of `grad_scale` / `found_inf` to the optimizer as attributes; the caller then runs the optimizer's
+        pieces itself (harness look-ahead schedule: step_decoder, lookahead_sum, step_tables) and calls release().
+        enabled: optional device word (any 4-byte dtype); 0 = nothing pending, skip the step and leave the scaler alone."""
         if getattr(optimizer, "flat_bucket", None) is None:
             raise _lib.NsigError("FusedGradScaler needs an optimizer built over a flat gradient bucket "
                                  "(WatermarkAdam(flat_bucket=...)); use torch.amp.GradScaler otherwise")
@@ -358,10 +406,20 @@ class FusedGradScaler:
                   _P(self._step_scale), _P(f["step"]) if f is not None else None, _P(self._scratch), _P(enabled))
         # 0-dim views: torch's fused Adam (the non-flat decoder path) broadcasts found_inf against its 0-dim step tensors
         optimizer.grad_scale, optimizer.found_inf = self._step_scale.reshape(()), self._found_inf.reshape(())
+
+    @staticmethod
+    def release(optimizer):
+        for a in ("grad_scale", "found_inf"):
+            if hasattr(optimizer, a):
+                delattr(optimizer, a)
+
+    def step(self, optimizer, enabled=None):
+        """check() + optimizer.step().  enabled: see check()."""
+        self.check(optimizer, enabled)
         try:
             return optimizer.step()
         finally:
-            del optimizer.grad_scale, optimizer.found_inf
+            self.release(optimizer)
 
     def update(self, new_scale=None):
         if new_scale is not None:

@@ -116,6 +116,12 @@ class GradSync:
     def zero_flat(self):
         self.flat.zero_()  # one fill: dL/dS (scatter-added by the field backward) and the decoder gradients both accumulate
 
+    def zero_decoder_grads(self):
+        self.flat[self.table_numel:].zero_()
+
+    def zero_table_grad(self):
+        self.flat[:self.table_numel].zero_()
+
     def reduce_flat(self):
         if not self.enabled or os.environ.get("NSIG_DIAG_SKIP_REDUCE") == "1":  # diagnosis only: wrong gradients
             return

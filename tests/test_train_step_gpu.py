@@ -314,16 +314,18 @@ def test_lr_schedule_acts_on_graph_replays():
     del sched
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_deferred_optimizer_equals_sequential_optimizer(graph):
+@pytest.mark.parametrize("graph,lookahead", [(False, True), (True, True), (True, False)])
+def test_deferred_optimizer_equals_sequential_optimizer(graph, lookahead):
     """harness defer_optimizer: the Adam update of step t issued at the start of step t+1 (next to its march) leaves, after
     flush_optimizer(), the same tables, decoder and scaler state as the sequential schedule, step for step; a flush in the
     middle (what update_extra_state needs) does not apply an update twice.  The scatter-add order of dL/dS is not
     deterministic and Adam's update is sign-like for near-zero gradients (see _close_frac), so the yardstick is the
-    run-to-run difference of two IDENTICAL sequential scenes."""
+    run-to-run difference of two IDENTICAL sequential scenes.
+    lookahead (default): S for the next step comes from nsig_msg_adam_lookahead_sum and the table update itself runs next to
+    the decoder (between the composite forward and the field backward)."""
     kw = dict(optimizer="fused", merged_render=True, fused_decoder=True, fused_losses=True, graph=graph)
-    a, a2, b = _scene(**kw), _scene(**kw), _scene(defer_optimizer=True, **kw)
-    assert b.defer_optimizer
+    a, a2, b = _scene(**kw), _scene(**kw), _scene(defer_optimizer=True, lookahead=lookahead, **kw)
+    assert b.defer_optimizer and b.lookahead == lookahead
     batches = _batches(a, 2)
     gen = torch.Generator().manual_seed(21)
     msgs = [a.new_message(gen) for _ in range(7)]
@@ -352,3 +354,59 @@ def test_deferred_optimizer_equals_sequential_optimizer(graph):
     assert worst <= max(1e-3, 3.0 * floor), (worst, floor)
     np.testing.assert_allclose(b.optimizer.steps.cpu().numpy(), a.optimizer.steps.cpu().numpy())
     assert a.scaler.get_scale() == b.scaler.get_scale()
+
+
+@pytest.mark.parametrize("skip,shard", [(False, False), (True, False), (False, True)])
+def test_lookahead_sum_is_bit_identical_to_update_then_sum(skip, shard):
+    """nsig_msg_adam_lookahead_sum(applied, next) == nsig_msg_adam_step(applied) followed by nsig_msg_table_sum(next), bit for
+    bit (same adam_elem, same accumulation order), without having touched tables or moments; the update that follows with
+    steps_prepared=1 leaves exactly what a stand-alone nsig_msg_adam_step leaves (steps, tables, moments).  Also with a
+    skipped step (found_inf = 1) and on a slice of the tables (sharded optimizer)."""
+    from nerf_signature_b200 import _lib
+    P = _lib.ptr
+    dev = torch.device("cuda:0")
+    md, log2_T = 6, 12
+    n = 2 << log2_T
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    def state():
+        gg = torch.Generator(device="cuda").manual_seed(11)
+        tabs = [torch.randn(n, device=dev, generator=gg) * 1e-2 for _ in range(2 * md)]
+        ms = [torch.randn(n, device=dev, generator=gg) * 1e-3 for _ in range(2 * md)]
+        vs = [torch.rand(n, device=dev, generator=gg) * 1e-6 for _ in range(2 * md)]
+        ptrs = torch.tensor([[t.data_ptr() for t in grp] for grp in (tabs, ms, vs)], dtype=torch.int64, device=dev)
+        steps = torch.arange(2 * md, dtype=torch.float32, device=dev) + 3.0
+        coef = torch.zeros(2 * md, 2, dtype=torch.float32, device=dev)
+        return tabs, ms, vs, ptrs, steps, coef
+
+    G = torch.randn(n, device=dev, generator=g) * 65536.0 * 1e-3
+    G[torch.rand(n, device=dev, generator=g) < 0.5] = 0.0
+    applied = torch.tensor([1, 0, 1, 1, 0, 0], dtype=torch.float32, device=dev)
+    nxt = torch.tensor([1, 1, 0, 1, 0, 1], dtype=torch.float32, device=dev)
+    scale = torch.tensor([65536.0], device=dev)
+    finf = torch.tensor([1.0 if skip else 0.0], device=dev)
+    lo, cnt = (1024, 2048) if shard else (0, 0)
+    hyper = (1e-2, 0.9, 0.99, 1e-15)
+
+    # reference order: update, then sum
+    tabs, ms, vs, ptrs, steps, coef = state()
+    _lib.call("nsig_msg_adam_step", P(ptrs), 2 * md, md, P(applied), P(G), P(steps), P(coef), P(scale), P(finf), *hyper,
+              log2_T, None, lo, cnt, 0)
+    S_ref = torch.full((n,), 7.0, device=dev)
+    _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, P(nxt), log2_T, P(S_ref), lo, cnt)
+    # look-ahead order
+    tabs2, ms2, vs2, ptrs2, steps2, coef2 = state()
+    before = [t.clone() for t in tabs2 + ms2 + vs2]
+    S = torch.full((n,), 7.0, device=dev)
+    _lib.call("nsig_msg_adam_lookahead_sum", P(ptrs2), 2 * md, md, P(applied), P(nxt), P(G), P(steps2), P(coef2), P(scale),
+              P(finf), *hyper, log2_T, None, lo, cnt, P(S))
+    for x, y in zip(before, tabs2 + ms2 + vs2):
+        assert torch.equal(x, y)                      # read-only
+    assert torch.equal(S, S_ref)                      # incl. the untouched 7.0 outside the slice
+    if not skip:
+        assert not torch.equal(S_ref[lo:lo + (cnt or n)], sum(tabs2[2 * i + int(nxt[i])] for i in range(md))[lo:lo + (cnt or n)])
+    _lib.call("nsig_msg_adam_step", P(ptrs2), 2 * md, md, P(applied), P(G), P(steps2), P(coef2), P(scale), P(finf), *hyper,
+              log2_T, None, lo, cnt, 1)
+    assert torch.equal(steps, steps2) and torch.equal(coef, coef2)
+    for x, y in zip(tabs + ms + vs, tabs2 + ms2 + vs2):
+        assert torch.equal(x, y)
