@@ -27,8 +27,11 @@
 
 namespace nsig {
 
-constexpr int kDecThreads = 256;
-constexpr int kDecWarps = 8;
+#ifndef NSIG_DEC_THREADS
+#define NSIG_DEC_THREADS 256
+#endif
+constexpr int kDecThreads = NSIG_DEC_THREADS;
+constexpr int kDecWarps = kDecThreads / 32;
 constexpr float kBnEps = 1e-3f;  // hidden_models.py:24
 
 enum InMode { IN_RAW = 0, IN_BNGELU = 1, IN_DZ = 2 };
@@ -118,6 +121,34 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 // positions x chunks per thread (items base + j*blockDim + tid), `commit` applies the transform and writes the tile.
 constexpr int kStagePF = 4;
 
+// (dy, dy * yhat) of one output element for the backward BatchNorm statistics; out of line for the same reason as below
+__device__ __noinline__ float2 bstat_terms(__half z, __half da, const BnCoef& co) {
+    const float zf = h2f(z);
+    const __half y = f2h(fmaf(zf, co.scale, co.shift));
+    const float dy = h2f(f2h(h2f(da) * gelu_grad_f(h2f(y))));
+    return make_float2(dy, dy * ((zf - co.mean) * co.rstd));
+}
+
+// 8 channels at a time, NOT inlined: the staging loops are unrolled for memory-level parallelism, and an inlined erff per
+// element per unrolled slot turned the prologue into thousands of straight-line instructions (instruction-fetch stalls)
+__device__ __noinline__ uint4 act8_from_z(uint4 v, const BnCoef* __restrict__ coef) {
+    uint4 out;
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+    __half* ho = reinterpret_cast<__half*>(&out);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ho[k] = act_from_z(hv[k], coef[k]);
+    return out;
+}
+__device__ __noinline__ uint4 dz8_from(uint4 v, uint4 v2, const BnCoef* __restrict__ coef) {
+    uint4 out;
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+    const __half* hz = reinterpret_cast<const __half*>(&v2);
+    __half* ho = reinterpret_cast<__half*>(&out);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ho[k] = dz_from(hv[k], hz[k], coef[k]);
+    return out;
+}
+
 template <int C, int SCH, int MODE>
 struct TileStager {
     static constexpr int STRIDE = C + 8, CHUNKS = C / 8;
@@ -155,20 +186,9 @@ struct TileStager {
             const int pos = i / CHUNKS, ck = i - pos * CHUNKS;
             uint4 out = make_uint4(0u, 0u, 0u, 0u);   // outside the image / padded channels: zero
             if (valid & (1u << j)) {
-                if (MODE == IN_RAW) {
-                    out = v[j];
-                } else {
-                    const __half* hv = reinterpret_cast<const __half*>(&v[j]);
-                    __half* ho = reinterpret_cast<__half*>(&out);
-                    if (MODE == IN_BNGELU) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) ho[k] = act_from_z(hv[k], coef[ck * 8 + k]);
-                    } else {
-                        const __half* hz = reinterpret_cast<const __half*>(&v2[j]);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) ho[k] = dz_from(hv[k], hz[k], coef[ck * 8 + k]);
-                    }
-                }
+                if (MODE == IN_RAW) out = v[j];
+                else if (MODE == IN_BNGELU) out = act8_from_z(v[j], coef + ck * 8);
+                else out = dz8_from(v[j], v2[j], coef + ck * 8);
             }
             *reinterpret_cast<uint4*>(tile + (size_t)pos * STRIDE + ck * 8) = out;
         }
@@ -207,7 +227,7 @@ struct ConvParams {
 template <int CIN, int SCH, int COUT, int MODE>
 __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* smem_raw, int item0, int item_step, int n_items,
                                          int strips) {
-    constexpr int STRIDE = CIN + 8, NT = COUT / 8, KS = CIN / 16, MB = 4;
+    constexpr int STRIDE = CIN + 8, NT = COUT / 8, KS = CIN / 16, MB = kDecWarps >= 16 ? 2 : 4;
     if (item0 >= n_items) return;
     __half* tile = reinterpret_cast<__half*>(smem_raw);                      // [(R+2)*(W+2)][STRIDE]
     BnCoef* coef = reinterpret_cast<BnCoef*>(tile + (size_t)(p.R + 2) * (p.W + 2) * STRIDE);
@@ -280,6 +300,32 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
 #pragma unroll
         for (int m = 0; m < MB; ++m) { c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f; }
         constexpr int KK = 9 * KS;
+        if constexpr (KS % 2 == 0) {
+            // a real loop over the 9 taps (only the KS k-steps of one tap are unrolled): the fully unrolled 36-k-step body
+            // made the kernel ~75 KB of straight-line code that every SM executes exactly once, and a fifth of the warp
+            // stall samples were instruction-fetch misses (stall_no_inst, profiles/r02_ncu_decoder.txt)
+#pragma unroll 1
+            for (int t = 0; t < 9; ++t) {
+                const int off = ((t / 3 - 1) * TW + (t % 3 - 1)) * STRIDE;
+#pragma unroll
+                for (int kp = 0; kp < KS / 2; ++kp) {
+                    uint32_t bf[4];
+                    ldsm_x4(bf, wlane + (t * (KS / 2) + kp) * 32);
+#pragma unroll
+                    for (int half_ = 0; half_ < 2; ++half_) {
+                        const int ks = 2 * kp + half_;
+#pragma unroll
+                        for (int m = 0; m < MB; ++m) {
+                            if (m < mcount) {
+                                uint32_t a[4];
+                                ldsm_x4(a, arow[m] + off + ks * 16);
+                                mma_16816(c[m], a, bf[2 * half_], bf[2 * half_ + 1]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int kp = 0; kp < (KK + 1) / 2; ++kp) {
             uint32_t bf[4];
@@ -307,6 +353,7 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
                 }
             }
         }
+        }
         // epilogue: rows g, g+8 of each m-tile; columns nt*8 + 2tig, +1
         const int col = nt * 8 + 2 * tig;
         const float bias0 = (p.bias && col < p.cout_valid) ? p.bias[col] : 0.f;
@@ -330,12 +377,9 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
                         const __half zh[2] = {__low2half(zz), __high2half(zz)}, dh[2] = {o0, o1};
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const BnCoef& co = coef_out[col + e];
-                            const float zf = h2f(zh[e]);
-                            const __half y = f2h(fmaf(zf, co.scale, co.shift));
-                            const float dy = h2f(f2h(h2f(dh[e]) * gelu_grad_f(h2f(y))));
-                            l1[e] += dy;
-                            l2[e] += dy * ((zf - co.mean) * co.rstd);
+                            const float2 t = bstat_terms(zh[e], dh[e], coef_out[col + e]);
+                            l1[e] += t.x;
+                            l2[e] += t.y;
                         }
                     } else {
                         const float f0 = h2f(o0), f1 = h2f(o1);
