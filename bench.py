@@ -534,8 +534,16 @@ def grad_check_1_vs_n(cx, content_rays=16384):
     tabs_n, tabs_1 = sn.model.msg_encoder.tables(), s1.model.msg_encoder.tables()
     upd = max(float((tabs_n[2 * i + b] - tabs_1[2 * i + b]).abs().max()) for i, b in enumerate(bits))
     untouched = max(float((tabs_n[2 * i + 1 - b] - tabs_1[2 * i + 1 - b]).abs().max()) for i, b in enumerate(bits))
+    # a rank's loss holds the image term of ITS content rays only (equal counts per rank): the mean over the ranks is the
+    # single-GPU loss
+    ln_mean = ln.detach().float().reshape(1).clone()
+    if cx.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ln_mean)
+        ln_mean /= cx.world
     out = {"content_rays": content_rays, "block_rays": int(sum(counts)), "dLdS_rel_l2": rel(Gn, G1),
-           "decoder_grads_rel_l2": rel(Dn, D1), "loss_rel": abs(float(ln) - float(l1)) / abs(float(l1)),
+           "decoder_grads_rel_l2": rel(Dn, D1), "loss_rel": abs(float(ln_mean) - float(l1)) / abs(float(l1)),
+           "loss_note": "mean over the ranks of the per-rank loss vs the single-GPU loss",
            "updated_tables_max_abs_diff": upd, "untouched_tables_max_abs_diff": untouched, "lr": 1e-2,
            "optimizer_sharded": sn.optimizer.shard is not None}
     del sn, s1

@@ -120,6 +120,116 @@ k_msg_adam(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const 
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same update with the data in flight held in SHARED MEMORY instead of registers: bulk asynchronous copies (TMA,
+// cp.async.bulk + mbarrier) stream [G | p | m | v] chunks of 256 float4 through a 4-stage ring, 256 threads update a chunk in
+// place and a bulk copy writes it back.  k_msg_adam needs ~100 registers x 256 threads per 48 KB of loads in flight, i.e. two
+// resident CTAs own 52 k of an SM's 64 k registers for the ~145 us the update streams, and the march of the parallel graph
+// branch (14 k registers per CTA) does not get a single CTA in: the two branches ran back to back (profiles/
+// r02_graph_offsets_final.txt: the march ends at 253 us whenever it starts).  Here a CTA holds 48 KB in flight with ~40
+// registers per thread, so HBM stays saturated while most of the register file is free for the latency-bound neighbour.
+// Items = (chunk, table) pairs, dealt to the CTAs as contiguous ranges; arithmetic = adam_elem (bit-identical to k_msg_adam).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTmaChunk = 256;                       // float4 per array and item
+constexpr int kTmaStages = 4;
+constexpr int kTmaStageBytes = 4 * kTmaChunk * 16;   // G, p, m, v
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_msg_adam_tma(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, const float* __restrict__ G,
+               const float* __restrict__ coef, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
+               float beta1, float beta2, float eps, uint32_t n_vec4, uint32_t vec4_begin) {
+    if (found_inf && *found_inf != 0.0f) return;
+    extern __shared__ __align__(128) unsigned char ring[];      // kTmaStages x [G | p | m | v]
+    __shared__ __align__(8) uint64_t full[kTmaStages];
+    __shared__ uint64_t s_ptr[3][NSIG_MAX_MSG_TABLES / 2];       // (param, exp_avg, exp_avg_sq) of the table each bit selects
+    __shared__ float s_coef[NSIG_MAX_MSG_TABLES / 2][2];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t mi = tid; mi < md; mi += blockDim.x) {
+        const uint32_t t = 2 * mi + (((uint32_t)(int)message[mi]) & 1u);
+        s_ptr[0][mi] = ptrs.table[t];
+        s_ptr[1][mi] = ptrs.table[ptrs.n_tables + t];
+        s_ptr[2][mi] = ptrs.table[2 * ptrs.n_tables + t];
+        s_coef[mi][0] = coef[2 * t];
+        s_coef[mi][1] = coef[2 * t + 1];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kTmaStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&full[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t pol = evict_first_policy();
+    const uint32_t n_chunks = (n_vec4 + kTmaChunk - 1) / kTmaChunk;
+    const uint64_t n_items = (uint64_t)n_chunks * md;
+    const uint64_t i0 = n_items * blockIdx.x / gridDim.x, i1 = n_items * (blockIdx.x + 1) / gridDim.x;
+    const float inv = grad_scale ? 1.0f / *grad_scale : 1.0f;
+    const float w1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+
+    auto issue_loads = [&](uint64_t item, int s) {              // thread 0 only
+        const uint32_t chunk = (uint32_t)(item / md), mi = (uint32_t)(item - (uint64_t)chunk * md);
+        const uint32_t v0 = chunk * kTmaChunk, nv = min((uint32_t)kTmaChunk, n_vec4 - v0), bytes = nv * 16;
+        const size_t off = ((size_t)vec4_begin + v0) * 4;
+        const uint32_t bar = smem_addr(&full[s]), base = smem_addr(ring + (size_t)s * kTmaStageBytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4 * bytes) : "memory");
+        bulk_load(base, G + off, bytes, bar, pol);
+        bulk_load(base + kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[0][mi]) + off, bytes, bar, pol);
+        bulk_load(base + 2 * kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[1][mi]) + off, bytes, bar, pol);
+        bulk_load(base + 3 * kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[2][mi]) + off, bytes, bar, pol);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kTmaStages && i0 + k < i1; ++k) issue_loads(i0 + k, k);
+
+    for (uint64_t item = i0; item < i1; ++item) {
+        const uint32_t k = (uint32_t)(item - i0), s = k % kTmaStages, parity = (k / kTmaStages) & 1u;
+        const uint32_t chunk = (uint32_t)(item / md), mi = (uint32_t)(item - (uint64_t)chunk * md);
+        const uint32_t v0 = chunk * kTmaChunk, nv = min((uint32_t)kTmaChunk, n_vec4 - v0);
+        {   // wait for the stage's four copies
+            const uint32_t bar = smem_addr(&full[s]);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        float4* st = reinterpret_cast<float4*>(ring + (size_t)s * kTmaStageBytes);
+        if (tid < nv) {
+            float4 g = st[tid], p = st[kTmaChunk + tid], m = st[2 * kTmaChunk + tid], v = st[3 * kTmaChunk + tid];
+            g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+            const float step_size = s_coef[mi][0], bc2_sqrt = s_coef[mi][1];
+            adam_elem(p.x, m.x, v.x, g.x, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+            adam_elem(p.y, m.y, v.y, g.y, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+            adam_elem(p.z, m.z, v.z, g.z, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+            adam_elem(p.w, m.w, v.w, g.w, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+            st[kTmaChunk + tid] = p; st[2 * kTmaChunk + tid] = m; st[3 * kTmaChunk + tid] = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            const size_t off = ((size_t)vec4_begin + v0) * 4;
+            const uint32_t base = smem_addr(st), bytes = nv * 16;
+            bulk_store(reinterpret_cast<float*>(s_ptr[0][mi]) + off, base + kTmaChunk * 16, bytes, pol);
+            bulk_store(reinterpret_cast<float*>(s_ptr[1][mi]) + off, base + 2 * kTmaChunk * 16, bytes, pol);
+            bulk_store(reinterpret_cast<float*>(s_ptr[2][mi]) + off, base + 3 * kTmaChunk * 16, bytes, pol);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (k >= 1) {   // the PREVIOUS item's write-back has left shared memory: refill its stage
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const uint64_t nxt = item - 1 + kTmaStages;
+                if (nxt < i1) issue_loads(nxt, (int)((k - 1) % kTmaStages));
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // Look-ahead table sum: S = sum_i table[2i + next_i] AS IT WILL BE once k_msg_adam has applied the pending update (the one
 // selected by `applied`), without writing anything but S.  A table that the pending update touches AND the next message
 // selects (next_i == applied_i) contributes p_new computed from (p, m, v, G) with the very same adam_elem; any other table
@@ -300,6 +410,23 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
     }
     const uint32_t n_vec4 = elem_count / 4;
     AdamPtrs ptrs{ptr_table, n_tables};
+    // NSIG_ADAM_TMA=<CTAs per SM> selects the shared-memory-staged kernel.  Measured (round 2, call X): bit-identical; alone 164 us
+    // vs 157 us for the register kernel; inside the step the march does overlap it then (ends at 200 us instead of 253 us) but
+    // the update stretches to 192 us beside it and the field forward starts at 251 us instead of 257 us - step 0.972-0.991 ms vs
+    // 0.955 ms.  The register kernel stays the default.
+    static const int tma_per_sm = [] { const char* e = getenv("NSIG_ADAM_TMA"); return e ? atoi(e) : 0; }();
+    if (tma_per_sm > 0 && 2 * message_dim <= NSIG_MAX_MSG_TABLES) {
+        const size_t smem = (size_t)kTmaStages * kTmaStageBytes;
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(k_msg_adam_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+        const uint64_t items = (uint64_t)div_up(n_vec4, (uint32_t)kTmaChunk) * message_dim;
+        const uint64_t cap = 148ull * (uint64_t)tma_per_sm;
+        const uint32_t grid = (uint32_t)(items < cap ? items : cap);
+        k_msg_adam_tma<<<grid, 256, smem, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
+                                                beta1, beta2, eps, n_vec4, elem_begin / 4);
+        NSIG_LAUNCH_CHECK();
+        return 0;
+    }
     const uint32_t grid = min(div_up(n_vec4, 256u), 148u * adam_ctas_per_sm());
     k_msg_adam<<<grid, 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
                                      beta1, beta2, eps, n_vec4, elem_begin / 4);
