@@ -85,6 +85,12 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     buf = (ctypes.c_float * 64)()
     base = ctypes.addressof(buf)
     aligned, odd = V(base + (-base) % 16), V(base + (-base) % 16 + 2)
+    # look-ahead table sum: needs both messages and an output; ranges must be multiples of 4 floats inside the table
+    assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, None, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, aligned, None) == -1
+    assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, None, None) == -1
+    assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 2, 8, aligned, None) == -1
+    assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 1 << 20, aligned, None) == -1
+    assert h.nsig_msg_adam_step(p, 8, 4, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 6, 0, None) == -1   # ragged range
     assert h.nsig_field_backward(p, p, 4, 1.0, p, p, p, odd, aligned, 1.0, None, 2048.0, 19, p, None, None, None, None) == -1
     # round-2 entry points: tcgen05 backward, fused-slot probe, one-kernel GradScaler, flat Adam
     assert h.nsig_field_backward_tc(None, None, 0, 1.0, None, None, None, None, None, 1.0, None, 2048.0, 19, None, None) == 0
