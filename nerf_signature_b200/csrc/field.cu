@@ -46,7 +46,13 @@ k_field_fwd(const FieldParams p, float* __restrict__ sigmas, float* __restrict__
         if (row0 >= M) continue;
         uint32_t fa[MT][2][4];
 #ifndef NSIG_GATHER_V2
+#ifndef NSIG_FWD_UNROLLED
+        // per-row encode code emitted once and looped over the thread's 4 rows: 0.2317 -> 0.2180 ms per 1.07 M samples against the
+        // fully unrolled body (-DNSIG_FWD_UNROLLED), which is instruction-fetch limited (profiles/r02_experiments.txt)
+        encode_rows_rolled<MT, H2>(fa, p, M, row0, g, tig);
+#else
         encode_rows<MT, H2>(fa, p, M, row0, g, tig);
+#endif
         if (feat_out) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -343,6 +349,14 @@ k_render_rays(const RenderParams p) {
             {
                 uint32_t fa[MT][2][4];
 #ifndef NSIG_GATHER_V2
+#ifndef NSIG_RENDER_UNROLLED
+                auto pos = [&](int mt, int h, float (&x)[3]) {
+                    const uint32_t row = min((uint32_t)(mt * 16 + h * 8 + g), nb - 1);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) x[a] = __fmul_rn(__fadd_rn(st_xyz[row * 3 + a], p.f.bound_add), p.f.bound_mul);
+                };
+                encode_positions_rolled<MT, H2>(fa, p.f, pos, g, tig);
+#else
                 float xn[MT][2][3];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
@@ -354,6 +368,7 @@ k_render_rays(const RenderParams p) {
                             xn[mt][h][a] = __fmul_rn(__fadd_rn(st_xyz[row * 3 + a], p.f.bound_add), p.f.bound_mul);
                     }
                 encode_positions<MT, H2>(fa, p.f, xn, g, tig);
+#endif
 #else
                 {
                     const uint32_t row = min((uint32_t)lane, nb - 1);

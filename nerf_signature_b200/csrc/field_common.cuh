@@ -334,6 +334,78 @@ __device__ __forceinline__ void encode_positions(uint32_t (&fa)[MT][2][4], const
                 fa[mt][j >> 1][2 * (j & 1) + h] = pack_h2(f[mt][h][j].x, f[mt][h][j].y);
 }
 
+// The same encode with the loop over the thread's 2*MT rows NOT unrolled: one copy of the per-row code (4 base levels + locate)
+// instead of 2*MT.  For kernels whose warps drift apart (k_render_rays: every warp marches its own ray, so the warps of an SM
+// partition sit in march, encode, MLP and composite code at the same time) the fully unrolled body does not fit the
+// instruction caches: ncu showed stall_no_instruction as the top stall (28 % of the samples, profiles/r02_ncu_render.txt).
+// pos(mt, h, x): the row's normalised position (a runtime (mt, h), e.g. read from shared or global memory).
+template <int MT, bool H2, typename PosFn>
+__device__ __forceinline__ void encode_positions_rolled(uint32_t (&fa)[MT][2][4], const FieldParams& p, PosFn pos, int g, int tig) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) fa[mt][ks][r] = 0u;
+    float2 top[MT][2];   // level tig + 12 of every row, kept in fp32 until the message feature has been added (tig == 3)
+#pragma unroll 1
+    for (int s = 0; s < 2 * MT; ++s) {
+        const int mt = s >> 1, h = s & 1;
+        float x[3];
+        pos(mt, h, x);
+        uint32_t packed[3];
+        float2 last = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int level = tig + 4 * j;
+            const LevelGeom L = p.base.geom[level];
+            const Voxel v = locate_fused(x[0], x[1], x[2], L);
+            const float2 f = H2 ? encode_level_fused_h2(p.base.th[level], v, p.mask, __ldg(p.base.inv_scale + level))
+                                : encode_level_fused(p.base.t[level], v, p.mask);
+            if (j < 3) packed[j] = pack_h2(f.x, f.y); else last = f;
+        }
+#pragma unroll
+        for (int m2 = 0; m2 < MT; ++m2)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+                if (s == m2 * 2 + h2) {   // level tig+4j -> k-step j>>1, register 2*(j&1)+h
+                    fa[m2][0][h2] = packed[0]; fa[m2][0][2 + h2] = packed[1]; fa[m2][1][h2] = packed[2];
+                    top[m2][h2] = last;
+                }
+    }
+    if (p.S != nullptr) {   // message feature, as in encode_positions
+#pragma unroll
+        for (int q = 0; q < (MT * 2 + 3) / 4; ++q) {
+            const int sel = q * 4 + tig;
+            float2 mine = make_float2(0.f, 0.f);
+            if (sel < MT * 2) {
+                float x[3];
+                pos(sel >> 1, sel & 1, x);
+                const Voxel v = locate_fused(x[0], x[1], x[2], p.msg_geom);
+                mine = encode_level_fused(p.S, v, p.mask);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int src = mt * 2 + h - q * 4;
+                    if (src >= 0 && src < 4) {
+                        const float mx = __shfl_sync(NSIG_FULL_MASK, mine.x, (g << 2) | src);
+                        const float my = __shfl_sync(NSIG_FULL_MASK, mine.y, (g << 2) | src);
+                        if (tig == 3) {
+                            top[mt][h].x = __fadd_rn(top[mt][h].x, mx);
+                            top[mt][h].y = __fadd_rn(top[mt][h].y, my);
+                        }
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) fa[mt][1][2 + h] = pack_h2(top[mt][h].x, top[mt][h].y);
+}
+
 template <int MT, bool H2 = false>
 __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
                                             uint32_t row0, int g, int tig) {
@@ -348,6 +420,18 @@ __device__ __forceinline__ void encode_rows(uint32_t (&fa)[MT][2][4], const Fiel
                 xn[mt][h][a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
         }
     encode_positions<MT, H2>(fa, p, xn, g, tig);
+}
+
+// encode_rows with the per-row code emitted once (encode_positions_rolled): positions are re-read per row
+template <int MT, bool H2 = false>
+__device__ __forceinline__ void encode_rows_rolled(uint32_t (&fa)[MT][2][4], const FieldParams& p, uint32_t M,
+                                                   uint32_t row0, int g, int tig) {
+    auto pos = [&](int mt, int h, float (&x)[3]) {
+        const uint32_t r = min(row0 + (uint32_t)(mt * 16 + h * 8 + g), M - 1);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)r * 3 + a), p.bound_add), p.bound_mul);
+    };
+    encode_positions_rolled<MT, H2>(fa, p, pos, g, tig);
 }
 
 // ---------------------------------------------------------------------------------------------------
