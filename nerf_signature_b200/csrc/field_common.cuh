@@ -348,11 +348,14 @@ __device__ __forceinline__ void encode_positions_rolled(uint32_t (&fa)[MT][2][4]
 #pragma unroll
             for (int r = 0; r < 4; ++r) fa[mt][ks][r] = 0u;
     float2 top[MT][2];   // level tig + 12 of every row, kept in fp32 until the message feature has been added (tig == 3)
+    float xnext[3];
+    pos(0, 0, xnext);
 #pragma unroll 1
     for (int s = 0; s < 2 * MT; ++s) {
-        const int mt = s >> 1, h = s & 1;
-        float x[3];
-        pos(mt, h, x);
+        // this row's position was requested one iteration ago; request the next row's now (its latency would otherwise be
+        // exposed at the head of every iteration: 11 % of the warp-stall samples sat on the first use of the position)
+        const float x[3] = {xnext[0], xnext[1], xnext[2]};
+        if (s + 1 < 2 * MT) pos((s + 1) >> 1, (s + 1) & 1, xnext);
         uint32_t packed[3];
         float2 last = make_float2(0.f, 0.f);
 #pragma unroll
