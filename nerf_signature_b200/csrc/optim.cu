@@ -167,6 +167,8 @@ k_msg_adam_tma(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, co
     }
     __syncthreads();
     const uint64_t pol = evict_first_policy();
+    uint64_t pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
     const uint32_t n_chunks = (n_vec4 + kTmaChunk - 1) / kTmaChunk;
     const uint64_t n_items = (uint64_t)n_chunks * md;
     const uint64_t i0 = n_items * blockIdx.x / gridDim.x, i1 = n_items * (blockIdx.x + 1) / gridDim.x;
@@ -179,7 +181,7 @@ k_msg_adam_tma(AdamPtrs ptrs, uint32_t md, const float* __restrict__ message, co
         const size_t off = ((size_t)vec4_begin + v0) * 4;
         const uint32_t bar = smem_addr(&full[s]), base = smem_addr(ring + (size_t)s * kTmaStageBytes);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4 * bytes) : "memory");
-        bulk_load(base, G + off, bytes, bar, pol);
+        bulk_load(base, G + off, bytes, bar, pol_keep);   // G is re-read for every table: it must stay in L2
         bulk_load(base + kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[0][mi]) + off, bytes, bar, pol);
         bulk_load(base + 2 * kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[1][mi]) + off, bytes, bar, pol);
         bulk_load(base + 3 * kTmaChunk * 16, reinterpret_cast<const float*>(s_ptr[2][mi]) + off, bytes, bar, pol);
