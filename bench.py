@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame inference leg")
     ap.add_argument("--no-defer", action="store_true",
                     help="run the optimizer at the end of each step instead of overlapping it with the next step's march")
+    ap.add_argument("--march-ahead", type=int, default=0, choices=[0, 1],
+                    help="1 = software-pipelined sample generation: near/far + march of batch t+1 run inside step t next to the "
+                         "decoder chain (harness.Scene(march_ahead=True)); main workload only")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the secondary legs (configs[2] 360 training, configs[4] sharded 262144-ray step, gradient "
                          "check, reference-composed CUDA step, configs[0] CPU render)")
@@ -317,11 +320,39 @@ def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_repla
     n_pool = len(host_batches)
     dev_batches = [scene.to_device(b) for b in host_batches]
     md = scene.cfg["message_dim"]
+    ahead = getattr(scene, "march_ahead", False)
+
+    class Feeder:
+        """Hands the scene one batch per step from a pool, with a fresh message.  march_ahead scenes are also told the
+        FOLLOWING batch and its message (that batch's input copy and march run during this step); the running index
+        continues across the warm-up / timed / roofline loops so every batch of the timed region was announced."""
+
+        def __init__(self, pool, host):
+            self.pool, self.host, self.i, self.msg = pool, host, 0, None
+
+        def _msg(self, slot):
+            m = scene.new_message(gen)
+            if self.host:                       # packed pinned batch: the message travels inside the flat buffer
+                self.pool[slot]["message"].copy_(m)
+                return self.pool[slot]["message"]
+            return m
+
+        def step(self):
+            cur = self.i % n_pool
+            self.i += 1
+            if not ahead:
+                return scene.train_step(self.pool[cur], self._msg(cur))
+            m = self.msg if self.msg is not None else self._msg(cur)
+            nxt = self.i % n_pool
+            self.msg = self._msg(nxt)
+            return scene.train_step(self.pool[cur], m, next_batch=self.pool[nxt], next_message=self.msg)
+
+    feed = Feeder(dev_batches, host=False)
     names = ["nsig_field_forward", "nsig_field_backward", "nsig_field_backward_masks", "nsig_field_backward_tc",
              "nsig_field_backward_tc_masks"]
     _lib.timing_enable(names)   # external event nodes when the step is captured
     for i in range(W):
-        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+        feed.step()
     if not scene.use_graph:
         _lib.timing_enable(names)
     if clocks is not None:
@@ -331,7 +362,7 @@ def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_repla
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
+        feed.step()
     scene.flush_optimizer()   # deferred-optimizer mode: the last step's Adam update belongs to the timed region
     e1.record()
     _barrier(cx)
@@ -343,8 +374,9 @@ def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_repla
     if not scene.use_graph:
         _lib.timing_enable(names)
     for i in range(roofline_replays):
-        scene.train_step(dev_batches[i % n_pool], scene.new_message(gen))
-        t = _lib.timing_read()          # synchronises; in graph mode = this replay's event pairs
+        feed.step()
+        # synchronises; in graph mode = this replay's event pairs (march_ahead: those of the graph that just ran)
+        t = _lib.timing_read(scene._ahead_last if ahead else None)
         s_, r_ = scene.samples_per_step()
         samples += s_; rays += r_
         if scene.use_graph:
@@ -364,12 +396,11 @@ def time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, roofline_repla
         pinned_msg = torch.empty(md, dtype=torch.float32).pin_memory()
         out["h2d_bytes"] = (pool[0]["_flat"].numel() * 4) if pool is not None else \
             (sum(v.nbytes for v in host_batches[0].values()) + md * 4)
+        hfeed = Feeder(pool, host=True) if pool is not None else None
 
         def host_step(i):
-            if pool is not None:
-                pb = pool[i % n_pool]
-                pb["message"].copy_(scene.new_message(gen))
-                loss, _, _ = scene.train_step(pb, pb["message"])
+            if hfeed is not None:
+                loss, _, _ = hfeed.step()      # one H2D copy of a packed batch (march_ahead: the NEXT step's batch)
                 return float(loss)
             for k, v in host_batches[i % n_pool].items():
                 pinned[k].copy_(torch.from_numpy(v))
@@ -607,7 +638,8 @@ def run_ours(args):
                 for k in ("rays_o", "rays_d", "gt"):
                     mine[k] = np.ascontiguousarray(np.concatenate([v[k] for v in views], axis=1)[:, rank::world])
             host_batches.append(mine)
-        scene = harness.Scene(cfg, dev, **skw)
+        scene = harness.Scene(cfg, dev, march_ahead=bool(args.march_ahead) and use_graph and args.render_mode == "merged",
+                              **skw)
     rays_per_step = host_batches[0]["rays_o"].shape[1] + int(np.prod(host_batches[0]["rays_o_block"].shape[:-1]))
     clocks = ClockSampler(local_rank) if rank == 0 else None
     res = time_scene(cx, scene, host_batches, K, W, gen, want_e2e=True, clocks=clocks)

@@ -78,6 +78,17 @@ int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
                           int32_t* rays, int32_t* counter, const float* noises,
                           void* scratch, nsig_stream_t stream);
 
+/* nsig_march_rays_train on a grid of at most `max_blocks` CTAs of 8 warps (0 = no limit): each warp walks rays
+ * n, n + 8 * max_blocks, ...  Same outputs bit for bit.  For a march that runs on a branch next to other kernels and
+ * must leave them room on every SM (the training harness issues the march of batch t+1 beside the decoder of step t);
+ * the reference has no counterpart (its march_rays_train always owns the device, raymarching.cu:312). */
+int nsig_march_rays_train_limited(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                  float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                  uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                  const float* fars, float* xyzs, float* dirs, float* deltas,
+                                  int32_t* rays, int32_t* counter, const float* noises,
+                                  void* scratch, uint32_t max_blocks, nsig_stream_t stream);
+
 /* Zero rows [counter[0], end) of the three sample buffers — the rows the reference gets from
  * torch.zeros (raymarching.py:205-207): end = min(align_up(counter[0]), M) with
  * align_up(m) = m + align - m % align (adds a full `align` when already aligned,
@@ -480,6 +491,20 @@ int nsig_msg_adam_lookahead_sum(const uint64_t* ptr_table, uint32_t n_tables, ui
                                 float lr, float beta1, float beta2, float eps, uint32_t log2_T,
                                 const float* lr_dev, uint32_t elem_begin, uint32_t elem_count, float* S,
                                 nsig_stream_t stream);
+
+/* nsig_msg_adam_step(message = message_applied) AND nsig_msg_table_sum(message_next) in one pass over the tables: S is
+ * accumulated while the update streams - from the freshly updated value where message_next selects the table being updated,
+ * from one extra read of the sibling table otherwise - in nsig_msg_table_sum's order, so S is bit-identical to the call
+ * pair.  A skipped update (*found_inf != 0) leaves the tables alone and sums them as they are.  Same arguments as
+ * nsig_msg_adam_lookahead_sum; with a slice (elem_begin / elem_count) only that slice of S is written.  Replaces
+ * optimizer.step() (utils_wtmk_disen.py:1178) + the next step's per-bit table selection
+ * (hash_encoding_wtmk_bit.py:99-116) when the caller knows the next message before it applies the update. */
+int nsig_msg_adam_step_sum(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
+                           const float* message_applied, const float* message_next, const float* G,
+                           float* steps, float* coef, const float* grad_scale, const float* found_inf,
+                           float lr, float beta1, float beta2, float eps, uint32_t log2_T,
+                           const float* lr_dev, uint32_t elem_begin, uint32_t elem_count, float* S,
+                           nsig_stream_t stream);
 
 /* torch.amp.GradScaler's per-step work (utils_wtmk_disen.py:1175-1181) over the flat gradient bucket in one launch:
  * non-finite check of flat[0..n) -> *found_inf (0/1); *step_scale = the scale this step's gradients carry (what the

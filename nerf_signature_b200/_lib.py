@@ -26,6 +26,8 @@ _SIGNATURES = {
     "nsig_packbits": ([_vp, _u32, _f32, _vp, _vp], 1),
     "nsig_march_rays_train": ([_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp, _vp], 3),
+    "nsig_march_rays_train_limited": ([_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, _vp, _vp, _u32, _vp], 3),
     "nsig_zero_sample_padding": ([_vp, _vp, _vp, _vp, _u32, _u32, _vp], 1),
     "nsig_composite_rays_train_forward": ([_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp], 1),
     "nsig_composite_rays_train_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp,
@@ -75,6 +77,8 @@ _SIGNATURES = {
                             _vp], lambda a: 1 if a[17] else 2),
     "nsig_msg_adam_lookahead_sum": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp,
                                      _u32, _u32, _vp, _vp], 2),
+    "nsig_msg_adam_step_sum": ([_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _vp,
+                                _u32, _u32, _vp, _vp], 2),
     "nsig_grad_check_update_scale": ([_vp, _u32, _vp, _vp, _f32, _f32, _c.c_int32, _vp, _vp, _vp, _vp, _vp, _vp], 1),
     "nsig_flat_adam_step": ([_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _f32, _vp, _f32, _f32, _f32, _vp], 1),
     "nsig_field_backward_tc": ([_vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _f32, _u32, _vp, _vp], 1),
@@ -158,6 +162,7 @@ def stream():
 
 _timing_names = ()
 _timing_events = []
+timing_tag = None   # label attached to the event pairs recorded from now on (a harness that captures several graphs)
 
 
 def timing_enable(names):
@@ -175,12 +180,14 @@ def timing_reset():
     _timing_events.clear()
 
 
-def timing_read():
+def timing_read(tag=None):
     """Synchronise and return {name: {"ms": total, "n": calls}} over the recorded event pairs (for graph
-    replays: the most recent replay).  Keeps the events."""
+    replays: the most recent replay; `tag` selects the pairs recorded while `timing_tag` had that value).  Keeps the events."""
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1 in _timing_events:
+    for name, e0, e1, t in _timing_events:
+        if tag is not None and t != tag:
+            continue
         d = out.setdefault(name, {"ms": 0.0, "n": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["n"] += 1
@@ -207,7 +214,7 @@ def call(name, *args):
         e0.record()
         rc = getattr(lib, name)(*args, stream())
         e1.record()
-        _timing_events.append((name, e0, e1))
+        _timing_events.append((name, e0, e1, timing_tag))
     else:
         rc = getattr(lib, name)(*args, stream())
     if rc != 0:

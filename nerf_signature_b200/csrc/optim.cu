@@ -293,6 +293,76 @@ k_msg_sum_ahead(AdamPtrs ptrs, uint32_t md, const float* __restrict__ applied, c
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Update AND the next message's table sum in one pass: the update of the tables `applied` selects (k_msg_adam's loop,
+// adam_elem) with S = sum_i table[2i + next_i] accumulated on the way - from the freshly updated value where the next message
+// selects the table being updated (next_i == applied_i), from one extra read of the sibling table otherwise (on average
+// half of the bits: +64 MiB of reads at message_dim 32 next to the update's 0.8 GB).  Replaces k_msg_adam followed by
+// k_msg_table_sum (message_dim x 4 MiB read again, one more kernel and one more cross-branch dependency on the step's
+// critical path: the field forward waits for S).  Accumulation order = k_msg_table_sum's, so S has the bits of
+// update-then-sum.  A skipped update (found_inf) leaves the tables alone and sums them as they are.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_msg_adam_sum(AdamPtrs ptrs, uint32_t md, const float* __restrict__ applied, const float* __restrict__ next,
+               const float* __restrict__ G, const float* __restrict__ coef, const float* __restrict__ grad_scale,
+               const float* __restrict__ found_inf, float beta1, float beta2, float eps, uint32_t n_vec4,
+               uint32_t vec4_begin, float* __restrict__ S) {
+    const bool skip = found_inf && *found_inf != 0.0f;
+    const uint64_t pol = evict_first_policy();
+    const float w1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    const uint64_t* P = ptrs.table;
+    const uint64_t* M = ptrs.table + ptrs.n_tables;
+    const uint64_t* V = ptrs.table + 2 * ptrs.n_tables;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += gridDim.x * blockDim.x) {
+        const size_t off = (size_t)(vec4_begin + i) * 4;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!skip) {
+            g = ld4_stream(G + off, pol);
+            if (grad_scale) {
+                const float inv = 1.0f / *grad_scale;
+                g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+            }
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t m0 = 0; m0 < md; m0 += kAdamUnroll) {
+            float4 p[kAdamUnroll], m[kAdamUnroll], v[kAdamUnroll], q[kAdamUnroll];
+            uint32_t t[kAdamUnroll];
+            bool same[kAdamUnroll];
+#pragma unroll
+            for (int u = 0; u < kAdamUnroll; ++u) {
+                const uint32_t mi = min(m0 + u, md - 1);
+                const uint32_t ba = ((uint32_t)(int)__ldg(applied + mi)) & 1u, bn = ((uint32_t)(int)__ldg(next + mi)) & 1u;
+                t[u] = 2 * mi + ba;
+                same[u] = !skip && bn == ba;      // uniform over the grid
+                if (!skip) {
+                    p[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(P + t[u])) + off, pol);
+                    m[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(M + t[u])) + off, pol);
+                    v[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(V + t[u])) + off, pol);
+                }
+                if (!same[u]) q[u] = ld4_stream(reinterpret_cast<const float*>(__ldg(P + 2 * mi + bn)) + off, pol);
+            }
+#pragma unroll
+            for (int u = 0; u < kAdamUnroll; ++u) {
+                if (m0 + u >= md) break;
+                if (!skip) {
+                    const float step_size = __ldg(coef + 2 * t[u]), bc2_sqrt = __ldg(coef + 2 * t[u] + 1);
+                    adam_elem(p[u].x, m[u].x, v[u].x, g.x, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].y, m[u].y, v[u].y, g.y, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].z, m[u].z, v[u].z, g.z, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    adam_elem(p[u].w, m[u].w, v[u].w, g.w, w1, beta2, omb2, step_size, bc2_sqrt, eps);
+                    st4_stream(reinterpret_cast<float*>(__ldg(P + t[u])) + off, p[u], pol);
+                    st4_stream(reinterpret_cast<float*>(__ldg(M + t[u])) + off, m[u], pol);
+                    st4_stream(reinterpret_cast<float*>(__ldg(V + t[u])) + off, v[u], pol);
+                }
+                const float4 s = same[u] ? p[u] : q[u];
+                acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+            }
+        }
+        *reinterpret_cast<float4*>(S + off) = acc;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // torch.amp.GradScaler's per-step work as ONE kernel over the flat gradient bucket [dL/dS | decoder gradients]
 // (nerf/utils_wtmk_disen.py:1175-1181: scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()):
 //   * the non-finite check of every gradient (GradScaler._unscale_grads_ -> _amp_foreach_non_finite_check_and_unscale_:
@@ -432,6 +502,29 @@ extern "C" int nsig_msg_adam_step(const uint64_t* ptr_table, uint32_t n_tables, 
     const uint32_t grid = min(div_up(n_vec4, 256u), 148u * adam_ctas_per_sm());
     k_msg_adam<<<grid, 256, 0, st>>>(ptrs, message_dim, message, G, coef, grad_scale, found_inf,
                                      beta1, beta2, eps, n_vec4, elem_begin / 4);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsig_msg_adam_step_sum(const uint64_t* ptr_table, uint32_t n_tables, uint32_t message_dim,
+                                      const float* message_applied, const float* message_next, const float* G,
+                                      float* steps, float* coef, const float* grad_scale, const float* found_inf,
+                                      float lr, float beta1, float beta2, float eps, uint32_t log2_T,
+                                      const float* lr_dev, uint32_t elem_begin, uint32_t elem_count, float* S,
+                                      nsig_stream_t stream) {
+    if (!ptr_table || !message_applied || !message_next || !G || !steps || !coef || !S) return NSIG_EINVAL;
+    if (message_dim == 0 || 2 * message_dim > n_tables || n_tables > NSIG_MAX_MSG_TABLES) return NSIG_EINVAL;
+    if (log2_T < 1 || log2_T > 30 || (((uintptr_t)G) & 15) || (((uintptr_t)S) & 15)) return NSIG_EINVAL;
+    if (adam_range(log2_T, elem_begin, elem_count)) return NSIG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_msg_adam_prepare<<<div_up(message_dim, 128), 128, 0, st>>>(message_dim, message_applied, steps, coef, found_inf,
+                                                                 (double)lr, lr_dev, (double)beta1, (double)beta2);
+    NSIG_LAUNCH_CHECK();
+    const uint32_t n_vec4 = elem_count / 4;
+    AdamPtrs ptrs{ptr_table, n_tables};
+    const uint32_t grid = min(div_up(n_vec4, 256u), 148u * adam_ctas_per_sm());
+    k_msg_adam_sum<<<grid, 256, 0, st>>>(ptrs, message_dim, message_applied, message_next, G, coef, grad_scale, found_inf,
+                                         beta1, beta2, eps, n_vec4, elem_begin / 4, S);
     NSIG_LAUNCH_CHECK();
     return 0;
 }

@@ -109,21 +109,22 @@ k_packbits(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __
 
 constexpr int kMarchWarps = 8;  // rays per CTA
 
-// pass 1: per-ray sample counts
+// pass 1: per-ray sample counts.  Warp-per-ray; the grid may be smaller than N / kMarchWarps (nsig_march_rays_train_limited:
+// a march that shares the SMs with other kernels), then every warp walks rays n, n + stride, ...
 __global__ void __launch_bounds__(kMarchWarps * 32)
 k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
               uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
               const float* __restrict__ fars, const float* __restrict__ noises,
               uint32_t* __restrict__ counts) {
-    const uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
-    if (n >= N) return;
     const int lane = threadIdx.x & 31;
     const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
-    const RayConst r = load_ray(rays_o, rays_d, n);
-    const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
-    const uint32_t cnt = warp_march<false>(r, c, grid, t0, fars[n], max_steps, nullptr, nullptr, nullptr, lane);
-    if (lane == 0) counts[n] = cnt;
+    for (uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5); n < N; n += gridDim.x * kMarchWarps) {
+        const RayConst r = load_ray(rays_o, rays_d, n);
+        const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
+        const uint32_t cnt = warp_march<false>(r, c, grid, t0, fars[n], max_steps, nullptr, nullptr, nullptr, lane);
+        if (lane == 0) counts[n] = cnt;
+    }
 }
 
 // exclusive scan of counts (single CTA of 1024 threads); updates the global counters the way the
@@ -170,7 +171,7 @@ k_march_scan(const uint32_t* __restrict__ counts, uint32_t N, uint32_t* __restri
     }
 }
 
-// pass 2: write samples and the rays table (id, offset, count)
+// pass 2: write samples and the rays table (id, offset, count); same ray-to-warp mapping as pass 1
 __global__ void __launch_bounds__(kMarchWarps * 32)
 k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
@@ -179,31 +180,31 @@ k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d
               const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
               float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
               int* __restrict__ rays) {
-    const uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
-    if (n >= N) return;
     const int lane = threadIdx.x & 31;
-    const uint32_t num_steps = counts[n], off = offsets[n];
-    if (lane == 0) {
-        rays[n * 3] = (int)n;
-        rays[n * 3 + 1] = (int)off;
-        rays[n * 3 + 2] = (int)num_steps;
-    }
-    if (num_steps == 0) return;
-    if (off + num_steps > M) {
-        // reservation overflow: ray dropped (raymarching.cu:416).  Offsets only grow, so exactly one
-        // dropped ray starts inside the buffer; it clears the tail the reference leaves zero-filled.
-        for (uint32_t i = off + lane; i < M; i += 32) {
-            xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
-            dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
-            deltas[(size_t)i * 2] = deltas[(size_t)i * 2 + 1] = 0.f;
-        }
-        return;
-    }
     const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
-    const RayConst r = load_ray(rays_o, rays_d, n);
-    const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
-    warp_march<true>(r, c, grid, t0, fars[n], num_steps, xyzs + (size_t)off * 3,
-                     dirs + (size_t)off * 3, deltas + (size_t)off * 2, lane);
+    for (uint32_t n = blockIdx.x * kMarchWarps + (threadIdx.x >> 5); n < N; n += gridDim.x * kMarchWarps) {
+        const uint32_t num_steps = counts[n], off = offsets[n];
+        if (lane == 0) {
+            rays[n * 3] = (int)n;
+            rays[n * 3 + 1] = (int)off;
+            rays[n * 3 + 2] = (int)num_steps;
+        }
+        if (num_steps == 0) continue;
+        if (off + num_steps > M) {
+            // reservation overflow: ray dropped (raymarching.cu:416).  Offsets only grow, so exactly one
+            // dropped ray starts inside the buffer; it clears the tail the reference leaves zero-filled.
+            for (uint32_t i = off + lane; i < M; i += 32) {
+                xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
+                dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
+                deltas[(size_t)i * 2] = deltas[(size_t)i * 2 + 1] = 0.f;
+            }
+            continue;
+        }
+        const RayConst r = load_ray(rays_o, rays_d, n);
+        const float t0 = perturbed_start(nears[n], noises ? noises[n] : 0.0f, c);
+        warp_march<true>(r, c, grid, t0, fars[n], num_steps, xyzs + (size_t)off * 3,
+                         dirs + (size_t)off * 3, deltas + (size_t)off * 2, lane);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -612,11 +613,11 @@ int nsig_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* 
 
 size_t nsig_march_rays_train_scratch_bytes(uint32_t N) { return (size_t)N * 2 * sizeof(uint32_t); }
 
-int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                          uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
-                          float* deltas, int32_t* rays, int32_t* counter, const float* noises,
-                          void* scratch, nsig_stream_t stream) {
+static int march_rays_train_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                                 float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                 void* scratch, uint32_t max_blocks, nsig_stream_t stream) {
     if (N == 0) return 0;
     if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !rays ||
         !counter || !scratch)
@@ -625,12 +626,13 @@ int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* counts = (uint32_t*)scratch;
     uint32_t* offsets = counts + N;
-    const uint32_t blocks = div_up(N, kMarchWarps);
+    const uint32_t all_blocks = div_up(N, kMarchWarps);
+    const uint32_t blocks = (max_blocks && max_blocks < all_blocks) ? max_blocks : all_blocks;
     // Measured (round 2, call Q): inside the training step the single-launch kernel is SLOWER than the three-kernel chain
     // (1.000 vs 0.967 ms per step; the march branch takes ~220 us either way next to the HBM-bound table Adam, and CTAs that
     // spin in the look-back keep SM slots the Adam and the remaining rays are waiting for), so it is opt-in: NSIG_MARCH_FUSED=1.
     static const bool fused = [] { const char* e = getenv("NSIG_MARCH_FUSED"); return e && e[0] == '1'; }();
-    if (fused) {
+    if (fused && blocks == all_blocks) {
         // scratch (2N words) as [ticket | pad | look-back state: one 64-bit word per CTA]
         const size_t state_bytes = 16 + (size_t)blocks * sizeof(unsigned long long);
         if (state_bytes <= (size_t)N * 2 * sizeof(uint32_t) && (((uintptr_t)scratch) & 7) == 0) {
@@ -654,6 +656,24 @@ int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
                                                        xyzs, dirs, deltas, rays);
     NSIG_LAUNCH_CHECK();
     return 0;
+}
+
+int nsig_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                          uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                          float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                          void* scratch, nsig_stream_t stream) {
+    return march_rays_train_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                                 deltas, rays, counter, noises, scratch, 0, stream);
+}
+
+int nsig_march_rays_train_limited(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                  uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                                  float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                  void* scratch, uint32_t max_blocks, nsig_stream_t stream) {
+    return march_rays_train_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                                 deltas, rays, counter, noises, scratch, max_blocks, stream);
 }
 
 int nsig_zero_sample_padding(float* xyzs, float* dirs, float* deltas, const int32_t* counter,

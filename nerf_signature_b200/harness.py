@@ -119,7 +119,7 @@ class Scene:
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
                  merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
                  shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False, shard_optimizer=None,
-                 lookahead=None):
+                 lookahead=None, march_ahead=False):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -138,7 +138,14 @@ class Scene:
         of step t+1 on the side stream that also builds the summed message table, next to the latency-bound march of step t+1
         (which needs neither the tables nor G).  Every kernel sees exactly the data it would see in the sequential order -
         Adam(t) still completes before the table sum of step t+1 - so results are unchanged; reads of the message tables
-        from outside (evaluation, checkpoints, update_extra_state) must call flush_optimizer() first (train_step does)."""
+        from outside (evaluation, checkpoints, update_extra_state) must call flush_optimizer() first (train_step does).
+        march_ahead (captured, merged step only): software-pipeline the sample generation.  near/far + march of batch t+1 read
+        only its rays and the occupancy bitfield, so they are issued inside step t on a branch next to the decoder's
+        chain of small latency-bound kernels (which leaves most of every SM idle), instead of at the head of step t+1 where
+        they compete with the HBM-saturating table Adam and finish 150 us late.  train_step(batch, message, next_batch=...,
+        next_message=...) announces the following batch; an unannounced batch is staged and marched on the spot (correct,
+        not overlapped).  Two input buffers / sample-buffer sets / graphs alternate.  Kernels and data are those of the
+        plain schedule; only when the march runs changes.  Not for configs that rebuild the bitfield (grid_update_every)."""
         from .nerf.network_wtmk_tcnn import NeRFNetwork
         from .optim import WatermarkAdam
         torch.manual_seed(seed)
@@ -213,8 +220,20 @@ class Scene:
         if lookahead is None:
             lookahead = os.environ.get("NSIG_LOOKAHEAD") == "1"
         self.lookahead = self.defer_optimizer and bool(lookahead) and merged_render
+        # deferred order: the pending update's kernel also builds S for the step that issues it (nsig_msg_adam_step_sum)
+        self.fuse_table_sum = self.defer_optimizer and not self.lookahead and os.environ.get("NSIG_NO_FUSED_SUM") != "1"
         if self.defer_optimizer:   # [message of the step whose update is pending (md) | pending flag (1)]
             self._opt_state = torch.zeros(cfg["message_dim"] + 1, dtype=torch.float32, device=device)
+        self.march_ahead = bool(march_ahead)
+        if self.march_ahead and not (graph and merged_render and shard_blocks is None
+                                     and not cfg.get("grid_update_every", 0)):
+            raise ValueError("march_ahead needs graph=True, merged_render=True, an unsharded batch and a config without "
+                             "grid_update_every (marched-ahead samples go stale when the occupancy bitfield changes)")
+        # grid limit of the marched-ahead kernels (CTAs of 8 warps): they must leave every SM room for a decoder CTA
+        self.march_ahead_blocks = int(os.environ.get("NSIG_MARCH_AHEAD_CTAS_PER_SM", "2")) * 148
+        self._ahead_p = 0           # parity: which input buffer / sample-buffer set holds the batch to train on next
+        self._ahead_token = None    # id() of the batch announced for the next call
+        self._ahead_last = 0
         self.iteration = 0
         self.keep_outputs = False   # parity tests: keep the step's rendered pixels and decoder logits in self.last
         self.last = None
@@ -238,7 +257,7 @@ class Scene:
             out[k] = t.to(self.device, non_blocking=True)
         return out
 
-    def _step_impl(self, batch, message):
+    def _step_impl(self, batch, message, ahead=None):
         """utils_wtmk_disen.py:1164-1181 + 579-646; `message` is a host tensor (torch-Adam path: the bits
         select which tables receive a gradient) or a device tensor (fused path: nothing on the host depends
         on the bits)."""
@@ -274,6 +293,8 @@ class Scene:
                     self.sync.zero_decoder_grads()
                     self.optimizer.lookahead_sum(msg_dev)
                 else:
+                    if self.fuse_table_sum:   # S of THIS step's message accumulated by the pending update's own pass
+                        self.optimizer.sum_with_next_step(msg_dev)
                     self.scaler.step(self.optimizer, enabled=self._opt_state[md:])
                     self.sync.zero_flat()
             if side is not None:
@@ -301,7 +322,18 @@ class Scene:
                 o_all = torch.cat([ob.reshape(1, nb, 3), batch["rays_o"]], dim=1)
                 d_all = torch.cat([batch["rays_d_block"].reshape(1, nb, 3), batch["rays_d"]], dim=1)
             out = model.render(o_all, d_all, message, staged=False, bg_color=1, perturb=False, force_all_rays=True,
-                               **self.opt)
+                               premarched=None if ahead is None else ahead[0], **self.opt)
+            if ahead is not None:
+                # samples of the NEXT batch (ahead = (this batch's sample buffers, next input buffer, its sample buffers)):
+                # a branch that starts behind the composite forward and runs beside the decoder; joined at the end of the step
+                mside = _lib.side_stream(self.device, 4)
+                main = torch.cuda.current_stream()
+                if mside is not None:
+                    mside.wait_stream(main)
+                with torch.cuda.stream(mside if mside is not None else main):
+                    model.march_ahead(ahead[1]["rays_o_all"], ahead[1]["rays_d_all"], ahead[2],
+                                      dt_gamma=self.opt["dt_gamma"], max_steps=self.opt["max_steps"],
+                                      max_blocks=self.march_ahead_blocks)
             if self.fused_losses:
                 pred, image_c = split_clamp(out["image"], nb)
                 image_c = image_c.view(batch["rays_o"].shape)
@@ -367,6 +399,10 @@ class Scene:
         else:
             self.scaler.step(self.optimizer)
             self.scaler.update()
+        if ahead is not None:
+            mside = _lib.side_stream(self.device, 4)
+            if mside is not None:
+                torch.cuda.current_stream().wait_stream(mside)
         return loss, lossi, lossw
 
     def flush_optimizer(self):
@@ -382,8 +418,9 @@ class Scene:
         self.model._S_cache = None
         self.model.msg_encoder.presummed = None
 
-    def _capture(self, batch, message):
-        """Warm up on a side stream, then record one step into a CUDA graph with static input buffers."""
+    def _capture(self, batch, message, next_batch=None, next_message=None):
+        """Warm up on a side stream, then record one step into a CUDA graph with static input buffers (march_ahead: two
+        buffers and two graphs - graph p trains on buffer p, whose samples exist, and marches buffer 1-p)."""
         from . import _lib
         # ONE flat static input buffer; the per-key entries are views of it.  Layout (floats):
         #   [rays_o_block | rays_o | rays_d_block | rays_d | gt | message]
@@ -397,15 +434,52 @@ class Scene:
             self._layout[k] = (o, tuple(batch[k].shape))
             o += batch[k].numel()
         self._layout["message"] = (o, (md,))
-        self._static_flat = torch.empty(o + md, dtype=torch.float32, device=self.device)
-        self._static = {k: self._static_flat[a:a + math.prod(shp)].view(shp) for k, (a, shp) in self._layout.items()}
-        if self.merged_render:
-            nb, nc = batch["rays_o_block"].numel() // 3, batch["rays_o"].numel() // 3
-            for a in ("o", "d"):
-                lo = self._layout[f"rays_{a}_block"][0]
-                self._static[f"rays_{a}_all"] = self._static_flat[lo:lo + 3 * (nb + nc)].view(1, nb + nc, 3)
+        nb, nc = batch["rays_o_block"].numel() // 3, batch["rays_o"].numel() // 3
+
+        def make_static():
+            flat = torch.empty(o + md, dtype=torch.float32, device=self.device)
+            views = {k: flat[a:a + math.prod(shp)].view(shp) for k, (a, shp) in self._layout.items()}
+            if self.merged_render:
+                for a in ("o", "d"):
+                    lo = self._layout[f"rays_{a}_block"][0]
+                    views[f"rays_{a}_all"] = flat[lo:lo + 3 * (nb + nc)].view(1, nb + nc, 3)
+            return flat, views
+
+        self._static_flat, self._static = make_static()
         self._copy_inputs(batch, message)
         side = torch.cuda.Stream()
+        if self.march_ahead:
+            self._statics = [(self._static_flat, self._static), make_static()]
+            self._pm = [self.model.march_buffers(nb + nc, self.opt["max_steps"], self.device) for _ in range(2)]
+            if next_batch is None:
+                next_batch, next_message = batch, message
+            self._copy_inputs(next_batch, next_message, which=1)
+            self._march_now(0)
+
+            def step(p):
+                st, other = self._statics[p][1], self._statics[1 - p][1]
+                return self._step_impl(st, st["message"], ahead=(self._pm[p], other, self._pm[1 - p]))
+
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(4):      # an even count: buffer 0 is the marched one again afterwards
+                    step(i % 2)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graphs, self._static_outs = [], []
+            _lib.timing_reset()
+            for p in range(2):
+                g = torch.cuda.CUDAGraph()
+                _lib.timing_tag = p
+                n0 = _lib.launch_count
+                with torch.cuda.graph(g):
+                    self._static_outs.append(step(p))
+                self.launches_per_step = _lib.launch_count - n0
+                self._graphs.append(g)
+            _lib.timing_tag = None
+            self._graph = self._graphs[0]
+            self._ahead_p = 0
+            return
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
@@ -422,15 +496,22 @@ class Scene:
         n_calls = 1 if self.merged_render else 2
         self._graph_rows = [(ls - k) % 16 for k in range(n_calls, 0, -1)]  # the march counters baked into the graph
 
-    def _copy_inputs(self, batch, message):
+    def _march_now(self, p):
+        """Samples of input buffer p, marched on the spot (priming, or a batch that was not announced)."""
+        st = self._statics[p][1]
+        self.model.march_ahead(st["rays_o_all"], st["rays_d_all"], self._pm[p], dt_gamma=self.opt["dt_gamma"],
+                               max_steps=self.opt["max_steps"])
+
+    def _copy_inputs(self, batch, message, which=None):
+        sflat, static = (self._static_flat, self._static) if which is None else self._statics[which]
         flat = batch.get("_flat") if isinstance(batch, dict) else None
-        if flat is not None and flat.numel() == self._static_flat.numel():
-            self._static_flat.copy_(flat, non_blocking=True)   # packed host batch (pinned_batch): one H2D copy
+        if flat is not None and flat.numel() == sflat.numel():
+            sflat.copy_(flat, non_blocking=True)   # packed host batch (pinned_batch): one H2D copy
             return
         for k, v in batch.items():
-            if k != "_flat":
-                self._static[k].copy_(v, non_blocking=True)
-        self._static["message"].copy_(message, non_blocking=True)
+            if k not in ("_flat", "message"):
+                static[k].copy_(v, non_blocking=True)
+        static["message"].copy_(message, non_blocking=True)
 
     def pinned_batch(self, batch_np):
         """A host batch in pinned memory, packed in the layout of the captured step's static input buffer (what a data
@@ -446,10 +527,16 @@ class Scene:
                 out[k].copy_(torch.from_numpy(batch_np[k]))
         return out
 
-    def train_step(self, batch, message):
+    def train_step(self, batch, message, next_batch=None, next_message=None):
         """One optimisation step; returns (loss, lossi, lossw) as device scalars (no host sync here).  Configs with
         `grid_update_every` also run NeRFRenderer.update_extra_state every that many iterations (the clean trainer's
-        cadence, nerf/utils.py:855-857; BASELINE configs[2] asks for it in watermark training too)."""
+        cadence, nerf/utils.py:855-857; BASELINE configs[2] asks for it in watermark training too).
+        march_ahead: `next_batch` / `next_message` announce the batch of the following call (its input copy and its
+        march happen during this step); the message of an announced batch is the one it was announced with."""
+        if self.march_ahead:
+            out = self._train_step_ahead(batch, message, next_batch, next_message)
+            self.iteration += 1
+            return out
         out = self._train_step(batch, message)
         self.iteration += 1
         every = self.cfg.get("grid_update_every", 0)
@@ -474,6 +561,26 @@ class Scene:
         self.model._S_cache = None
         return self._static_out
 
+    def _train_step_ahead(self, batch, message, next_batch, next_message):
+        if self._graph is None:
+            self._capture(batch, message, next_batch, next_message)
+            self._ahead_token = None
+        p = self._ahead_p
+        if self._ahead_token is None or self._ahead_token != id(batch):
+            self._copy_inputs(batch, message, which=p)     # not announced: stage and march it now
+            self._march_now(p)
+        if next_batch is not None:
+            self._copy_inputs(next_batch, message if next_message is None else next_message, which=1 - p)
+            self._ahead_token = id(next_batch)
+        else:   # nothing announced: the graph re-marches whatever buffer 1-p holds; the next call stages its own batch
+            self._ahead_token = None
+        self.optimizer.sync_lr()
+        self._graphs[p].replay()
+        self.model._S_cache = None
+        self._ahead_last = p
+        self._ahead_p = 1 - p
+        return self._static_outs[p]
+
     def _counter_rows(self):
         if self.use_graph and getattr(self, "_graph_rows", None) is not None:
             return self._graph_rows
@@ -483,6 +590,9 @@ class Scene:
     def samples_per_step(self):
         """Measured (samples, rays) of the two most recent render calls = one training step (reads the march
         counters the kernels left on the device)."""
+        if self.march_ahead and self._graph is not None:
+            r = self._pm[self._ahead_last]["counter"].tolist()
+            return r[0], r[1]
         rows = self.model.step_counter[self._counter_rows()].tolist()
         return sum(r[0] for r in rows), sum(r[1] for r in rows)
 

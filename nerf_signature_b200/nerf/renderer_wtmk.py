@@ -204,7 +204,43 @@ class NeRFRenderer(nn.Module):
                   _P(xyzs), _P(dirs), _P(deltas), _P(rays), _P(counter), _P(noises), _P(_scratch(N, dev)))
         return xyzs, dirs, deltas, rays
 
-    def run_cuda(self, rays_o, rays_d, message=None, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+    def march_buffers(self, n_rays, max_steps=1024, device=None):
+        """Persistent worst-case-sized sample buffers of `march_ahead` for `n_rays` rays (a captured step bakes their
+        addresses): nears/fars [N], xyzs/dirs [N*max_steps,3], deltas [N*max_steps,2], rays [N,3] i32, counter i32[2]."""
+        dev = self.density_bitfield.device if device is None else device
+        M = n_rays * max_steps
+        f32 = dict(dtype=torch.float32, device=dev)
+        return {"nears": torch.empty(n_rays, **f32), "fars": torch.empty(n_rays, **f32),
+                "xyzs": torch.empty(M, 3, **f32), "dirs": torch.empty(M, 3, **f32), "deltas": torch.empty(M, 2, **f32),
+                "rays": torch.empty(n_rays, 3, dtype=torch.int32, device=dev),
+                "counter": torch.zeros(2, dtype=torch.int32, device=dev), "max_steps": max_steps, "n_rays": n_rays}
+
+    @torch.no_grad()
+    def march_ahead(self, rays_o, rays_d, bufs, dt_gamma=0, max_steps=1024, max_blocks=0):
+        """Sample generation of a training render call (near_far_from_aabb + march_rays_train with force_all_rays=True,
+        perturb=False: reference renderer_wtmk.py:268-286) issued AHEAD of the call that renders the rays, into `bufs`
+        (march_buffers).  The march reads only the rays and the occupancy bitfield - neither the tables nor any gradient -
+        so a training loop can run it for batch t+1 next to the latency-bound decoder kernels of step t.  The results
+        are handed to run_cuda(..., premarched=bufs); they are valid until `density_bitfield` changes.
+        max_blocks > 0 limits the march kernels' grids (nsig_march_rays_train_limited) so that the kernels it runs
+        beside still find room on every SM; outputs are bit-identical."""
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        N = rays_o.shape[0]
+        if N != bufs["n_rays"] or max_steps != bufs["max_steps"]:
+            raise ValueError(f"march_ahead: buffers were sized for {bufs['n_rays']} rays x {bufs['max_steps']} steps, "
+                             f"got {N} x {max_steps}")
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        _lib.call("nsig_near_far_from_aabb", _P(rays_o), _P(rays_d), _P(aabb), N, float(self.min_near),
+                  _P(bufs["nears"]), _P(bufs["fars"]))
+        bufs["counter"].zero_()
+        _lib.call("nsig_march_rays_train_limited", _P(rays_o), _P(rays_d), _P(self.density_bitfield), float(self.bound),
+                  float(dt_gamma), int(max_steps), N, int(self.cascade), int(self.grid_size), N * max_steps,
+                  _P(bufs["nears"]), _P(bufs["fars"]), _P(bufs["xyzs"]), _P(bufs["dirs"]), _P(bufs["deltas"]),
+                  _P(bufs["rays"]), _P(bufs["counter"]), _P(None), _P(_scratch(N, rays_o.device)), int(max_blocks))
+        return bufs
+
+    def run_cuda(self, rays_o, rays_d, message=None, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4, premarched=None, **kwargs):
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.contiguous().view(-1, 3).float()
         rays_d = rays_d.contiguous().view(-1, 3).float()
@@ -212,7 +248,13 @@ class NeRFRenderer(nn.Module):
         N = rays_o.shape[0]
         device = rays_o.device
 
-        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        if premarched is not None:
+            if not self.training or perturb or N != premarched["n_rays"] or max_steps != premarched["max_steps"]:
+                raise ValueError("premarched samples need the training branch, perturb=False and the ray count / max_steps "
+                                 "they were marched with")
+            nears, fars = premarched["nears"], premarched["fars"]
+        else:
+            nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
 
         if self.bg_radius > 0:
             sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
@@ -225,11 +267,15 @@ class NeRFRenderer(nn.Module):
         if self.training:
             if message is not None and hasattr(self, "prefetch_summed_table"):
                 self.prefetch_summed_table(message)  # the table sum overlaps the march (side stream)
-            counter = self.step_counter[self.local_step % 16]
-            counter.zero_()
-            self.local_step += 1
+            if premarched is not None:   # marched ahead of this call (march_ahead): the live prefix length is its own counter
+                counter = premarched["counter"]
+                xyzs, dirs, deltas, rays = (premarched[k] for k in ("xyzs", "dirs", "deltas", "rays"))
+            else:
+                counter = self.step_counter[self.local_step % 16]
+                counter.zero_()
+                self.local_step += 1
 
-            xyzs, dirs, deltas, rays = self._march_train_nosync(rays_o, rays_d, nears, fars, counter, perturb, force_all_rays, dt_gamma, max_steps)
+                xyzs, dirs, deltas, rays = self._march_train_nosync(rays_o, rays_d, nears, fars, counter, perturb, force_all_rays, dt_gamma, max_steps)
 
             # sigmas already include density_scale (folded into the fused kernel, reference L294)
             sigmas, rgbs = self.field(xyzs, dirs, message, count=counter)

@@ -333,11 +333,32 @@ class WatermarkAdam(torch.optim.Optimizer):
         self._model._S_cache = None
         return self._S_ahead
 
+    def sum_with_next_step(self, next_message):
+        """Fold the NEXT forward's table sum into the next step()/step_tables(): the update kernel then also accumulates
+        S = sum_i table[2i + next_message_i] over the updated tables (nsig_msg_adam_step_sum, bit-identical to update-then-
+        sum) and hands it to the encoder as the pre-summed table of `next_message` - the separate pass over message_dim
+        tables and its kernel disappear from the head of the next forward.  One use; None cancels."""
+        self._sum_next = next_message
+
     @torch.no_grad()
     def step_tables(self):
         """The message tables' share of step(): one Adam kernel over the tables the message selects; joins the decoder's
         side stream (step_decoder) into the current stream."""
-        if self._train_tables:
+        nxt, self._sum_next = getattr(self, "_sum_next", None), None
+        if self._train_tables and nxt is not None and not getattr(self, "_steps_prepared", False):
+            group, beta1, beta2 = self._table_call_args()
+            md = self.enc.message_dim
+            if getattr(self, "_S_ahead", None) is None:
+                self._S_ahead = torch.empty_like(self.tables[0])
+            nx = nxt.to(device=self.G.device, dtype=torch.float32)
+            _lib.call("nsig_msg_adam_step_sum", _P(self._ptrs), len(self.tables), md, _P(self.message), _P(nx), _P(self.G),
+                      _P(self.steps), _P(self._coef), _P(getattr(self, "grad_scale", None)),
+                      _P(getattr(self, "found_inf", None)), float(group["lr"]), beta1, beta2, float(group["eps"]),
+                      self.enc.log2_hashmap_size, _P(self._lr_dev), self.shard[0] if self.shard else 0,
+                      self.shard[1] if self.shard else 0, _P(self._S_ahead))
+            self.enc.presummed = (nxt, self._S_ahead)
+            self._model._S_cache = None
+        elif self._train_tables:
             group, beta1, beta2 = self._table_call_args()
             md = self.enc.message_dim
             prepared = 1 if getattr(self, "_steps_prepared", False) else 0

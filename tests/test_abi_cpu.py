@@ -91,6 +91,13 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 2, 8, aligned, None) == -1
     assert h.nsig_msg_adam_lookahead_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 1 << 20, aligned, None) == -1
     assert h.nsig_msg_adam_step(p, 8, 4, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 6, 0, None) == -1   # ragged range
+    # update + next message's table sum in one pass: same contract as the look-ahead sum
+    assert h.nsig_msg_adam_step_sum(p, 8, 4, p, None, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, aligned, None) == -1
+    assert h.nsig_msg_adam_step_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, odd, None) == -1
+    assert h.nsig_msg_adam_step_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 2, 8, aligned, None) == -1
+    # grid-limited march: the unlimited entry's validation
+    assert h.nsig_march_rays_train_limited(p, p, p, 1.0, 0.0, 1024, 4, 0, 128, 64, p, p, p, p, p, p, p, None, p, 296, None) == -1  # C=0
+    assert h.nsig_march_rays_train_limited(p, p, p, 1.0, 0.0, 1024, 0, 1, 128, 64, p, p, p, p, p, p, p, None, p, 296, None) == 0   # no rays
     assert h.nsig_field_backward(p, p, 4, 1.0, p, p, p, odd, aligned, 1.0, None, 2048.0, 19, p, None, None, None, None) == -1
     # round-2 entry points: tcgen05 backward, fused-slot probe, one-kernel GradScaler, flat Adam
     assert h.nsig_field_backward_tc(None, None, 0, 1.0, None, None, None, None, None, 1.0, None, 2048.0, 19, None, None) == 0

@@ -314,18 +314,19 @@ def test_lr_schedule_acts_on_graph_replays():
     del sched
 
 
-@pytest.mark.parametrize("graph,lookahead", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("graph,lookahead", [(False, True), (True, True), (True, False), (False, False)])
 def test_deferred_optimizer_equals_sequential_optimizer(graph, lookahead):
     """harness defer_optimizer: the Adam update of step t issued at the start of step t+1 (next to its march) leaves, after
     flush_optimizer(), the same tables, decoder and scaler state as the sequential schedule, step for step; a flush in the
     middle (what update_extra_state needs) does not apply an update twice.  The scatter-add order of dL/dS is not
     deterministic and Adam's update is sign-like for near-zero gradients (see _close_frac), so the yardstick is the
     run-to-run difference of two IDENTICAL sequential scenes.
-    lookahead (default): S for the next step comes from nsig_msg_adam_lookahead_sum and the table update itself runs next to
-    the decoder (between the composite forward and the field backward)."""
+    lookahead: S for the next step comes from nsig_msg_adam_lookahead_sum and the table update itself runs next to
+    the decoder (between the composite forward and the field backward).  Without it (default) the pending update's kernel
+    also accumulates S for the step that issues it (nsig_msg_adam_step_sum)."""
     kw = dict(optimizer="fused", merged_render=True, fused_decoder=True, fused_losses=True, graph=graph)
     a, a2, b = _scene(**kw), _scene(**kw), _scene(defer_optimizer=True, lookahead=lookahead, **kw)
-    assert b.defer_optimizer and b.lookahead == lookahead
+    assert b.defer_optimizer and b.lookahead == lookahead and b.fuse_table_sum == (not lookahead)
     batches = _batches(a, 2)
     gen = torch.Generator().manual_seed(21)
     msgs = [a.new_message(gen) for _ in range(7)]
@@ -410,3 +411,131 @@ def test_lookahead_sum_is_bit_identical_to_update_then_sum(skip, shard):
     assert torch.equal(steps, steps2) and torch.equal(coef, coef2)
     for x, y in zip(tabs + ms + vs, tabs2 + ms2 + vs2):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("skip,shard", [(False, False), (True, False), (False, True)])
+def test_adam_step_sum_is_bit_identical_to_update_then_sum(skip, shard):
+    """nsig_msg_adam_step_sum(applied, next) == nsig_msg_adam_step(applied) followed by nsig_msg_table_sum(next): tables,
+    moments, steps, coefficients and S, bit for bit - also with a skipped step (found_inf = 1: tables untouched, S of the
+    tables as they are) and on a slice (sharded optimizer: nothing outside the slice is written, S included)."""
+    from nerf_signature_b200 import _lib
+    P = _lib.ptr
+    dev = torch.device("cuda:0")
+    md, log2_T = 7, 12          # odd message_dim: the unrolled loop's tail
+    n = 2 << log2_T
+    g = torch.Generator(device="cuda").manual_seed(5)
+
+    def state():
+        gg = torch.Generator(device="cuda").manual_seed(13)
+        tabs = [torch.randn(n, device=dev, generator=gg) * 1e-2 for _ in range(2 * md)]
+        ms = [torch.randn(n, device=dev, generator=gg) * 1e-3 for _ in range(2 * md)]
+        vs = [torch.rand(n, device=dev, generator=gg) * 1e-6 for _ in range(2 * md)]
+        ptrs = torch.tensor([[t.data_ptr() for t in grp] for grp in (tabs, ms, vs)], dtype=torch.int64, device=dev)
+        steps = torch.arange(2 * md, dtype=torch.float32, device=dev) + 3.0
+        coef = torch.zeros(2 * md, 2, dtype=torch.float32, device=dev)
+        return tabs, ms, vs, ptrs, steps, coef
+
+    G = torch.randn(n, device=dev, generator=g) * 65536.0 * 1e-3
+    G[torch.rand(n, device=dev, generator=g) < 0.5] = 0.0
+    applied = torch.tensor([1, 0, 1, 1, 0, 0, 1], dtype=torch.float32, device=dev)
+    nxt = torch.tensor([1, 1, 0, 1, 0, 1, 1], dtype=torch.float32, device=dev)
+    scale = torch.tensor([65536.0], device=dev)
+    finf = torch.tensor([1.0 if skip else 0.0], device=dev)
+    lo, cnt = (1024, 2048) if shard else (0, 0)
+    hyper = (1e-2, 0.9, 0.99, 1e-15)
+
+    tabs, ms, vs, ptrs, steps, coef = state()
+    before = [t.clone() for t in tabs + ms + vs]
+    _lib.call("nsig_msg_adam_step", P(ptrs), 2 * md, md, P(applied), P(G), P(steps), P(coef), P(scale), P(finf), *hyper,
+              log2_T, None, lo, cnt, 0)
+    S_ref = torch.full((n,), 7.0, device=dev)
+    _lib.call("nsig_msg_table_sum", _lib.pointer_array(tabs), md, P(nxt), log2_T, P(S_ref), lo, cnt)
+
+    tabs2, ms2, vs2, ptrs2, steps2, coef2 = state()
+    S = torch.full((n,), 7.0, device=dev)
+    _lib.call("nsig_msg_adam_step_sum", P(ptrs2), 2 * md, md, P(applied), P(nxt), P(G), P(steps2), P(coef2), P(scale),
+              P(finf), *hyper, log2_T, None, lo, cnt, P(S))
+    assert torch.equal(S, S_ref)
+    assert torch.equal(steps, steps2) and torch.equal(coef, coef2)
+    for x, y in zip(tabs + ms + vs, tabs2 + ms2 + vs2):
+        assert torch.equal(x, y)
+    changed = sum(int(not torch.equal(x, y)) for x, y in zip(before, tabs2 + ms2 + vs2))
+    assert changed == (0 if skip else 3 * md)
+    # argument validation
+    with pytest.raises(_lib.NsigError):
+        _lib.call("nsig_msg_adam_step_sum", P(ptrs2), 2 * md, md, P(applied), None, P(G), P(steps2), P(coef2), P(scale),
+                  P(finf), *hyper, log2_T, None, lo, cnt, P(S))
+    with pytest.raises(_lib.NsigError):
+        _lib.call("nsig_msg_adam_step_sum", P(ptrs2), 2 * md, md, P(applied), P(nxt), P(G), P(steps2), P(coef2), P(scale),
+                  P(finf), *hyper, log2_T, None, 2, 6, P(S))
+
+
+def test_premarched_render_is_bit_identical():
+    """NeRFRenderer.march_ahead + run_cuda(premarched=...) == run_cuda marching by itself: same kernels, same arguments."""
+    from nerf_signature_b200 import harness
+    s = _scene(optimizer="fused", merged_render=True)
+    model = s.model
+    b = harness.make_batch(s.cfg, seed=77)
+    o = torch.from_numpy(b["rays_o"]).cuda()
+    d = torch.from_numpy(b["rays_d"]).cuda()
+    msg = s.new_message(torch.Generator().manual_seed(1)).cuda()
+    kw = dict(staged=False, bg_color=1, perturb=False, force_all_rays=True, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4)
+    with torch.no_grad():
+        ref = model.render(o, d, msg, **kw)
+        rows = model.step_counter[(model.local_step - 1) % 16].tolist()
+        bufs = model.march_buffers(o.shape[1])
+        model.march_ahead(o, d, bufs)
+        out = model.render(o, d, msg, premarched=bufs, **kw)
+        # grid-limited march (nsig_march_rays_train_limited: 5 CTAs walk all the rays) - the same bits
+        lim = model.march_buffers(o.shape[1])
+        model.march_ahead(o, d, lim, max_blocks=5)
+    assert bufs["counter"].tolist() == rows
+    for k in ("image", "depth", "weights_sum"):
+        assert torch.equal(out[k], ref[k]), k
+    m = rows[0]
+    assert lim["counter"].tolist() == rows and torch.equal(lim["rays"], bufs["rays"])
+    for k in ("nears", "fars"):
+        assert torch.equal(lim[k], bufs[k]), k
+    for k in ("xyzs", "dirs", "deltas"):
+        assert torch.equal(lim[k][:m], bufs[k][:m]), k
+    with pytest.raises(ValueError):
+        model.render(o[:, :100], d[:, :100], msg, premarched=bufs, **kw)
+    with pytest.raises(ValueError):
+        model.march_ahead(o[:, :100], d[:, :100], bufs)
+
+
+def test_march_ahead_schedule_equals_plain_schedule():
+    """harness march_ahead: the samples of batch t+1 are generated inside step t (next to the decoder), from a second input
+    buffer, by a second graph - losses, sample counts, tables and decoder must be those of the plain captured step on the same
+    batch / message sequence, whether a batch was announced (overlapped march) or not (marched on the spot).  Yardstick: two
+    identical plain scenes (the scatter-add order of dL/dS is not deterministic)."""
+    kw = dict(optimizer="fused", merged_render=True, fused_decoder=True, fused_losses=True, graph=True, defer_optimizer=True)
+    a, a2, b = _scene(**kw), _scene(**kw), _scene(march_ahead=True, **kw)
+    batches = _batches(a, 3)
+    gen = torch.Generator().manual_seed(31)
+    msgs = [a.new_message(gen) for _ in range(9)]
+    # capture warm-ups: 3 steps (plain) / 4 steps (march_ahead, both buffers) on (batches[0], msgs[0])
+    a._capture(batches[0], msgs[0]); a2._capture(batches[0], msgs[0])
+    b._capture(batches[0], msgs[0], batches[0], msgs[0])
+    a.train_step(batches[0], msgs[0]); a2.train_step(batches[0], msgs[0])
+    for i, m in enumerate(msgs):
+        cur = batches[i % 3]
+        la = [float(x) for x in a.train_step(cur, m)]
+        la2 = [float(x) for x in a2.train_step(cur, m)]
+        if i in (4, 5) or i + 1 == len(msgs):   # nothing announced for steps 5 and 6: they are staged + marched on the spot
+            lb = b.train_step(cur, m)
+        else:
+            lb = b.train_step(cur, m, next_batch=batches[(i + 1) % 3], next_message=msgs[i + 1])
+        lb = [float(x) for x in lb]
+        assert b.samples_per_step() == a.samples_per_step(), i
+        for k in range(3):
+            floor = abs(la2[k] - la[k]) / abs(la[k])
+            assert abs(lb[k] - la[k]) / abs(la[k]) <= max(2e-4, 3.0 * floor), (i, k, la, la2, lb)
+    for s in (a, a2, b):
+        s.flush_optimizer()
+    torch.cuda.synchronize()
+    floor = max(_bad_frac(x, y) for x, y in zip(_msg_tables(a2), _msg_tables(a)))
+    worst = max(_bad_frac(x, y) for x, y in zip(_msg_tables(b), _msg_tables(a)))
+    assert worst <= max(1e-4, 3.0 * floor), (worst, floor)
+    with pytest.raises(ValueError):
+        _scene(march_ahead=True, optimizer="fused", merged_render=True, graph=False)
