@@ -376,6 +376,11 @@ size_t nsig_decoder_workspace_bytes(uint32_t B, uint32_t H, uint32_t W, uint32_t
 size_t nsig_decoder_weights_bytes(uint32_t num_blocks);
 int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks, uint32_t num_bits,
                                  uint32_t redundancy, void* weights, nsig_stream_t stream);
+
+/* Parity probe of the decoder kernels' activation arithmetic: gelu[i] = fp16(GELU(y[i])), gelu_grad[i] = fp16(GELU'(y[i]))
+ * for n fp16 values, through the very device functions the conv kernels apply while staging their tiles (nn.GELU(), exact /
+ * erf form: hidden_models.py:26).  Lets a test sweep all 2^16 fp16 inputs against torch and against float64. */
+int nsig_decoder_gelu_probe(const void* y, uint32_t n, void* gelu, void* gelu_grad, nsig_stream_t stream);
 int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W, uint32_t num_blocks,
                          uint32_t num_bits, uint32_t redundancy, const float* const* params, void* workspace,
                          float* logits, const void* prepared_weights, nsig_stream_t stream);

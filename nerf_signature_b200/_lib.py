@@ -70,6 +70,7 @@ _SIGNATURES = {
     "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
                               lambda a: 2 * (a[4] + 1) + 3 + (1 if a[10] is not None else 0)),
     "nsig_decoder_prepare_weights": ([_vp, _u32, _u32, _u32, _vp, _vp], 1),
+    "nsig_decoder_gelu_probe": ([_vp, _u32, _vp, _vp, _vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
