@@ -36,6 +36,19 @@ constexpr float kBnEps = 1e-3f;  // hidden_models.py:24
 
 enum InMode { IN_RAW = 0, IN_BNGELU = 1, IN_DZ = 2 };
 
+// -DNSIG_DEC_TRACE (tools/build_variant.py, never in the shipped library): CTA 0 of every conv launch stamps %globaltimer at its
+// phase boundaries; nsig_debug_dec_trace copies the stamps out (tools/dec_trace.py).
+#ifdef NSIG_DEC_TRACE
+__device__ unsigned long long g_dec_trace[64][12];
+__device__ unsigned int g_dec_trace_n;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DEC_TRACE_BEGIN() unsigned int tr_slot = 0; if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { tr_slot = atomicAdd(&g_dec_trace_n, 1u) & 63u; g_dec_trace[tr_slot][0] = gtime(); }
+#define DEC_TRACE(k) if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dec_trace[tr_slot][k] = gtime();
+#else
+#define DEC_TRACE_BEGIN()
+#define DEC_TRACE(k)
+#endif
+
 // per-channel constants of one BatchNorm layer, derived from the raw sums
 struct BnCoef {
     float scale, shift;   // y = z*scale + shift  (scale = gamma*rstd, shift = beta - mean*scale)
@@ -241,6 +254,7 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
     __half* wsm = reinterpret_cast<__half*>(coef_out + COUT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
     const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
+    DEC_TRACE_BEGIN();
     // Asynchronous copy of the weights (up to 74 KB from L2), issued first: it completes while the BatchNorm
     // coefficients are derived and the input tile is staged and transformed.  Reading every weight fragment straight from
     // global memory inside the k-loop instead exposed an L2 round trip every few k-steps on a kernel whose math is ~1 us.
@@ -260,14 +274,18 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
     // the first batch of input-tile loads is in flight while the BatchNorm coefficients (their own L2 round trip +
     // fp64 arithmetic) are derived: one exposed memory latency in the prologue instead of two
     TileStager<CIN, SCH, MODE> stager;
+    DEC_TRACE(1);
     stager.issue(p.src, p.src2, 0, b, r0, R, p.H, p.W);
+    DEC_TRACE(2);
     if (first && MODE != IN_RAW) {
         for (int ch = threadIdx.x; ch < SCH; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
         if (bstats)
             for (int ch = threadIdx.x; ch < COUT; ch += blockDim.x) coef_out[ch] = bn_coef(p.bn_out, ch, false);
         __syncthreads();
     }
+    DEC_TRACE(3);
     stager.commit(tile, coef, 0, R, p.W);
+    DEC_TRACE(4);
     {
         const int total = (R + 2) * (p.W + 2) * (CIN / 8), step = kStagePF * (int)blockDim.x;
         for (int base = step; base < total; base += step) {
@@ -276,7 +294,9 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
         }
     }
     if (first) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    DEC_TRACE(5);
     __syncthreads();
+    DEC_TRACE(6);
 
     const int P = R * p.W, TW = p.W + 2, m_tiles = (P + 15) / 16, m_groups = (m_tiles + MB - 1) / MB;
     if (p.act_out) {  // materialise the centre rows of the transformed tile
@@ -287,6 +307,7 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
                 *reinterpret_cast<const uint4*>(tile + ((size_t)(rr + 1) * TW + (ww + 1)) * STRIDE + ck * 8);
         }
     }
+    DEC_TRACE(7);
     for (int item = warp; item < m_groups * NT; item += kDecWarps) {
         const int mg = item / NT, nt = item - mg * NT;
         const __half* arow[MB];
@@ -358,6 +379,7 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
             }
         }
         }
+        DEC_TRACE(8);
         // epilogue: rows g, g+8 of each m-tile; columns nt*8 + 2tig, +1
         const int col = nt * 8 + 2 * tig;
         const float bias0 = (p.bias && col < p.cout_valid) ? p.bias[col] : 0.f;
@@ -406,7 +428,9 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
             }
         }
     }
+    DEC_TRACE(9);
     __syncthreads();   // the tile is restaged for the CTA's next item
+    DEC_TRACE(10);
   }
 }
 
@@ -1151,6 +1175,21 @@ int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks
     NSIG_LAUNCH_CHECK();
     return 0;
 }
+
+#ifdef NSIG_DEC_TRACE
+int nsig_debug_dec_trace(unsigned long long* host_out /* [64][12] */, unsigned int* host_n, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, g_dec_trace, sizeof(unsigned long long) * 64 * 12);
+    cudaMemcpyFromSymbol(host_n, g_dec_trace_n, sizeof(unsigned int));
+    if (reset) {
+        static unsigned long long z[64][12];
+        unsigned int zero = 0;
+        cudaMemcpyToSymbol(g_dec_trace, z, sizeof(z));
+        cudaMemcpyToSymbol(g_dec_trace_n, &zero, sizeof(zero));
+    }
+    return 0;
+}
+#endif
 
 int nsig_decoder_gelu_probe(const void* y, uint32_t n, void* gelu, void* gelu_grad, nsig_stream_t stream) {
     if (n == 0) return 0;
