@@ -44,9 +44,18 @@ __device__ unsigned int g_dec_trace_n;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define DEC_TRACE_BEGIN() unsigned int tr_slot = 0; if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { tr_slot = atomicAdd(&g_dec_trace_n, 1u) & 63u; g_dec_trace[tr_slot][0] = gtime(); }
 #define DEC_TRACE(k) if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dec_trace[tr_slot][k] = gtime();
+__device__ unsigned long long g_wg_trace[64][12];
+__device__ unsigned int g_wg_trace_n;
+#define WG_TRACE_BEGIN() unsigned int wg_slot = 0; if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { wg_slot = atomicAdd(&g_wg_trace_n, 1u) & 63u; g_wg_trace[wg_slot][0] = gtime(); g_wg_trace[wg_slot][11] = wg_slot; }
+#define WG_TRACE(k) if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_wg_trace[wg_slot][k] = gtime();
+// the final reduction of tap 0 runs in whichever group's CTA drew the last ticket: it stamps the most recent slot
+#define WG_TRACE_LAST(k) if (blockIdx.x == 0 && threadIdx.x == 0) g_wg_trace[(g_wg_trace_n - 1u) & 63u][k] = gtime();
 #else
 #define DEC_TRACE_BEGIN()
 #define DEC_TRACE(k)
+#define WG_TRACE_BEGIN()
+#define WG_TRACE(k)
+#define WG_TRACE_LAST(k)
 #endif
 
 // per-channel constants of one BatchNorm layer, derived from the raw sums
@@ -194,7 +203,10 @@ struct TileStager {
         }
     }
 
-    __device__ __forceinline__ void commit(__half* tile, const BnCoef* __restrict__ coef, int base, int R, int W) const {
+    // element (pos, 8-channel chunk ck) lands at tile + pos * pos_stride + ck * ck_stride (halfs): row-major [pos][C + 8] by
+    // default; the tcgen05 kernel passes (8, positions * 8) = the no-swizzle K-major core-matrix layout [ck][pos][8]
+    __device__ __forceinline__ void commit(__half* tile, const BnCoef* __restrict__ coef, int base, int R, int W,
+                                           int pos_stride = STRIDE, int ck_stride = 8) const {
         const int TW = W + 2, total = (R + 2) * TW * CHUNKS;
 #pragma unroll
         for (int j = 0; j < kStagePF; ++j) {
@@ -207,7 +219,7 @@ struct TileStager {
                 else if (MODE == IN_BNGELU) out = act8_from_z(v[j], coef + ck * 8);
                 else out = dz8_from(v[j], v2[j], coef + ck * 8);
             }
-            *reinterpret_cast<uint4*>(tile + (size_t)pos * STRIDE + ck * 8) = out;
+            *reinterpret_cast<uint4*>(tile + (size_t)pos * pos_stride + (size_t)ck * ck_stride) = out;
         }
     }
 };
@@ -217,6 +229,7 @@ struct ConvParams {
     const __half* src2;    // z (IN_DZ)
     BnSrc bn;              // BatchNorm state of the input transform
     const __half* w;       // [COUT][9][CIN] fp16 (already rotated/transposed for data gradients)
+    const __half* w_tc;    // the same 64x64 layer as [9 taps][64 x 64] in the UMMA canonical layout (k_dec_conv_tc), or null
     const float* bias;     // [COUT] or null
     __half* dst;           // [B,H,W,COUT]
     __half* act_out;       // optional [B,H,W,SCH]: the transformed input (a_{l-1} forward, dz_l backward) is written
@@ -443,6 +456,231 @@ k_dec_conv(const ConvParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The 64 -> 64 convolution on tcgen05 + TMEM (default; NSIG_DEC_TC=0 selects k_dec_conv).  Same contract as k_dec_conv<64,64,64,MODE> (staging, transforms,
+// act_out, outputs, statistics); what changes is the contraction.  The phase trace of the mma.sync kernel
+// (profiles/r02_decoder_phase_trace.txt) shows its k-loop as the largest phase (3.7 us forward / 4.9 us data gradient of
+// 8.3 / 13.4 us): 864 m16n8k16 MMAs and 1008 ldmatrix.x4 per CTA, every warp re-reading the whole activation tile from
+// shared memory for its 8 output channels.  Here the tile is written ONCE in the UMMA K-major core-matrix layout
+// [8-channel chunk][position][8 halfs] (positions = the strip with its halo, row-major over the PADDED width W + 2) and the
+// tensor core reads it: output row m = r * (W + 2) + c needs, for tap (dy, dx), input position m + (1 + dy) * (W + 2) + 1 + dx -
+// a shift of the operand's START ADDRESS by 16 bytes per position (rows are 16 bytes apart throughout this layout, so any
+// shift keeps every 8-row core matrix contiguous).  36 MMAs (M = 128, N = 64, K = 16) issued by one thread accumulate all
+// 9 taps in 64 TMEM columns; rows of the padding columns (c >= W) and past the strip are computed and dropped.
+// Weights: [tap][64 x 64] in the canonical layout of field_tc.cu (leading byte offset 128, stride byte offset 1024).
+// ---------------------------------------------------------------------------------------------------------------
+namespace tcv {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory matrix descriptor (no swizzle, version 1): start address, leading / stride byte offsets in 16-byte units
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();   // a lost completion must fail loudly, never hang the GPU
+    }
+}
+#define NSIG_DEC_TMEM_LD16(taddr, v)                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"  \
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),         \
+                   "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])    \
+                 : "r"(taddr))
+constexpr uint32_t kCols = 64;
+constexpr int kWBytes = 9 * 64 * 64 * 2;
+// positions of the A operand that must be addressable: the largest tap offset 2 * (W + 2) + 2 plus 128 rows
+// (= 1 mod 8: the 8 channel chunks of a position then start 16 bytes apart modulo 128 - conflict-free tile stores)
+__host__ __device__ inline int npos_alloc(int W) { return (2 * (W + 2) + 2 + 128 + 7) / 8 * 8 + 1; }
+__host__ __device__ inline size_t smem_bytes(int R, int W) {
+    return (size_t)kWBytes + (((size_t)8 * npos_alloc(W) * 16 + 127) / 128 * 128) + (size_t)R * W * 64 * 2 + 2 * 64 * sizeof(BnCoef) + 4 * 64 * 2 * sizeof(float) + 64;
+}
+}  // namespace tcv
+
+template <int MODE>
+__global__ void __launch_bounds__(kDecThreads)
+k_dec_conv_tc(const ConvParams p) {
+    constexpr int C = 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, r0 = blockIdx.x * p.R, R = min(p.R, p.H - r0), TW = p.W + 2, P = R * p.W, Mrows = R * TW;
+    const int NposA = tcv::npos_alloc(p.W);
+    __half* wsm = reinterpret_cast<__half*>(smem_raw);
+    __half* atile = reinterpret_cast<__half*>(smem_raw + tcv::kWBytes);                  // [8][NposA][8]
+    __half* otile = atile + ((size_t)8 * NposA * 8 + 63) / 64 * 64;                      // [P][64] fp16 outputs of the strip
+    BnCoef* coef = reinterpret_cast<BnCoef*>(otile + (size_t)p.R * p.W * C);
+    BnCoef* coef_out = coef + C;
+    float* red = reinterpret_cast<float*>(coef_out + C);                                 // [4][64][2] statistics partials
+    uint64_t* mbar_store = reinterpret_cast<uint64_t*>(red + 4 * 64 * 2);      // [0] accumulator complete, [1] weights arrived
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_store + 2);
+    const uint32_t mbar = tcv::smem_u32(mbar_store), mbar_w = tcv::smem_u32(mbar_store + 1);
+    const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
+    DEC_TRACE_BEGIN();
+
+    // weights: 72 KB already in the operand layout (k_dec_prep_weights) -> 9 bulk asynchronous copies issued by one thread
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_w));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_w), "r"((uint32_t)tcv::kWBytes) : "memory");
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(tcv::smem_u32(wsm) + t * 8192), "l"(p.w_tc + (size_t)t * 4096), "r"(8192u), "r"(mbar_w) : "memory");
+    }
+    DEC_TRACE(11);
+    __syncwarp();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tcv::smem_u32(tmem_slot)), "n"(tcv::kCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+
+    DEC_TRACE(1);
+    TileStager<C, C, MODE> stager;
+    stager.issue(p.src, p.src2, 0, b, r0, R, p.H, p.W);
+    DEC_TRACE(2);
+    for (int ch = tid; ch < C; ch += blockDim.x) coef[ch] = bn_coef(p.bn, ch, MODE == IN_DZ);
+    if (bstats)
+        for (int ch = tid; ch < C; ch += blockDim.x) coef_out[ch] = bn_coef(p.bn_out, ch, false);
+    __syncthreads();
+    DEC_TRACE(3);
+    stager.commit(atile, coef, 0, R, p.W, 8, NposA * 8);
+    {
+        const int total = (R + 2) * TW * (C / 8), step = kStagePF * (int)blockDim.x;
+        for (int base = step; base < total; base += step) {
+            stager.issue(p.src, p.src2, base, b, r0, R, p.H, p.W);
+            stager.commit(atile, coef, base, R, p.W, 8, NposA * 8);
+        }
+    }
+    DEC_TRACE(4);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes (the tile) -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    DEC_TRACE(5);
+
+    if (tid == 0) {
+        // instruction descriptor: D = fp32 (bit 4), A = B = fp16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t chunk_bytes = (uint32_t)NposA * 16;
+        // descriptors differ in their start-address field only (16-byte units, no carry out of its 14 bits)
+        const uint64_t da0 = tcv::make_desc(tcv::smem_u32(atile), chunk_bytes, 128);
+        const uint64_t db0 = tcv::make_desc(tcv::smem_u32(wsm), 128, 1024);
+        const uint32_t kstep = (2 * chunk_bytes) >> 4, trow = (uint32_t)TW;
+        tcv::mbar_wait(mbar_w, 0);     // weights in shared memory (async proxy writes: no proxy fence needed)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                tcv::mma_f16_ss(tmem_d, da0 + (uint64_t)((t / 3) * trow + (t % 3) + ks * kstep),
+                                db0 + (uint64_t)(t * 512 + ks * 16), idesc, (t | ks) ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    }
+    DEC_TRACE(6);
+    if (p.act_out) {  // materialise the centre rows of the transformed tile (while the tensor core works)
+        for (int i = tid; i < P * 8; i += blockDim.x) {
+            const int pix = i >> 3, ck = i & 7, rr = pix / p.W, ww = pix - rr * p.W;
+            *reinterpret_cast<uint4*>(p.act_out + (((size_t)b * p.H + r0 + rr) * p.W + ww) * C + ck * 8) =
+                *reinterpret_cast<const uint4*>(atile + (size_t)ck * NposA * 8 + (size_t)((rr + 1) * TW + (ww + 1)) * 8);
+        }
+    }
+    DEC_TRACE(7);
+    tcv::mbar_wait(mbar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DEC_TRACE(8);
+
+    // accumulators -> fp16 outputs in shared memory: warp w reads TMEM lanes 32 * (w % 4).., columns 32 * (w / 4)..
+    {
+        const int q = warp & 3, hf = warp >> 2;
+        if (32 * q < Mrows) {
+            float v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * hf);
+            NSIG_DEC_TMEM_LD16(taddr, v);
+            NSIG_DEC_TMEM_LD16(taddr + 16, (&v[16]));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int m = 32 * q + lane, rr = m / TW, cc = m - rr * TW;
+            if (m < Mrows && cc < p.W) {
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = 32 * hf + 2 * j;
+                    const float b0 = p.bias ? p.bias[col] : 0.f, b1 = p.bias ? p.bias[col + 1] : 0.f;
+                    const __half2 h = __halves2half2(f2h(v[2 * j] + b0), f2h(v[2 * j + 1] + b1));
+                    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(otile + (size_t)(rr * p.W + cc) * C + 32 * hf);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(tcv::kCols));
+    DEC_TRACE(9);
+
+    // the strip's outputs are contiguous in the NHWC tensor
+    {
+        uint4* gdst = reinterpret_cast<uint4*>(p.dst + ((size_t)b * p.H + r0) * p.W * C);
+        const uint4* osrc = reinterpret_cast<const uint4*>(otile);
+        for (int i = tid; i < P * 8; i += blockDim.x) gdst[i] = osrc[i];
+    }
+    // statistics of the (fp16-rounded) outputs: thread (channel, part) walks every 4th pixel
+    double* const sums_dst = bstats ? p.out_bsums : p.out_sums;
+    if (sums_dst) {
+        const int ch = tid & 63, part = tid >> 6;
+        float s1 = 0.f, s2 = 0.f;
+        if (bstats) {
+            const __half* zsrc = p.z_out + ((size_t)b * p.H + r0) * p.W * C + ch;
+            constexpr int PF = 8, STEP = kDecThreads / 64;   // z of 8 pixels requested together (one L2 round trip, not eight)
+            for (int pix0 = part; pix0 < P; pix0 += PF * STEP) {
+                __half zv[PF];
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int pix = pix0 + j * STEP;
+                    zv[j] = pix < P ? zsrc[(size_t)pix * C] : f2h(0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int pix = pix0 + j * STEP;
+                    if (pix < P) {
+                        const float2 t = bstat_terms(zv[j], otile[(size_t)pix * C + ch], coef_out[ch]);
+                        s1 += t.x;
+                        s2 += t.y;
+                    }
+                }
+            }
+        } else {
+            for (int pix = part; pix < P; pix += kDecThreads / 64) {
+                const float f = h2f(otile[(size_t)pix * C + ch]);
+                s1 += f;
+                s2 += f * f;
+            }
+        }
+        red[(part * 64 + ch) * 2] = s1;
+        red[(part * 64 + ch) * 2 + 1] = s2;
+        __syncthreads();
+        if (tid < 128) {
+            const int c2 = tid & 63, which = tid >> 6;
+            float acc = 0.f;
+#pragma unroll
+            for (int pt = 0; pt < kDecThreads / 64; ++pt) acc += red[(pt * 64 + c2) * 2 + which];
+            atomicAdd(sums_dst + which * C + c2, (double)acc);
+        }
+    }
+    DEC_TRACE(10);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // backward statistics of one layer: bsums[0][c] += sum dy, bsums[1][c] += sum dy*yhat   (dy = da * GELU'(BN(z)))
 // grid = any, grid-stride over pixels; C channels (64 or 8)
 // ---------------------------------------------------------------------------------------------------------------
@@ -517,9 +755,13 @@ struct WgradParams {
     int B, H, W, R, cin_real, cout_real;
 };
 
+constexpr int kWgradBatchMax = 8;
+struct WgradBatch { WgradParams p[kWgradBatchMax]; };   // blockIdx.z selects the layer (layers of one shape in ONE launch)
+
 template <int CIN, int COUT, int DCH>
 __global__ void __launch_bounds__(kDecThreads)
-k_dec_wgrad(const WgradParams p) {
+k_dec_wgrad(const WgradBatch q) {
+    const WgradParams& p = q.p[blockIdx.z];
     constexpr int ASTR = CIN + 8, DSTR = COUT + 8, MT = COUT / 16, NT = CIN / 8, ITEMS = MT * NT;
     constexpr int PER_WARP = (ITEMS + kDecWarps - 1) / kDecWarps;          // 4 (64x64), 1 (64x16 or 16x64)
     constexpr int NT_PER = PER_WARP;                                        // a warp's items share one m-tile
@@ -545,19 +787,25 @@ k_dec_wgrad(const WgradParams p) {
     const int n_img = ((int)p.B - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
     const int n_items = n_img * spi;
     const size_t buf_halfs = (size_t)Pmax * (ASTR + DSTR);
+    // pix / W by multiplication (exact for pix, W < 2^16): the two runtime divisions per 16-byte copy made ISSUING one item's
+    // copies take 2.1 us (phase trace of this kernel)
+    const uint32_t w_magic = 0xFFFFFFFFu / (uint32_t)p.W + 1u;
     auto stage = [&](int k, int which) {
         const int b = blockIdx.y + (k / spi) * gridDim.y, r0 = (k % spi) * p.R;
         const int R = min(p.R, p.H - r0), P = R * p.W, Ppad = (P + 15) / 16 * 16;
         __half* at = atile + which * buf_halfs;
         __half* dt = at + (size_t)Pmax * ASTR;
+        const __half* a_img = p.a + (size_t)b * p.H * p.W * CIN;
+        const __half* d_img = p.dz + ((size_t)b * p.H + r0) * p.W * DCH;   // the strip's dz rows are contiguous
         for (int i = threadIdx.x; i < Ppad * (CIN / 8); i += blockDim.x) {
             const int pix = i / (CIN / 8), ck = i - pix * (CIN / 8);
             const __half* src = p.a;
             uint32_t bytes = 0;
             if (pix < P) {
-                const int rr = r0 + pix / p.W + dy, ww = pix % p.W + dx;
+                const int prow = (int)__umulhi((uint32_t)pix, w_magic);
+                const int rr = r0 + prow + dy, ww = pix - prow * p.W + dx;
                 if (rr >= 0 && rr < p.H && ww >= 0 && ww < p.W) {
-                    src = p.a + (((size_t)b * p.H + rr) * p.W + ww) * CIN + ck * 8;
+                    src = a_img + (size_t)(rr * p.W + ww) * CIN + ck * 8;
                     bytes = 16;
                 }
             }
@@ -569,7 +817,7 @@ k_dec_wgrad(const WgradParams p) {
             const __half* src = p.dz;
             uint32_t bytes = 0;
             if (pix < P && ck * 8 < DCH) {
-                src = p.dz + (((size_t)b * p.H + r0 + pix / p.W) * p.W + pix % p.W) * DCH + ck * 8;
+                src = d_img + (size_t)pix * DCH + ck * 8;
                 bytes = 16;
             }
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dt + (size_t)pix * DSTR + ck * 8);
@@ -577,7 +825,9 @@ k_dec_wgrad(const WgradParams p) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    WG_TRACE_BEGIN();
     if (n_items > 0) stage(0, 0);
+    WG_TRACE(1);
     for (int k = 0; k < n_items; ++k) {
         if (k + 1 < n_items) {
             stage(k + 1, (k + 1) & 1);
@@ -608,6 +858,7 @@ k_dec_wgrad(const WgradParams p) {
             }
         }
         __syncthreads();   // everybody is done with buffer k&1 before item k+2 is copied into it
+        WG_TRACE(2 + (k < 2 ? k : 1));
     }
     if (p.partial == nullptr) {
         if (t == 4 && bco < p.cout_real) atomicAdd(p.db + bco, dbias);
@@ -647,38 +898,64 @@ k_dec_wgrad(const WgradParams p) {
                 *reinterpret_cast<float2*>(mine + co * CIN + ci) = make_float2(c[j][2 * h], c[j][2 * h + 1]);
             }
     }
+    if (p.tickets == nullptr) return;   // the groups are summed by k_dec_wgrad_reduce (one launch for all layers, after the join)
     __shared__ unsigned int s_ticket;
+    WG_TRACE(4);
     __threadfence();
     __syncthreads();
+    WG_TRACE(5);
     if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + t, 1u);
     __syncthreads();
+    WG_TRACE(6);
     if (s_ticket != gridDim.y - 1) return;
+    WG_TRACE_LAST(7);
     __threadfence();   // acquire: the other groups' partials were fenced before their tickets
     const float* base = p.partial + (size_t)t * (COUT * CIN);
-    constexpr int NE = COUT * CIN / kDecThreads;     // elements per thread: all their loads of one group are in flight at once
-    float acc[NE];
+    // thread owns NQ groups of 4 consecutive elements (16-byte loads); the groups are summed in group order (deterministic)
+    constexpr int NQ = COUT * CIN / (4 * kDecThreads);            // 4 (64x64), 1 (64x16 / 16x64)
+    constexpr int GU = NQ >= 4 ? 4 : 8;                            // groups whose loads are in flight together
+    float4 acc[NQ];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
-    constexpr int GU = NE >= 16 ? 4 : 8;             // groups whose loads are in flight together (same summation order)
+    for (int e = 0; e < NQ; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (unsigned int grp = 0; grp < gridDim.y; grp += GU) {
-        float v[GU][NE];
+        float4 v[GU][NQ];
 #pragma unroll
         for (int u = 0; u < GU; ++u)
 #pragma unroll
-            for (int e = 0; e < NE; ++e)
-                v[u][e] = (grp + u < gridDim.y) ? __ldcg(base + (size_t)(grp + u) * 10 * (COUT * CIN) + e * kDecThreads + threadIdx.x) : 0.f;
+            for (int e = 0; e < NQ; ++e)
+                v[u][e] = (grp + u < gridDim.y)
+                              ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(grp + u) * 10 * (COUT * CIN)) + e * kDecThreads + threadIdx.x)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < GU; ++u)
             if (grp + u < gridDim.y) {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) acc[e] += v[u][e];
+                for (int e = 0; e < NQ; ++e) {
+                    acc[e].x += v[u][e].x; acc[e].y += v[u][e].y; acc[e].z += v[u][e].z; acc[e].w += v[u][e].w;
+                }
             }
     }
+    // dW += acc, this CTA being the sole writer of tap t: all the old values are requested first - as "load, add, store"
+    // per element the compiler must keep the (possibly aliasing) accesses in order, i.e. dependent L2 round trips
+    WG_TRACE_LAST(8);
+    float oldw[NQ][4];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-        const int i = e * kDecThreads + (int)threadIdx.x, co = i / CIN, ci = i - co * CIN;
-        if (co < p.cout_real && ci < p.cin_real) p.dW[((size_t)co * p.cin_real + ci) * 9 + t] += acc[e];   // sole writer of tap t
+    for (int e = 0; e < NQ; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = (e * kDecThreads + (int)threadIdx.x) * 4 + c, co = i / CIN, ci = i - co * CIN;
+            oldw[e][c] = (co < p.cout_real && ci < p.cin_real) ? __ldcg(p.dW + ((size_t)co * p.cin_real + ci) * 9 + t) : 0.f;
+        }
+#pragma unroll
+    for (int e = 0; e < NQ; ++e) {
+        const float a4[4] = {acc[e].x, acc[e].y, acc[e].z, acc[e].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = (e * kDecThreads + (int)threadIdx.x) * 4 + c, co = i / CIN, ci = i - co * CIN;
+            if (co < p.cout_real && ci < p.cin_real) p.dW[((size_t)co * p.cin_real + ci) * 9 + t] = oldw[e][c] + a4[c];
+        }
     }
+    WG_TRACE_LAST(9);
     if (t == 4 && (int)threadIdx.x < p.cout_real) {
         float acc = 0.f;
         for (unsigned int grp = 0; grp < gridDim.y; ++grp)
@@ -688,11 +965,69 @@ k_dec_wgrad(const WgradParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Second phase of the weight gradients for ALL layers in one launch: dW[co][ci][tap] += sum over the image groups (in group
+// order: deterministic, the same additions the ticket scheme's last CTA performed) of the partials k_dec_wgrad stored;
+// db likewise.  The ticket scheme ended every weight-gradient kernel with 9 CTAs summing 16 groups x 16 KB and writing dW with
+// stride-36-byte read-modify-writes while the other 135 CTAs had left: 7 of the kernel's 12.5 us (phase trace), nine times
+// per backward, next to the data-gradient chain whose stragglers it slowed.  grid = (37, layers): block x = tap * 4 + quarter
+// of the [COUT x CIN] partial (1024 elements, 4 per thread), block 36 = the bias.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradReduceParams {
+    const float* partial[17];
+    float* dW[17];
+    float* db[17];
+    int n_elem[17];                 // COUT * CIN of the layer's (padded) partial
+    int cin_pad[17], cin_real[17], cout_real[17];
+    int groups;
+};
+__global__ void __launch_bounds__(256)
+k_dec_wgrad_reduce(const WgradReduceParams q) {
+    const int l = blockIdx.y, N = q.n_elem[l], G = q.groups;
+    const float* __restrict__ part = q.partial[l];
+    if (blockIdx.x == 36) {
+        if ((int)threadIdx.x < q.cout_real[l]) {
+            float acc = 0.f;
+            for (int g = 0; g < G; ++g) acc += __ldcg(part + ((size_t)g * 10 + 9) * N + threadIdx.x);
+            q.db[l][threadIdx.x] += acc;
+        }
+        return;
+    }
+    const int t = blockIdx.x >> 2, e4 = (blockIdx.x & 3) * 256 + (int)threadIdx.x;
+    if (e4 * 4 >= N) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g0 = 0; g0 < G; g0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = g0 + u < G ? __ldcg(reinterpret_cast<const float4*>(part + ((size_t)(g0 + u) * 10 + t) * N) + e4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (g0 + u < G) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    const int cin_pad = q.cin_pad[l], cin_real = q.cin_real[l], cout_real = q.cout_real[l];
+    float* __restrict__ dW = q.dW[l];
+    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+    float oldw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int i = e4 * 4 + c, co = i / cin_pad, ci = i - co * cin_pad;
+        oldw[c] = (co < cout_real && ci < cin_real) ? __ldcg(dW + ((size_t)co * cin_real + ci) * 9 + t) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int i = e4 * 4 + c, co = i / cin_pad, ci = i - co * cin_pad;
+        if (co < cout_real && ci < cin_real) dW[((size_t)co * cin_real + ci) * 9 + t] = oldw[c] + a4[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // parameter preparation: fp16 conv weights in [COUT_PAD][9][CIN_PAD] (forward) and the rotated / transposed copy
 // [CIN_PAD][9][COUT_PAD] with tap 8-t (data gradient), from torch's fp32 [cout][cin][3][3].
 // ---------------------------------------------------------------------------------------------------------------
 struct PrepParams {
     const float* w[17]; __half* wf[17]; __half* wr[17];
+    __half* wf_tc[17]; __half* wr_tc[17];   // 64 -> 64 layers: [tap][64 x 64] canonical (rows = conv outputs, k = conv inputs)
     int cout[17], cin[17], cout_pad[17], cin_pad[17];
 };
 __global__ void __launch_bounds__(256)
@@ -711,6 +1046,16 @@ k_dec_prep_weights(const PrepParams q) {
         {   // data-gradient layout: i = (ci, t, co) holds w[co][ci][8 - t]
             const int ci = i / (9 * cout_pad), rem = i - ci * 9 * cout_pad, t = rem / cout_pad, co = rem - t * cout_pad;
             wr[i] = (co < cout && ci < cin) ? f2h(w[((size_t)co * cin + ci) * 9 + (8 - t)]) : f2h(0.f);
+        }
+    }
+    if (q.wf_tc[l] != nullptr) {   // element (row r, tap t, k) of either orientation -> t * 4096 + canonical(r, k) halfs
+        __half* __restrict__ wf_tc = q.wf_tc[l];
+        __half* __restrict__ wr_tc = q.wr_tc[l];
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < 64 * 9 * 64; i += gridDim.x * 256) {
+            const int r = i / 576, rem = i - r * 576, t = rem >> 6, k = rem & 63;
+            const int dst = t * 4096 + (r >> 3) * 512 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
+            wf_tc[dst] = f2h(w[((size_t)r * 64 + k) * 9 + t]);            // forward: r = co, k = ci
+            wr_tc[dst] = f2h(w[((size_t)k * 64 + r) * 9 + (8 - t)]);      // data gradient: r = ci, k = co, taps mirrored
         }
     }
 }
@@ -981,6 +1326,7 @@ struct DecLayout {
     size_t n_pix;
     size_t off_x0, off_z[kMaxLayers + 1], off_a[kMaxLayers + 1], off_da[2], off_dz[kMaxLayers + 1], off_da9, off_dx0, off_pooled;
     size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_sums[kMaxLayers + 1], off_bsums[kMaxLayers + 1];
+    size_t off_wf_tc[kMaxLayers + 1], off_wr_tc[kMaxLayers + 1];   // UMMA-layout copies of the 64 -> 64 layers (0 = none)
     size_t off_sums_begin, sums_bytes, off_barrier, off_tickets, off_partial[kMaxLayers + 1], total;
 };
 
@@ -1006,6 +1352,10 @@ DecLayout make_layout(int B, int H, int W, int L) {
         const int cin = l == 0 ? 16 : 64, cout = l == L ? 16 : 64;
         d.off_wf[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
         d.off_wr[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
+        if (l > 0 && l < L) {
+            d.off_wf_tc[l] = o; o = align_up(o + (size_t)64 * 9 * 64 * 2);
+            d.off_wr_tc[l] = o; o = align_up(o + (size_t)64 * 9 * 64 * 2);
+        }
     }
     d.off_sums_begin = o;
     for (int l = 0; l <= L; ++l) {
@@ -1025,7 +1375,7 @@ DecLayout make_layout(int B, int H, int W, int L) {
 }
 
 // fp16 weights of every layer in both orientations, as one buffer (nsig_decoder_prepare_weights): offsets of layer l
-struct WeightLayout { size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], total; };
+struct WeightLayout { size_t off_wf[kMaxLayers + 1], off_wr[kMaxLayers + 1], off_wf_tc[kMaxLayers + 1], off_wr_tc[kMaxLayers + 1], total; };
 WeightLayout make_weight_layout(int L) {
     WeightLayout w{};
     size_t o = 0;
@@ -1033,15 +1383,23 @@ WeightLayout make_weight_layout(int L) {
         const int cin = l == 0 ? 16 : 64, cout = l == L ? 16 : 64;
         w.off_wf[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
         w.off_wr[l] = o; o = align_up(o + (size_t)cout * 9 * cin * 2);
+        if (l > 0 && l < L) {
+            w.off_wf_tc[l] = o; o = align_up(o + (size_t)64 * 9 * 64 * 2);
+            w.off_wr_tc[l] = o; o = align_up(o + (size_t)64 * 9 * 64 * 2);
+        }
     }
     w.total = o;
     return w;
 }
-PrepParams make_prep(const float* const* params, int L, int nb, unsigned char* base, const size_t* off_wf, const size_t* off_wr) {
+PrepParams make_prep(const float* const* params, int L, int nb, unsigned char* base, const size_t* off_wf, const size_t* off_wr,
+                     const size_t* off_wf_tc, const size_t* off_wr_tc) {
     PrepParams q{};
     for (int l = 0; l <= L; ++l) {
         q.w[l] = params[4 * l];
         q.wf[l] = reinterpret_cast<__half*>(base + off_wf[l]); q.wr[l] = reinterpret_cast<__half*>(base + off_wr[l]);
+        if (l > 0 && l < L) {
+            q.wf_tc[l] = reinterpret_cast<__half*>(base + off_wf_tc[l]); q.wr_tc[l] = reinterpret_cast<__half*>(base + off_wr_tc[l]);
+        }
         q.cin[l] = l == 0 ? 3 : 64; q.cout[l] = l == L ? nb : 64; q.cin_pad[l] = l == 0 ? 16 : 64; q.cout_pad[l] = l == L ? 16 : 64;
     }
     return q;
@@ -1055,6 +1413,27 @@ int conv_rows(int B, int H, int W) {
     if (want < R) R = want;
     return R < H ? R : H;
 }
+// the tcgen05 conv needs the strip's rows over the padded width as one M = 128 operand
+bool conv_tc_enabled() {
+    static const bool on = [] { const char* e = getenv("NSIG_DEC_TC"); return !(e && e[0] == '0'); }();   // default on; NSIG_DEC_TC=0: mma.sync kernels
+    return on;
+}
+template <int MODE>
+int launch_conv_tc(ConvParams p, cudaStream_t st) {
+    p.R = conv_rows(p.B, p.H, p.W);
+    const size_t smem = tcv::smem_bytes(p.R, p.W);
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(k_dec_conv_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    k_dec_conv_tc<MODE><<<dim3((p.H + p.R - 1) / p.R, p.B), kDecThreads, smem, st>>>(p);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
+bool conv_tc_fits(const ConvParams& p) {
+    const int R = conv_rows(p.B, p.H, p.W);
+    return conv_tc_enabled() && kDecThreads == 256 && R * (p.W + 2) <= 128 && tcv::smem_bytes(R, p.W) <= 200 * 1024 &&
+           p.cout_valid == 64 && p.w_tc != nullptr && (((uintptr_t)p.w_tc) & 15) == 0;
+}
+
 // image rows per weight-gradient step: as many pixels as fit next to each other in ~160 KB of shared memory
 int wgrad_rows(int H, int W, int cin, int cout) {
     const size_t per_pix = (size_t)(cin + 8 + cout + 8) * 2;
@@ -1076,23 +1455,32 @@ int launch_conv(ConvParams p, cudaStream_t st) {
     return 0;
 }
 
-template <int CIN, int COUT, int DCH>
-int launch_wgrad(WgradParams p, cudaStream_t st) {
-    p.R = wgrad_rows(p.H, p.W, CIN, COUT);
-    if (p.R <= 0) return NSIG_EINVAL;
-    const size_t smem = 2 * (size_t)((p.R * p.W + 15) / 16 * 16) * (CIN + 8 + COUT + 8) * 2;
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+int wgrad_groups(int B) {
     static const int g_max = [] {
         const char* e = getenv("NSIG_DEC_WGRAD_G");
         const int v = e ? atoi(e) : 0;
         return v > 0 ? (v < kWgradGroupsMax ? v : kWgradGroupsMax) : 16;
     }();
-    const int G = p.B < g_max ? p.B : g_max;   // image groups: 9*G CTAs, each adds its [COUT x CIN] partial with atomics
-    k_dec_wgrad<CIN, COUT, DCH><<<dim3(9, G), kDecThreads, smem, st>>>(p);
+    return B < g_max ? B : g_max;
+}
+
+template <int CIN, int COUT, int DCH>
+int launch_wgrad_batch(const WgradParams* layers, int n, cudaStream_t st) {
+    if (n < 1 || n > kWgradBatchMax) return NSIG_EINVAL;
+    WgradBatch q{};
+    const int R = wgrad_rows(layers[0].H, layers[0].W, CIN, COUT);
+    if (R <= 0) return NSIG_EINVAL;
+    for (int i = 0; i < n; ++i) { q.p[i] = layers[i]; q.p[i].R = R; }
+    const size_t smem = 2 * (size_t)((R * layers[0].W + 15) / 16 * 16) * (CIN + 8 + COUT + 8) * 2;
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(k_dec_wgrad<CIN, COUT, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    const int G = wgrad_groups(layers[0].B);   // image groups: 9*G CTAs per layer, each stores (or atomically adds) its [COUT x CIN] partial
+    k_dec_wgrad<CIN, COUT, DCH><<<dim3(9, G, n), kDecThreads, smem, st>>>(q);
     NSIG_LAUNCH_CHECK();
     return 0;
 }
+template <int CIN, int COUT, int DCH>
+int launch_wgrad(WgradParams p, cudaStream_t st) { return launch_wgrad_batch<CIN, COUT, DCH>(&p, 1, st); }
 
 // Side stream of the backward chain.  The data-gradient convs form a dependent chain (layer l needs the statistics of
 // da_l); the weight gradient of layer l only needs a_{l-1} (forward) and dz_l (written by the data-gradient conv of
@@ -1170,7 +1558,7 @@ int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks
     const int L = (int)num_blocks, nb = (int)(num_bits * redundancy);
     if (!params || !weights || L < 1 || L > kMaxLayers || nb < 1 || nb > 8) return NSIG_EINVAL;
     const WeightLayout wl = make_weight_layout(L);
-    const PrepParams q = make_prep(params, L, nb, reinterpret_cast<unsigned char*>(weights), wl.off_wf, wl.off_wr);
+    const PrepParams q = make_prep(params, L, nb, reinterpret_cast<unsigned char*>(weights), wl.off_wf, wl.off_wr, wl.off_wf_tc, wl.off_wr_tc);
     k_dec_prep_weights<<<dim3(16, L + 1), 256, 0, (cudaStream_t)stream>>>(q);
     NSIG_LAUNCH_CHECK();
     return 0;
@@ -1181,11 +1569,18 @@ int nsig_debug_dec_trace(unsigned long long* host_out /* [64][12] */, unsigned i
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(host_out, g_dec_trace, sizeof(unsigned long long) * 64 * 12);
     cudaMemcpyFromSymbol(host_n, g_dec_trace_n, sizeof(unsigned int));
+    if (reset == 2) {   // the weight-gradient kernels' stamps instead
+        cudaMemcpyFromSymbol(host_out, g_wg_trace, sizeof(unsigned long long) * 64 * 12);
+        cudaMemcpyFromSymbol(host_n, g_wg_trace_n, sizeof(unsigned int));
+        return 0;
+    }
     if (reset) {
         static unsigned long long z[64][12];
         unsigned int zero = 0;
         cudaMemcpyToSymbol(g_dec_trace, z, sizeof(z));
         cudaMemcpyToSymbol(g_dec_trace_n, &zero, sizeof(zero));
+        cudaMemcpyToSymbol(g_wg_trace, z, sizeof(z));
+        cudaMemcpyToSymbol(g_wg_trace_n, &zero, sizeof(zero));
     }
     return 0;
 }
@@ -1217,7 +1612,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
     auto D64 = [&](size_t off) { return reinterpret_cast<double*>(ws + off); };
     cudaError_t e = cudaMemsetAsync(ws + d.off_sums_begin, 0, d.sums_bytes, st);
     if (e != cudaSuccess) return (int)e;
-    const PrepParams q = make_prep(params, L, nb, ws, d.off_wf, d.off_wr);
+    const PrepParams q = make_prep(params, L, nb, ws, d.off_wf, d.off_wr, d.off_wf_tc, d.off_wr_tc);
     const WeightLayout wl = make_weight_layout(L);
     const unsigned char* pw = reinterpret_cast<const unsigned char*>(prepared_weights);
     auto WF = [&](int l) { return pw ? reinterpret_cast<const __half*>(pw + wl.off_wf[l]) : H16(d.off_wf[l]); };
@@ -1226,6 +1621,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
         p.w = WF(l); p.bias = params[4 * l + 1]; p.dst = H16(d.off_z[l]); p.out_sums = D64(d.off_sums[l]);
+        if (l > 0 && l < L) p.w_tc = pw ? reinterpret_cast<const __half*>(pw + wl.off_wf_tc[l]) : H16(d.off_wf_tc[l]);
         p.cout_valid = l == L ? nb : 64;
         if (l == 0) {
             p.src = H16(d.off_x0);
@@ -1283,6 +1679,7 @@ int nsig_decoder_forward(const float* image, uint32_t B, uint32_t H, uint32_t W,
         ConvParams p = conv_params(l);
         int rc;
         if (l == 0) rc = launch_conv<16, 16, 64, IN_RAW>(p, st);
+        else if (l < L && conv_tc_fits(p)) rc = launch_conv_tc<IN_BNGELU>(p, st);
         else rc = l == L ? launch_conv<64, 64, 8, IN_BNGELU>(p, st) : launch_conv<64, 64, 64, IN_BNGELU>(p, st);
         if (rc) return rc;
     }
@@ -1321,8 +1718,47 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
     SideStream* side = side_stream_for_current_device();
     // weight-gradient reduction: tickets + partials (deterministic, default) or fp32 atomics (NSIG_DEC_WGRAD_ATOMIC=1)
     static const bool two_phase = [] { const char* e = getenv("NSIG_DEC_WGRAD_ATOMIC"); return !(e && e[0] == '1'); }();
+    // second phase: one reduction launch for all layers behind the join (default) or, NSIG_DEC_WGRAD_TICKETS=1, inside every
+    // weight-gradient kernel by the CTA that draws the last ticket of its tap (round-2 scheme; same bits)
+    static const bool ticket_reduce = [] { const char* e = getenv("NSIG_DEC_WGRAD_TICKETS"); return e && e[0] == '1'; }();
     const __half* da = H16(d.off_da9);
     const int stat_blocks = n_pix / 64 < 64 ? (n_pix / 64 > 0 ? n_pix / 64 : 1) : 64;
+    // NSIG_DEC_WGRAD_LATE=1: all weight-gradient kernels are issued behind the data-gradient chain (on the side streams, next to
+    // each other) instead of next to it, layer by layer
+    // Schedule of the weight gradients.  Default: ALL of them behind the data-gradient chain - the 64 -> 64 layers as ONE launch
+    // (blockIdx.z = layer) and the two odd-shaped layers next to it on the side streams.  Issued layer by layer next to the
+    // chain (NSIG_DEC_WGRAD_EARLY=1, the round-2 schedule) every data-gradient kernel waited ~7 us instead of ~3 us for its
+    // predecessor's stragglers (phase trace: profiles/r02_decoder_phase_trace.txt).
+    static const bool wgrad_late = [] { const char* e = getenv("NSIG_DEC_WGRAD_EARLY"); return !(e && e[0] == '1'); }();
+    auto wgrad_params = [&](int l) {
+        WgradParams w{};
+        w.dz = H16(d.off_dz[l]); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
+        w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
+        w.a = l == 0 ? H16(d.off_x0) : H16(d.off_a[l - 1]);
+        if (two_phase) {
+            w.partial = reinterpret_cast<float*>(ws + d.off_partial[l]);
+            if (ticket_reduce) w.tickets = reinterpret_cast<unsigned int*>(ws + d.off_tickets) + 16 * l;
+        }
+        return w;
+    };
+    auto fork_to = [&](int slot, cudaStream_t& wst) -> int {   // side stream `slot` continues from the current point of st
+        wst = st;
+        if (side) {
+            cudaError_t e = cudaEventRecord(side->fork[slot], st);
+            wst = side->stream[slot % side->n];
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(wst, side->fork[slot], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return 0;
+    };
+    auto wgrad_layer = [&](int l) -> int {
+        cudaStream_t wst;
+        if (int rc = fork_to(l, wst)) return rc;
+        const WgradParams w = wgrad_params(l);
+        if (l == 0) return launch_wgrad<16, 64, 64>(w, wst);
+        if (l == L) return launch_wgrad<64, 16, 8>(w, wst);
+        return launch_wgrad<64, 64, 64>(w, wst);
+    };
     for (int l = L; l >= 0; --l) {
         BnSrc bn{D64(d.off_sums[l]), D64(d.off_bsums[l]), params[4 * l + 2], params[4 * l + 3], inv_n, l == L ? 8 : 64, l == L ? nb : 64};
         // (1) backward statistics = dbeta, dgamma.  Only the last block needs a pass of its own (its da comes from the
@@ -1335,6 +1771,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         ConvParams p{};
         p.B = (int)B; p.H = (int)H; p.W = (int)W;
         p.src = da; p.src2 = H16(d.off_z[l]); p.bn = bn; p.w = WR(l); p.act_out = H16(d.off_dz[l]);
+        if (l > 0 && l < L) p.w_tc = pw ? reinterpret_cast<const __half*>(pw + wl.off_wr_tc[l]) : H16(d.off_wr_tc[l]);
         __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
         p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
         if (l > 0) {   // outputs are da_{l-1}: accumulate layer l-1's backward statistics on the way out
@@ -1345,29 +1782,29 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         int rc;
         if (l == L) rc = launch_conv<16, 8, 64, IN_DZ>(p, st);
         else if (l == 0) rc = launch_conv<64, 64, 16, IN_DZ>(p, st);
+        else if (conv_tc_fits(p)) rc = launch_conv_tc<IN_DZ>(p, st);
         else rc = launch_conv<64, 64, 64, IN_DZ>(p, st);
         if (rc) return rc;
         // (3) weight / bias gradient from the materialised a_{l-1} and dz_l, on the side stream
-        cudaStream_t wst = st;
-        if (side) {
-            cudaError_t e = cudaEventRecord(side->fork[l], st);
-            wst = side->stream[l % side->n];
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(wst, side->fork[l], 0);
-            if (e != cudaSuccess) return (int)e;
+        if (!wgrad_late) {
+            rc = wgrad_layer(l);
+            if (rc) return rc;
         }
-        WgradParams w{};
-        w.dz = H16(d.off_dz[l]); w.dW = grads[4 * l]; w.db = grads[4 * l + 1];
-        w.B = (int)B; w.H = (int)H; w.W = (int)W; w.cin_real = l == 0 ? 3 : 64; w.cout_real = l == L ? nb : 64;
-        w.a = l == 0 ? H16(d.off_x0) : H16(d.off_a[l - 1]);
-        if (two_phase) {
-            w.partial = reinterpret_cast<float*>(ws + d.off_partial[l]);
-            w.tickets = reinterpret_cast<unsigned int*>(ws + d.off_tickets) + 16 * l;
-        }
-        if (l == 0) rc = launch_wgrad<16, 64, 64>(w, wst);
-        else if (l == L) rc = launch_wgrad<64, 16, 8>(w, wst);
-        else rc = launch_wgrad<64, 64, 64>(w, wst);
-        if (rc) return rc;
         da = out;
+    }
+    if (wgrad_late) {
+        cudaStream_t wst;
+        if (int rc = fork_to(0, wst)) return rc;
+        for (int l0 = 1; l0 < L; l0 += kWgradBatchMax) {   // the 64 -> 64 layers, up to 8 per launch
+            WgradParams mid[kWgradBatchMax];
+            int n = 0;
+            for (int l = l0; l < L && n < kWgradBatchMax; ++l) mid[n++] = wgrad_params(l);
+            if (int rc = launch_wgrad_batch<64, 64, 64>(mid, n, wst)) return rc;
+        }
+        if (int rc = fork_to(1, wst)) return rc;
+        if (int rc = launch_wgrad<16, 64, 64>(wgrad_params(0), wst)) return rc;
+        if (int rc = fork_to(2, wst)) return rc;
+        if (int rc = launch_wgrad<64, 16, 8>(wgrad_params(L), wst)) return rc;
     }
     if (side) {
         for (int k = 0; k < side->n && k <= L; ++k) {
@@ -1375,6 +1812,19 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join[k], 0);
             if (e != cudaSuccess) return (int)e;
         }
+    }
+    if (two_phase && !ticket_reduce) {
+        WgradReduceParams r{};
+        for (int l = 0; l <= L; ++l) {
+            const int cin_pad = l == 0 ? 16 : 64, cout_pad = l == L ? 16 : 64;
+            r.partial[l] = reinterpret_cast<const float*>(ws + d.off_partial[l]);
+            r.dW[l] = grads[4 * l]; r.db[l] = grads[4 * l + 1];
+            r.n_elem[l] = cin_pad * cout_pad; r.cin_pad[l] = cin_pad;
+            r.cin_real[l] = l == 0 ? 3 : 64; r.cout_real[l] = l == L ? nb : 64;
+        }
+        r.groups = wgrad_groups((int)B);
+        k_dec_wgrad_reduce<<<dim3(37, L + 1), 256, 0, st>>>(r);
+        NSIG_LAUNCH_CHECK();
     }
     BnGradParams q{};
     for (int l = 0; l <= L; ++l) {

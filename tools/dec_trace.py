@@ -70,7 +70,23 @@ def main():
                 last = st[k]
         gap = (st[0] - prev_end) if prev_end is not None else 0
         prev_end = last
-        print(f"{i:3d} {gap:7d} " + " ".join(f"{x:9d}" for x in d) + f" {last - st[0]:8d}")
+        extra = f"  [stamp 11 at +{r[11] - st[0]}]" if r[11] else ""
+        print(f"{i:3d} {gap:7d} " + " ".join(f"{x:9d}" for x in d) + f" {last - st[0]:8d}" + extra)
+    wgrad_rows(lib)
+
+
+def wgrad_rows(lib):
+    import ctypes
+    buf = (ctypes.c_ulonglong * (64 * 12))()
+    n = ctypes.c_uint(0)
+    lib.nsig_debug_dec_trace(buf, ctypes.byref(n), 2)
+    rows = [[buf[i * 12 + k] for k in range(12)] for i in range(min(n.value, 64))]
+    rows.sort(key=lambda r: r[0])
+    print(f"{n.value} weight-gradient launches; ns from entry (CTA (tap 0, group 0), thread 0; 7-9: the CTA that reduces tap 0)")
+    print("  #  staged0   item0   item1  stored  fenced  ticket | last: start  summed  written")
+    for i, r in enumerate(rows):
+        rel = [(r[k] - r[0]) if r[k] else 0 for k in range(1, 10)]
+        print(f"{i:3d} " + " ".join(f"{x:7d}" for x in rel[:6]) + "  |     " + " ".join(f"{x:7d}" for x in rel[6:]))
 
 
 if __name__ == "__main__":
