@@ -377,6 +377,16 @@ size_t nsig_decoder_weights_bytes(uint32_t num_blocks);
 int nsig_decoder_prepare_weights(const float* const* params, uint32_t num_blocks, uint32_t num_bits,
                                  uint32_t redundancy, void* weights, nsig_stream_t stream);
 
+/* Deferred tail of nsig_decoder_backward.  After nsig_decoder_defer_weight_grads(1), a backward returns as soon as the INPUT
+ * gradient (dimage) and the BatchNorm gradients are enqueued on `stream`; the conv weight / bias gradients are still being
+ * computed on the library's side streams and `grads` / `workspace` must stay untouched and alive until
+ * nsig_decoder_finish_backward(stream) has been called: it makes `stream` wait for them and enqueues the deterministic
+ * reduction into `grads`.  A caller whose next kernels only need dimage (the renderer's backward,
+ * utils_wtmk_disen.py:1175) overlaps them with the decoder's weight gradients this way.  No-op when nothing is pending; a new
+ * backward finishes a forgotten tail first.  Process-wide switch, one pending backward per device. */
+int nsig_decoder_defer_weight_grads(int on);
+int nsig_decoder_finish_backward(nsig_stream_t stream);
+
 /* Parity probe of the decoder kernels' activation arithmetic: gelu[i] = fp16(GELU(y[i])), gelu_grad[i] = fp16(GELU'(y[i]))
  * for n fp16 values, through the very device functions the conv kernels apply while staging their tiles (nn.GELU(), exact /
  * erf form: hidden_models.py:26).  Lets a test sweep all 2^16 fp16 inputs against torch and against float64. */

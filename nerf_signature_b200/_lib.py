@@ -71,6 +71,7 @@ _SIGNATURES = {
                               lambda a: 2 * (a[4] + 1) + 3 + (1 if a[10] is not None else 0)),
     "nsig_decoder_prepare_weights": ([_vp, _u32, _u32, _u32, _vp, _vp], 1),
     "nsig_decoder_gelu_probe": ([_vp, _u32, _vp, _vp, _vp], 1),
+    "nsig_decoder_finish_backward": ([_vp], 1),
     "nsig_color_forward": ([_vp, _vp, _u32, _vp, _vp, _vp], 1),
     "nsig_render_rays": ([_vp, _vp, _u32, _vp, _f32, _f32, _vp, _u32, _u32, _f32, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _f32,
                           _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], 1),
@@ -89,7 +90,8 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["nsig_version", "nsig_march_rays_train_scratch_bytes",
                                                 "nsig_grid_sample_cells_scratch_bytes", "nsig_allreduce_grid",
-                                                "nsig_decoder_workspace_bytes", "nsig_decoder_weights_bytes"])
+                                                "nsig_decoder_workspace_bytes", "nsig_decoder_weights_bytes",
+                                                "nsig_decoder_defer_weight_grads"])
 
 _lib = None
 _lock = threading.Lock()
@@ -127,6 +129,8 @@ def load():
         lib.nsig_decoder_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32]
         lib.nsig_decoder_weights_bytes.restype = _sz
         lib.nsig_decoder_weights_bytes.argtypes = [_u32]
+        lib.nsig_decoder_defer_weight_grads.restype = _c.c_int
+        lib.nsig_decoder_defer_weight_grads.argtypes = [_c.c_int]
         lib.nsig_allreduce_grid.restype = _u32
         lib.nsig_allreduce_grid.argtypes = []
         _lib = lib

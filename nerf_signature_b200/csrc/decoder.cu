@@ -1526,6 +1526,39 @@ SideStream* side_stream_for_current_device() {
 
 }  // namespace
 
+namespace {
+// Deferred tail of nsig_decoder_backward (nsig_decoder_defer_weight_grads): the weight-gradient kernels are left running on the
+// side streams and the caller's stream goes on with what needs the INPUT gradient only; nsig_decoder_finish_backward joins them
+// and launches the group reduction.  One pending backward per device.
+struct DeferredTail {
+    bool pending = false;
+    bool reduce = false;
+    nsig::WgradReduceParams r{};
+    int layers = 0;
+};
+DeferredTail g_deferred[64];
+bool g_defer_on = false;
+
+int finish_deferred_locked(int dev, cudaStream_t st) {
+    DeferredTail& t = g_deferred[dev];
+    if (!t.pending) return 0;
+    t.pending = false;
+    SideStream* side = side_stream_for_current_device();
+    if (side) {
+        for (int k = 0; k < side->n; ++k) {
+            cudaError_t e = cudaEventRecord(side->join[k], side->stream[k]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join[k], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (t.reduce) {
+        nsig::k_dec_wgrad_reduce<<<dim3(37, t.layers), 256, 0, st>>>(t.r);
+        NSIG_LAUNCH_CHECK();
+    }
+    return 0;
+}
+}  // namespace
+
 namespace nsig {
 // parity probe: the decoder kernels' own GELU / GELU' device functions applied to n fp16 values
 __global__ void __launch_bounds__(256)
@@ -1716,6 +1749,9 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
 
     std::lock_guard<std::mutex> lock(g_side_mutex);
     SideStream* side = side_stream_for_current_device();
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    if (int rc = finish_deferred_locked(cur_dev, st)) return rc;   // an earlier deferred tail nobody finished
     // weight-gradient reduction: tickets + partials (deterministic, default) or fp32 atomics (NSIG_DEC_WGRAD_ATOMIC=1)
     static const bool two_phase = [] { const char* e = getenv("NSIG_DEC_WGRAD_ATOMIC"); return !(e && e[0] == '1'); }();
     // second phase: one reduction launch for all layers behind the join (default) or, NSIG_DEC_WGRAD_TICKETS=1, inside every
@@ -1806,26 +1842,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         if (int rc = fork_to(2, wst)) return rc;
         if (int rc = launch_wgrad<64, 16, 8>(wgrad_params(L), wst)) return rc;
     }
-    if (side) {
-        for (int k = 0; k < side->n && k <= L; ++k) {
-            cudaError_t e = cudaEventRecord(side->join[k], side->stream[k]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join[k], 0);
-            if (e != cudaSuccess) return (int)e;
-        }
-    }
-    if (two_phase && !ticket_reduce) {
-        WgradReduceParams r{};
-        for (int l = 0; l <= L; ++l) {
-            const int cin_pad = l == 0 ? 16 : 64, cout_pad = l == L ? 16 : 64;
-            r.partial[l] = reinterpret_cast<const float*>(ws + d.off_partial[l]);
-            r.dW[l] = grads[4 * l]; r.db[l] = grads[4 * l + 1];
-            r.n_elem[l] = cin_pad * cout_pad; r.cin_pad[l] = cin_pad;
-            r.cin_real[l] = l == 0 ? 3 : 64; r.cout_real[l] = l == L ? nb : 64;
-        }
-        r.groups = wgrad_groups((int)B);
-        k_dec_wgrad_reduce<<<dim3(37, L + 1), 256, 0, st>>>(r);
-        NSIG_LAUNCH_CHECK();
-    }
+    // what remains on the caller's stream does not depend on the weight gradients: issued first, so that it runs next to them
     BnGradParams q{};
     for (int l = 0; l <= L; ++l) {
         q.bsums[l] = D64(d.off_bsums[l]); q.dgamma[l] = grads[4 * l + 2]; q.dbeta[l] = grads[4 * l + 3];
@@ -1837,7 +1854,52 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         k_dec_input_grad<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(H16(d.off_dx0), n_pix, dimage);
         NSIG_LAUNCH_CHECK();
     }
+    const bool defer = g_defer_on && side != nullptr && wgrad_late;
+    if (side && !defer) {
+        for (int k = 0; k < side->n && k <= L; ++k) {
+            cudaError_t e = cudaEventRecord(side->join[k], side->stream[k]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join[k], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (defer) {
+        DeferredTail& t = g_deferred[cur_dev];
+        t.pending = true;
+        t.reduce = false;
+        t.layers = L + 1;
+    }
+    if (two_phase && !ticket_reduce) {
+        WgradReduceParams r{};
+        for (int l = 0; l <= L; ++l) {
+            const int cin_pad = l == 0 ? 16 : 64, cout_pad = l == L ? 16 : 64;
+            r.partial[l] = reinterpret_cast<const float*>(ws + d.off_partial[l]);
+            r.dW[l] = grads[4 * l]; r.db[l] = grads[4 * l + 1];
+            r.n_elem[l] = cin_pad * cout_pad; r.cin_pad[l] = cin_pad;
+            r.cin_real[l] = l == 0 ? 3 : 64; r.cout_real[l] = l == L ? nb : 64;
+        }
+        r.groups = wgrad_groups((int)B);
+        if (defer) {
+            g_deferred[cur_dev].reduce = true;
+            g_deferred[cur_dev].r = r;
+        } else {
+            k_dec_wgrad_reduce<<<dim3(37, L + 1), 256, 0, st>>>(r);
+            NSIG_LAUNCH_CHECK();
+        }
+    }
     return 0;
+}
+
+int nsig_decoder_defer_weight_grads(int on) {
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    g_defer_on = on != 0;
+    return 0;
+}
+
+int nsig_decoder_finish_backward(nsig_stream_t stream) {
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return NSIG_EINVAL;
+    return finish_deferred_locked(dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

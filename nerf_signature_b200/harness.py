@@ -211,6 +211,9 @@ class Scene:
             # fp16 weight copies of the decoder: converted behind every optimizer update (on its side stream) instead of at the
             # head of every decoder forward, i.e. off the step's critical path
             self.model.prepare_decoder_weights()
+        # the decoder backward hands back the block-pixel gradient first and finishes its weight gradients next to the composite /
+        # field backward (decoder_ops.finish_backward after loss.backward()); NSIG_NO_DEC_DEFER=1 joins them inside the call
+        self.model.defer_decoder_weight_grads = self.fused_decoder and os.environ.get("NSIG_NO_DEC_DEFER") != "1"
         self.overlap_decoder = overlap_decoder and not merged_render
         self.defer_optimizer = bool(defer_optimizer) and self.fused and use_fs   # needs the one-kernel scaler's skip flag
         # look-ahead schedule of the deferred optimizer (see _step_impl).  Opt-in (lookahead=True or NSIG_LOOKAHEAD=1): measured
@@ -388,6 +391,9 @@ class Scene:
         if self.keep_outputs:
             self.last = {"pred": pred.detach(), "image_c": image_c.detach(), "decoded": decoded.detach()}
         self.scaler.scale(loss).backward()
+        if self.fused_decoder:   # deferred tail of the decoder backward (its weight gradients ran next to the renderer's backward)
+            from .nerf.decoder_ops import finish_backward
+            finish_backward()
         if self.flat_sync:
             self.sync.reduce_flat()
         else:

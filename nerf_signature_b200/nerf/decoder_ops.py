@@ -35,10 +35,23 @@ def decoder_params(decoder):
     return ps
 
 
+_deferred_keep = []   # workspaces / gradient scratch of backward calls whose weight-gradient tail is still pending
+
+
+def finish_backward():
+    """Join the deferred tail of the last fused-decoder backward (decode(..., defer_weight_grads=True)) into the current stream:
+    after this call the decoder's conv weight / bias gradients are complete in stream order.  No-op when nothing is pending."""
+    if _deferred_keep:
+        _lib.call("nsig_decoder_finish_backward")
+        for g, tmp in [f for item in _deferred_keep for f in item[1]]:
+            g.add_(tmp)
+        _deferred_keep.clear()
+
+
 class _fused_decode(Function):
     @staticmethod
     def forward(ctx, image, meta, prepared, *params):
-        num_blocks, num_bits, redundancy = meta
+        num_blocks, num_bits, redundancy, ctx.defer = meta
         image = image.contiguous().float()
         B, H, W, _ = image.shape
         dev = image.device
@@ -83,11 +96,23 @@ class _fused_decode(Function):
                 grads.append(tmp)
                 fixups.append((p.grad, tmp))
         dimage = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if ctx.need_image else None
-        _lib.call("nsig_decoder_backward", _P(dlogits.contiguous().float()), B, H, W, num_blocks, num_bits, redundancy,
-                  _lib.pointer_array([p.detach().contiguous() for p in params]), _lib.pointer_array(grads), _P(ctx.ws),
-                  _P(dimage), _P(ctx.prepared))
-        for g, tmp in fixups:
-            g.add_(tmp)
+        if ctx.defer:
+            # the call returns with the weight gradients still running on the library's side streams: the workspace (their
+            # partials) and the gradient buffers must outlive it - parked until finish_backward()
+            finish_backward()
+            _lib.load().nsig_decoder_defer_weight_grads(1)
+        try:
+            _lib.call("nsig_decoder_backward", _P(dlogits.contiguous().float()), B, H, W, num_blocks, num_bits, redundancy,
+                      _lib.pointer_array([p.detach().contiguous() for p in params]), _lib.pointer_array(grads), _P(ctx.ws),
+                      _P(dimage), _P(ctx.prepared))
+        finally:
+            if ctx.defer:
+                _lib.load().nsig_decoder_defer_weight_grads(0)
+        if ctx.defer:
+            _deferred_keep.append((ctx.ws, fixups, grads))
+        else:
+            for g, tmp in fixups:
+                g.add_(tmp)
         ctx.ws = None
         return (dimage, None, None) + (None,) * len(params)
 
@@ -114,14 +139,17 @@ class PreparedWeights:
                   self.decoder.num_bits, self.decoder.redundancy, _P(self.buffer))
 
 
-def decode(decoder, image, prepared=None):
+def decode(decoder, image, prepared=None, defer_weight_grads=False):
     """logits [B, num_bits] of `image` [B,H,W,3] (fp32, in [0,1]); fused kernels when the decoder has the
-    reference architecture, the plain module (under autocast) otherwise.  prepared: optional PreparedWeights of `decoder`."""
+    reference architecture, the plain module (under autocast) otherwise.  prepared: optional PreparedWeights of `decoder`.
+    defer_weight_grads: the backward returns once the image gradient is enqueued; the decoder's weight gradients are complete
+    only after finish_backward() (a training loop calls it once the rest of its backward is issued, so the renderer's
+    backward kernels run next to the decoder's weight gradients)."""
     ps = decoder_params(decoder) if image.is_cuda else None
     if ps is None:
         from .hidden_models import normalize_img
         with torch.autocast("cuda", dtype=torch.float16, enabled=image.is_cuda):
             return decoder(normalize_img(image.permute(0, 3, 1, 2)))
     num_blocks = len(ps) // 4 - 1
-    return _fused_decode.apply(image, (num_blocks, decoder.num_bits, decoder.redundancy),
+    return _fused_decode.apply(image, (num_blocks, decoder.num_bits, decoder.redundancy, bool(defer_weight_grads)),
                                prepared.buffer if prepared is not None else None, *ps)

@@ -166,7 +166,8 @@ class NeRFNetwork(NeRFRenderer):
         """msg_decoder(normalization(image.permute(0, 3, 1, 2))) for rendered blocks `image` [B,H,W,3] in [0,1], with
         float16-autocast arithmetic (utils_wtmk_disen.py:592-595), through the fused decoder kernels."""
         from .decoder_ops import decode
-        return decode(self.msg_decoder, image, getattr(self, "_dec_prepared", None))
+        return decode(self.msg_decoder, image, getattr(self, "_dec_prepared", None),
+                      defer_weight_grads=getattr(self, "defer_decoder_weight_grads", False) and torch.is_grad_enabled())
 
     def prepare_decoder_weights(self, enable=True):
         """Keep the decoder's fp16 weight copies in a persistent buffer (decoder_ops.PreparedWeights) instead of converting

@@ -163,3 +163,41 @@ def test_gelu_arithmetic_over_all_fp16_inputs():
     assert int((dg != exact_grad).sum()) < 0.01 * n, int((dg != exact_grad).sum())
     with pytest.raises(_lib.NsigError):
         _lib.call("nsig_decoder_gelu_probe", P(y), n, None, P(dg))
+
+
+def test_deferred_weight_gradients_equal_the_joined_backward():
+    """decode(..., defer_weight_grads=True): the backward hands back the image gradient with the conv weight gradients still on
+    the library's side streams; after decoder_ops.finish_backward() every gradient is bit-identical to the backward that joins
+    them itself (same kernels, same deterministic reduction).  A second backward without finish_backward() completes the first
+    one's tail before it starts (gradients accumulate into .grad)."""
+    from nerf_signature_b200.nerf import decoder_ops
+    dec = _decoder(3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    image = torch.rand(32, 12, 12, 3, device="cuda", generator=g)
+    gout = torch.randn(32, 1, device="cuda", generator=g) * 64.0
+    o_ref, di_ref, gp_ref = _run_fused(dec, image, gout)
+
+    def run(defer):
+        img = image.clone().requires_grad_(True)
+        out = decoder_ops.decode(dec, img, defer_weight_grads=defer)
+        (out * gout).sum().backward()
+        return out.detach(), img.grad.detach()
+
+    dec.zero_grad(set_to_none=True)
+    o, di = run(True)
+    junk = torch.randn(1 << 22, device="cuda").sin_()          # work on the caller's stream between backward and finish
+    decoder_ops.finish_backward()
+    torch.cuda.synchronize()
+    assert torch.equal(o, o_ref) and torch.equal(di, di_ref)
+    for p, ref in zip(dec.parameters(), gp_ref):
+        assert torch.equal(p.grad, ref)
+    # two deferred backwards in a row, one finish at the end: .grad holds exactly the sum of both
+    dec.zero_grad(set_to_none=True)
+    run(True)
+    run(True)
+    decoder_ops.finish_backward()
+    decoder_ops.finish_backward()      # idempotent
+    torch.cuda.synchronize()
+    for p, ref in zip(dec.parameters(), gp_ref):
+        torch.testing.assert_close(p.grad, 2 * ref, rtol=1e-6, atol=1e-6 * float(ref.abs().max()))
+    del junk
