@@ -523,6 +523,7 @@ k_dec_conv_tc(const ConvParams p) {
     const uint32_t mbar = tcv::smem_u32(mbar_store), mbar_w = tcv::smem_u32(mbar_store + 1);
     const bool bstats = MODE == IN_DZ && p.out_bsums != nullptr;
     DEC_TRACE_BEGIN();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the chain may start its prologue
 
     // weights: 72 KB already in the operand layout (k_dec_prep_weights) -> 9 bulk asynchronous copies issued by one thread
     if (tid == 0) {
@@ -543,6 +544,10 @@ k_dec_conv_tc(const ConvParams p) {
     }
 
     DEC_TRACE(1);
+    // Programmatic dependent launch: everything above (barriers, the 72 KB weight fetch, the TMEM allocation) touches nothing
+    // the preceding kernel of the chain writes, so this grid may start while that one is still running; from here on its
+    // outputs (activations, statistics) are needed.  No-op when the kernel was launched without the attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     TileStager<C, C, MODE> stager;
     stager.issue(p.src, p.src2, 0, b, r0, R, p.H, p.W);
     DEC_TRACE(2);
@@ -965,12 +970,123 @@ k_dec_wgrad(const WgradBatch q) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the 64 -> 64 layers with ALL NINE TAPS in one CTA (k_dec_wgrad loads a and dz once PER TAP: 9 x the
+// traffic, 9 x the CTAs; behind the data-gradient chain, where all layers' weight gradients run at once, the batched launch of
+// 1008 such CTAs took 40-70 us).  grid = (G image groups, layers); 16 warps: warp (mt = w / 4, pair = w % 4) keeps the
+// [16 cout x 16 cin] block of all 9 taps in registers (72 accumulators) while the CTA walks its images: the image's a tile is
+// staged WITH its halo (padded width W + 2, zero outside) and dz next to it, double-buffered by 16-byte asynchronous copies;
+// per 16-pixel k-step the dz fragment is loaded once and reused for the 9 taps, whose a fragments are the same ldmatrix rows
+// shifted by dy * (W + 2) + dx.  Partials go to the same [group][tap] slots k_dec_wgrad fills, in the same order of
+// accumulation over pixels and images (same bits); k_dec_wgrad_reduce sums the groups.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgAllThreads = 512;
+__global__ void __launch_bounds__(kWgAllThreads, 1)
+k_dec_wgrad_all(const WgradBatch q) {
+    constexpr int C = 64, ASTR = C + 8, DSTR = C + 8;
+    const WgradParams& p = q.p[blockIdx.y];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int TW = p.W + 2, NPAD = (p.H + 2) * TW, P = p.H * p.W, Ppad = (P + 15) / 16 * 16;
+    const size_t buf_halfs = (size_t)NPAD * ASTR + (size_t)Ppad * DSTR;
+    __half* buf0 = reinterpret_cast<__half*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
+    const int mt = warp >> 2, nt0 = (warp & 3) * 2;
+    const uint32_t w_magic = 0xFFFFFFFFu / (uint32_t)p.W + 1u, tw_magic = 0xFFFFFFFFu / (uint32_t)TW + 1u;
+    float c[9][2][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { c[t][j][0] = c[t][j][1] = c[t][j][2] = c[t][j][3] = 0.f; }
+    float dbias = 0.f;
+    const int bco = tid & 63, bpart = tid >> 6;
+    const int n_img = ((int)p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    auto stage = [&](int k, int which) {
+        const int b = blockIdx.x + k * gridDim.x;
+        __half* at = buf0 + which * buf_halfs;
+        __half* dt = at + (size_t)NPAD * ASTR;
+        const __half* a_img = p.a + (size_t)b * P * C;
+        const __half* d_img = p.dz + (size_t)b * P * C;
+        for (int i = tid; i < NPAD * 8; i += kWgAllThreads) {
+            const int pos = i >> 3, ck = i & 7;
+            const int tr = (int)__umulhi((uint32_t)pos, tw_magic), tc = pos - tr * TW;
+            const int rr = tr - 1, ww = tc - 1;
+            const __half* src = p.a;
+            uint32_t bytes = 0;
+            if (rr >= 0 && rr < p.H && ww >= 0 && ww < p.W) { src = a_img + (size_t)(rr * p.W + ww) * C + ck * 8; bytes = 16; }
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(at + (size_t)pos * ASTR + ck * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        for (int i = tid; i < Ppad * 8; i += kWgAllThreads) {
+            const int pix = i >> 3, ck = i & 7;
+            const __half* src = p.dz;
+            uint32_t bytes = 0;
+            if (pix < P) { src = d_img + (size_t)pix * C + ck * 8; bytes = 16; }
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dt + (size_t)pix * DSTR + ck * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_img > 0) stage(0, 0);
+    for (int k = 0; k < n_img; ++k) {
+        if (k + 1 < n_img) {
+            stage(k + 1, (k + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const __half* at = buf0 + (k & 1) * buf_halfs;
+        const __half* dt = at + (size_t)NPAD * ASTR;
+        if (bco < p.cout_real)
+            for (int pix = bpart; pix < P; pix += kWgAllThreads / 64) dbias += h2f(dt[(size_t)pix * DSTR + bco]);
+        for (int k0 = 0; k0 < Ppad; k0 += 16) {
+            uint32_t a[4];
+            ldsm_x4_trans(a, dt + (size_t)(k0 + (lane & 7) + ((lane >> 4) << 3)) * DSTR + mt * 16 + (((lane >> 3) & 1) << 3));
+            // this lane's B row of the k-step: pixel k0 + (lane & 15) at the centre tap, in padded-tile coordinates
+            const int pix = min(k0 + (lane & 15), P - 1);
+            const int prow = (int)__umulhi((uint32_t)pix, w_magic);
+            const __half* brow = at + (size_t)((prow + 1) * TW + (pix - prow * p.W) + 1) * ASTR + nt0 * 8;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int off = ((t / 3 - 1) * TW + (t % 3 - 1)) * ASTR;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t bb[2];
+                    ldsm_x2_trans(bb, brow + off + j * 8);
+                    mma_16816(c[t][j], a, bb[0], bb[1]);
+                }
+            }
+        }
+        __syncthreads();   // everybody is done with buffer k&1 before image k+2 is copied into it
+    }
+    // partials: slot (group, tap) as [cout][cin]; slot (group, 9) = the group's bias partial
+    __shared__ float s_db[kWgAllThreads];
+    s_db[tid] = dbias;
+    __syncthreads();
+    if (tid < 64) {
+        float acc = 0.f;
+        for (int part = 0; part < kWgAllThreads / 64; ++part) acc += s_db[part * 64 + tid];
+        p.partial[((size_t)blockIdx.x * 10 + 9) * (C * C) + tid] = acc;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        float* mine = p.partial + ((size_t)blockIdx.x * 10 + t) * (C * C);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int co = mt * 16 + h * 8 + g, ci = (nt0 + j) * 8 + 2 * tig;
+                *reinterpret_cast<float2*>(mine + co * C + ci) = make_float2(c[t][j][2 * h], c[t][j][2 * h + 1]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Second phase of the weight gradients for ALL layers in one launch: dW[co][ci][tap] += sum over the image groups (in group
 // order: deterministic, the same additions the ticket scheme's last CTA performed) of the partials k_dec_wgrad stored;
 // db likewise.  The ticket scheme ended every weight-gradient kernel with 9 CTAs summing 16 groups x 16 KB and writing dW with
 // stride-36-byte read-modify-writes while the other 135 CTAs had left: 7 of the kernel's 12.5 us (phase trace), nine times
-// per backward, next to the data-gradient chain whose stragglers it slowed.  grid = (37, layers): block x = tap * 4 + quarter
-// of the [COUT x CIN] partial (1024 elements, 4 per thread), block 36 = the bias.
+// per backward, next to the data-gradient chain whose stragglers it slowed.  grid = (17, layers).
 // ---------------------------------------------------------------------------------------------------------------
 struct WgradReduceParams {
     const float* partial[17];
@@ -982,9 +1098,12 @@ struct WgradReduceParams {
 };
 __global__ void __launch_bounds__(256)
 k_dec_wgrad_reduce(const WgradReduceParams q) {
+    // block (x, layer): x < 16 = 256 consecutive elements (co, ci) of the [COUT x CIN] partial, ALL nine taps - a thread's nine
+    // results are 36 contiguous bytes of dW[co][ci][3][3] and a warp's a contiguous 1152: coalesced read-modify-write (one block
+    // per tap wrote dW with stride-36-byte accesses: 21 us under ncu for 16 MB of partials); x == 16 = the bias
     const int l = blockIdx.y, N = q.n_elem[l], G = q.groups;
     const float* __restrict__ part = q.partial[l];
-    if (blockIdx.x == 36) {
+    if (blockIdx.x == 16) {
         if ((int)threadIdx.x < q.cout_real[l]) {
             float acc = 0.f;
             for (int g = 0; g < G; ++g) acc += __ldcg(part + ((size_t)g * 10 + 9) * N + threadIdx.x);
@@ -992,33 +1111,33 @@ k_dec_wgrad_reduce(const WgradReduceParams q) {
         }
         return;
     }
-    const int t = blockIdx.x >> 2, e4 = (blockIdx.x & 3) * 256 + (int)threadIdx.x;
-    if (e4 * 4 >= N) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int g0 = 0; g0 < G; g0 += 8) {
-        float4 v[8];
+    const int e = blockIdx.x * 256 + (int)threadIdx.x;
+    if (e >= N) return;
+    float acc[9];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            v[u] = g0 + u < G ? __ldcg(reinterpret_cast<const float4*>(part + ((size_t)(g0 + u) * 10 + t) * N) + e4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    for (int g0 = 0; g0 < G; g0 += 4) {      // groups in order (deterministic): 4 groups x 9 taps of loads in flight
+        float v[4][9];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (g0 + u < G) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                v[u][t] = g0 + u < G ? __ldcg(part + ((size_t)(g0 + u) * 10 + t) * N + e) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (g0 + u < G) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc[t] += v[u][t];
+            }
     }
-    const int cin_pad = q.cin_pad[l], cin_real = q.cin_real[l], cout_real = q.cout_real[l];
-    float* __restrict__ dW = q.dW[l];
-    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-    float oldw[4];
+    const int cin_pad = q.cin_pad[l], co = e / cin_pad, ci = e - co * cin_pad;
+    if (co >= q.cout_real[l] || ci >= q.cin_real[l]) return;
+    float* __restrict__ dst = q.dW[l] + ((size_t)co * q.cin_real[l] + ci) * 9;
+    float oldw[9];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int i = e4 * 4 + c, co = i / cin_pad, ci = i - co * cin_pad;
-        oldw[c] = (co < cout_real && ci < cin_real) ? __ldcg(dW + ((size_t)co * cin_real + ci) * 9 + t) : 0.f;
-    }
+    for (int t = 0; t < 9; ++t) oldw[t] = __ldcg(dst + t);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int i = e4 * 4 + c, co = i / cin_pad, ci = i - co * cin_pad;
-        if (co < cout_real && ci < cin_real) dW[((size_t)co * cin_real + ci) * 9 + t] = oldw[c] + a4[c];
-    }
+    for (int t = 0; t < 9; ++t) dst[t] = oldw[t] + acc[t];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1424,7 +1543,24 @@ int launch_conv_tc(ConvParams p, cudaStream_t st) {
     const size_t smem = tcv::smem_bytes(p.R, p.W);
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_dec_conv_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    k_dec_conv_tc<MODE><<<dim3((p.H + p.R - 1) / p.R, p.B), kDecThreads, smem, st>>>(p);
+    // NSIG_DEC_PDL=1: launched with programmatic stream serialization - the grid may begin once every CTA of the preceding
+    // kernel has executed griddepcontrol.launch_dependents (k_dec_conv_tc does at entry; any other kernel implicitly when it
+    // completes) and blocks in griddepcontrol.wait until that kernel has completed and flushed.  Measured (round 2, call BI):
+    // the kernels do start up to 22 us early and sit in the wait with their weights loaded, but forward+backward takes 271 us
+    // instead of 265 us - what a kernel boundary costs here is the completion + flush + wake-up, not the launch.  Off by default.
+    static const bool pdl = [] { const char* e = getenv("NSIG_DEC_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((p.H + p.R - 1) / p.R, p.B);
+    cfg.blockDim = dim3(kDecThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_dec_conv_tc<MODE>, p);
+    if (e != cudaSuccess) return (int)e;
     NSIG_LAUNCH_CHECK();
     return 0;
 }
@@ -1481,6 +1617,27 @@ int launch_wgrad_batch(const WgradParams* layers, int n, cudaStream_t st) {
 }
 template <int CIN, int COUT, int DCH>
 int launch_wgrad(WgradParams p, cudaStream_t st) { return launch_wgrad_batch<CIN, COUT, DCH>(&p, 1, st); }
+
+// the all-taps kernel needs two whole images (a with halo + dz) in shared memory and the two-phase reduction
+size_t wgrad_all_smem(int H, int W) {
+    const size_t P = (size_t)H * W, Ppad = (P + 15) / 16 * 16;
+    return 2 * ((size_t)(H + 2) * (W + 2) + Ppad) * 72 * 2;
+}
+bool wgrad_all_fits(const WgradParams& p) {
+    static const bool on = [] { const char* e = getenv("NSIG_DEC_WGRAD_PER_TAP"); return !(e && e[0] == '1'); }();
+    return on && p.partial != nullptr && p.tickets == nullptr && wgrad_all_smem(p.H, p.W) <= 200 * 1024 && p.H * p.W < 65536;
+}
+int launch_wgrad_all(const WgradParams* layers, int n, cudaStream_t st) {
+    if (n < 1 || n > kWgradBatchMax) return NSIG_EINVAL;
+    WgradBatch q{};
+    for (int i = 0; i < n; ++i) q.p[i] = layers[i];
+    const size_t smem = wgrad_all_smem(layers[0].H, layers[0].W);
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(k_dec_wgrad_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    k_dec_wgrad_all<<<dim3(wgrad_groups(layers[0].B), n), kWgAllThreads, smem, st>>>(q);
+    NSIG_LAUNCH_CHECK();
+    return 0;
+}
 
 // Side stream of the backward chain.  The data-gradient convs form a dependent chain (layer l needs the statistics of
 // da_l); the weight gradient of layer l only needs a_{l-1} (forward) and dz_l (written by the data-gradient conv of
@@ -1552,7 +1709,7 @@ int finish_deferred_locked(int dev, cudaStream_t st) {
         }
     }
     if (t.reduce) {
-        nsig::k_dec_wgrad_reduce<<<dim3(37, t.layers), 256, 0, st>>>(t.r);
+        nsig::k_dec_wgrad_reduce<<<dim3(17, t.layers), 256, 0, st>>>(t.r);
         NSIG_LAUNCH_CHECK();
     }
     return 0;
@@ -1835,7 +1992,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
             WgradParams mid[kWgradBatchMax];
             int n = 0;
             for (int l = l0; l < L && n < kWgradBatchMax; ++l) mid[n++] = wgrad_params(l);
-            if (int rc = launch_wgrad_batch<64, 64, 64>(mid, n, wst)) return rc;
+            if (int rc = wgrad_all_fits(mid[0]) ? launch_wgrad_all(mid, n, wst) : launch_wgrad_batch<64, 64, 64>(mid, n, wst)) return rc;
         }
         if (int rc = fork_to(1, wst)) return rc;
         if (int rc = launch_wgrad<16, 64, 64>(wgrad_params(0), wst)) return rc;
@@ -1882,7 +2039,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
             g_deferred[cur_dev].reduce = true;
             g_deferred[cur_dev].r = r;
         } else {
-            k_dec_wgrad_reduce<<<dim3(37, L + 1), 256, 0, st>>>(r);
+            k_dec_wgrad_reduce<<<dim3(17, L + 1), 256, 0, st>>>(r);
             NSIG_LAUNCH_CHECK();
         }
     }
