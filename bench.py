@@ -727,7 +727,8 @@ def run_ours(args):
                    "optimizer": ("WatermarkAdam (fused message-table Adam + torch fused Adam for the decoder)"
                                  if args.optimizer == "fused" else "torch.optim.Adam(fused)") + " + GradScaler",
                    "optimizer_schedule": ("deferred: Adam of step t runs at the start of step t+1 next to its march (same data "
-                                          "dependencies, flushed inside the timed region after the last step)"
+                                          "dependencies, flushed inside the timed region after the last step); the update kernel "
+                                          "also accumulates the next message's summed table"
                                           if (use_graph and not args.no_defer) else "end of step"),
                    "step": ("one CUDA graph replay per step" if use_graph else "eager") +
                            {"merged": "; both render passes in one call over [block rays | content rays]",
@@ -736,7 +737,8 @@ def run_ours(args):
                                        "next to the content pass"}[args.render_mode],
                    "l2": "inputs larger than L2: 64 MiB base tables + %d MiB message tables selected by a fresh message "
                          "each step + per-step sample buffers vs 126 MB L2" % (4 * md),
-                   "decoder": "plain PyTorch module (autocast)" if args.torch_decoder else "fused kernels (csrc/decoder.cu)",
+                   "decoder": "plain PyTorch module (autocast)" if args.torch_decoder else ("fused kernels (csrc/decoder.cu): 64->64 convs on tcgen05 + TMEM, weight gradients behind the data-gradient chain "
+                                "and joined after the renderer's backward"),
                    "losses": "plain torch expressions" if args.torch_losses else "loss-head kernels (csrc/wtmk_loss.cu)",
                    "parallelism": f"ray-sharded dp{world}" + ("; content rays of the N views dealt out ray by ray (balanced "
                                                                  "sample counts), watermark blocks per rank" if world > 1 else ""),
