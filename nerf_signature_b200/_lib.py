@@ -70,8 +70,9 @@ _SIGNATURES = {
     "nsig_decoder_backward": ([_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
                               # head, last block's statistics, L+1 data-gradient convs, weight gradients (the 64->64 layers as
                               # one launch per 8 layers + first + last layer), their reduction (counted here also when it is
-                              # deferred to nsig_decoder_finish_backward), BatchNorm gradients, input gradient
-                              lambda a: (a[4] + 1) + 2 + (-(-max(a[4] - 1, 0) // 8) + 2) + 1 + 1 + (1 if a[10] is not None else 0)),
+                              # deferred to nsig_decoder_finish_backward), BatchNorm gradients (the input gradient is written
+                              # by the first layer's data-gradient conv)
+                              lambda a: (a[4] + 1) + 2 + (-(-max(a[4] - 1, 0) // 8) + 2) + 1 + 1),
     "nsig_decoder_prepare_weights": ([_vp, _u32, _u32, _u32, _vp, _vp], 1),
     "nsig_decoder_gelu_probe": ([_vp, _u32, _vp, _vp, _vp], 1),
     "nsig_decoder_finish_backward": ([_vp], 0),   # (its reduction launch is counted with nsig_decoder_backward)

@@ -243,6 +243,8 @@ struct ConvParams {
     double* out_bsums;     // [2][COUT] or null
     int B, H, W, R;        // R = image rows per CTA
     int cout_valid;        // outputs >= cout_valid are written as zero (channel padding)
+    float* dimage;         // optional (first layer's data gradient): [B,H,W,3] fp32 = output channels 0..2 / std of the input
+                           // normalisation, written by the epilogue (saves the conversion kernel behind the chain)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -411,6 +413,12 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
                     if (col + 1 >= p.cout_valid) o1 = f2h(0.f);
                     const size_t oidx = (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col;
                     *reinterpret_cast<__half2*>(p.dst + oidx) = __halves2half2(o0, o1);
+                    if (MODE == IN_DZ && p.dimage != nullptr && col < 3) {   // d(image) = d(x0) / std (k_dec_input_grad's arithmetic)
+                        const float stdv[4] = {0.229f, 0.224f, 0.225f, 1.0f};
+                        float* di = p.dimage + ((((size_t)b * p.H + r0 + rr) * p.W + ww)) * 3;
+                        di[col] = __fdiv_rn(h2f(o0), stdv[col]);
+                        if (col + 1 < 3) di[col + 1] = __fdiv_rn(h2f(o1), stdv[col + 1]);
+                    }
                     if (bstats) {   // backward statistics of the layer whose da this is (same arithmetic as k_dec_bwd_stats)
                         const __half2 zz = *reinterpret_cast<const __half2*>(p.z_out + oidx);
                         const __half zh[2] = {__low2half(zz), __high2half(zz)}, dh[2] = {o0, o1};
@@ -1967,6 +1975,7 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         if (l > 0 && l < L) p.w_tc = pw ? reinterpret_cast<const __half*>(pw + wl.off_wr_tc[l]) : H16(d.off_wr_tc[l]);
         __half* out = l == 0 ? H16(d.off_dx0) : H16(d.off_da[l & 1]);
         p.dst = out; p.cout_valid = l == 0 ? 3 : 64;
+        if (l == 0) p.dimage = dimage;   // the input gradient leaves the chain's last kernel directly
         if (l > 0) {   // outputs are da_{l-1}: accumulate layer l-1's backward statistics on the way out
             p.z_out = H16(d.off_z[l - 1]);
             p.bn_out = BnSrc{D64(d.off_sums[l - 1]), nullptr, params[4 * (l - 1) + 2], params[4 * (l - 1) + 3], inv_n, 64, 64};
@@ -1999,16 +2008,18 @@ int nsig_decoder_backward(const float* dlogits, uint32_t B, uint32_t H, uint32_t
         if (int rc = fork_to(2, wst)) return rc;
         if (int rc = launch_wgrad<64, 16, 8>(wgrad_params(L), wst)) return rc;
     }
-    // what remains on the caller's stream does not depend on the weight gradients: issued first, so that it runs next to them
-    BnGradParams q{};
-    for (int l = 0; l <= L; ++l) {
-        q.bsums[l] = D64(d.off_bsums[l]); q.dgamma[l] = grads[4 * l + 2]; q.dbeta[l] = grads[4 * l + 3];
-        q.c_pad[l] = l == L ? 8 : 64; q.c_real[l] = l == L ? nb : 64;
-    }
-    k_dec_bn_grads<<<L + 1, 64, 0, st>>>(q);
-    NSIG_LAUNCH_CHECK();
-    if (dimage) {
-        k_dec_input_grad<<<(unsigned)((d.n_pix + 255) / 256), 256, 0, st>>>(H16(d.off_dx0), n_pix, dimage);
+    // BatchNorm parameter gradients (= the backward statistics): nothing on the caller's stream needs them - with the weight
+    // gradients on a side stream (the last one used above, or the caller's stream without side streams)
+    {
+        cudaStream_t bst = st;
+        if (side && wgrad_late) bst = side->stream[2 % side->n];
+        else if (side) { if (int rc = fork_to(0, bst)) return rc; }
+        BnGradParams q{};
+        for (int l = 0; l <= L; ++l) {
+            q.bsums[l] = D64(d.off_bsums[l]); q.dgamma[l] = grads[4 * l + 2]; q.dbeta[l] = grads[4 * l + 3];
+            q.c_pad[l] = l == L ? 8 : 64; q.c_real[l] = l == L ? nb : 64;
+        }
+        k_dec_bn_grads<<<L + 1, 64, 0, bst>>>(q);
         NSIG_LAUNCH_CHECK();
     }
     const bool defer = g_defer_on && side != nullptr && wgrad_late;
