@@ -96,6 +96,9 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert h.nsig_msg_adam_step_sum(p, 8, 4, p, None, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, aligned, None) == -1
     assert h.nsig_msg_adam_step_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 0, 0, odd, None) == -1
     assert h.nsig_msg_adam_step_sum(p, 8, 4, p, p, aligned, p, p, None, None, 1e-2, 0.9, 0.99, 1e-15, 12, None, 2, 8, aligned, None) == -1
+    # deferred decoder tail: a process-wide switch (no CUDA call), restored at once
+    assert h.nsig_decoder_defer_weight_grads(1) == 0 and h.nsig_decoder_defer_weight_grads(0) == 0
+    assert h.nsig_decoder_gelu_probe(None, 0, None, None, None) == 0 and h.nsig_decoder_gelu_probe(p, 8, None, p, None) == -1
     # grid-limited march: the unlimited entry's validation
     assert h.nsig_march_rays_train_limited(p, p, p, 1.0, 0.0, 1024, 4, 0, 128, 64, p, p, p, p, p, p, p, None, p, 296, None) == -1  # C=0
     assert h.nsig_march_rays_train_limited(p, p, p, 1.0, 0.0, 1024, 0, 1, 128, 64, p, p, p, p, p, p, p, None, p, 296, None) == 0   # no rays
