@@ -413,7 +413,7 @@ __device__ __forceinline__ void conv_cta(const ConvParams& p, unsigned char* sme
                     if (col + 1 >= p.cout_valid) o1 = f2h(0.f);
                     const size_t oidx = (((size_t)b * p.H + r0 + rr) * p.W + ww) * COUT + col;
                     *reinterpret_cast<__half2*>(p.dst + oidx) = __halves2half2(o0, o1);
-                    if (MODE == IN_DZ && p.dimage != nullptr && col < 3) {   // d(image) = d(x0) / std (k_dec_input_grad's arithmetic)
+                    if (MODE == IN_DZ && p.dimage != nullptr && col < 3) {   // d(image) = d(x0) / std (normalize_img backward: hidden_models.py)
                         const float stdv[4] = {0.229f, 0.224f, 0.225f, 1.0f};
                         float* di = p.dimage + ((((size_t)b * p.H + r0 + rr) * p.W + ww)) * 3;
                         di[col] = __fdiv_rn(h2f(o0), stdv[col]);
@@ -1201,16 +1201,6 @@ k_dec_prep_input(const float* __restrict__ img, int n_pix, __half* __restrict__ 
     *reinterpret_cast<uint4*>(x0 + (size_t)i * 16) = *reinterpret_cast<const uint4*>(o);
     *reinterpret_cast<uint4*>(x0 + (size_t)i * 16 + 8) = *reinterpret_cast<const uint4*>(o + 8);
 }
-// dx0 [B,H,W,16] fp16 -> dimg [B,H,W,3] fp32 = dx0 / std
-__global__ void __launch_bounds__(256)
-k_dec_input_grad(const __half* __restrict__ dx0, int n_pix, float* __restrict__ dimg) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_pix) return;
-    const float std[3] = {0.229f, 0.224f, 0.225f};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) dimg[(size_t)i * 3 + k] = __fdiv_rn(h2f(dx0[(size_t)i * 16 + k]), std[k]);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // head: a9 = GELU(BN(z9)) [B,H,W,8 (nb real)] -> AdaptiveAvgPool2d(1) -> Linear(nb, nb) -> sum over redundancy.
 // One CTA per image.  Backward: dlogits[B,num_bits] -> dlin_w, dlin_b (+=), da9 [B,H,W,8] fp16.
