@@ -40,6 +40,49 @@ def test_library_exports_every_declared_symbol(lib):
     assert exported == set(decl), exported ^ set(decl)  # C linkage, no stray mangled nsig entry points
 
 
+_C_TYPES = {"uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "int": ctypes.c_int, "float": ctypes.c_float,
+            "double": ctypes.c_double, "uint64_t": ctypes.c_uint64, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+            "nsig_stream_t": ctypes.c_void_p}
+
+
+def declared_prototypes():
+    """{name: (return type, [ctypes type of every parameter])} parsed from include/nsig.h."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for ret, name, params in re.findall(r"\b([A-Za-z_][A-Za-z0-9_ \*]*?)\s*\b(nsig_[A-Za-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        types = []
+        for prm in params.split(","):
+            prm = prm.strip()
+            if prm in ("", "void"):
+                continue
+            if "*" in prm:
+                types.append(ctypes.c_void_p)
+            else:
+                toks = prm.replace("const", "").split()
+                assert len(toks) == 2, f"{name}: cannot parse parameter '{prm}'"
+                types.append(_C_TYPES[toks[0]])
+        protos[name] = (" ".join(ret.split()), types)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_parameter_by_parameter(lib):
+    """The binding passes scalars by ctypes argtypes: a count or type drift between include/nsig.h (which the .cu files
+    compile against through nsig_common.cuh) and _lib._SIGNATURES would silently shift every later argument."""
+    protos = declared_prototypes()
+    assert sorted(protos) == declared_symbols()
+    handle = lib.load()
+    for name, (ret, types) in protos.items():
+        fn = getattr(handle, name)
+        assert list(fn.argtypes or []) == types, f"{name}: argtypes differ from the header"
+        want_ret = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "uint32_t": ctypes.c_uint32,
+                    "const char*": ctypes.c_char_p}[ret.replace(" *", "*")]
+        assert fn.restype is want_ret, f"{name}: restype {fn.restype} vs header '{ret}'"
+        if name in lib._SIGNATURES:   # every status-returning entry point ends with the stream it runs on
+            assert ret == "int" and types[-1] is ctypes.c_void_p
+
+
 def test_library_is_sm100a_only_and_has_no_torch_dependency(lib):
     assert lib.version().startswith("nsig_b200") and "sm_100a" in lib.version()
     out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
