@@ -1,9 +1,12 @@
 """CPU tests (-m "not gpu") of the host-side mirror of the reference interface: module structure,
 state-dict keys, freezing policy, level resolutions, synthetic batch shapes.  No kernels run."""
 import inspect
+import os
 
 import numpy as np
 import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_raymarching_module_has_the_reference_callables_and_signatures():
@@ -91,6 +94,47 @@ def test_synthetic_batch_shapes_match_the_reference_provider():
     np.testing.assert_allclose(np.linalg.norm(b["rays_o"], axis=-1), 4.0311 * 0.8, atol=1e-4)
     b2 = harness.make_batch(cfg, seed=0)
     assert all(np.array_equal(b[k], b2[k]) for k in b)  # seeded
+
+
+def test_workloads_carry_the_parameters_baseline_json_names():
+    """harness.CONFIGS vs the prose of BASELINE.json configs[1], [2], [4] (the numbers the bench lines are quoted on)."""
+    import json
+    from nerf_signature_b200 import harness
+    cfgs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    c1, c2, c4 = harness.CONFIGS["blender_wtmk"], harness.CONFIGS["360_wtmk"], harness.CONFIGS["shard262144_wtmk"]
+    assert "bound 1.0, scale 0.8, dt_gamma 0" in cfgs[1] and "message_dim 32, 32x32 codebook, num_rays 4096" in cfgs[1]
+    assert (c1["bound"], c1["scale"], c1["dt_gamma"], c1["message_dim"], c1["num_rows"], c1["num_cols"], c1["num_rays"]) == \
+        (1.0, 0.8, 0.0, 32, 32, 32, 4096)
+    assert "scale 0.33, dt_gamma 0" in cfgs[2] and "num_rays 4096, message_dim 32" in cfgs[2] and "every 16 iters" in cfgs[2]
+    assert (c2["scale"], c2["dt_gamma"], c2["message_dim"], c2["num_rays"], c2["grid_update_every"]) == (0.33, 0.0, 32, 4096, 16)
+    assert c2["bound"] > 1.0                                   # unbounded scene: more than one cascade
+    assert "262144 rays/step" in cfgs[4] and "message_dim 48" in cfgs[4]
+    assert (c4["num_rays"], c4["message_dim"]) == (262144, 48)
+    # configs[1]'s step: 4096 content rays + message_dim blocks of (400/32)^2 pixels = 8704 rays
+    assert c1["num_rays"] + c1["message_dim"] * (c1["H"] // c1["num_rows"]) * (c1["W"] // c1["num_cols"]) == 8704
+
+
+def test_shard_batch_partitions_one_global_batch_exactly():
+    """the ranks' shards of configs[4]-shaped batches are contiguous, disjoint, complete and balanced,
+    for the content rays (with their ground truth) and for the flattened watermark-block rays."""
+    from nerf_signature_b200 import harness
+    cfg = dict(harness.CONFIGS["shard262144_wtmk"], num_rays=1000 + 3)        # ragged on purpose
+    g = harness.make_batch(cfg, seed=3)
+    md, pH, pW = g["rays_o_block"].shape[:3]
+    assert (md, pH, pW) == (48, 12, 12)
+    for world in (1, 2, 3, 4, 8):
+        shards = [harness.shard_batch(g, r, world) for r in range(world)]
+        assert all(s[1] == (md, pH, pW) for s in shards)
+        counts = shards[0][2]
+        assert all(s[2] == counts for s in shards) and sum(counts) == md * pH * pW
+        assert [s[0]["rays_o_block"].shape[0] for s in shards] == counts and max(counts) - min(counts) <= 1
+        for key, full in (("rays_o_block", g["rays_o_block"].reshape(-1, 3)), ("rays_d_block", g["rays_d_block"].reshape(-1, 3))):
+            assert np.array_equal(np.concatenate([s[0][key] for s in shards], axis=0), full)
+        for key in ("rays_o", "rays_d", "gt"):
+            assert np.array_equal(np.concatenate([s[0][key] for s in shards], axis=1), g[key])
+        sizes = [s[0]["rays_o"].shape[1] for s in shards]
+        assert max(sizes) - min(sizes) <= 1 and all(s[0]["gt"].shape == s[0]["rays_o"].shape for s in shards)
+        assert all(a.flags["C_CONTIGUOUS"] for s in shards for a in s[0].values())   # handed to pinned copies as they are
 
 
 def test_fused_index_identity_double_multiply_equals_fp32_division():
