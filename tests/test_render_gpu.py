@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from nerf_signature_b200 import synthetic as syn
+from conftest import record_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +57,83 @@ def test_fused_renderer_matches_reference_loop(bound, rays_fn, dt_gamma, sigma_g
         c = net.render(ro, rd, msg, staged=True, max_ray_batch=400, bg_color=1, perturb=False, dt_gamma=dt_gamma,
                        max_steps=1024, T_thresh=1e-4)
     np.testing.assert_allclose(c["image"].cpu().numpy(), img_a, rtol=1e-6, atol=1e-7)
+
+
+def _oracle_frame(oracle_cpu, net, rays_o, rays_d, msg, bound, T_thresh):
+    """The frame the oracle gives for these rays: C oracle march + hash encoders, torch-fp32 MLP oracle, and the INFERENCE
+    composite rule restated in fp64 - composite_rays accumulates a sample and THEN stops if the transmittance BEFORE it was
+    below T_thresh (raymarching.cu:868-883), one sample later than composite_rays_train (raymarching.cu:548-551).  With
+    perturb off the inference march (raymarching.cu:701-800) visits the lattice points of the training march
+    (raymarching.cu:312-480), so the training march supplies the samples.  Returns (image on white, weights_sum, samples
+    marched, samples consumed, image under the TRAINING rule by the C oracle)."""
+    from oracle import field_oracle as fo
+    N = rays_o.shape[0]
+    bitfield = net.density_bitfield.cpu().numpy()
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    xyz, dirs, deltas, rays, cnt = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield, 1, 128, on, of)
+    m = int(cnt[0])
+    xn = ((xyz[:m] + np.float32(bound)) * np.float32(0.5 / bound)).astype(np.float32)
+    tabs = [e.weight.detach().cpu().numpy() for e in net.encoder.embeddings]
+    feat = oracle_cpu.hash_encode_forward(xn, tabs, net.encoder.resolutions, 19)
+    mt = [e.weight.detach().cpu().numpy() for e in net.msg_encoder.embeddings]
+    feat[:, 30:32] += oracle_cpu.msg_encode_forward(xn, mt, msg, net.msg_encoder.resolution, 19)
+    sig, rgb, _, _ = fo.mlp_forward(torch.from_numpy(feat), torch.from_numpy(dirs[:m]),
+                                    net.sigma_net.params.detach().cpu(), net.color_net.params.detach().cpu())
+    sig, rgb = sig.numpy(), rgb.numpy()
+    ws_t, _, img_t = oracle_cpu.composite_rays_train_forward(sig, rgb, deltas[:m], rays, T_thresh)
+    alpha = 1.0 - np.exp(-sig.astype(np.float64) * deltas[:m, 0].astype(np.float64))
+    img, ws, used = np.zeros((N, 3)), np.zeros(N), 0
+    for n in range(N):
+        lo, c = int(rays[n, 1]), int(rays[n, 2])
+        for k in range(lo, lo + c):
+            T = 1.0 - ws[n]
+            w = alpha[k] * T
+            ws[n] += w
+            img[n] += w * rgb[k]
+            used += 1
+            if T < T_thresh:
+                break
+    return (img + (1 - ws)[:, None]).astype(np.float32), ws.astype(np.float32), m, used, img_t + (1 - ws_t)[:, None]
+
+
+@pytest.mark.parametrize("sigma_gain,T_thresh", [(0.0, 1e-4), (0.6, 1e-4), (12.0, 1e-2)])
+def test_fused_renderer_matches_cpu_oracle(oracle_cpu, sigma_gain, T_thresh):
+    """nsig_render_rays DIRECTLY against the oracle (not through the repo's own alive-ray loop).  Cases 1-2: no ray
+    reaches T_thresh, every marched sample is consumed, 1e-3 (north_star; observed 2e-6).  Case 3: a dense scene in which
+    rays are killed after ~17 % of their samples.  Measured on a B200 against the TRAINING-rule composite the kernel's
+    frame was at most 3.3613e-3 away; the oracle's own inference-rule and training-rule frames differ by at most
+    3.3610e-3 (the one extra sample the inference rule accumulates), i.e. the kernel follows the inference rule.  The
+    round's GPU budget ended before the direct comparison with the inference-rule frame could be re-run, so the bound
+    asserted for case 3 is the one that FOLLOWS from that measurement (3.4e-3 + one sample's weight < T_thresh), not
+    the tight one; conftest.record_parity logs the observed error."""
+    md, N, bound = 8, 600, 1.0
+    net = _net(bound, md, sigma_gain=sigma_gain)
+    rays_o, rays_d = syn.blender_rays(N, seed=23)
+    msg = np.random.RandomState(4).randint(0, 2, size=md).astype(np.float32)
+    with torch.no_grad():
+        net.fused_inference = True
+        out = net.render(torch.from_numpy(rays_o)[None].cuda(), torch.from_numpy(rays_d)[None].cuda(),
+                         torch.from_numpy(msg).cuda(), staged=False, bg_color=1, perturb=False, dt_gamma=0.0,
+                         max_steps=1024, T_thresh=T_thresh)
+    n_samples = int(net.last_render_samples)
+    image = out["image"].cpu().numpy().reshape(-1, 3)
+    img, ws, m, used, img_train_rule = _oracle_frame(oracle_cpu, net, rays_o, rays_d, msg, bound, T_thresh)
+    assert np.abs(img - 1.0).max() > 0.05           # the scene is visible
+    dense = sigma_gain > 10
+    if dense:
+        assert used < 0.25 * m and used <= n_samples < 0.8 * m     # killed rays; the kernel evaluates 32 samples at a time
+        assert np.abs(img - img_train_rule).max() < T_thresh        # the two rules differ by one sample's weight
+    else:
+        assert used == m == n_samples                               # nothing terminates: every marched sample is consumed
+        assert np.abs(img - img_train_rule).max() < 1e-5
+    per_ray = np.abs(image - img).max(axis=1)
+    err = float(per_ray.max())
+    record_parity("render_rays_vs_cpu_oracle", {"sigma_gain": sigma_gain, "T_thresh": T_thresh, "image_max_abs": err,
+                                                "samples": n_samples, "oracle_samples": m, "oracle_samples_consumed": used})
+    assert err < (1e-3 + 1.5 * T_thresh if dense else 1e-3), err
+    if "weights_sum" in out and not dense:
+        assert np.abs(out["weights_sum"].cpu().numpy().reshape(-1) - ws).max() < 1e-3
 
 
 def test_fused_renderer_early_termination_saves_samples():
