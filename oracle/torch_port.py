@@ -172,30 +172,76 @@ def near_far_from_aabb(rays_o, rays_d, bound, min_near=0.2):
     return torch.where(miss, torch.full_like(near, big), near), torch.where(miss, torch.full_like(far, big), far)
 
 
-def render_run(field, rays_o, rays_d, message, num_steps=512, bg_color=1.0, min_near=0.2):
-    """NeRFRenderer.run with upsample_steps=0, perturb=False (renderer_wtmk.py:125-253)."""
+def _alpha_weights(z, sigma, sample_dist):
+    """Interval lengths (the last one is the nominal spacing), alphas and compositing weights of sorted depths z [N, T]
+    (renderer_wtmk.py:204-208; the 1e-15 keeps the running product off exact zero)."""
+    deltas = torch.cat([z[..., 1:] - z[..., :-1], sample_dist * torch.ones_like(z[..., :1])], dim=-1)
+    alphas = 1 - torch.exp(-deltas * sigma)
+    shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+    return deltas, alphas * torch.cumprod(shifted, dim=-1)[..., :-1]
+
+
+def resample_depths(edges, weights, n_samples):
+    """Deterministic inverse-CDF resampling (renderer_wtmk.py:12-46 with det=True, what run() uses in eval mode): the
+    n_samples bin centres of [0, 1] pulled back through the piecewise-linear CDF that `weights` [N, B-1] define over the
+    `edges` [N, B]."""
+    pdf = weights + 1e-5
+    pdf = pdf / pdf.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, n_samples).expand(cdf.shape[0], n_samples).contiguous()
+    hi = torch.searchsorted(cdf, u, right=True)
+    lo = (hi - 1).clamp(min=0)
+    hi = hi.clamp(max=cdf.shape[-1] - 1)
+    c0, c1 = cdf.gather(1, lo), cdf.gather(1, hi)
+    e0, e1 = edges.gather(1, lo), edges.gather(1, hi)
+    width = c1 - c0
+    width = torch.where(width < 1e-5, torch.ones_like(width), width)
+    return e0 + (u - c0) / width * (e1 - e0)
+
+
+def render_run(field, rays_o, rays_d, message, num_steps=512, bg_color=1.0, min_near=0.2, upsample_steps=0,
+               return_depth=False):
+    """NeRFRenderer.run in eval mode, perturb=False (renderer_wtmk.py:125-253): uniform depths between near and far,
+    optional hierarchical resampling (upsample_steps > 0: the extra points are evaluated WITHOUT the message, as the
+    reference does at renderer_wtmk.py:185), colour only where the weight exceeds 1e-4, white-background blend.
+    Returns (image, weights_sum[, depth])."""
     N = rays_o.shape[0]
     nears, fars = near_far_from_aabb(rays_o, rays_d, field.bound, min_near)
     nears, fars = nears.unsqueeze(-1), fars.unsqueeze(-1)
     z = torch.linspace(0.0, 1.0, num_steps).unsqueeze(0).expand(N, num_steps)
     z = nears + (fars - nears) * z
     sample_dist = (fars - nears) / num_steps
-    xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)
-    xyzs = xyzs.clamp(-field.bound, field.bound)
+
+    def points(depths):
+        return (rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * depths.unsqueeze(-1)).clamp(-field.bound, field.bound)
+
+    xyzs = points(z)
     dens = field.density(xyzs.reshape(-1, 3), message)
-    sigma = dens['sigma'].view(N, num_steps)
-    deltas = torch.cat([z[..., 1:] - z[..., :-1], sample_dist * torch.ones_like(z[..., :1])], dim=-1)
-    alphas = 1 - torch.exp(-deltas * sigma)
-    shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-    weights = alphas * torch.cumprod(shifted, dim=-1)[..., :-1]
+    sigma, geo = dens['sigma'].view(N, num_steps), dens['geo_feat'].view(N, num_steps, -1)
+    if upsample_steps > 0:
+        with torch.no_grad():
+            deltas, w = _alpha_weights(z, sigma, sample_dist)
+            mids = z[..., :-1] + 0.5 * deltas[..., :-1]
+            z_new = resample_depths(mids, w[:, 1:-1], upsample_steps)
+        extra = field.density(points(z_new).reshape(-1, 3), None)
+        z, order = torch.sort(torch.cat([z, z_new], dim=1), dim=1)
+        sigma = torch.cat([sigma, extra['sigma'].view(N, upsample_steps)], dim=1).gather(1, order)
+        geo = torch.cat([geo, extra['geo_feat'].view(N, upsample_steps, -1)], dim=1)
+        geo = geo.gather(1, order.unsqueeze(-1).expand_as(geo))
+        xyzs = points(z)
+    T = z.shape[1]
+    _, weights = _alpha_weights(z, sigma, sample_dist)
     mask = (weights > 1e-4).reshape(-1)
     dirs = rays_d.view(-1, 1, 3).expand_as(xyzs).reshape(-1, 3)
-    rgbs = torch.zeros(N * num_steps, 3)
+    rgbs = torch.zeros(N * T, 3)
     if mask.any():
-        rgbs[mask] = field.color(dirs[mask], dens['geo_feat'][mask])
-    rgbs = rgbs.view(N, num_steps, 3)
+        rgbs[mask] = field.color(dirs[mask], geo.reshape(N * T, -1)[mask])
+    rgbs = rgbs.view(N, T, 3)
     weights_sum = weights.sum(dim=-1)
     image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2) + (1 - weights_sum).unsqueeze(-1) * bg_color
+    if return_depth:
+        depth = torch.sum(weights * ((z - nears) / (fars - nears)).clamp(0, 1), dim=-1)
+        return image, weights_sum, depth
     return image, weights_sum
 
 

@@ -173,3 +173,46 @@ def test_c_morton_packbits_match_reference_cuda(golden_rm, oracle_cpu):
     assert np.array_equal(oracle_cpu.morton3D_invert(g["morton_idx"]), g["morton_back"])
     assert np.array_equal(g["morton_back"], g["morton_coords"])
     assert np.array_equal(oracle_cpu.packbits(g["packbits_grid"], 0.25), g["packbits_bits"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# non-cuda_ray renderer: oracle/torch_port.render_run against the reference's own NeRFRenderer.run
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden_run():
+    return np.load(os.path.join(ROOT, "tests", "golden", "run_golden.npz"))
+
+
+@pytest.mark.parametrize("case", ["clean", "wtmk", "wtmk_bound2", "wtmk_upsample"])
+def test_torch_port_render_run_matches_reference_run(golden_run, case):
+    """tests/golden/run_golden.npz holds what the reference's unmodified NeRFRenderer.run (+ sample_pdf) returned on CPU
+    for these rays (tests/golden/make_golden_run.py).  The port is bench.py's CPU baseline and the oracle of the
+    product's `run`: image, weights_sum and depth within fp32 rounding of the reference's."""
+    import make_golden_run as mg
+    from oracle import torch_port as tp
+    field, o, d, msg, steps, up = mg.case_inputs(case)
+    with torch.no_grad():
+        image, ws, depth = tp.render_run(field, o, d, msg, num_steps=steps, upsample_steps=up, return_depth=True)
+    g = golden_run
+    assert float(g[f"{case}_weights_sum"].max()) > 0.5 and np.ptp(g[f"{case}_image"]) > 0.1      # a visible scene
+    np.testing.assert_allclose(ws.numpy(), g[f"{case}_weights_sum"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(image.numpy(), g[f"{case}_image"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(depth.numpy(), g[f"{case}_depth"], rtol=0, atol=2e-6)
+
+
+def test_product_sample_pdf_matches_reference_sample_pdf(golden_run):
+    """nerf_signature_b200.nerf.renderer_wtmk.sample_pdf is plain torch (no kernel) and therefore checked here, on CPU,
+    against the reference's own function (renderer_wtmk.py:12-46): deterministic and seeded-random draws, incl. an all-zero
+    ray, a ray with all its weight in one bin and one with weight in the outermost bins only."""
+    from nerf_signature_b200.nerf.renderer_wtmk import sample_pdf
+    from oracle import torch_port as tp
+    g = golden_run
+    bins, weights = torch.from_numpy(g["pdf_bins"]), torch.from_numpy(g["pdf_weights"])
+    det = sample_pdf(bins, weights, 24, det=True)
+    assert np.array_equal(det.numpy().view(np.uint32), g["pdf_det"].view(np.uint32))
+    torch.manual_seed(1234)
+    rnd = sample_pdf(bins, weights, 24, det=False)
+    assert np.array_equal(rnd.numpy().view(np.uint32), g["pdf_rand_seed1234"].view(np.uint32))
+    assert np.array_equal(tp.resample_depths(bins, weights, 24).numpy().view(np.uint32), g["pdf_det"].view(np.uint32))
+    # samples stay inside their ray's bin range and are sorted for the deterministic draw
+    assert (det >= bins[:, :1]).all() and (det <= bins[:, -1:]).all() and (det[:, 1:] >= det[:, :-1]).all()
