@@ -164,3 +164,18 @@ def test_fused_index_identity_double_multiply_equals_fp32_division():
         assert np.array_equal(q_ref.view(np.uint32), q_fused.view(np.uint32)), res
         n += x.size
     assert n > 3 * 10 ** 7
+
+
+def test_trunc_exp_forward_is_exp_and_gradient_is_clamped():
+    """activation.py:5-18 of the reference: fp32 exp forward, gradient g * exp(clamp(x, -15, 15)) - a pre-activation
+    beyond +-15 keeps a bounded gradient; half inputs are computed in fp32."""
+    from nerf_signature_b200.activation import trunc_exp
+    x = torch.tensor([-20.0, -15.0, -1.0, 0.0, 2.5, 15.0, 20.0], requires_grad=True)
+    y = trunc_exp(x)
+    assert torch.equal(y, torch.exp(x.detach()))
+    g = torch.tensor([1.0, 2.0, -1.0, 0.5, 1.0, 1.0, 3.0])
+    y.backward(g)
+    assert torch.equal(x.grad, g * torch.exp(x.detach().clamp(-15, 15)))
+    assert float(x.grad[-1]) == 3.0 * float(torch.exp(torch.tensor(15.0)))          # not exp(20)
+    h = torch.tensor([0.5, 3.0], dtype=torch.float16)
+    assert trunc_exp(h).dtype == torch.float32 and torch.equal(trunc_exp(h), torch.exp(h.float()))
