@@ -5,7 +5,8 @@ PARITY UNPINNED for the MLP arithmetic: tiny-cuda-nn is an unvendored, unpinned,
 dependency of the reference (nerf/network_wtmk_tcnn.py:7,52-88) and the reference has
 no test or golden vector for it.  What is pinned: the SH basis (against the reference's own
 hash_encoding.SHEncoder, tests/golden/hash_golden.npz `sh_*`), the network wiring
-(network_wtmk_tcnn.py:97-124) and the hash features (oracle/hash_oracle.c, bit-exact against the
+(network_wtmk_tcnn.py:97-176: against the reference's own forward / density / color bodies run unmodified on CPU around
+stand-ins for the tcnn modules, tests/golden/field_golden.npz, tests/test_field_oracle_cpu.py) and the hash features (oracle/hash_oracle.c, bit-exact against the
 reference modules).  The MLP follows nerf/"network copy.py":33-68 (bias-free Linear + ReLU) with the
 storage precision of this implementation made explicit: fp16 weights, fp16 inputs and hidden
 activations, fp32 accumulation.
