@@ -245,7 +245,7 @@ def render_run(field, rays_o, rays_d, message, num_steps=512, bg_color=1.0, min_
     return image, weights_sum
 
 
-def train_step(field, decoder, batch, message, lambda_w=0.005, lambda_i=1.0, num_steps=512):
+def train_step(field, decoder, batch, message, lambda_w=0.005, lambda_i=1.0, num_steps=512, return_terms=False):
     """One watermark training step (utils_wtmk_disen.py:579-646 + 1175): two render passes, decoder,
     losses, backward.  batch: rays_o_block/rays_d_block [md,pH,pW,3], rays_o/rays_d [n,3], gt [n,3]."""
     blk_o, blk_d = batch['rays_o_block'], batch['rays_d_block']
@@ -260,4 +260,6 @@ def train_step(field, decoder, batch, message, lambda_w=0.005, lambda_i=1.0, num
     lossw = F.binary_cross_entropy_with_logits(decoded * 10.0, message.unsqueeze(-1), reduction='mean')
     loss = lambda_w * lossw + lambda_i * lossi
     loss.backward()
+    if return_terms:
+        return float(loss.detach()), float(lossi.detach()), float(lossw.detach()), pred.detach()
     return float(loss.detach())

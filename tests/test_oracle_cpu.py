@@ -216,3 +216,41 @@ def test_product_sample_pdf_matches_reference_sample_pdf(golden_run):
     assert np.array_equal(tp.resample_depths(bins, weights, 24).numpy().view(np.uint32), g["pdf_det"].view(np.uint32))
     # samples stay inside their ray's bin range and are sorted for the deterministic draw
     assert (det >= bins[:, :1]).all() and (det <= bins[:, -1:]).all() and (det[:, 1:] >= det[:, :-1]).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# one watermark training step: oracle/torch_port.train_step against the reference's own Trainer.train_step
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["md4", "md8_lw1"])
+def test_torch_port_train_step_matches_reference_train_step(case):
+    """tests/golden/trainstep_golden.npz holds what the reference's unmodified Trainer.train_step body
+    (utils_wtmk_disen.py:579-646; tests/golden/make_golden_trainstep.py) computed on CPU: the three losses, the clamped
+    block pixels handed to the decoder, and the gradients autograd delivered to the message tables and the decoder.  The
+    port (bench.py's CPU baseline step; the semantics harness.Scene and nerf.loss_ops follow) reproduces them, and only the
+    tables the message selects receive a gradient."""
+    import make_golden_trainstep as mg
+    from nerf_signature_b200.nerf.hidden_models import get_hidden_decoder_multi_views
+    from oracle import torch_port as tp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trainstep_golden.npz"))
+    field, batch, message, lw, li, seed = mg.case_inputs(case)
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.manual_seed(seed)
+        decoder = get_hidden_decoder_multi_views(num_bits=1, redundancy=1, num_blocks=8, input_ch=3, channels=64)
+        loss, lossi, lossw, pred = tp.train_step(field, decoder, batch, message, lambda_w=lw, lambda_i=li,
+                                                 num_steps=mg.NUM_STEPS, return_terms=True)
+    finally:
+        torch.set_num_threads(threads)
+    got = mg.summarize(field, decoder, (loss, lossi, lossw))
+    np.testing.assert_allclose(got["losses"], g[f"{case}_losses"], rtol=1e-5)
+    assert abs(loss - (lw * lossw + li * lossi)) < 1e-6 * max(1.0, abs(loss))
+    np.testing.assert_allclose(pred.numpy(), g[f"{case}_pred_rgb"], rtol=0, atol=2e-6)
+    want_sums = g[f"{case}_table_grad_sums"]
+    selected = np.zeros(len(field.msg_tables), bool)
+    selected[[2 * i + int(b) for i, b in enumerate(message.tolist())]] = True
+    assert np.array_equal(want_sums > 0, selected) and np.array_equal(got["table_grad_sums"] > 0, selected)
+    np.testing.assert_allclose(got["table_grad_sums"], want_sums, rtol=1e-3)
+    ref0 = g[f"{case}_table_grad_0"]
+    assert np.abs(got["table_grad_0"] - ref0).max() <= 1e-3 * np.abs(ref0).max()
+    np.testing.assert_allclose(got["decoder_grad_norms"], g[f"{case}_decoder_grad_norms"], rtol=1e-3)
