@@ -132,6 +132,13 @@ def test_fused_renderer_matches_cpu_oracle(oracle_cpu, sigma_gain, T_thresh):
     record_parity("render_rays_vs_cpu_oracle", {"sigma_gain": sigma_gain, "T_thresh": T_thresh, "image_max_abs": err,
                                                 "samples": n_samples, "oracle_samples": m, "oracle_samples_consumed": used})
     assert err < (1e-3 + 1.5 * T_thresh if dense else 1e-3), err
+    # ... and against the frame the REFERENCE'S OWN run_cuda loop returned for this network and these rays
+    # (tests/golden/runcuda_golden.npz; tests/test_runcuda_oracle_cpu.py shows it equals the oracle frame above to 5e-6)
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runcuda_golden.npz"))
+    key = {0.0: "gain0", 0.6: "gain0.6", 12.0: "gain12_dense"}[sigma_gain]
+    err_ref = float(np.abs(image - gold[f"{key}_eval_image"]).max())
+    assert err_ref < (1e-3 + 1.5 * T_thresh if dense else 1e-3), err_ref
     if "weights_sum" in out and not dense:
         assert np.abs(out["weights_sum"].cpu().numpy().reshape(-1) - ws).max() < 1e-3
 
