@@ -1,7 +1,10 @@
 """CPU tests (-m "not gpu") of checkpoint compatibility (reference nerf/utils_wtmk_disen.py:1385-1517):
 a CLEAN torch-ngp/tiny-cuda-nn-layout checkpoint loads into the watermark network with strict=False semantics, the
 tiny-cuda-nn parameter conversion is the documented one, mean_count/mean_density are restored, and save/load round-trips."""
+import os
+
 import numpy as np
+import pytest
 import torch
 
 from nerf_signature_b200 import checkpoint as ck
@@ -84,3 +87,81 @@ def test_save_load_round_trip_is_not_converted_twice(tmp_path):
     for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(va, vb), k
     assert b.mean_count == 99 and b.mean_density == 1.5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference Trainer's OWN save_checkpoint / load_checkpoint bodies, run unmodified on this repo's network
+# ---------------------------------------------------------------------------------------------------------------------
+REF = os.environ.get("NSIG_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "nerf", "utils_wtmk_disen.py")),
+                    reason="needs the reference sources (build container only)")
+def test_reference_trainer_checkpoint_methods_work_unchanged_on_this_network(tmp_path):
+    """`Trainer.save_checkpoint / load_checkpoint` (utils_wtmk_disen.py:1385-1517) work unchanged with
+    this package's NeRFNetwork.  The two method bodies are cut out of the reference source with `ast` and run as they are
+    on a stub Trainer holding OUR network, a torch Adam over get_params, a LambdaLR and a GradScaler: the file has the
+    reference's layout, a second network restored from it by the reference's loader is identical, and this package's own
+    loader reads the same file (flagged as native only by its own writer, so here the tcnn conversion is switched off)."""
+    import glob as _glob
+    import types
+    import make_golden_field as mgf
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+
+    fns = mgf.cut_methods(os.path.join(REF, "nerf", "utils_wtmk_disen.py"), {"save_checkpoint", "load_checkpoint"})
+    env = {"torch": torch, "os": os, "glob": _glob}
+    for f in fns.values():
+        exec(compile(f, "ref:utils_wtmk_disen", "exec"), env)
+
+    def trainer(net, lr=1e-2):
+        t = types.SimpleNamespace(name="ngp", epoch=0, global_step=0, model=net, ema=None, device="cpu", max_keep_ckpt=2,
+                                  ckpt_path=str(tmp_path), best_path=str(tmp_path / "best.pth"), log=lambda *a, **k: None,
+                                  stats={"loss": [], "valid_loss": [], "results": [], "checkpoints": [], "best_result": None})
+        t.optimizer = torch.optim.Adam(net.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
+        t.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(t.optimizer, lambda it: 0.1 ** min(it / 100, 1))
+        t.scaler = torch.amp.GradScaler("cpu", enabled=False)
+        return t
+
+    torch.manual_seed(0)
+    a = NeRFNetwork(bound=1, cuda_ray=True, message_dim=2)
+    a.mean_count, a.mean_density = 777, 0.125
+    with torch.no_grad():
+        a.density_grid.uniform_(0, 1)
+        a.msg_encoder.embeddings[1].weight.add_(0.5)
+    ta = trainer(a)
+    # one optimizer step so that the optimizer state is not empty (message table 1 and the decoder get gradients)
+    loss = a.msg_encoder.embeddings[1].weight.square().sum() + sum(p.square().sum() for p in a.msg_decoder.parameters())
+    loss.backward()
+    ta.optimizer.step()
+    ta.lr_scheduler.step()
+    ta.epoch, ta.global_step = 3, 42
+    env["save_checkpoint"](ta, full=True)
+    path = tmp_path / "ngp_ep0003.pth"
+    assert path.is_file() and ta.stats["checkpoints"] == [str(path)]
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"epoch", "global_step", "stats", "mean_count", "mean_density", "optimizer", "lr_scheduler", "scaler", "model"} <= set(raw)
+    assert raw["mean_count"] == 777 and raw["mean_density"] == 0.125
+    assert {"sigma_net.params", "color_net.params", "density_grid", "density_bitfield", "step_counter",
+            "encoder.embeddings.0.weight", "msg_encoder.embeddings.3.weight"} <= set(raw["model"])
+
+    # ---- the reference's loader restores a second network (latest checkpoint found by its own glob) ----
+    torch.manual_seed(1)
+    b = NeRFNetwork(bound=1, cuda_ray=True, message_dim=2)
+    tb = trainer(b)
+    env["load_checkpoint"](tb)
+    assert (tb.epoch, tb.global_step, b.mean_count, b.mean_density) == (3, 42, 777, 0.125)
+    for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(va, vb), k
+    sa, sb = ta.optimizer.state_dict(), tb.optimizer.state_dict()
+    assert sa["param_groups"] == sb["param_groups"] and sa["state"].keys() == sb["state"].keys() and sa["state"]
+    assert all(torch.equal(sa["state"][k]["exp_avg"], sb["state"][k]["exp_avg"]) for k in sa["state"])
+    assert tb.lr_scheduler.last_epoch == 1
+
+    # ---- and this package's loader reads the file the reference wrote ----
+    torch.manual_seed(2)
+    c = NeRFNetwork(bound=1, cuda_ray=True, message_dim=2)
+    info = ck.load_checkpoint(c, str(path), map_location="cpu", tcnn=False)
+    assert info["missing_keys"] == [] and info["unexpected_keys"] == [] and info["epoch"] == 3 and info["global_step"] == 42
+    for (k, va), (_, vc) in zip(a.state_dict().items(), c.state_dict().items()):
+        assert torch.equal(va, vc), k
+    assert c.mean_count == 777 and c.mean_density == 0.125
