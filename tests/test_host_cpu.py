@@ -4,6 +4,7 @@ import inspect
 import os
 
 import numpy as np
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -179,3 +180,44 @@ def test_trunc_exp_forward_is_exp_and_gradient_is_clamped():
     assert torch.equal(x.grad[-1], torch.tensor(3.0) * torch.exp(torch.tensor(15.0)))   # exp(15), not exp(20)
     h = torch.tensor([0.5, 3.0], dtype=torch.float16)
     assert trunc_exp(h).dtype == torch.float32 and torch.equal(trunc_exp(h), torch.exp(h.float()))
+
+
+REF = os.environ.get("NSIG_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "nerf", "renderer_wtmk.py")),
+                    reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("cuda_ray", [True, False])
+def test_render_chunks_rays_like_the_reference_render(cuda_ray):
+    """NeRFRenderer.render (renderer_wtmk.py:541-574) against the reference's own method body run on the same stub runner:
+    the same sequence of (batch entry, ray range, message, kwargs) calls and the same assembled image / depth, staged and
+    unstaged, ragged last chunk and B > 1 included."""
+    import types
+    import make_golden_field as mgf
+    from nerf_signature_b200.nerf.network_wtmk_tcnn import NeRFNetwork
+    env = {"torch": torch}
+    exec(compile(mgf.cut_methods(os.path.join(REF, "nerf", "renderer_wtmk.py"), {"render"})["render"], "ref:render", "exec"), env)
+
+    def make_runner(log):
+        def runner(rays_o, rays_d, message, **kw):
+            log.append((tuple(rays_o.shape), float(rays_o[0, 0, 0]), None if message is None else message.tolist(), sorted(kw.items())))
+            return {"image": rays_o * 2 + rays_d, "depth": rays_o[..., 0] - rays_d[..., 1], "weights_sum": rays_o[..., 2]}
+        return runner
+
+    net = NeRFNetwork(bound=1, cuda_ray=cuda_ray, message_dim=2)
+    torch.manual_seed(0)
+    rays_o, rays_d, msg = torch.randn(2, 1000, 3), torch.randn(2, 1000, 3), torch.tensor([1.0, 0.0])
+    for staged, chunk in ((False, 4096), (True, 4096), (True, 300), (True, 1000), (True, 1)):
+        if chunk == 1:
+            rays_o, rays_d = rays_o[:, :7], rays_d[:, :7]
+        log_a, log_b = [], []
+        name = "run_cuda" if cuda_ray else "run"
+        setattr(net, name, make_runner(log_a))
+        stub = types.SimpleNamespace(cuda_ray=cuda_ray, run_cuda=make_runner(log_b), run=make_runner(log_b))
+        kw = dict(bg_color=1, perturb=False, dt_gamma=0.0)
+        got = net.render(rays_o, rays_d, msg, staged=staged, max_ray_batch=chunk, **kw)
+        want = env["render"](stub, rays_o, rays_d, msg, staged=staged, max_ray_batch=chunk, **kw)
+        assert log_a == log_b and len(log_a) == (2 * -(-rays_o.shape[1] // chunk) if staged else 1)
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
