@@ -119,7 +119,7 @@ class Scene:
     def __init__(self, cfg, device, seed=0, lr=1e-2, fp16=True, table_scale=1.0, optimizer="fused", graph=False,
                  merged_render=False, fused_decoder=False, fused_losses=False, overlap_decoder=False,
                  shard_blocks=None, distributed=True, fused_scaler=None, defer_optimizer=False, shard_optimizer=None,
-                 lookahead=None, march_ahead=False):
+                 lookahead=None, march_ahead=False, distortion="none"):
         """optimizer: "fused" = optim.WatermarkAdam (one kernel for the message tables, capture-safe);
         "torch" = torch.optim.Adam over get_params, exactly as main_nerf_wtmk.py:107 builds it.
         graph: capture the whole step (both render passes, decoder, losses, backward, optimizer, scaler)
@@ -239,6 +239,15 @@ class Scene:
         self._ahead_last = 0
         self.iteration = 0
         self.keep_outputs = False   # parity tests: keep the step's rendered pixels and decoder logits in self.last
+        # training-time attack on the rendered blocks before the decoder (Trainer.distortion_layer, CLI --distortion);
+        # 'none' (default) adds nothing to the step
+        from .nerf.distortion import CAPTURABLE, KINDS
+        if distortion not in KINDS:
+            raise ValueError(f"distortion must be one of {KINDS}, got {distortion!r}")
+        if graph and distortion not in CAPTURABLE:
+            raise ValueError(f"distortion {distortion!r} draws its parameter on the host (as the reference does) and cannot be "
+                             "captured in a CUDA graph: use graph=False")
+        self.distortion = distortion
         self.last = None
         self._graph = None
         self._static = None
@@ -365,6 +374,9 @@ class Scene:
         if gather is not None:
             pred = gather(pred)
         pred = pred.reshape(block_shape)
+        if self.distortion != "none":   # utils_wtmk_disen.py:594: decoder sees the attacked blocks, the loss the clean ones
+            from .nerf.distortion import distortion_layer
+            pred = distortion_layer(pred, self.distortion)
         side = _lib.side_stream(self.device, 2) if self.overlap_decoder else None
         main = torch.cuda.current_stream()
         if side is not None:     # fork: the decoder chain runs next to the content pass below

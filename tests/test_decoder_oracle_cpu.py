@@ -58,3 +58,44 @@ def test_normalisation_is_torchvision_normalize():
     dec = hm.get_hidden_decoder_multi_views(num_bits=1, num_blocks=8)
     assert not any("running" in k for k in dec.state_dict())
     assert all(abs(m.eps - 1e-3) < 1e-12 for m in dec.modules() if isinstance(m, torch.nn.BatchNorm2d))
+
+
+REF = os.environ.get("NSIG_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "nerf", "utils_wtmk_disen.py")),
+                    reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("kind", ["none", "noise", "rotation", "scaling", "blurring", "brightness"])
+def test_distortion_layer_matches_reference_body(kind):
+    """nerf.distortion.distortion_layer against Trainer.distortion_layer (utils_wtmk_disen.py:551-577), cut out of the
+    reference source and run unmodified: identical output bits from the same generator state, same gradient to the pixels."""
+    import types
+    import torchvision.transforms as T
+    import make_golden_field as mgf
+    from nerf_signature_b200.nerf.distortion import distortion_layer
+    env = {"torch": torch, "F": torch.nn.functional, "T": T}
+    exec(compile(mgf.cut_methods(os.path.join(REF, "nerf", "utils_wtmk_disen.py"), {"distortion_layer"})["distortion_layer"],
+                 "ref:distortion_layer", "exec"), env)
+    g = torch.Generator().manual_seed(7)
+    pixels = torch.rand(6, 12, 12, 3, generator=g)
+    outs = []
+    for fn in (lambda p: env["distortion_layer"](types.SimpleNamespace(distortion=kind), p), lambda p: distortion_layer(p, kind)):
+        p = pixels.clone().requires_grad_(True)
+        torch.manual_seed(123)
+        out = fn(p)
+        (out * torch.linspace(0, 1, out.numel()).view(out.shape)).sum().backward()
+        outs.append((out.detach(), p.grad))
+    (want, gwant), (got, ggot) = outs
+    assert got.shape == want.shape and torch.equal(got, want)
+    assert torch.equal(ggot, gwant)
+    if kind == "scaling":
+        assert got.shape[:2] == (6, 12) and got.shape[3] == 3 and 9 <= got.shape[2] <= 15      # only the width is resampled
+    elif kind != "none":
+        assert got.shape == pixels.shape and not torch.equal(got, pixels)
+
+
+def test_distortion_layer_rejects_unknown_kinds():
+    from nerf_signature_b200.nerf.distortion import distortion_layer, KINDS, CAPTURABLE
+    assert set(CAPTURABLE) < set(KINDS)
+    with pytest.raises(ValueError):
+        distortion_layer(torch.zeros(1, 2, 2, 3), "jpeg")
