@@ -199,3 +199,16 @@ def test_product_package_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(pkg, "csrc")):
         for f in files:
             assert "oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_every_entry_point_validates_before_touching_cuda(lib):
+    """Error behaviour of the boundary, for ALL status-returning entry points at once: NULL pointers with non-zero sizes
+    are NSIG_EINVAL (-1); all-zero sizes are a no-op (0) or, where even an empty call needs a valid configuration,
+    NSIG_EINVAL.  This container has no GPU: a positive status (a cudaError_t such as cudaErrorNoDevice) would mean the
+    entry point reached the CUDA runtime before checking its arguments - and none may crash."""
+    h = lib.load()
+    for size in (4, 0):
+        for name, (argtypes, _) in lib._SIGNATURES.items():
+            args = [None if t is ctypes.c_void_p else 1.0 if t in (ctypes.c_float, ctypes.c_double) else size for t in argtypes]
+            rc = getattr(h, name)(*args)
+            assert rc == -1 if size else rc in (0, -1), (name, size, rc)
