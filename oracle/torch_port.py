@@ -9,12 +9,13 @@ cores (kind = "port": /root/reference is Python and cannot travel to the GPU box
   * hash_encoding.py:114-195            SHEncoder degree 4 (stands in for tcnn SphericalHarmonics)
   * nerf/"network copy.py":33-68        bias-free Linear + ReLU MLPs (stand in for tcnn FullyFusedMLP)
   * nerf/network_wtmk_tcnn.py:97-176    forward / density / color wiring
-  * nerf/renderer_wtmk.py:125-253       NeRFRenderer.run (non-cuda_ray: uniform samples, upsample_steps=0)
+  * nerf/renderer_wtmk.py:12-46,125-253 NeRFRenderer.run (non-cuda_ray: uniform samples + optional hierarchical resampling)
   * raymarching.cu:108-144              near_far_from_aabb restated in torch (the reference calls CUDA here)
   * nerf/utils_wtmk_disen.py:579-646    train_step losses (BCE x temp 10 on decoded bits + MSE)
 
-Pinned against tests/golden/hash_golden.npz (outputs of the reference modules) by
-tests/test_oracle_cpu.py.
+Pinned by tests/test_oracle_cpu.py against outputs of the reference's own code: tests/golden/hash_golden.npz (the encoder
+modules), tests/golden/run_golden.npz (NeRFRenderer.run + sample_pdf, incl. upsample_steps > 0) and
+tests/golden/trainstep_golden.npz (Trainer.train_step: losses, block pixels, gradients).
 """
 import math
 
