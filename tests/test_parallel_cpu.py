@@ -155,3 +155,82 @@ def test_flat_gradient_bucket_gloo_world_size_2():
     results = mgr.dict()
     mp.spawn(_flat_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def _decoder_worker(rank, world, port, results):
+    """SURVEY 8(e) with the REAL HiDDeN decoder (BatchNorm on batch statistics): a 'table' produces the block pixels; rank r
+    renders the contiguous slice r of the flattened block rays (harness.shard_batch's partitioning), the pixels are
+    all-gathered, every rank decodes the FULL batch, and after the rank-mean exchange the table and decoder gradients equal
+    the single-process ones.  Without the all-gather (each rank decoding its own blocks) they would not."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.nn.functional as F
+        from nerf_signature_b200.nerf.hidden_models import get_hidden_decoder_multi_views, normalize_img
+        torch.set_num_threads(1)
+        md, ph, pw = 6, 5, 4
+        nb = md * ph * pw                                            # 120 block rays; 2 ranks: 60 each = 3 whole blocks
+        g = torch.Generator().manual_seed(5)
+        table0 = torch.rand(nb, 3, generator=g)                      # stands in for the message tables: pixel = sigmoid(table)
+        message = torch.randint(0, 2, (md,), generator=g).float()
+        gt = torch.rand(50, 3, generator=g)
+        content_w0 = torch.rand(50, 3, generator=g)                  # a content-ray path that also depends on "the tables"
+
+        def make():
+            torch.manual_seed(9)
+            dec = get_hidden_decoder_multi_views(num_bits=1, redundancy=1, num_blocks=3, input_ch=3, channels=16)
+            return torch.nn.Parameter(table0.clone()), torch.nn.Parameter(content_w0.clone()), dec
+
+        def loss_fn(dec, pixels_full, content_pred, n_content_total, content_gt):
+            pred = pixels_full.view(md, ph, pw, 3).clamp(0, 1)
+            decoded = dec(normalize_img(pred.permute(0, 3, 1, 2)))
+            lossw = F.binary_cross_entropy_with_logits(decoded * 10.0, message.unsqueeze(-1), reduction="mean")
+            lossi_sum = F.mse_loss(content_pred, content_gt, reduction="none").sum() / (3 * n_content_total)
+            return lossw, lossi_sum
+
+        # ---- single process ----
+        t1, c1, d1 = make()
+        lw, li = loss_fn(d1, torch.sigmoid(t1), torch.sigmoid(c1), 50, gt)
+        (0.005 * lw + 1.0 * li).backward()
+
+        # ---- sharded: contiguous ranges of the block rays and of the content rays ----
+        t2, c2, d2 = make()
+        blo, bhi = parallel.shard_range(nb, rank, world)
+        clo, chi = parallel.shard_range(50, rank, world)
+        counts = [parallel.shard_range(nb, r, world)[1] - parallel.shard_range(nb, r, world)[0] for r in range(world)]
+        local_px = torch.sigmoid(t2[blo:bhi])
+        full_px = parallel.all_gather_pixels(local_px, counts, grad_scale=world)
+        lw2, li2 = loss_fn(d2, full_px, torch.sigmoid(c2[clo:chi]), 50, gt[clo:chi])
+        # every rank holds the FULL watermark loss (its table gradient slice x world) and its share of the content loss x world
+        (0.005 * lw2 + 1.0 * li2 * world).backward()
+        sync = parallel.GradSync()
+        sync.reduce_params([t2, c2] + list(d2.parameters()))
+        assert torch.allclose(lw2.detach(), lw.detach(), atol=1e-6)
+        assert torch.allclose(t2.grad, t1.grad, atol=1e-7, rtol=1e-4), float((t2.grad - t1.grad).abs().max())
+        assert torch.allclose(c2.grad, c1.grad, atol=1e-8, rtol=1e-5)
+        for pa, pb in zip(d2.parameters(), d1.parameters()):
+            assert torch.allclose(pa.grad, pb.grad, atol=1e-6, rtol=1e-3), float((pa.grad - pb.grad).abs().max())
+
+        # ---- what the all-gather is for: per-rank decoding (local BatchNorm statistics) gives a different gradient ----
+        t3, _, d3 = make()
+        n_loc = (bhi - blo) // (ph * pw)
+        pred3 = torch.sigmoid(t3[blo:bhi]).view(n_loc, ph, pw, 3)
+        dec3 = d3(normalize_img(pred3.permute(0, 3, 1, 2)))
+        mlo = blo // (ph * pw)
+        F.binary_cross_entropy_with_logits(dec3 * 10.0, message[mlo:mlo + n_loc].unsqueeze(-1), reduction="mean").backward()
+        sync.reduce_params([t3])
+        assert (t3.grad * 0.005 - t1.grad).abs().max() > 1e-2 * t1.grad.abs().max()
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_sharded_blocks_with_the_real_decoder_gloo_world_size_2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_decoder_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
