@@ -92,3 +92,101 @@ def test_backend_has_no_cpu_path():
         backend._backend.morton3D(torch.zeros(4, 3, dtype=torch.int32), 4, torch.zeros(4, dtype=torch.int32))
     with pytest.raises(_lib.NsigError):
         backend._backend.packbits(torch.zeros(4, 16)[:, ::2], 1, 0.5, torch.zeros(1, dtype=torch.uint8))   # strided view
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's UNMODIFIED raymarching/raymarching.py on top of the shim
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "raymarching", "raymarching.py")),
+                    reason="needs the reference sources (build container only)")
+def test_reference_raymarching_module_runs_unmodified_on_the_backend(monkeypatch, oracle_cpu):
+    """The drop-in claim end to end, as far as a GPU-less box allows: the reference's own raymarching.py (autograd
+    Functions, buffer allocation, `.item()` on the counter, alignment padding, in-place alive-ray state) is loaded
+    unmodified with `.backend` resolved to this package's shim, and every call it makes lands in the C ABI with arguments
+    the entry points accept.  The device is faked (`.cuda()` is the identity, `_lib.call` dispatches to the C oracle, whose
+    functions have the argument order of raymarching.h), so the NUMBERS are the oracle's; what is tested is the calling
+    convention between the real caller and the shim - shapes, dtypes, argument order, outputs written in place."""
+    import ctypes
+    import sys
+    import types
+    import numpy as np
+    from nerf_signature_b200 import synthetic as syn
+
+    olib = oracle_cpu.lib()
+
+    def fake_call(name, *args):
+        sig = list(_lib._SIGNATURES[name][0])[:-1]                    # without the stream
+        args = list(args)
+        if name == "nsig_march_rays_train":                           # the oracle needs no scratch
+            args, sig = args[:-1], sig[:-1]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        fn = getattr(olib, "oracle_" + name[len("nsig_"):])
+        fn.restype = None
+        fn(*[a if t is ctypes.c_void_p else t(a) for a, t in zip(args, sig)])
+
+    monkeypatch.setattr(_lib, "call", fake_call)
+    monkeypatch.setattr(backend, "_P", lambda t: None if t is None else ctypes.c_void_p(t.data_ptr()))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    pkg = types.ModuleType("ref_raymarching_pkg")
+    pkg.__path__ = []
+    monkeypatch.setitem(sys.modules, "ref_raymarching_pkg", pkg)
+    monkeypatch.setitem(sys.modules, "ref_raymarching_pkg.backend", backend)
+    monkeypatch.setitem(sys.modules, "_raymarching", None)            # the compiled extension is not importable
+    rm = types.ModuleType("ref_raymarching_pkg.raymarching")
+    rm.__package__ = "ref_raymarching_pkg"
+    src = open(os.path.join(REF, "raymarching", "raymarching.py")).read()
+    exec(compile(src, os.path.join(REF, "raymarching", "raymarching.py"), "exec"), rm.__dict__)
+    assert rm._backend is backend._backend
+
+    C, H, bound, max_steps, N = 2, 128, 2.0, 256, 200
+    rng = np.random.default_rng(3)
+    grid = syn.sphere_grid(C).astype(np.float32)
+    grid *= (rng.uniform(size=grid.shape) < 0.9)
+    rays_o, rays_d = syn.blender_rays(N, seed=3)
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    t = torch.from_numpy
+    # ---- utilities ----
+    nears, fars = rm.near_far_from_aabb(t(rays_o), t(rays_d), t(aabb), 0.2)
+    on, of = oracle_cpu.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    assert np.array_equal(nears.numpy(), on) and np.array_equal(fars.numpy(), of)
+    coords = rng.integers(0, 128, size=(1000, 3)).astype(np.int32)
+    idx = rm.morton3D(t(coords))
+    assert np.array_equal(idx.numpy(), oracle_cpu.morton3D(coords))
+    assert np.array_equal(rm.morton3D_invert(idx).numpy(), coords)
+    bitfield = rm.packbits(t(grid), 0.5)
+    assert bitfield.dtype == torch.uint8 and np.array_equal(bitfield.numpy(), oracle_cpu.packbits(grid.reshape(-1), 0.5))
+    # ---- training: march (force_all_rays, align 128) + differentiable composite ----
+    counter = torch.zeros(2, dtype=torch.int32)
+    xyzs, dirs, deltas, rays = rm.march_rays_train(t(rays_o), t(rays_d), bound, bitfield, C, H, nears, fars, counter, -1, False, 128,
+                                                   True, 0, max_steps)
+    ox, od, odl, orays, ocnt = oracle_cpu.march_rays_train(rays_o, rays_d, bound, bitfield.numpy(), C, H, on, of, max_steps=max_steps)
+    m = int(ocnt[0])
+    assert np.array_equal(counter.numpy(), ocnt) and np.array_equal(rays.numpy(), orays)
+    assert xyzs.shape[0] == m + 128 - m % 128 and np.array_equal(xyzs[:m].numpy(), ox[:m]) and not xyzs[m:].any()
+    sig = torch.rand(xyzs.shape[0], requires_grad=True)
+    rgb = torch.rand(xyzs.shape[0], 3, requires_grad=True)
+    ws, depth, image = rm.composite_rays_train(sig, rgb, deltas, rays, 1e-4)
+    ows, odepth, oimg = oracle_cpu.composite_rays_train_forward(sig.detach().numpy(), rgb.detach().numpy(), deltas.numpy(), orays, 1e-4)
+    assert np.array_equal(ws.detach().numpy(), ows) and np.array_equal(image.detach().numpy(), oimg)
+    g_ws, g_img = torch.randn(N), torch.randn(N, 3)
+    (ws * g_ws).sum().add((image * g_img).sum()).backward()
+    ogs, ogc = oracle_cpu.composite_rays_train_backward(g_ws.numpy(), g_img.numpy(), sig.detach().numpy(), rgb.detach().numpy(),
+                                                        deltas.numpy(), orays, ows, oimg, 1e-4)
+    assert np.array_equal(sig.grad.numpy(), ogs) and np.array_equal(rgb.grad.numpy(), ogc)
+    # ---- inference: one iteration of the alive-ray loop, in-place state ----
+    n_step = 4
+    alive = torch.arange(N, dtype=torch.int32)
+    rays_t = nears.clone()
+    x2, d2, dl2 = rm.march_rays(N, n_step, alive, rays_t, t(rays_o), t(rays_d), bound, bitfield, C, H, nears, fars, 128, False, 0,
+                                max_steps)
+    assert x2.shape[0] == N * n_step + 128 - (N * n_step) % 128
+    sg = torch.rand(x2.shape[0], n_step).T.reshape(-1)[:x2.shape[0]] * 20
+    sg[n_step:2 * n_step] = 500.0                                     # ray 1 is opaque: killed by this call
+    cl = torch.rand(x2.shape[0], 3)
+    wsum, dep, img = torch.zeros(N), torch.zeros(N), torch.zeros(N, 3)
+    o_alive, o_t = alive.numpy().copy(), rays_t.numpy().copy()
+    o_ws, o_dep, o_img = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    rm.composite_rays(N, n_step, alive, rays_t, sg, cl, dl2, wsum, dep, img, 1e-2)
+    oracle_cpu.composite_rays(N, n_step, o_alive, o_t, sg.numpy(), cl.numpy(), dl2.numpy(), o_ws, o_dep, o_img, 1e-2)
+    assert np.array_equal(alive.numpy(), o_alive) and alive[1] == -1 and alive[0] == 0
+    assert np.array_equal(wsum.numpy(), o_ws) and np.array_equal(img.numpy(), o_img) and np.array_equal(rays_t.numpy(), o_t)
