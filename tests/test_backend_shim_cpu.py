@@ -2,10 +2,14 @@
 `raymarching/backend.py` (the pybind11 call surface of raymarching/src/raymarching.h:7-18 over the C ABI): the ten names,
 their parameter lists, and that every argument reaches the C entry point in the position include/nsig.h gives the parameter
 of the same name.  No kernel runs: `_lib.call` is replaced by a recorder."""
+import ctypes
 import inspect
 import os
 import re
+import sys
+import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -97,36 +101,60 @@ def test_backend_has_no_cpu_path():
 # ---------------------------------------------------------------------------------------------------------------------
 # the reference's UNMODIFIED raymarching/raymarching.py on top of the shim
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "raymarching", "raymarching.py")),
-                    reason="needs the reference sources (build container only)")
-def test_reference_raymarching_module_runs_unmodified_on_the_backend(monkeypatch, oracle_cpu):
-    """The drop-in claim end to end, as far as a GPU-less box allows: the reference's own raymarching.py (autograd
-    Functions, buffer allocation, `.item()` on the counter, alignment padding, in-place alive-ray state) is loaded
-    unmodified with `.backend` resolved to this package's shim, and every call it makes lands in the C ABI with arguments
-    the entry points accept.  The device is faked (`.cuda()` is the identity, `_lib.call` dispatches to the C oracle, whose
-    functions have the argument order of raymarching.h), so the NUMBERS are the oracle's; what is tested is the calling
-    convention between the real caller and the shim - shapes, dtypes, argument order, outputs written in place."""
-    import ctypes
-    import sys
-    import types
-    import numpy as np
-    from nerf_signature_b200 import synthetic as syn
+class _HostPtr:
+    """What `_P(tensor)` returns on the faked device: the raw host address for ctypes, plus the tensor itself for the two
+    entry points that have no C-oracle counterpart and are emulated in Python."""
 
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self._as_parameter_ = ctypes.c_void_p(tensor.data_ptr())
+
+
+@pytest.fixture
+def fake_device(monkeypatch, oracle_cpu):
+    """`.cuda()` is the identity, `_lib.call` dispatches to the C oracle (whose functions have the argument order of
+    raymarching.h) and `_P` hands out host addresses: the Python layers above the C ABI run on a box without a GPU, the
+    NUMBERS are the oracle's.  nsig_zero_sample_padding (no oracle counterpart) is emulated from its contract in nsig.h."""
+    from nerf_signature_b200.raymarching import raymarching as pkg_rm
     olib = oracle_cpu.lib()
 
     def fake_call(name, *args):
-        sig = list(_lib._SIGNATURES[name][0])[:-1]                    # without the stream
         args = list(args)
+        if name == "nsig_zero_sample_padding":
+            xyzs, dirs, deltas, counter, align, M = [a.tensor if isinstance(a, _HostPtr) else a for a in args]
+            m = int(counter[0])
+            end = M if align == 0 else min(m + align - m % align, M)
+            for buf in (xyzs, dirs, deltas):
+                buf.view(-1, buf.shape[-1])[m:end] = 0
+            return
+        sig = list(_lib._SIGNATURES[name][0])[:-1]                    # without the stream
         if name == "nsig_march_rays_train":                           # the oracle needs no scratch
             args, sig = args[:-1], sig[:-1]
         assert len(args) == len(sig), (name, len(args), len(sig))
         fn = getattr(olib, "oracle_" + name[len("nsig_"):])
         fn.restype = None
         fn(*[a if t is ctypes.c_void_p else t(a) for a, t in zip(args, sig)])
+        if name == "nsig_march_rays_train":
+            # contract of nsig.h the reference kernel does not have (its wrapper zero-fills everything beforehand): when
+            # rays are dropped for lack of room, the rows after the last kept ray are cleared by the kernel itself
+            M, xyzs, dirs, deltas, rays, counter = args[9], args[12].tensor, args[13].tensor, args[14].tensor, args[15].tensor, args[16].tensor
+            if int(counter[0]) > M:
+                ends = (rays[:, 1] + rays[:, 2]).long()
+                kept = ends[ends <= M]
+                last = int(kept.max()) if kept.numel() else 0
+                for buf in (xyzs, dirs, deltas):
+                    buf[last:M] = 0
 
+    ptr = lambda t: None if t is None else _HostPtr(t)                # noqa: E731
     monkeypatch.setattr(_lib, "call", fake_call)
-    monkeypatch.setattr(backend, "_P", lambda t: None if t is None else ctypes.c_void_p(t.data_ptr()))
+    monkeypatch.setattr(backend, "_P", ptr)
+    monkeypatch.setattr(pkg_rm, "_P", ptr)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    return oracle_cpu
+
+
+def _load_reference_raymarching(monkeypatch):
+    """raymarching/raymarching.py of the reference, unmodified, with `.backend` resolved to this package's shim."""
     pkg = types.ModuleType("ref_raymarching_pkg")
     pkg.__path__ = []
     monkeypatch.setitem(sys.modules, "ref_raymarching_pkg", pkg)
@@ -134,9 +162,26 @@ def test_reference_raymarching_module_runs_unmodified_on_the_backend(monkeypatch
     monkeypatch.setitem(sys.modules, "_raymarching", None)            # the compiled extension is not importable
     rm = types.ModuleType("ref_raymarching_pkg.raymarching")
     rm.__package__ = "ref_raymarching_pkg"
-    src = open(os.path.join(REF, "raymarching", "raymarching.py")).read()
-    exec(compile(src, os.path.join(REF, "raymarching", "raymarching.py"), "exec"), rm.__dict__)
+    path = os.path.join(REF, "raymarching", "raymarching.py")
+    exec(compile(open(path).read(), path, "exec"), rm.__dict__)
     assert rm._backend is backend._backend
+    return rm
+
+
+needs_reference = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "raymarching", "raymarching.py")),
+                                     reason="needs the reference sources (build container only)")
+
+
+@needs_reference
+def test_reference_raymarching_module_runs_unmodified_on_the_backend(monkeypatch, fake_device):
+    """The drop-in claim end to end, as far as a GPU-less box allows: the reference's own raymarching.py (autograd
+    Functions, buffer allocation, `.item()` on the counter, alignment padding, in-place alive-ray state) is loaded
+    unmodified with `.backend` resolved to this package's shim, and every call it makes lands in the C ABI with arguments
+    the entry points accept.  The device is faked (fixture above), so the NUMBERS are the oracle's; what is tested is the
+    calling convention between the real caller and the shim - shapes, dtypes, argument order, outputs written in place."""
+    from nerf_signature_b200 import synthetic as syn
+    oracle_cpu = fake_device
+    rm = _load_reference_raymarching(monkeypatch)
 
     C, H, bound, max_steps, N = 2, 128, 2.0, 256, 200
     rng = np.random.default_rng(3)
@@ -190,3 +235,87 @@ def test_reference_raymarching_module_runs_unmodified_on_the_backend(monkeypatch
     oracle_cpu.composite_rays(N, n_step, o_alive, o_t, sg.numpy(), cl.numpy(), dl2.numpy(), o_ws, o_dep, o_img, 1e-2)
     assert np.array_equal(alive.numpy(), o_alive) and alive[1] == -1 and alive[0] == 0
     assert np.array_equal(wsum.numpy(), o_ws) and np.array_equal(img.numpy(), o_img) and np.array_equal(rays_t.numpy(), o_t)
+
+
+@needs_reference
+def test_package_wrappers_behave_like_the_reference_wrappers(monkeypatch, fake_device):
+    """nerf_signature_b200.raymarching (the package's own autograd shells: no worst-case zero fill, only the padding rows
+    cleared, no empty_cache) against the reference's raymarching.py on the same faked device: same shapes, same alignment
+    padding rule (a full `align` is added when the count is already aligned), same zero rows, same counter updates, same
+    in-place semantics, same gradients - in force_all_rays mode, in mean_count mode (fixed-size buffers, all rows returned)
+    and when the buffers are too small and rays are dropped."""
+    from nerf_signature_b200 import synthetic as syn
+    from nerf_signature_b200 import raymarching as pkg
+    ref = _load_reference_raymarching(monkeypatch)
+    C, H, bound, max_steps, N = 2, 128, 2.0, 128, 150
+    rng = np.random.default_rng(11)
+    grid = syn.sphere_grid(C).astype(np.float32)
+    grid *= (rng.uniform(size=grid.shape) < 0.9)
+    rays_o, rays_d = syn.blender_rays(N, seed=11)
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    t = torch.from_numpy
+
+    def same(a, b):
+        assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
+
+    for fn_args in ((t(rays_o), t(rays_d), t(aabb), 0.2), (t(rays_o), t(rays_d), t(aabb))):
+        for a, b in zip(pkg.near_far_from_aabb(*fn_args), ref.near_far_from_aabb(*fn_args)):
+            same(a, b)
+    nears, fars = ref.near_far_from_aabb(t(rays_o), t(rays_d), t(aabb), 0.2)
+    same(pkg.sph_from_ray(t(rays_o), t(rays_d), 3.0), ref.sph_from_ray(t(rays_o), t(rays_d), 3.0))
+    coords = t(rng.integers(0, 128, size=(777, 3)).astype(np.int32))
+    same(pkg.morton3D(coords), ref.morton3D(coords))
+    same(pkg.morton3D_invert(ref.morton3D(coords)), ref.morton3D_invert(ref.morton3D(coords)))
+    bitfield = ref.packbits(t(grid), 0.5)
+    same(pkg.packbits(t(grid), 0.5), bitfield)
+    reuse_a, reuse_b = torch.full_like(bitfield, 255), torch.full_like(bitfield, 255)
+    out_a, out_b = pkg.packbits(t(grid), 0.5, reuse_a), ref.packbits(t(grid), 0.5, reuse_b)        # caller's buffer, in place
+    assert out_a.data_ptr() == reuse_a.data_ptr() and out_b.data_ptr() == reuse_b.data_ptr()
+    same(reuse_a, reuse_b)
+
+    def march(mod, mean_count, force_all_rays, align):
+        counter = torch.zeros(2, dtype=torch.int32)
+        out = mod.march_rays_train(t(rays_o), t(rays_d), bound, bitfield, C, H, nears, fars, counter, mean_count, False, align,
+                                   force_all_rays, 0, max_steps)
+        return out, counter
+
+    total = int(march(ref, -1, True, -1)[1][0])
+    assert total > 128
+    for mean_count, force, align in ((-1, True, 128), (-1, True, -1), (0, False, 128), (total + 300, False, 128),
+                                     (total, False, 128), (total // 2, False, 128), (total + 5, True, 64)):
+        (pa, ca), (pb, cb) = march(pkg, mean_count, force, align), march(ref, mean_count, force, align)
+        same(ca, cb)
+        for a, b in zip(pa, pb):                                   # xyzs, dirs, deltas (padding rows included), rays
+            same(a, b)
+    # differentiable composite on the aligned buffers
+    (xyzs, dirs, deltas, rays), _ = march(ref, -1, True, 128)
+    base_s, base_c = torch.rand(xyzs.shape[0]) * 5, torch.rand(xyzs.shape[0], 3)
+    g_ws, g_img = torch.randn(N), torch.randn(N, 3)
+    res = []
+    for mod in (pkg, ref):
+        s, c = base_s.clone().requires_grad_(True), base_c.clone().requires_grad_(True)
+        ws, depth, image = mod.composite_rays_train(s, c, deltas, rays, 1e-4)
+        ((ws * g_ws).sum() + (image * g_img).sum()).backward()
+        res.append((ws.detach(), depth.detach(), image.detach(), s.grad, c.grad))
+    for a, b in zip(*res):
+        same(a, b)
+    # inference: three iterations of the alive-ray loop, state carried in place
+    state = []
+    for mod in (pkg, ref):
+        alive, rays_t = torch.arange(N, dtype=torch.int32), nears.clone()
+        wsum, dep, img = torch.zeros(N), torch.zeros(N), torch.zeros(N, 3)
+        gen = torch.Generator().manual_seed(4)
+        shapes = []
+        for it in range(3):
+            n_alive, n_step = alive.shape[0], 2 + it
+            x, d, dl = mod.march_rays(n_alive, n_step, alive, rays_t, t(rays_o), t(rays_d), bound, bitfield, C, H, nears, fars,
+                                      128, False, 0, max_steps)
+            shapes.append(tuple(x.shape))
+            sg = torch.rand(x.shape[0], generator=gen) * 36
+            cl = torch.rand(x.shape[0], 3, generator=gen)
+            mod.composite_rays(n_alive, n_step, alive, rays_t, sg, cl, dl, wsum, dep, img, 1e-2)
+            alive = alive[alive >= 0]
+        state.append((alive, rays_t, wsum, dep, img, torch.tensor(shapes)))
+    for a, b in zip(*state):
+        same(a, b)
+    assert 0 < state[0][0].shape[0] < N                               # some rays were killed, some are still alive
