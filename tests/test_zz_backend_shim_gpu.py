@@ -54,8 +54,8 @@ def test_utilities_through_the_backend(oracle_cpu):
     _backend.packbits(dev(grid.reshape(-1)), n_bytes, 0.5, bitfield)
     assert np.array_equal(host(bitfield), oracle_cpu.packbits(grid.reshape(-1), 0.5))
     sph = torch.empty(N, 2, device="cuda")
-    _backend.sph_from_ray(dev(rays_o), dev(rays_d), 3.0, N, sph)
-    np.testing.assert_allclose(host(sph), oracle_cpu.sph_from_ray(rays_o, rays_d, 3.0), rtol=1e-4, atol=1e-5)
+    _backend.sph_from_ray(dev(rays_o), dev(rays_d), 4.0, N, sph)
+    np.testing.assert_allclose(host(sph), oracle_cpu.sph_from_ray(rays_o, rays_d, 4.0), rtol=1e-4, atol=1e-5)
 
 
 def test_training_march_and_composite_through_the_backend(oracle_cpu):
