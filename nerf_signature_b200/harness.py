@@ -245,8 +245,8 @@ class Scene:
         if distortion not in KINDS:
             raise ValueError(f"distortion must be one of {KINDS}, got {distortion!r}")
         if graph and distortion not in CAPTURABLE:
-            raise ValueError(f"distortion {distortion!r} draws its parameter on the host (as the reference does) and cannot be "
-                             "captured in a CUDA graph: use graph=False")
+            raise ValueError(f"distortion {distortion!r} runs in the eager step only (four of the attacks draw a parameter on the "
+                             "host, as the reference does; 'noise' was never measured inside the captured step): use graph=False")
         self.distortion = distortion
         self.last = None
         self._graph = None
